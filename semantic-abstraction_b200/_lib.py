@@ -1,0 +1,89 @@
+"""ctypes binding of libsemabs_b200.so (the C ABI declared in include/semabs_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, an exception is raised.
+torch is used only as the owner of device memory / streams (`tensor.data_ptr()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libsemabs_b200.so"
+
+_lib = None
+
+
+class SemabsError(RuntimeError):
+    pass
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("aux", C.c_void_p),
+        ("aux_rows", C.c_int32),
+        ("ld_aux", C.c_int32),
+        ("out_f32", C.c_void_p),
+        ("ld_out", C.c_int32),
+        ("out_f16", C.c_void_p),
+        ("ld_out16", C.c_int32),
+        ("out_f16_splits", C.c_int32),
+        ("act", C.c_int32),
+        ("scale_cols", C.c_int32),
+        ("scale", C.c_float),
+    ]
+
+
+ACT_NONE, ACT_QUICKGELU, ACT_QUICKGELU_GRAD = 0, 1, 2
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if os.environ.get("SEMABS_B200_AUTOBUILD", "0") == "1":
+            from . import build as _build
+
+            _build.build()
+        else:
+            raise SemabsError(
+                f"{LIB_PATH} is missing: run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                "There is no CPU / PyTorch fallback for this path."
+            )
+    l = C.CDLL(str(LIB_PATH))
+    l.semabs_last_error.restype = C.c_char_p
+    l.semabs_abi_version.restype = C.c_int
+    _lib = l
+    return l
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = lib().semabs_last_error()
+        raise SemabsError(f"libsemabs_b200 call failed (status {status}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda, "libsemabs_b200 works on device memory only (no CPU fallback)"
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def i32(v) -> C.c_int32:
+    return C.c_int32(int(v))
+
+
+def f32(v) -> C.c_float:
+    return C.c_float(float(v))

@@ -1,0 +1,59 @@
+// Host-side helpers shared by every translation unit of libsemabs_b200.so: status/last-error plumbing for the
+// C ABI, the lazily resolved cuTensorMapEncodeTiled entry point (no link-time dependency on libcuda) and
+// small device math helpers used by several kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace sb {
+
+// ---- C-ABI status ----------------------------------------------------------------------------------
+void set_last_error(const char* fmt, ...);
+int num_sms();
+
+#define SB_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      sb::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 1;                                                                               \
+    }                                                                                         \
+  } while (0)
+
+#define SB_REQUIRE(cond, ...)         \
+  do {                                \
+    if (!(cond)) {                    \
+      sb::set_last_error(__VA_ARGS__); \
+      return 2;                       \
+    }                                 \
+  } while (0)
+
+// ---- TMA descriptors -------------------------------------------------------------------------------
+// rank-R tiled tensor map over fp16 data. dims/box innermost first; strides_bytes[i] = byte stride of dim i+1.
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, CUtensorMapSwizzle swizzle);
+
+// ---- device math -----------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
+// QuickGELU (reference: CLIP/clip/model_explainability.py:197-199): x * sigmoid(1.702 x)
+__device__ __forceinline__ float quick_gelu(float x) { return x * sigmoidf_precise(1.702f * x); }
+__device__ __forceinline__ float quick_gelu_grad(float x) {
+  float s = sigmoidf_precise(1.702f * x);
+  return s + 1.702f * x * s * (1.0f - s);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace sb

@@ -1,0 +1,306 @@
+// Persistent, warp-specialised TN GEMM for sm_100a: TMA (128B-swizzled tiles) -> smem ring -> tcgen05.mma with
+// fp32 accumulators in TMEM (double-buffered) -> tcgen05.ld epilogue with fused bias / QuickGELU / residual.
+//
+//   C[M,N] = epi( A[M, splits*K] * B[N,K]^T )           A, B fp16 K-major
+//
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (warp w owns TMEM lanes [32*(w%4), +32)).
+// Replaces F.linear call sites of the reference ViT (see include/semabs_b200.h for file:line).
+#include "../../include/semabs_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sb {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;  // 64 fp16 = 128 bytes = one swizzle-128B row
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KiB alignment
+};
+
+struct EpiParams {
+  const float* bias;
+  const float* residual;
+  const float* aux;
+  int aux_rows;
+  int ld_aux;
+  float* out_f32;
+  int ld_out;
+  __half* out_f16;
+  int ld_out16;
+  int out_f16_splits;
+  int act;
+  int scale_cols;
+  float scale;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                   int kblocks_total, int kblocks_wrap_b, EpiParams ep) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* tmem_full = empty_bar + S::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t / num_n, n_blk = t % num_n;
+        for (int kb = 0; kb < kblocks_total; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * S::STAGE_BYTES;
+          uint8_t* sB = sA + S::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          tma_load_2d(sA, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d(sB, &tmB, &full_bar[stage], (kb % kblocks_wrap_b) * GEMM_BK, n_blk * BN);
+          if (++stage == S::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks_total; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + S::A_BYTES;
+          const uint64_t da = make_smem_desc(a_addr, 16, 1024, SW_128B);
+          const uint64_t db = make_smem_desc(b_addr, 16, 1024, SW_128B);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128B swizzle row: +2 in the 16-byte address field
+            umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == S::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t / num_n, n_blk = t % num_n;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * GEMM_BM + q * 32 + lane;
+      const bool row_ok = row < M;
+      const float* aux_row = nullptr;
+      if (ep.act == SEMABS_ACT_QUICKGELU_GRAD && row_ok) aux_row = ep.aux + size_t(row % ep.aux_rows) * ep.ld_aux;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 32), r);
+        tc_wait_ld();
+        const int col0 = n_blk * BN + c * 32;
+        if (row_ok && col0 < N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + j);
+              v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+            }
+          }
+          if (col0 < ep.scale_cols) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < ep.scale_cols) v[j] *= ep.scale;
+          }
+          if (ep.act == SEMABS_ACT_QUICKGELU_GRAD) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 u = *reinterpret_cast<const float4*>(aux_row + col0 + j);
+              v[j] *= quick_gelu_grad(u.x), v[j + 1] *= quick_gelu_grad(u.y);
+              v[j + 2] *= quick_gelu_grad(u.z), v[j + 3] *= quick_gelu_grad(u.w);
+            }
+          }
+          if (ep.residual) {
+            const float* rr = ep.residual + size_t(row) * ep.ld_out + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 x = *reinterpret_cast<const float4*>(rr + j);
+              v[j] += x.x, v[j + 1] += x.y, v[j + 2] += x.z, v[j + 3] += x.w;
+            }
+          }
+          if (ep.out_f32) {
+            float* o = ep.out_f32 + size_t(row) * ep.ld_out + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          if (ep.out_f16) {
+            if (ep.act == SEMABS_ACT_QUICKGELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+            }
+            __half* o = ep.out_f16 + size_t(row) * ep.ld_out16 + col0;
+            __align__(16) __half2 h[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(o)[j] = reinterpret_cast<const uint4*>(h)[j];
+            if (ep.out_f16_splits == 2) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float2 f = __half22float2(h[j]);
+                h[j] = __floats2half2_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(o + N)[j] = reinterpret_cast<const uint4*>(h)[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int kblocks_total,
+                       int kblocks_wrap_b, const EpiParams& ep, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  static bool configured = false;
+  if (!configured) {
+    SB_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  const int num_tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  gemm_f16_tn_kernel<BN><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, M, N, kblocks_total, kblocks_wrap_b, ep);
+  SB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sb
+
+extern "C" int semabs_gemm_f16(const void* A, int32_t lda, const void* B, int32_t ldb, int32_t M, int32_t N,
+                               int32_t K, int32_t a_splits, const semabs_gemm_epilogue* e, void* stream) {
+  using namespace sb;
+  SB_REQUIRE(A && B && e, "semabs_gemm_f16: null pointer");
+  SB_REQUIRE(M > 0 && N > 0 && K > 0, "semabs_gemm_f16: bad shape M=%d N=%d K=%d", M, N, K);
+  SB_REQUIRE(a_splits == 1 || a_splits == 2, "semabs_gemm_f16: a_splits must be 1 or 2");
+  SB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "semabs_gemm_f16: K/lda/ldb must be multiples of 8");
+  SB_REQUIRE(N % 32 == 0, "semabs_gemm_f16: N must be a multiple of 32 (got %d)", N);
+  SB_REQUIRE(a_splits == 1 || K % GEMM_BK == 0, "semabs_gemm_f16: split-A needs K %% 64 == 0");
+  SB_REQUIRE(e->out_f32 || e->out_f16, "semabs_gemm_f16: no output buffer");
+  SB_REQUIRE(e->act != SEMABS_ACT_QUICKGELU_GRAD || (e->aux && e->aux_rows > 0), "semabs_gemm_f16: aux missing");
+  SB_REQUIRE(e->ld_out % 4 == 0 && e->ld_out16 % 8 == 0 && e->ld_aux % 4 == 0, "semabs_gemm_f16: bad output pitch");
+
+  const int kblocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const int BN = (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {uint64_t(a_splits) * uint64_t(K), uint64_t(M)};
+    uint64_t str[1] = {uint64_t(lda) * 2};
+    uint32_t box[2] = {GEMM_BK, GEMM_BM};
+    if (int rc = make_tmap_f16(&tmA, A, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  }
+  {
+    uint64_t dims[2] = {uint64_t(K), uint64_t(N)};
+    uint64_t str[1] = {uint64_t(ldb) * 2};
+    uint32_t box[2] = {GEMM_BK, uint32_t(BN)};
+    if (int rc = make_tmap_f16(&tmB, B, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  }
+  EpiParams ep;
+  ep.bias = e->bias;
+  ep.residual = e->residual;
+  ep.aux = e->aux;
+  ep.aux_rows = e->aux_rows;
+  ep.ld_aux = e->ld_aux;
+  ep.out_f32 = e->out_f32;
+  ep.ld_out = e->ld_out;
+  ep.out_f16 = reinterpret_cast<__half*>(e->out_f16);
+  ep.ld_out16 = e->ld_out16;
+  ep.out_f16_splits = e->out_f16_splits;
+  ep.act = e->act;
+  ep.scale_cols = e->scale_cols;
+  ep.scale = e->scale;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int kb_total = kblocks * a_splits;
+  if (BN == 128) return launch_gemm<128>(tmA, tmB, M, N, kb_total, kblocks, ep, st);
+  if (BN == 64) return launch_gemm<64>(tmA, tmB, M, N, kb_total, kblocks, ep, st);
+  return launch_gemm<32>(tmA, tmB, M, N, kb_total, kblocks, ep, st);
+}

@@ -1,0 +1,82 @@
+"""tcgen05/TMA GEMM (semabs_gemm_f16) vs torch fp32/fp64 matmul on the same fp16-rounded inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a16, b16):
+    return (a16.double() @ b16.double().t()).float()
+
+
+@pytest.mark.parametrize(
+    "M,N,K",
+    [(128, 128, 64), (256, 128, 128), (300, 384, 192), (8224, 3072, 1024), (1000, 64, 640), (77, 32, 512), (4096, 512, 1024)],
+)
+def test_gemm_plain(M, N, K):
+    from semabs_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).half()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm_f16(a, b, out_f32=out)
+    torch.cuda.synchronize()
+    ref = _ref(a, b)
+    err = (out - ref).abs().max().item()
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
+
+
+def test_gemm_split_is_fp32_accurate():
+    from semabs_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(7)
+    M, N, K = 520, 256, 1024
+    a = torch.randn(M, K, device="cuda", generator=g)
+    b = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).half()
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm_f16(ops.split_f16(a), b, a_splits=2, out_f32=out)
+    ref = (a.double() @ b.double().t()).float()
+    assert (out - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
+    out1 = torch.empty(M, N, device="cuda")
+    ops.gemm_f16(a.half(), b, out_f32=out1)
+    assert (out1 - ref).abs().max().item() > (out - ref).abs().max().item()
+
+
+def test_gemm_epilogues():
+    from semabs_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, N, K = 514, 256, 128
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    base = _ref(a, b)
+
+    # bias + column scaling + residual, fp32 and fp16 (split) outputs
+    o32 = torch.empty(M, N, device="cuda")
+    o16 = torch.empty(M, 2 * N, device="cuda", dtype=torch.float16)
+    ops.gemm_f16(a, b, bias=bias, residual=res, out_f32=o32, out_f16=o16, out_f16_splits=2, scale_cols=128, scale=0.125)
+    ref = base + bias
+    ref[:, :128] *= 0.125
+    ref = ref + res
+    assert torch.allclose(o32, ref, atol=1e-4, rtol=1e-5)
+    recon = o16[:, :N].float() + o16[:, N:].float()
+    assert torch.allclose(recon, o32, atol=1e-5, rtol=1e-5)
+
+    # quickgelu: fp32 = pre-activation, fp16 = activation
+    u = torch.empty(M, N, device="cuda")
+    gq = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    ops.gemm_f16(a, b, bias=bias, act=ops.ACT_QUICKGELU, out_f32=u, out_f16=gq)
+    pre = base + bias
+    assert torch.allclose(u, pre, atol=1e-4, rtol=1e-5)
+    assert torch.allclose(gq.float(), pre * torch.sigmoid(1.702 * pre), atol=2e-3, rtol=2e-3)
+
+    # quickgelu grad with row-broadcast aux (aux_rows divides M)
+    aux = torch.randn(M // 2, N, device="cuda", generator=g)
+    d = torch.empty(M, N, device="cuda")
+    ops.gemm_f16(a, b, aux=aux, act=ops.ACT_QUICKGELU_GRAD, out_f32=d)
+    s = torch.sigmoid(1.702 * aux)
+    gr = (s + 1.702 * aux * s * (1 - s)).repeat(2, 1)
+    assert torch.allclose(d, base * gr, atol=1e-4, rtol=1e-4)
