@@ -67,6 +67,80 @@ typedef struct semabs_gemm_epilogue {
 int semabs_gemm_f16(const void* A, int32_t lda, const void* B, int32_t ldb, int32_t M, int32_t N, int32_t K,
                     int32_t a_splits, const semabs_gemm_epilogue* ep, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * CLIP ViT / text-transformer stages other than the GEMMs (vit_ops.cu, vit_attn.cu).
+ * fp16 outputs named *16 are [rows, splits*width]: hi part in columns [0,width), lo part (splits == 2) after it.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Patch-embedding operand (conv1 with stride == kernel, CLIP/clip/model_explainability.py:304-310,325):
+ * tiles [B,3,R,R] fp32 -> out16 [B*(R/patch)^2, splits*Kpad], column (c*patch + i)*patch + j, zero padded. */
+int semabs_vit_im2col(const float* tiles, void* out16, int32_t B, int32_t R, int32_t patch, int32_t Kpad,
+                      int32_t splits, void* stream);
+
+/* LayerNorm in fp32, eps 1e-5 (model_explainability.py:188-194). Row m is read at x + m*x_stride.
+ * Any of y32 [M,d], y16 [M,splits*d], mean [M], rstd [M] may be NULL (at least one of y32 / y16 is required). */
+int semabs_layernorm_fwd(const float* x, int64_t x_stride, const float* gamma, const float* beta, float* y32,
+                         void* y16, float* mean, float* rstd, int32_t M, int32_t d, int32_t splits, void* stream);
+
+/* Token assembly + ln_pre (VisionTransformer.forward, model_explainability.py:326-344):
+ * x_out[b,t,:] = LN((t == 0 ? cls : patch[b,t-1,:]) + pos[t,:]).  `pos` is the table the reference would add
+ * (already passed through its interpolate_positional_emb quirk, auxiliary.py:24-38, when T != 50). */
+int semabs_vit_embed_lnpre(const float* patch, const float* cls, const float* pos, const float* gamma,
+                           const float* beta, float* x_out, int32_t B, int32_t T, int32_t d, void* stream);
+
+/* LayerNorm input-gradient for M stacked cotangent rows that share x_rows forward rows (row m uses forward row
+ * m % x_rows): dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) + dres, g = dy*gamma.  Output rows may be strided
+ * (out_stride / out16_stride in elements); dres (optional) uses out_stride.  Replaces the LayerNorm node of the
+ * torch.autograd.grad call at CLIP/clip/clip_gradcam.py:90-97. */
+int semabs_layernorm_bwd(const float* dy, const float* dres, const float* x, int64_t x_stride, int32_t x_rows,
+                         const float* mean, const float* rstd, const float* gamma, float* dx32, int64_t out_stride,
+                         void* dx16, int64_t out16_stride, int32_t M, int32_t d, int32_t splits, void* stream);
+
+/* Multi-head self-attention forward, head dim 64 (multi_head_attention_forward, CLIP/clip/auxiliary.py:260-337).
+ * qkv [B*T, 3d] fp32 with q pre-scaled (auxiliary.py:207); probs (optional) [B*H, T, T] fp32 = softmax(q k^T)
+ * (what the reference stores through its hook, :334); o32 (optional) [B*T, d]; o16 (optional) [B*T, splits*d].
+ * causal != 0 applies the text transformer's mask (model_explainability.py:452-458). */
+int semabs_attn_fwd(const float* qkv, float* probs, float* o32, void* o16, int32_t B, int32_t T, int32_t H,
+                    int32_t causal, int32_t splits, void* stream);
+
+/* Attention backward for P stacked cotangents + the relevance term of ClipGradcam.interpret
+ * (clip_gradcam.py:90-126).  dO16 [P*B*T, ld_do] fp16 is the gradient w.r.t. the pre-out-proj attention output.
+ *   dA = dO V^T ;  wpart[pb,h,j] = (1/H) sum_i r[pb,i] * relu?(dA ⊙ A)[i,j]   (relu iff positive_only)
+ *   dS = A ⊙ (dA - rowsum(dA ⊙ A)) ; dQ = scale dS K ; dK = dS^T Q ; dV = A^T dO -> dqkv16 [P*B*T, splits*3d]
+ * delta_ws is a [P*B*H*T] fp32 workspace.  need_dqkv == 0 computes the relevance term only. */
+int semabs_attn_bwd(const float* qkv, const float* probs, const float* o32, const void* dO16, int32_t ld_do,
+                    const float* r, float* delta_ws, float* wpart, void* dqkv16, int32_t P, int32_t B, int32_t T,
+                    int32_t H, int32_t splits, int32_t positive_only, int32_t need_dqkv, void* stream);
+
+/* logits[b,p] = 100 * f_b/|f_b| . W[:,p] (ClipGradcam.forward, clip_gradcam.py:58-68) and the cotangent seed
+ * d logits[b,p] / d f_b -> seed16 [P*B, splits*E] (row p*B + b). Either output may be NULL. W is [E,P] fp32. */
+int semabs_clip_logit_seed(const float* f, const float* W, float* logits, void* seed16, int32_t B, int32_t P,
+                           int32_t E, int32_t splits, void* stream);
+
+/* Rollout restricted to row 0 of R (clip_gradcam.py:81-84,124-127): r <- e_0, then per block r += sum_h wpart. */
+int semabs_rollout_init(float* r, int32_t PB, int32_t T, void* stream);
+int semabs_rollout_update(float* r, const float* wpart, int32_t PB, int32_t H, int32_t T, void* stream);
+
+/* Text side: x[n,t,:] = token_embedding[tokens[n,t]] + positional_embedding[t] (CLIP.encode_text,
+ * model_explainability.py:468-471); W[e,c] = mean_t feat[c*nt+t, e]/|feat[c*nt+t,:]| (zeroshot_classifier,
+ * clip_gradcam.py:12-27). tokens is int32 on the device. */
+int semabs_text_embed(const int32_t* tokens, const float* table, const float* pos, float* x, int32_t n_texts,
+                      int32_t ctx, int32_t d, void* stream);
+int semabs_zeroshot_weights(const float* feat, float* W, int32_t n_classes, int32_t n_templates, int32_t E,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Tile-pyramid assembly (assemble.cu) — ClipWrapper.get_clip_saliency_convolve, CLIP/clip/__init__.py:205-236.
+ * rel [P, n_tiles, g, g] fp32; tile_desc int32 [n_tiles,3] = (row0, col0, size) in the reference's tile-creation
+ * order (__init__.py:257-273); size_order = distinct tile sizes in cropping_augmentations order. Per size the
+ * bilinear (align_corners=False) up-sampled tiles are added in order into an fp16 accumulator (the reference's
+ * .half() buffers, :149-153,:227-229), divided by the coverage count (init 1e-5, :249-253); sizes are averaged.
+ * out [P,H,W] fp32.  semabs_flip_average: rel = (rel + flip_x(rel_flipped)) / 2 (:170-204), [n_maps, g, g].
+ * ---------------------------------------------------------------------------------------------------------- */
+int semabs_tile_assemble(const float* rel, const int32_t* tile_desc, int32_t n_tiles, const int32_t* size_order,
+                         int32_t n_sizes, int32_t g, int32_t H, int32_t W, int32_t P, float* out, void* stream);
+int semabs_flip_average(float* rel, const float* rel_flipped, int64_t n_maps, int32_t g, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,230 @@
+"""Host-side mirror of the reference's `CLIP.clip` public surface for the relevancy path: `saliency_configs`,
+`ClipWrapper` (singleton, same classmethods and keyword arguments; reference CLIP/clip/__init__.py:19-282) and
+`ClipGradcam` (clip_gradcam.py:30-142).  Host work is limited to what the reference also does on the host
+(PIL crop/resize/normalise, tokenisation, tile enumeration); every tensor op runs in libsemabs_b200.so.
+"""
+from __future__ import annotations
+
+import itertools
+from typing import List, Sequence
+
+import numpy as np
+import torch
+from PIL import Image
+
+from .. import ops
+from .engine import ClipEngine
+from .model import load_state_dict, pack_clip_weights
+from .tokenizer import tokenize
+
+saliency_configs = {
+    # same pyramid / TTA specs as the reference (CLIP/clip/__init__.py:19-41)
+    "ours": lambda img_dim: {
+        "distractor_labels": {},
+        "horizontal_flipping": True,
+        "augmentations": 5,
+        "imagenet_prompt_ensemble": False,
+        "positive_attn_only": True,
+        "cropping_augmentations": [
+            {"tile_size": img_dim, "stride": img_dim // 4},
+            {"tile_size": int(img_dim * 2 / 3), "stride": int(img_dim * 2 / 3) // 4},
+            {"tile_size": img_dim // 2, "stride": (img_dim // 2) // 4},
+            {"tile_size": img_dim // 4, "stride": (img_dim // 4) // 4},
+        ],
+    },
+    "chefer_et_al": lambda img_dim: {
+        "distractor_labels": {},
+        "horizontal_flipping": False,
+        "augmentations": 0,
+        "imagenet_prompt_ensemble": False,
+        "positive_attn_only": True,
+        "cropping_augmentations": [{"tile_size": img_dim, "stride": img_dim // 4}],
+    },
+}
+
+_MEAN = torch.tensor((0.48145466, 0.4578275, 0.40821073)).view(1, 3, 1, 1)
+_STD = torch.tensor((0.26862954, 0.26130258, 0.27577711)).view(1, 3, 1, 1)
+
+
+def preprocess_tiles(tiles_u8: Sequence[np.ndarray], n_px: int) -> torch.Tensor:
+    """The reference's `_transform` (clip_explainability.py:98-108) on a list of uint8 crops: PIL bicubic resize of
+    the shorter side to 224 (hard-coded there), centre crop/pad to n_px, /255, normalise. Host side, like the
+    reference (it is the reference's declared bottleneck, __init__.py:275; a device version is a 'next' row)."""
+    out = torch.empty(len(tiles_u8), 3, n_px, n_px)
+    for i, t in enumerate(tiles_u8):
+        img = Image.fromarray(t).convert("RGB")
+        w, h = img.size
+        nw, nh = (224, int(224 * h / w)) if w <= h else (int(224 * w / h), 224)
+        arr = torch.from_numpy(np.array(img.resize((nw, nh), Image.BICUBIC), dtype=np.uint8)).permute(2, 0, 1)
+        if (nh, nw) != (n_px, n_px):
+            if nh < n_px or nw < n_px:
+                pl, pt = max((n_px - nw) // 2, 0), max((n_px - nh) // 2, 0)
+                pr, pb = max((n_px - nw + 1) // 2, 0), max((n_px - nh + 1) // 2, 0)
+                arr = torch.nn.functional.pad(arr, (pl, pr, pt, pb))
+                nh, nw = arr.shape[1:]
+            top, left = int(round((nh - n_px) / 2.0)), int(round((nw - n_px) / 2.0))
+            arr = arr[:, top : top + n_px, left : left + n_px]
+        out[i] = arr.float().div(255)
+    return (out - _MEAN) / _STD
+
+
+class ClipGradcam:
+    """Drop-in for the reference class of the same name: `ClipGradcam(...)(x, o)` -> relevance [P,B,g,g]."""
+
+    def __init__(self, clip_model_name: str, classes: List[str], templates: List[str], device, num_layers=10,
+                 positive_attn_only=False, fwd_splits=2, bwd_splits=1, seed=0, **load_kwargs):
+        sd = load_state_dict(clip_model_name, load_kwargs.get("download_root"), seed=seed)
+        self.synthetic = "__synthetic__" in sd
+        sd.pop("__synthetic__", None)
+        self.clip_model_name = clip_model_name
+        self.device = torch.device(device)
+        self.weights = pack_clip_weights(clip_model_name, sd, self.device, first_rollout_block=num_layers + 1)
+        self.engine = ClipEngine(self.weights, self.device, num_layers=num_layers, fwd_splits=fwd_splits,
+                                 bwd_splits=bwd_splits)
+        self.n_px = self.weights.input_resolution
+        self.preprocess = lambda pil_img: preprocess_tiles([np.array(pil_img)], self.n_px)[0]
+        self.templates = templates
+        self.num_layers = num_layers
+        self.positive_attn_only = positive_attn_only
+        self.target_classes = None
+        self.class_to_language_feature = {}
+        self.set_classes(classes)
+
+    def set_classes(self, classes):
+        """zeroshot_classifier + dict keyed by label (duplicates collapse, as in clip_gradcam.py:134-142)."""
+        self.target_classes = classes
+        texts = list(itertools.chain(*[[t.format(c) for t in self.templates] for c in classes]))
+        W = self.engine.zeroshot_weights(tokenize(texts), len(classes), len(self.templates))
+        self.class_to_language_feature = {c: W[:, [i]] for i, c in enumerate(classes)}
+
+    def __call__(self, x: torch.Tensor, o: Sequence[str]):
+        W = torch.cat([self.class_to_language_feature[p] for p in o], dim=1).contiguous()
+        x = x.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        return self.engine.relevancy(x, W, positive_attn_only=self.positive_attn_only)
+
+    forward = __call__
+
+
+class ClipWrapper:
+    # SINGLETON WRAPPER (class-level state like the reference, __init__.py:44-51: one instance per process)
+    clip_gradcam = None
+    device = None
+    jittering_transforms = None
+    engine_kwargs: dict = {}
+
+    def __init__(self, clip_model_type, device, **kwargs):
+        import torchvision
+
+        ClipWrapper.device = torch.device(device)
+        ClipWrapper.jittering_transforms = torchvision.transforms.ColorJitter(
+            brightness=0.6, contrast=0.6, saturation=0.6, hue=0.1
+        )
+        ClipWrapper.clip_gradcam = ClipGradcam(
+            clip_model_name=clip_model_type, classes=[""], templates=["{}"], device=ClipWrapper.device, **kwargs
+        )
+
+    @classmethod
+    def check_initialized(cls, clip_model_type="ViT-B/32", **kwargs):
+        if cls.clip_gradcam is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("semabs_b200.ClipWrapper needs a CUDA device: there is no CPU path")
+            ClipWrapper(clip_model_type=clip_model_type, device="cuda", **kwargs)
+
+    @classmethod
+    def reset(cls):
+        cls.clip_gradcam = None
+
+    @classmethod
+    def get_clip_text_feature(cls, string):
+        cls.check_initialized()
+        return cls.clip_gradcam.engine.encode_text(tokenize(string, context_length=77)).squeeze().cpu().numpy()
+
+    @classmethod
+    def get_clip_saliency(cls, img, text_labels, prompts, distractor_labels=set(), use_lavt=False, **kwargs):
+        """Same contract as the reference (__init__.py:103-133): returns (maps [P,H,W] fp32 on CPU,
+        text features [P,E] on CPU)."""
+        cls.check_initialized()
+        if use_lavt:
+            raise NotImplementedError("LAVT localisation is outside the hot path (SURVEY.md §8)")
+        cls.clip_gradcam.templates = prompts
+        cls.clip_gradcam.set_classes(list(text_labels))
+        text_label_features = torch.stack(list(cls.clip_gradcam.class_to_language_feature.values()), dim=0)
+        text_label_features = text_label_features.squeeze(dim=-1).cpu()
+        text_maps = cls.get_clip_saliency_convolve(img=img, text_labels=text_labels, **kwargs)
+        if len(distractor_labels) > 0:
+            distractor_labels = set(distractor_labels) - set(text_labels)
+            cls.clip_gradcam.set_classes(list(distractor_labels))
+            distractor_maps = cls.get_clip_saliency_convolve(img=img, text_labels=list(distractor_labels), **kwargs)
+            text_maps -= distractor_maps.mean(dim=0)
+        return text_maps.cpu(), text_label_features.squeeze(dim=-1)
+
+    @classmethod
+    def get_clip_saliency_device(cls, tile_imgs, tile_desc, size_order, text_labels, H, W, horizontal_flipping=False,
+                                 positive_attn_only=False, tile_batch_size=32, prompt_batch_size=32):
+        """Device half of get_clip_saliency_convolve: preprocessed tiles [n,3,R,R] (host or device) -> maps
+        [P,H,W] on the device."""
+        gc = cls.clip_gradcam
+        gc.positive_attn_only = positive_attn_only
+        dev = cls.device
+        tile_imgs = tile_imgs.to(dev, non_blocking=True)
+        labels = list(text_labels)
+
+        def run(tiles):
+            return torch.cat(
+                [
+                    torch.cat(
+                        [gc(x=tiles[t : t + tile_batch_size], o=labels[p : p + prompt_batch_size]).clone()
+                         for t in range(0, len(tiles), tile_batch_size)],
+                        dim=1,
+                    )
+                    for p in range(0, len(labels), prompt_batch_size)
+                ],
+                dim=0,
+            ).contiguous()  # fmt: skip
+
+        rel = run(tile_imgs)
+        if horizontal_flipping:
+            # flipping the tile is pure data movement (__init__.py:170-173)
+            rel = ops.flip_average(rel, run(tile_imgs.flip(-1).contiguous()))
+        out = torch.empty(len(labels), H, W, device=dev)
+        desc = torch.as_tensor(np.ascontiguousarray(tile_desc), dtype=torch.int32).to(dev)
+        order = torch.as_tensor(list(size_order), dtype=torch.int32).to(dev)
+        return ops.tile_assemble(rel, desc, order, H, W, out)
+
+    @classmethod
+    def get_clip_saliency_convolve(cls, text_labels, horizontal_flipping=False, positive_attn_only: bool = False,
+                                   tile_batch_size=32, prompt_batch_size=32, tile_interpolate_batch_size=32, **kwargs):
+        tile_desc, tile_imgs, size_order = cls.create_tiles(**kwargs)
+        H, W = kwargs["img"].shape[:2]
+        out = cls.get_clip_saliency_device(tile_imgs, tile_desc, size_order, text_labels, H, W, horizontal_flipping,
+                                           positive_attn_only, tile_batch_size, prompt_batch_size)
+        return out.cpu()
+
+    @classmethod
+    def create_tiles(cls, img, augmentations, cropping_augmentations, **kwargs):
+        """Tile enumeration in the reference's order (__init__.py:238-282): image copies (original + ColorJitter
+        draws) -> crop sizes -> column offset -> row offset. Returns (tile_desc int32 [n,3] = (row0,col0,size),
+        preprocessed tiles [n,3,R,R] fp32 (pinned host memory), size order)."""
+        assert type(img) == np.ndarray
+        cls.check_initialized()
+        img_pil = Image.fromarray(img)
+        images = [np.array(img_pil)]
+        for _ in range(augmentations):
+            images.append(np.array(cls.jittering_transforms(img_pil)))
+        desc, crops = [], []
+        for im in images:
+            for aug in cropping_augmentations:
+                ts, st = aug["tile_size"], aug["stride"]
+                for y in np.arange(0, im.shape[1] - ts + 1, st):
+                    if y >= im.shape[0]:
+                        continue
+                    for x in np.arange(0, im.shape[0] - ts + 1, st):
+                        if x >= im.shape[1]:
+                            continue
+                        desc.append((int(x), int(y), int(ts)))
+                        crops.append(im[x : x + ts, y : y + ts])
+        tiles = preprocess_tiles(crops, cls.clip_gradcam.n_px)
+        if torch.cuda.is_available():
+            tiles = tiles.pin_memory()
+        size_order = list(dict.fromkeys(a["tile_size"] for a in cropping_augmentations))
+        return np.array(desc, dtype=np.int32).reshape(-1, 3), tiles, size_order

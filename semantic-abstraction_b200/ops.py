@@ -67,3 +67,90 @@ def split_f16(x: torch.Tensor) -> torch.Tensor:
     hi = x.half()
     lo = (x - hi.float()).half()
     return torch.cat([hi, lo], dim=1).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ViT / text transformer stages
+# ---------------------------------------------------------------------------------------------------------
+def _i64(v):
+    return C.c_int64(int(v))
+
+
+def vit_im2col(tiles, out16, patch, kpad, splits):
+    B, _, R, _ = tiles.shape
+    assert tiles.dtype == torch.float32 and tiles.is_contiguous()
+    check(lib().semabs_vit_im2col(ptr(tiles), ptr(out16), i32(B), i32(R), i32(patch), i32(kpad), i32(splits), stream_ptr()))
+
+
+def layernorm_fwd(x, gamma, beta, *, M, d, x_stride=None, y32=None, y16=None, mean=None, rstd=None, splits=1):
+    check(
+        lib().semabs_layernorm_fwd(
+            ptr(x), _i64(d if x_stride is None else x_stride), ptr(gamma), ptr(beta), ptr(y32), ptr(y16), ptr(mean),
+            ptr(rstd), i32(M), i32(d), i32(splits), stream_ptr(),
+        )
+    )
+
+
+def vit_embed_lnpre(patch, cls, pos, gamma, beta, x_out, B, T, d):
+    check(lib().semabs_vit_embed_lnpre(ptr(patch), ptr(cls), ptr(pos), ptr(gamma), ptr(beta), ptr(x_out), i32(B), i32(T), i32(d), stream_ptr()))
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx32, *, M, d, x_rows, x_stride=None, dres=None, out_stride=None, dx16=None,
+                  out16_stride=None, splits=1):
+    check(
+        lib().semabs_layernorm_bwd(
+            ptr(dy), ptr(dres), ptr(x), _i64(d if x_stride is None else x_stride), i32(x_rows), ptr(mean), ptr(rstd),
+            ptr(gamma), ptr(dx32), _i64(d if out_stride is None else out_stride), ptr(dx16),
+            _i64(splits * d if out16_stride is None else out16_stride), i32(M), i32(d), i32(splits), stream_ptr(),
+        )
+    )
+
+
+def attn_fwd(qkv, *, B, T, H, probs=None, o32=None, o16=None, causal=False, splits=1):
+    check(lib().semabs_attn_fwd(ptr(qkv), ptr(probs), ptr(o32), ptr(o16), i32(B), i32(T), i32(H), i32(int(causal)), i32(splits), stream_ptr()))
+
+
+def attn_bwd(qkv, probs, o32, dO16, ld_do, r, delta_ws, wpart, dqkv16, *, P, B, T, H, splits=1, positive_only=True,
+             need_dqkv=True):
+    check(
+        lib().semabs_attn_bwd(
+            ptr(qkv), ptr(probs), ptr(o32), ptr(dO16), i32(ld_do), ptr(r), ptr(delta_ws), ptr(wpart), ptr(dqkv16),
+            i32(P), i32(B), i32(T), i32(H), i32(splits), i32(int(positive_only)), i32(int(need_dqkv)), stream_ptr(),
+        )
+    )
+
+
+def clip_logit_seed(f, W, *, B, P, E, logits=None, seed16=None, splits=1):
+    check(lib().semabs_clip_logit_seed(ptr(f), ptr(W), ptr(logits), ptr(seed16), i32(B), i32(P), i32(E), i32(splits), stream_ptr()))
+
+
+def rollout_init(r, PB, T):
+    check(lib().semabs_rollout_init(ptr(r), i32(PB), i32(T), stream_ptr()))
+
+
+def rollout_update(r, wpart, PB, H, T):
+    check(lib().semabs_rollout_update(ptr(r), ptr(wpart), i32(PB), i32(H), i32(T), stream_ptr()))
+
+
+def text_embed(tokens, table, pos, x, n_texts, ctx, d):
+    assert tokens.dtype == torch.int32
+    check(lib().semabs_text_embed(ptr(tokens), ptr(table), ptr(pos), ptr(x), i32(n_texts), i32(ctx), i32(d), stream_ptr()))
+
+
+def zeroshot_weights(feat, W, n_classes, n_templates, E):
+    check(lib().semabs_zeroshot_weights(ptr(feat), ptr(W), i32(n_classes), i32(n_templates), i32(E), stream_ptr()))
+
+
+def tile_assemble(rel, tile_desc, size_order, H, W, out):
+    P, n, g, _ = rel.shape
+    assert rel.is_contiguous() and tile_desc.dtype == torch.int32 and size_order.dtype == torch.int32
+    check(lib().semabs_tile_assemble(ptr(rel), ptr(tile_desc), i32(n), ptr(size_order), i32(size_order.numel()), i32(g),
+                                     i32(H), i32(W), i32(P), ptr(out), stream_ptr()))
+    return out
+
+
+def flip_average(rel, rel_flipped):
+    g = rel.shape[-1]
+    assert rel.is_contiguous() and rel_flipped.is_contiguous() and rel.shape == rel_flipped.shape
+    check(lib().semabs_flip_average(ptr(rel), ptr(rel_flipped), _i64(rel.numel() // (g * g)), i32(g), stream_ptr()))
+    return rel

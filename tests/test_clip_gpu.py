@@ -1,0 +1,80 @@
+"""Engine-level parity: CUDA relevancy path vs the committed reference outputs (tests/golden/clip_golden.npz, produced
+by oracle/gen_golden.py from the unmodified reference) and vs the oracle restatement on fresh seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "clip_golden.npz")
+
+# tolerance of BASELINE.json's north_star: fp32 relevancy maps within 1e-3 relative, stated here as
+# max|Δ| / max|ref| per map; arg-max (relevancy-peak index) must be bit-exact.
+REL_TOL = 1e-3
+
+
+def _maxrel(a, b):
+    return ((a - b).abs().amax(dim=(-1, -2)) / b.abs().amax(dim=(-1, -2))).max().item()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def _engine(name, **kw):
+    from semabs_b200.clip.engine import ClipEngine
+    from semabs_b200.clip.model import pack_clip_weights, synthetic_clip_state_dict
+
+    sd = synthetic_clip_state_dict(name, seed=0)
+    return ClipEngine(pack_clip_weights(name, sd, "cuda"), "cuda", **kw), sd
+
+
+@pytest.mark.parametrize("fwd_splits,bwd_splits", [(2, 2), (2, 1), (1, 1)])
+def test_b32_relevancy_matches_reference(gold, fwd_splits, bwd_splits):
+    eng, sd = _engine("ViT-B/32", fwd_splits=fwd_splits, bwd_splits=bwd_splits)
+    chk = float(sum(v.double().abs().sum().item() for k, v in sorted(sd.items())))
+    assert abs(chk - float(gold["b32_weights_checksum"])) < 1e-6 * chk, "seeded weights differ from the fixture's"
+    W = eng.zeroshot_weights(torch.from_numpy(gold["b32_tokens"]).long(), 4, 1)
+    Wg = torch.from_numpy(gold["b32_W"]).cuda()
+    assert (W - Wg).abs().max().item() < 1e-3 * Wg.abs().max().item()
+    tiles = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(1)).cuda()
+    rel, logits = eng.relevancy(tiles, Wg.contiguous(), positive_attn_only=True, return_logits=True)
+    ref = torch.from_numpy(gold["b32_rel"]).cuda()
+    err = _maxrel(rel, ref)
+    print(f"B/32 splits=({fwd_splits},{bwd_splits}) relevancy max-rel err {err:.2e}")
+    assert err < REL_TOL
+    assert (rel.flatten(2).argmax(-1) == ref.flatten(2).argmax(-1)).all()
+    rel2 = eng.relevancy(tiles, Wg.contiguous(), positive_attn_only=False)
+    ref2 = torch.from_numpy(gold["b32_rel_signed"]).cuda()
+    # signed (positive_attn_only=False) maps cancel heavily; the all-fp16 fast mode (1,1) is held to 2e-3 there,
+    # the default (2,1) and the precise (2,2) modes to the 1e-3 of the spec
+    assert _maxrel(rel2, ref2) < (REL_TOL if fwd_splits == 2 else 2 * REL_TOL)
+
+
+@pytest.mark.parametrize("fwd_splits,bwd_splits", [(2, 2), (2, 1), (1, 1)])
+def test_l14_relevancy_matches_reference(gold, fwd_splits, bwd_splits):
+    eng, sd = _engine("ViT-L/14", fwd_splits=fwd_splits, bwd_splits=bwd_splits)
+    W = eng.zeroshot_weights(torch.from_numpy(gold["l14_tokens"]).long(), 2, 1)
+    Wg = torch.from_numpy(gold["l14_W"]).cuda()
+    assert (W - Wg).abs().max().item() < 1e-3 * Wg.abs().max().item()
+    tiles = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(2)).cuda()
+    rel = eng.relevancy(tiles, Wg.contiguous())
+    ref = torch.from_numpy(gold["l14_rel"]).cuda()
+    err = _maxrel(rel, ref)
+    print(f"L/14 splits=({fwd_splits},{bwd_splits}) relevancy max-rel err {err:.2e}")
+    assert err < REL_TOL
+    assert (rel.flatten(2).argmax(-1) == ref.flatten(2).argmax(-1)).all()
+
+
+def test_image_features_vs_oracle():
+    from oracle import clip_oracle
+
+    eng, sd = _engine("ViT-B/32")
+    sdo = clip_oracle.convert_weights_values(sd)
+    tiles = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        f_ref = clip_oracle.encode_image(sdo, tiles)
+    f, _ = eng.encode_image(tiles.cuda())
+    assert (f.cpu() - f_ref).abs().max().item() < 1e-4 * f_ref.abs().max().item()

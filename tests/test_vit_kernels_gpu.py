@@ -1,0 +1,120 @@
+"""Unit parity of the non-GEMM ViT kernels against plain torch fp32 on the same device."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def _recon(y16, d, splits):
+    return y16[:, :d].float() + (y16[:, d:].float() if splits == 2 else 0)
+
+
+@pytest.mark.parametrize("splits", [1, 2])
+def test_layernorm_fwd_bwd(splits):
+    from semabs_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(0)
+    M, d, P = 37, 768, 3
+    x = torch.randn(M, d, device=dev, generator=g) * 2 + 0.5
+    gamma = 1 + 0.1 * torch.randn(d, device=dev, generator=g)
+    beta = 0.1 * torch.randn(d, device=dev, generator=g)
+    y32 = torch.empty(M, d, device=dev)
+    y16 = torch.empty(M, splits * d, device=dev, dtype=torch.float16)
+    mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)
+    ops.layernorm_fwd(x, gamma, beta, M=M, d=d, y32=y32, y16=y16, mean=mean, rstd=rstd, splits=splits)
+    ref = F.layer_norm(x, (d,), gamma, beta, 1e-5)
+    assert torch.allclose(y32, ref, atol=2e-6, rtol=1e-5)
+    tol = 1e-6 if splits == 2 else 2e-3
+    assert torch.allclose(_recon(y16, d, splits), ref, atol=tol * 4, rtol=tol)
+
+    dy = torch.randn(P * M, d, device=dev, generator=g)
+    dres = torch.randn(P * M, d, device=dev, generator=g)
+    dx = torch.empty(P * M, d, device=dev)
+    dx16 = torch.empty(P * M, splits * d, device=dev, dtype=torch.float16)
+    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, M=P * M, d=d, x_rows=M, dres=dres, dx16=dx16, splits=splits)
+    xr = x.repeat(P, 1).requires_grad_(True)
+    F.layer_norm(xr, (d,), gamma, beta, 1e-5).backward(dy)
+    refdx = xr.grad + dres
+    assert torch.allclose(dx, refdx, atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("T,H,causal", [(50, 12, False), (257, 16, False), (77, 8, True)])
+def test_attn_fwd(T, H, causal):
+    from semabs_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(T)
+    B, d = 3, H * 64
+    qkv = torch.randn(B * T, 3 * d, device=dev, generator=g)
+    qkv[:, :d] *= 0.125 * 2.0
+    probs = torch.empty(B * H, T, T, device=dev)
+    o32 = torch.empty(B * T, d, device=dev)
+    o16 = torch.empty(B * T, 2 * d, device=dev, dtype=torch.float16)
+    ops.attn_fwd(qkv, B=B, T=T, H=H, probs=probs, o32=o32, o16=o16, causal=causal, splits=2)
+    q, k, v = (t.reshape(B, T, H, 64).permute(0, 2, 1, 3) for t in qkv.view(B, T, 3 * d).chunk(3, -1))
+    s = q @ k.transpose(-1, -2)
+    if causal:
+        s = s + torch.full((T, T), float("-inf"), device=dev).triu_(1)
+    a = s.softmax(-1)
+    o = (a @ v).permute(0, 2, 1, 3).reshape(B * T, d)
+    assert torch.allclose(probs.view(B, H, T, T), a, atol=1e-6, rtol=1e-4)
+    assert torch.allclose(o32, o, atol=1e-5, rtol=1e-4)
+    assert torch.allclose(_recon(o16, d, 2), o, atol=1e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("T,H", [(50, 12), (257, 16)])
+def test_attn_bwd(T, H):
+    from semabs_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(T + 1)
+    B, P, d = 2, 3, H * 64
+    qkv = torch.randn(B * T, 3 * d, device=dev, generator=g)
+    qkv[:, :d] *= 0.125 * 1.5
+    probs = torch.empty(B * H, T, T, device=dev)
+    o32 = torch.empty(B * T, d, device=dev)
+    ops.attn_fwd(qkv, B=B, T=T, H=H, probs=probs, o32=o32)
+    dO = torch.randn(P * B * T, d, device=dev, generator=g).half()
+    r = torch.rand(P * B, T, device=dev, generator=g)
+    delta = torch.empty(P * B * H, T, device=dev)
+    wpart = torch.full((P * B * H, T), float("nan"), device=dev)
+    dqkv16 = torch.full((P * B * T, 2 * 3 * d), float("nan"), device=dev, dtype=torch.float16)
+    ops.attn_bwd(qkv, probs, o32, dO, d, r, delta, wpart, dqkv16, P=P, B=B, T=T, H=H, splits=2, positive_only=True)
+    torch.cuda.synchronize()
+
+    # torch reference (fp32, same fp16-rounded dO)
+    dOf = dO.float().view(P, B, T, H, 64).permute(0, 1, 3, 2, 4)  # P,B,H,T,hd
+    q, k, v = (t.reshape(B, T, H, 64).permute(0, 2, 1, 3) for t in qkv.view(B, T, 3 * d).chunk(3, -1))
+    A = probs.view(B, H, T, T)
+    G = dOf @ v.transpose(-1, -2)[None]  # P,B,H,T,T
+    cam = (G * A[None]).clamp(min=0)
+    w_ref = torch.einsum("pbi,pbhij->pbhj", r.view(P, B, T), cam) / H
+    assert torch.allclose(wpart.view(P, B, H, T), w_ref, atol=2e-3 * w_ref.abs().max().item(), rtol=2e-3)
+    D = (G * A[None]).sum(-1, keepdim=True)
+    dS = A[None] * (G - D)
+    dq = (dS @ k[None]) * 0.125
+    dk = dS.transpose(-1, -2) @ q[None]
+    dv = A[None].transpose(-1, -2).expand(P, -1, -1, -1, -1) @ dOf
+    ref = torch.cat([t.permute(0, 1, 3, 2, 4).reshape(P * B * T, d) for t in (dq, dk, dv)], dim=1)
+    got = dqkv16[:, : 3 * d].float() + dqkv16[:, 3 * d :].float()
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() < 4e-3 * scale, ((got - ref).abs().max().item(), scale)
+
+
+def test_logit_seed():
+    from semabs_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(5)
+    B, P, E = 5, 3, 512
+    f = torch.randn(B, E, device=dev, generator=g)
+    W = torch.randn(E, P, device=dev, generator=g) / E**0.5
+    logits = torch.empty(B, P, device=dev)
+    seed16 = torch.empty(P * B, 2 * E, device=dev, dtype=torch.float16)
+    ops.clip_logit_seed(f, W, B=B, P=P, E=E, logits=logits, seed16=seed16, splits=2)
+    fr = f.clone().requires_grad_(True)
+    lg = 100.0 * (fr / fr.norm(dim=-1, keepdim=True)) @ W
+    assert torch.allclose(logits, lg, atol=1e-4, rtol=1e-5)
+    for p in range(P):
+        (gr,) = torch.autograd.grad(lg[:, p].sum(), fr, retain_graph=True)
+        got = _recon(seed16[p * B : (p + 1) * B], E, 2)
+        assert torch.allclose(got, gr, atol=1e-5, rtol=1e-3)
