@@ -1,0 +1,322 @@
+"""Benchmark of the hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One step = one pass of the relevancy hot path over one batch of synthetic input per GPU:
+BASELINE.json configs[1] — 8 images 336x336 RGB, ViT-L/14 (seeded random-init weights: no checkpoints offline),
+5-size crop pyramid (285 tiles / image, no jitter / flip), 16 labels -> 128 relevancy maps [336,336] per step per GPU.
+`value` = relevancy maps / s with the preprocessed tiles already resident in HBM; `e2e` = the same metric through
+ClipWrapper (host uint8 images -> PIL tile preprocessing -> H2D -> kernels -> D2H of the fp32 maps).
+The second half of BASELINE.json's metric (voxel grids / s, configs[2]: ResidualUNet3D 128^3 x 32 ch, batch 4) is
+measured in the same run and reported under "voxel".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+LABELS16 = ["basketball jersey", "nintendo switch", "television", "ping pong table", "vase", "fireplace",
+            "abstract painting of a vespa", "carpet", "wall", "microwave", "cabinet", "fire extinguisher", "mirror",
+            "woven chair", "globe", "leather sofa"]  # fmt: skip
+PROMPT = "a photograph of a {} in a home."
+PYRAMID = [{"tile_size": s, "stride": s // 4} for s in (336, 224, 168, 112, 84)]  # 1+9+25+81+169 = 285 tiles
+IMG = 336
+IMAGES_PER_STEP = 8
+MODEL = "ViT-L/14"
+# algorithmic work (SURVEY.md §8d / BASELINE.md §3): per tile 162.0 GF forward + 89.1 GF backward per label
+GF_FWD_TILE, GF_BWD_TILE_LABEL = 162.0, 89.1
+UNET_GF_PER_GRID = {16: 340.8, 32: 1363.2}
+UNET_GB_PER_GRID_FP32 = {16: 3.35, 32: 6.71}
+
+
+def synth_image(seed):
+    return np.random.default_rng(seed).integers(0, 256, (IMG, IMG, 3), dtype=np.uint8)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle (CPU restatement pinned bit-exactly to the reference) on a bounded sample
+# ---------------------------------------------------------------------------------------------------------
+def cpu_relevancy_sample(n_tiles=2, n_labels=16, repeats=1):
+    """Times the reference algorithm (oracle/clip_oracle.py; /root/reference cannot travel to the GPU box) on
+    n_tiles x n_labels of the SAME workload (ViT-L/14 tiles of a 336^2 synthetic image) with all host threads and
+    extrapolates linearly in tile count to maps/s of the full 285-tile pyramid."""
+    from oracle import clip_oracle
+    from semabs_b200.clip.model import synthetic_clip_state_dict
+
+    torch.set_num_threads(os.cpu_count())
+    sd = clip_oracle.convert_weights_values(synthetic_clip_state_dict(MODEL, seed=0))
+    img = synth_image(0)
+    desc = clip_oracle.enumerate_tiles(img.shape, PYRAMID)
+    pick = [0, len(desc) - 1, len(desc) // 2, len(desc) // 3][:n_tiles]
+    tiles = torch.stack([clip_oracle.preprocess_tile(img[r : r + s, c : c + s]) for r, c, s in desc[pick]])
+    g = torch.Generator().manual_seed(0)
+    W = torch.randn(768, n_labels, generator=g)
+    W = (W / W.norm(dim=0, keepdim=True)).contiguous()
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        clip_oracle.relevancy(sd, tiles, W)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts))
+    tile_label_per_s = n_tiles * n_labels / t
+    maps_per_s = tile_label_per_s / len(desc)  # one map needs all 285 tiles of its image
+    return {"value": maps_per_s, "unit": "relevancy-maps/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{n_tiles} tiles x {n_labels} labels of the 285-tile pyramid (ViT-L/14, fp32, torch CPU, "
+                      f"{torch.get_num_threads()} threads) in {t:.1f} s, extrapolated linearly in tile count"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_relevancy_sample(1, 2)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = cpu_relevancy_sample(2, 16)
+        vals.append(r["value"])
+    dt = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    r["value"] = v
+    line = {"impl": "reference", "metric": "relevancy-maps/sec/GPU (336^2, 5 scales, 16 labels)", "value": v,
+            "unit": "relevancy-maps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: ViT-L/14, 336^2, 5-size pyramid (285 tiles), 16 labels; CPU: bounded sample",
+                       "model_weights": "seeded random init"},
+            "cpu_baseline": r, "e2e": {"value": v, "unit": "relevancy-maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=IMAGES_PER_STEP)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-voxel", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from semabs_b200 import ops
+    from semabs_b200.clip import ClipWrapper
+    from semabs_b200.clip.tokenizer import tokenize
+
+    ClipWrapper.reset()
+    ClipWrapper(MODEL, dev, seed=0)
+    gc = ClipWrapper.clip_gradcam
+    eng = gc.engine
+    gc.templates = [PROMPT]
+    gc.set_classes(LABELS16)
+    cfg = dict(augmentations=0, cropping_augmentations=PYRAMID)
+    imgs = [synth_image(rank * 1000 + i) for i in range(args.images)]
+    P = len(LABELS16)
+
+    # ---- device-resident inputs for `value` ----
+    pre = [ClipWrapper.create_tiles(img=im, **cfg) for im in imgs]
+    dev_tiles = [t.to(dev) for (_, t, _) in pre]
+    n_tiles = pre[0][0].shape[0]
+
+    def step_device():
+        out = None
+        for (desc, _, order), tl in zip(pre, dev_tiles):
+            out = ClipWrapper.get_clip_saliency_device(tl, desc, order, LABELS16, IMG, IMG, positive_attn_only=True)
+        return out
+
+    def step_e2e():
+        last = None
+        for im in imgs:
+            maps = ClipWrapper.get_clip_saliency_convolve(img=im, text_labels=LABELS16, positive_attn_only=True, **cfg)
+            last = maps
+        return last
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item(), t[1].item()
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.GEMM_PROFILE.enable()
+    launches0 = eng.kernel_launches
+    ms_dev, _ = timed(step_device, args.steps)
+    launches = eng.kernel_launches - launches0 + args.steps * args.images  # + one assembly kernel per image
+    gemm_prof = ops.GEMM_PROFILE.collect()
+    clocks = sampler.stop() if rank == 0 else None
+    maps_per_step = args.images * P
+    value = world * maps_per_step * args.steps / (ms_dev / 1e3)
+
+    # ---- e2e through the public API (host images, PIL preprocessing, H2D, D2H) ----
+    step_e2e()
+    _, wall_e2e = timed(step_e2e, max(1, args.steps // 2))
+    e2e_steps = max(1, args.steps // 2)
+    e2e_value = world * maps_per_step * e2e_steps / (wall_e2e / 1e3)
+    h2d = args.images * n_tiles * 3 * 224 * 224 * 4
+    d2h = args.images * P * IMG * IMG * 4
+
+    pk = peaks()
+    flops_per_map = (GF_FWD_TILE + P * GF_BWD_TILE_LABEL) * 1e9 * n_tiles / P
+    roofline = {"bound": "tensor", "kernel": "gemm_f16_tn_kernel (tcgen05)", "achieved": gemm_prof["tflops"], "peak": pk["tflops"],
+                "unit": "TFLOP/s", "frac": gemm_prof["tflops"] / pk["tflops"], "traffic": None,
+                "peak_source": pk["src"] + " (sustained bf16 cuBLAS)", "gemm_launches": gemm_prof["launches"],
+                "gemm_time_share_of_step": gemm_prof["ms"] / ms_dev,
+                "whole_path_algorithmic_tflops": value / world * flops_per_map / 1e12,
+                "whole_path_frac": value / world * flops_per_map / 1e12 / pk["tflops"]}
+
+    voxel = None
+    if not args.skip_voxel:
+        voxel = bench_voxel(dev, world, dist if world > 1 else None, pk)
+
+    if rank == 0:
+        cpu = None if args.skip_cpu else cpu_relevancy_sample(2, 16)
+        line = {"metric": "relevancy-maps/sec/GPU (336^2, 5 scales, 16 labels)", "value": value, "unit": "relevancy-maps/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 MMA / f32 accumulate (fwd hi+lo split)",
+                "data": "synthetic",
+                "config": {"workload": f"configs[1]: {MODEL} (seeded random init), {args.images} images 336x336 per GPU per step, "
+                                       f"{n_tiles} tiles/image (5 crop sizes), {P} labels, no jitter/flip",
+                           "l2_policy": "inputs larger than L2: per-step working set ~6 GB of saved activations + 1.4 GB tiles",
+                           "fwd_splits": eng.fwd_splits, "bwd_splits": eng.bwd_splits},
+                "e2e": {"value": e2e_value, "unit": "relevancy-maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "note": "ClipWrapper.get_clip_saliency_convolve: host PIL tile preprocessing inside the timed region"},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "voxel": voxel}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_voxel(dev, world, dist, pk, C=32, N=4, steps=5, warmup=3):
+    """configs[2]: ResidualUNet3D inference, 128^3 x 32 channels, batch 4 (6 levels, 8 groups)."""
+    from semabs_b200.unet3d import ResidualUNet3D
+
+    torch.manual_seed(0)
+    m = ResidualUNet3D(in_channels=C, out_channels=C, f_maps=C, num_groups=8, num_levels=6).to(dev)
+    x = torch.randn(N, C, 128, 128, 128, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+    for _ in range(warmup):
+        m(x)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = m.kernel_launches
+    e0.record()
+    for _ in range(steps):
+        y = m(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    # e2e: host NCDHW fp32 in pinned memory -> device -> forward -> host
+    xh = x.cpu().pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        yh = m(xh.to(dev, non_blocking=True)).cpu()
+    torch.cuda.synchronize()
+    e2e = 2 * N / (time.perf_counter() - t0) * world
+    grids_s = world * N * steps / (ms / 1e3)
+    per_gpu = grids_s / world
+    return {"metric": "voxel-grids/sec/GPU (128^3, 32 ch)", "value": grids_s, "unit": "voxel-grids/s", "ms_per_step": ms / steps,
+            "batch": N, "precise": m.precise, "gpu_launches": m.kernel_launches - l0,
+            "e2e": {"value": e2e, "unit": "voxel-grids/s", "h2d_bytes_per_step": N * C * 128**3 * 4, "d2h_bytes_per_step": N * C * 128**3 * 4},
+            "roofline": {"bound": "hbm", "achieved": per_gpu * UNET_GB_PER_GRID_FP32[C], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": per_gpu * UNET_GB_PER_GRID_FP32[C] / pk["hbm_gbs"], "traffic": None,
+                         "tensor_tflops": per_gpu * UNET_GF_PER_GRID[C] / 1e3, "tensor_frac": per_gpu * UNET_GF_PER_GRID[C] / 1e3 / pk["tflops"],
+                         "note": "whole-forward algorithmic bytes (BASELINE.md byte rule, fp32 I/O) / time"}}
+
+
+if __name__ == "__main__":
+    main()

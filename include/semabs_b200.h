@@ -141,6 +141,76 @@ int semabs_tile_assemble(const float* rel, const int32_t* tile_desc, int32_t n_t
                          int32_t n_sizes, int32_t g, int32_t H, int32_t W, int32_t P, float* out, void* stream);
 int semabs_flip_average(float* rel, const float* rel_flipped, int64_t n_maps, int32_t g, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Residual 3-D UNet stages (conv3d.cu, unet_ops.cu) — reference unet3d.py.
+ * Internal activation layout is channels-last: raw fp32 [N,D,H,W,C] and, as MMA operand, fp16
+ * [N,D,H,W,a_splits*C] (hi | lo). GroupNorm statistics buffers are fp64 [N,G,2] = (sum, sum of squares) and must
+ * be zeroed by the caller before the producing kernel runs.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Implicit-GEMM convolution on tcgen05, TMA im2col by taps.
+ *   kind 0: nn.Conv3d 3x3x3, padding 1, no bias (unet3d.py:16-17,55-61); weights w16 [C_out, w_splits*27*C_in],
+ *           slice t = (kd*3+kh)*3+kw, i.e. conv.weight.permute(0,2,3,4,1)
+ *   kind 1: 1x1x1 conv (final_conv, unet3d.py:578); w16 [C_out, w_splits*C_in]
+ *   kind 2: nn.ConvTranspose3d k3 s2 p1 with output_size = 2x input (Upsampling, unet3d.py:428-440), one output
+ *           parity class per call (parity bit2 = z, bit1 = y, bit0 = x; 8 calls cover the output);
+ *           w16 [C_out, w_splits*27*C_in] = upsample.weight.permute(1,2,3,4,0)
+ * precise != 0 (needs a_splits == w_splits == 2) accumulates x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (≈ fp32 accuracy).
+ * Epilogue: + bias[C_out] (opt) + residual (opt, fp32, same layout as out32), ReLU (opt); writes out32
+ * [N,Do,Ho,Wo,C_out] and/or out16 [.., o16_splits*C_out]; accumulates `stats` of what it wrote for a GroupNorm
+ * with `groups` groups over C_out (opt). C_in must be 16, 32 or a multiple of 64; C_out a multiple of 16;
+ * D,H,W powers of two with D*H*W >= 32. */
+int semabs_conv3d(const void* x16, int32_t a_splits, const void* w16, int32_t w_splits, int32_t kind, int32_t parity,
+                  int32_t N, int32_t D, int32_t H, int32_t W, int32_t C_in, int32_t C_out, int32_t precise,
+                  const float* bias, const float* residual, int32_t relu, float* out32, void* out16,
+                  int32_t o16_splits, double* stats, int32_t groups, void* stream);
+
+/* Module-boundary layout conversions: x [N,C,S] fp32 (NCDHW, S = D*H*W) <-> y [N,S,Cpad] channels-last
+ * (channels >= C zero-filled). The forward direction also accumulates the statistics for the first GroupNorm
+ * (groups == 1 when C < num_groups, unet3d.py:72-73). */
+int semabs_ncdhw_to_ndhwc(const float* x, float* y, int32_t N, int64_t S, int32_t C, int32_t Cpad, int32_t groups,
+                          double* stats, void* stream);
+int semabs_ndhwc_to_ncdhw(const float* x, float* y, int32_t N, int64_t S, int32_t C, void* stream);
+
+/* nn.GroupNorm apply (unet3d.py:78-83; biased variance, eps 1e-5, affine): x raw fp32 [N,S,C] + stats ->
+ * y16 [N,S,splits*C]. gamma/beta are [C] (zero for padded channels >= C_real). */
+int semabs_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* y16,
+                           int32_t N, int64_t S, int32_t C, int32_t C_real, int32_t groups, int32_t splits,
+                           void* stream);
+
+/* nn.MaxPool3d(2) (Encoder.forward, unet3d.py:298,313-317) + statistics of the pooled tensor. */
+int semabs_maxpool3d_2(const float* x, float* y, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C,
+                       int32_t groups, double* stats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Point <-> voxel stages of SemAbs3D / SemAbsVOOL (points.cu) — reference net.py.
+ * Grid description (HOST pointers, 3 values each): neg_lc = -lower_corner, scale = (shape-1)/(uc-lc) computed
+ * in fp32 like VirtualGrid.get_points_grid_idxs (net.py:84-113), shape = (X,Y,Z).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* pts_feat_extractor (Linear(3+F,h) LeakyReLU Linear(h,h) LeakyReLU Linear(h,C); net.py:358-367,395-404) fused with
+ * VirtualGrid.scatter_points (net.py:185-201) using the reduce method the reference really applies: MEAN, empty
+ * voxels 0.  xyz [N/xyz_div, npts, 3] (sample n reads batch n/xyz_div: SemAbs3D repeats xyz over patches,
+ * net.py:386-390), feat [N, npts, F].  Weights are TRANSPOSED ([in][out]) fp32 device arrays.  use_mlp == 0
+ * scatters the raw features.  Output vol [N, X*Y*Z, Cpad] channels-last fp32 (this call zeroes it and `cnt`
+ * [N, X*Y*Z]); `stats` (optional, zeroed by caller) receives the statistics of the UNet's first GroupNorm. */
+int semabs_points_to_voxels(const float* xyz, int32_t xyz_div, const float* feat, int32_t N, int32_t npts, int32_t F,
+                            int32_t use_mlp, int32_t hidden, int32_t C, const float* w1t, const float* b1,
+                            const float* w2t, const float* b2, const float* w3t, const float* b3,
+                            const float* neg_lc, const float* scale, const int32_t* shape, float* vol, float* cnt,
+                            int32_t Cpad, int32_t groups, double* stats, void* stream);
+
+/* ImplicitVolumetricDecoder.forward (net.py:215-256): trilinear feature fetch (grid_sample bilinear / border /
+ * align_corners=True fed (x,y,z) in (W,H,D) order, indices normalised by shape instead of shape-1 — both quirks
+ * reproduced) + Linear(Cin,Hs) LeakyReLU Linear(Hs,out_dim). vol0/vol1 channels-last [N,X,Y,Z,C0] (vol1 optional:
+ * the VOOL sampler reads target | reference volumes, net.py:556). query [N,nq,3]. With emb [N,out_dim] the output
+ * is cosine_similarity(mlp_out, emb[n]) / temperature -> out [N,nq] (PointingAttention.cosine_sim, net.py:300-309);
+ * otherwise out [N,nq,out_dim]. */
+int semabs_sample_decode(const float* vol0, const float* vol1, int32_t C0, const float* query, int32_t N, int32_t nq,
+                         const float* neg_lc, const float* scale, const int32_t* shape, int32_t concat_xyz,
+                         const float* w1t, const float* b1, const float* w2t, const float* b2, int32_t Hs,
+                         int32_t out_dim, const float* emb, float temperature, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,213 @@
+// Bandwidth-bound stages of the residual 3-D UNet (reference unet3d.py): GroupNorm apply (statistics come from the
+// producer's epilogue, see conv3d.cu), 2x2x2 max-pool with fused statistics for the next GroupNorm
+// (Encoder.forward, unet3d.py:313-317), and the NCDHW <-> channels-last conversions at the module boundary.
+// All kernels: grid (x, N); a thread owns one channel quad (float4) so its GroupNorm group is loop-invariant and
+// statistics are reduced registers -> shared (fp32) -> global (fp64 atomics, a few per CTA).
+#include "../../include/semabs_b200.h"
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int EW_THREADS = 256;
+
+struct QuadStats {
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;  // channels (0,1) and (2,3) of the quad
+  __device__ __forceinline__ void add(const float4& v) {
+    s0 += v.x + v.y, q0 += v.x * v.x + v.y * v.y;
+    s1 += v.z + v.w, q1 += v.z * v.z + v.w * v.w;
+  }
+};
+
+// reduce the per-thread quad statistics of a CTA into stats[n, g, 2]
+__device__ __forceinline__ void flush_quad_stats(const QuadStats& qs, int cq, int cpg, int groups, double* stats_n) {
+  __shared__ float sm[16];
+  if (threadIdx.x < 16) sm[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int g0 = (4 * cq) / cpg, g1 = (4 * cq + 2) / cpg;
+  // warp-level pre-reduction when the whole warp maps to one group
+  atomicAdd(&sm[2 * g0], qs.s0);
+  atomicAdd(&sm[2 * g0 + 1], qs.q0);
+  atomicAdd(&sm[2 * g1], qs.s1);
+  atomicAdd(&sm[2 * g1 + 1], qs.q1);
+  __syncthreads();
+  if (threadIdx.x < 2 * groups) atomicAdd(stats_n + threadIdx.x, double(sm[threadIdx.x]));
+}
+
+// ---- NCDHW fp32 -> channels-last fp32 (channel-padded with zeros) + statistics -----------------------
+__global__ void __launch_bounds__(EW_THREADS)
+ncdhw_to_ndhwc_kernel(const float* __restrict__ x, float* __restrict__ y, long long S, int C, int Cpad, int groups,
+                      double* __restrict__ stats) {
+  const int n = blockIdx.y;
+  const int qpc = Cpad / 4;               // quads per voxel
+  const int vpb = EW_THREADS / qpc;       // voxels per CTA iteration
+  const int cq = threadIdx.x % qpc, vl = threadIdx.x / qpc;
+  const float* xn = x + size_t(n) * C * S;
+  float* yn = y + size_t(n) * S * Cpad;
+  QuadStats qs;
+  for (long long v = (long long)blockIdx.x * vpb + vl; v < S; v += (long long)gridDim.x * vpb) {
+    float4 o;
+    const int c = 4 * cq;
+    o.x = c + 0 < C ? xn[size_t(c + 0) * S + v] : 0.f;
+    o.y = c + 1 < C ? xn[size_t(c + 1) * S + v] : 0.f;
+    o.z = c + 2 < C ? xn[size_t(c + 2) * S + v] : 0.f;
+    o.w = c + 3 < C ? xn[size_t(c + 3) * S + v] : 0.f;
+    *reinterpret_cast<float4*>(yn + size_t(v) * Cpad + c) = o;
+    qs.add(o);
+  }
+  if (stats) {
+    const int cpg = groups == 1 ? Cpad : C / groups;
+    flush_quad_stats(qs, cq, cpg < 2 ? 2 : cpg, groups, stats + size_t(n) * groups * 2);
+  }
+}
+
+// ---- channels-last fp32 -> NCDHW fp32 -------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+ndhwc_to_ncdhw_kernel(const float* __restrict__ x, float* __restrict__ y, long long S, int C) {
+  // tile transpose through shared memory: 32 voxels x 32 channels
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long v0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
+  for (int r = ty; r < 32; r += 8) {
+    const long long v = v0 + r;
+    tile[r][tx] = (v < S && c0 + tx < C) ? x[(size_t(n) * S + v) * C + c0 + tx] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const long long v = v0 + tx;
+    if (c < C && v < S) y[(size_t(n) * C + c) * S + v] = tile[tx][r];
+  }
+}
+
+// ---- GroupNorm apply: raw fp32 channels-last + (sum, sumsq) -> normalised fp16 (hi | lo) ------------------
+// torch.nn.GroupNorm semantics (unet3d.py:78-83): biased variance over (C/G) x D x H x W, eps 1e-5, affine.
+__global__ void __launch_bounds__(EW_THREADS)
+gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, __half* __restrict__ y, long long S, int C, int groups, int cpg,
+                double inv_count, int splits) {
+  __shared__ float s_scale[1024], s_shift[1024];
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = min(c / cpg, groups - 1);
+    const double mean = stats[(size_t(n) * groups + g) * 2] * inv_count;
+    double var = stats[(size_t(n) * groups + g) * 2 + 1] * inv_count - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = float(1.0 / sqrt(var + 1e-5));
+    const float sc = rstd * gamma[c];
+    s_scale[c] = sc;
+    s_shift[c] = beta[c] - float(mean) * sc;
+  }
+  __syncthreads();
+  const int qpc = C / 4, vpb = EW_THREADS / qpc;
+  const int cq = threadIdx.x % qpc, vl = threadIdx.x / qpc, c = 4 * cq;
+  const float4 sc = make_float4(s_scale[c], s_scale[c + 1], s_scale[c + 2], s_scale[c + 3]);
+  const float4 sh = make_float4(s_shift[c], s_shift[c + 1], s_shift[c + 2], s_shift[c + 3]);
+  const float* xn = x + size_t(n) * S * C;
+  __half* yn = y + size_t(n) * S * splits * C;
+  for (long long v = (long long)blockIdx.x * vpb + vl; v < S; v += (long long)gridDim.x * vpb) {
+    const float4 a = *reinterpret_cast<const float4*>(xn + size_t(v) * C + c);
+    const float o0 = fmaf(a.x, sc.x, sh.x), o1 = fmaf(a.y, sc.y, sh.y), o2 = fmaf(a.z, sc.z, sh.z), o3 = fmaf(a.w, sc.w, sh.w);
+    const __half2 h0 = __floats2half2_rn(o0, o1), h1 = __floats2half2_rn(o2, o3);
+    __half* dst = yn + size_t(v) * splits * C + c;
+    *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    if (splits == 2) {
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      const __half2 l0 = __floats2half2_rn(o0 - f0.x, o1 - f0.y), l1 = __floats2half2_rn(o2 - f1.x, o3 - f1.y);
+      *reinterpret_cast<uint2*>(dst + C) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    }
+  }
+}
+
+// ---- MaxPool3d(2) + statistics of the pooled tensor --------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+maxpool2_kernel(const float* __restrict__ x, float* __restrict__ y, int D, int H, int W, int C, int groups,
+                double* __restrict__ stats) {
+  const int n = blockIdx.y;
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2;
+  const long long So = (long long)Do * Ho * Wo;
+  const int qpc = C / 4, vpb = EW_THREADS / qpc;
+  const int cq = threadIdx.x % qpc, vl = threadIdx.x / qpc, c = 4 * cq;
+  const float* xn = x + size_t(n) * D * H * W * C;
+  float* yn = y + size_t(n) * So * C;
+  QuadStats qs;
+  for (long long v = (long long)blockIdx.x * vpb + vl; v < So; v += (long long)gridDim.x * vpb) {
+    const int xo = int(v % Wo), yo = int((v / Wo) % Ho), zo = int(v / ((long long)Wo * Ho));
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const size_t src = ((size_t(2 * zo + dz) * H + (2 * yo + dy)) * W + (2 * xo + dx)) * C + c;
+          const float4 a = *reinterpret_cast<const float4*>(xn + src);
+          m.x = fmaxf(m.x, a.x), m.y = fmaxf(m.y, a.y), m.z = fmaxf(m.z, a.z), m.w = fmaxf(m.w, a.w);
+        }
+    *reinterpret_cast<float4*>(yn + size_t(v) * C + c) = m;
+    qs.add(m);
+  }
+  if (stats) flush_quad_stats(qs, cq, C / groups, groups, stats + size_t(n) * groups * 2);
+}
+
+static int ew_grid(long long S, int vpb) {
+  long long need = (S + vpb - 1) / vpb;
+  long long cap = (long long)num_sms() * 8;
+  return int(need < cap ? need : cap);
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" int semabs_ncdhw_to_ndhwc(const float* x, float* y, int32_t N, int64_t S, int32_t C, int32_t Cpad,
+                                     int32_t groups, double* stats, void* stream) {
+  SB_REQUIRE(x && y && N > 0 && S > 0 && C > 0 && Cpad >= C && Cpad % 4 == 0 && (EW_THREADS % (Cpad / 4)) == 0,
+             "semabs_ncdhw_to_ndhwc: bad arguments (Cpad=%d)", Cpad);
+  SB_REQUIRE(!stats || (groups >= 1 && groups <= 8 && (groups == 1 || (C == Cpad && C % groups == 0 && (C / groups) % 2 == 0))),
+             "semabs_ncdhw_to_ndhwc: unsupported GroupNorm grouping C=%d groups=%d", C, groups);
+  const int vpb = EW_THREADS / (Cpad / 4);
+  dim3 grid(ew_grid(S, vpb), N);
+  ncdhw_to_ndhwc_kernel<<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, y, S, C, Cpad, groups, stats);
+  SB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int semabs_ndhwc_to_ncdhw(const float* x, float* y, int32_t N, int64_t S, int32_t C, void* stream) {
+  SB_REQUIRE(x && y && N > 0 && S > 0 && C > 0, "semabs_ndhwc_to_ncdhw: bad arguments");
+  dim3 grid((unsigned)((S + 31) / 32), (C + 31) / 32, N);
+  ndhwc_to_ncdhw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, S, C);
+  SB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int semabs_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta,
+                                      void* y16, int32_t N, int64_t S, int32_t C, int32_t C_real, int32_t groups,
+                                      int32_t splits, void* stream) {
+  SB_REQUIRE(x && stats && gamma && beta && y16 && N > 0 && S > 0, "semabs_groupnorm_apply: null pointer");
+  SB_REQUIRE(C % 4 == 0 && C <= 1024 && (EW_THREADS % (C / 4)) == 0 && groups >= 1 && groups <= 8 && C_real <= C,
+             "semabs_groupnorm_apply: unsupported channel count %d", C);
+  const int cpg = groups == 1 ? C : C_real / groups;
+  const double inv_count = 1.0 / (double(S) * double(groups == 1 ? C_real : cpg));
+  const int vpb = EW_THREADS / (C / 4);
+  dim3 grid(ew_grid(S, vpb), N);
+  gn_apply_kernel<<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, stats, gamma, beta, (__half*)y16, S, C, groups, cpg,
+                                                                 inv_count, splits);
+  SB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int semabs_maxpool3d_2(const float* x, float* y, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C,
+                                  int32_t groups, double* stats, void* stream) {
+  SB_REQUIRE(x && y && N > 0 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "semabs_maxpool3d_2: bad arguments");
+  SB_REQUIRE(C % 4 == 0 && (EW_THREADS % (C / 4)) == 0, "semabs_maxpool3d_2: unsupported channel count %d", C);
+  SB_REQUIRE(!stats || (groups >= 1 && groups <= 8 && C % groups == 0 && (C / groups) % 2 == 0),
+             "semabs_maxpool3d_2: unsupported GroupNorm grouping");
+  const int vpb = EW_THREADS / (C / 4);
+  const long long So = (long long)(D / 2) * (H / 2) * (W / 2);
+  dim3 grid(ew_grid(So, vpb), N);
+  maxpool2_kernel<<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, y, D, H, W, C, groups, stats);
+  SB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -9,6 +9,28 @@ from . import _lib
 from ._lib import ACT_NONE, ACT_QUICKGELU, ACT_QUICKGELU_GRAD, GemmEpilogue, check, f32, i32, lib, ptr, stream_ptr
 
 
+class _GemmProfile:
+    """Optional CUDA-event bracket around every GEMM launch (bench.py's live roofline measurement)."""
+
+    def __init__(self):
+        self.on = False
+        self.recs = []
+
+    def enable(self):
+        self.on, self.recs = True, []
+
+    def collect(self):
+        torch.cuda.synchronize()
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self.recs)
+        flops = sum(f for _, _, f in self.recs)
+        n = len(self.recs)
+        self.on, self.recs = False, []
+        return {"ms": ms, "launches": n, "tflops": (flops / (ms * 1e-3) / 1e12) if ms > 0 else 0.0, "flops": flops}
+
+
+GEMM_PROFILE = _GemmProfile()
+
+
 def gemm_f16(
     a: torch.Tensor,
     b: torch.Tensor,
@@ -53,12 +75,19 @@ def gemm_f16(
         assert out_f32.dtype == torch.float32 and out_f32.shape == (M, N)
     if out_f16 is not None:
         assert out_f16.dtype == torch.float16 and out_f16.shape == (M, out_f16_splits * N)
+    prof = GEMM_PROFILE.on
+    if prof:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(
         lib().semabs_gemm_f16(
             ptr(a), i32(a.stride(0)), ptr(b), i32(b.stride(0)), i32(M), i32(N), i32(K), i32(a_splits),
             C.byref(ep), stream_ptr(),
         )
     )
+    if prof:
+        e1.record()
+        GEMM_PROFILE.recs.append((e0, e1, 2.0 * M * N * K))  # algorithmic FLOPs (hi/lo passes not double counted)
     return out_f32 if out_f32 is not None else out_f16
 
 
@@ -154,3 +183,73 @@ def flip_average(rel, rel_flipped):
     assert rel.is_contiguous() and rel_flipped.is_contiguous() and rel.shape == rel_flipped.shape
     check(lib().semabs_flip_average(ptr(rel), ptr(rel_flipped), _i64(rel.numel() // (g * g)), i32(g), stream_ptr()))
     return rel
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 3-D UNet stages
+# ---------------------------------------------------------------------------------------------------------
+CONV_3X3X3, CONV_1X1X1, CONV_TRANSPOSE_PARITY = 0, 1, 2
+
+
+def conv3d(x16, w16, *, kind, N, D, H, W, C_in, C_out, a_splits=1, w_splits=1, parity=0, precise=False, bias=None,
+           residual=None, relu=False, out32=None, out16=None, o16_splits=1, stats=None, groups=0):
+    check(
+        lib().semabs_conv3d(
+            ptr(x16), i32(a_splits), ptr(w16), i32(w_splits), i32(kind), i32(parity), i32(N), i32(D), i32(H), i32(W),
+            i32(C_in), i32(C_out), i32(int(precise)), ptr(bias), ptr(residual), i32(int(relu)), ptr(out32), ptr(out16),
+            i32(o16_splits), ptr(stats), i32(groups), stream_ptr(),
+        )
+    )
+
+
+def ncdhw_to_ndhwc(x, y, *, N, S, C, Cpad, groups=1, stats=None):
+    check(lib().semabs_ncdhw_to_ndhwc(ptr(x), ptr(y), i32(N), _i64(S), i32(C), i32(Cpad), i32(groups), ptr(stats), stream_ptr()))
+
+
+def ndhwc_to_ncdhw(x, y, *, N, S, C):
+    check(lib().semabs_ndhwc_to_ncdhw(ptr(x), ptr(y), i32(N), _i64(S), i32(C), stream_ptr()))
+
+
+def groupnorm_apply(x, stats, gamma, beta, y16, *, N, S, C, C_real, groups, splits=1):
+    check(lib().semabs_groupnorm_apply(ptr(x), ptr(stats), ptr(gamma), ptr(beta), ptr(y16), i32(N), _i64(S), i32(C),
+                                       i32(C_real), i32(groups), i32(splits), stream_ptr()))
+
+
+def maxpool3d_2(x, y, *, N, D, H, W, C, groups=1, stats=None):
+    check(lib().semabs_maxpool3d_2(ptr(x), ptr(y), i32(N), i32(D), i32(H), i32(W), i32(C), i32(groups), ptr(stats), stream_ptr()))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# point <-> voxel stages
+# ---------------------------------------------------------------------------------------------------------
+_cf, _ci = C.c_float, C.c_int32
+
+
+def _host3(vals, ctype):
+    return (ctype * 3)(*vals)
+
+
+def points_to_voxels(xyz, feat, grid, *, N, npts, F, xyz_div, mlp, C_out, vol, cnt, Cpad, groups=1, stats=None):
+    """grid = (neg_lc[3], scale[3], shape[3]) host values; mlp = None or (w1t,b1,w2t,b2,w3t,b3, hidden)."""
+    neg_lc, scale, shape = grid
+    w = mlp[:6] if mlp is not None else (None,) * 6
+    hidden = mlp[6] if mlp is not None else 0
+    check(
+        lib().semabs_points_to_voxels(
+            ptr(xyz), i32(xyz_div), ptr(feat), i32(N), i32(npts), i32(F), i32(int(mlp is not None)), i32(hidden), i32(C_out),
+            ptr(w[0]), ptr(w[1]), ptr(w[2]), ptr(w[3]), ptr(w[4]), ptr(w[5]), _host3(neg_lc, _cf),
+            _host3(scale, _cf), _host3(shape, _ci), ptr(vol), ptr(cnt), i32(Cpad), i32(groups), ptr(stats), stream_ptr(),
+        )
+    )
+
+
+def sample_decode(vol0, vol1, C0, query, grid, *, N, nq, concat_xyz, w1t, b1, w2t, b2, Hs, out_dim, out, emb=None,
+                  temperature=1.0):
+    neg_lc, scale, shape = grid
+    check(
+        lib().semabs_sample_decode(
+            ptr(vol0), ptr(vol1), i32(C0), ptr(query), i32(N), i32(nq), _host3(neg_lc, _cf), _host3(scale, _cf),
+            _host3(shape, _ci), i32(int(concat_xyz)), ptr(w1t), ptr(b1), ptr(w2t), ptr(b2), i32(Hs), i32(out_dim),
+            ptr(emb), f32(temperature), ptr(out), stream_ptr(),
+        )
+    )

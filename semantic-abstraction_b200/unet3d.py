@@ -1,0 +1,270 @@
+"""ResidualUNet3D on the B200 kernels — host-side mirror of the reference module of the same name
+(reference: unet3d.py:658-689 on top of Abstract3DUNet :481-621, ExtResNetBlock :190-259, Encoder :262-317,
+Decoder/Upsampling :320-444).
+
+The nn.Module tree exists only to own parameters under the reference's state-dict key names
+(`encoders.0.basic_module.conv1.groupnorm.weight`, `decoders.0.upsampling.upsample.weight`, `final_conv.bias`, ...)
+and — being built in the reference's construction order from stock torch containers — to draw identical
+initial values under the same torch seed.  forward() never calls those containers: it issues the C-ABI kernels
+(GroupNorm-apply -> implicit-GEMM conv with fused ReLU / residual / next-GroupNorm statistics; max-pool with fused
+statistics; transposed conv as 8 parity classes with fused skip-sum), on channels-last buffers.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+F16, F32, F64 = torch.float16, torch.float32, torch.float64
+
+
+def number_of_features_per_level(init_channel_number, num_levels):
+    return [init_channel_number * 2**k for k in range(num_levels)]
+
+
+def _pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+class SingleConv(nn.Sequential):
+    """'gc[r]' unit: GroupNorm(in) -> Conv3d(3x3x3, pad 1, no bias) [-> ReLU] (create_conv, unet3d.py:20-95)."""
+
+    def __init__(self, in_channels, out_channels, order="gcr", num_groups=8):
+        super().__init__()
+        assert order in ("gcr", "gc"), "only the reference's ResidualUNet3D layer order 'gcr' is implemented"
+        if in_channels < num_groups:
+            num_groups = 1  # unet3d.py:72-73
+        self.add_module("groupnorm", nn.GroupNorm(num_groups=num_groups, num_channels=in_channels))
+        self.add_module("conv", nn.Conv3d(in_channels, out_channels, 3, padding=1, bias=False))
+        self.relu = "r" in order
+        self.num_groups = num_groups
+
+
+class ExtResNetBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, order="gcr", num_groups=8, **kwargs):
+        super().__init__()
+        self.conv1 = SingleConv(in_channels, out_channels, order, num_groups)
+        self.conv2 = SingleConv(out_channels, out_channels, order, num_groups)
+        self.conv3 = SingleConv(out_channels, out_channels, order.replace("r", ""), num_groups)
+
+
+class Encoder(nn.Module):
+    def __init__(self, in_channels, out_channels, apply_pooling=True, conv_layer_order="gcr", num_groups=8):
+        super().__init__()
+        self.pooling = nn.MaxPool3d(kernel_size=(2, 2, 2)) if apply_pooling else None
+        self.basic_module = ExtResNetBlock(in_channels, out_channels, order=conv_layer_order, num_groups=num_groups)
+
+
+class Upsampling(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.upsample = nn.ConvTranspose3d(in_channels, out_channels, kernel_size=3, stride=(2, 2, 2), padding=1)
+
+
+class Decoder(nn.Module):
+    def __init__(self, in_channels, out_channels, conv_layer_order="gcr", num_groups=8):
+        super().__init__()
+        self.upsampling = Upsampling(in_channels, out_channels)
+        self.basic_module = ExtResNetBlock(out_channels, out_channels, order=conv_layer_order, num_groups=num_groups)
+
+
+def _split_pack(w2d: torch.Tensor, splits: int) -> torch.Tensor:
+    """[Co, K] fp32 -> [Co, splits*K] fp16 (hi | lo)."""
+    hi = w2d.half()
+    if splits == 1:
+        return hi.contiguous()
+    lo = (w2d - hi.float()).half()
+    return torch.cat([hi, lo], dim=1).contiguous()
+
+
+class ResidualUNet3D(nn.Module):
+    """Same constructor arguments as the reference. `precise=True` (default) runs every convolution as
+    x_hi·w_hi + x_lo·w_hi + x_hi·w_lo on fp16 tensor-core MMAs with fp32 accumulation (≈ fp32 accuracy: the voxel
+    logits have to match the fp32 reference to 1e-3); `precise=False` is the single-pass fp16 mode."""
+
+    def __init__(self, in_channels, out_channels, f_maps=64, num_groups=8, num_levels=5, final_sigmoid=False,
+                 layer_order="gcr", is_segmentation=False, precise=True, **kwargs):
+        super().__init__()
+        if isinstance(f_maps, int):
+            f_maps = number_of_features_per_level(f_maps, num_levels=num_levels)
+        self.f_maps = list(f_maps)
+        self.in_channels, self.out_channels, self.num_groups = in_channels, out_channels, num_groups
+        self.precise = precise
+        encoders = []
+        for i, out_f in enumerate(f_maps):
+            encoders.append(Encoder(in_channels if i == 0 else f_maps[i - 1], out_f, apply_pooling=i > 0,
+                                    conv_layer_order=layer_order, num_groups=num_groups))
+        self.encoders = nn.ModuleList(encoders)
+        rev = list(reversed(f_maps))
+        self.decoders = nn.ModuleList(
+            [Decoder(rev[i], rev[i + 1], conv_layer_order=layer_order, num_groups=num_groups) for i in range(len(rev) - 1)]
+        )
+        self.final_conv = nn.Conv3d(f_maps[0], out_channels, 1)
+        assert not is_segmentation, "final activation is not used on the hot path (reference default is_segmentation=False)"
+        self._pack: Dict[str, torch.Tensor] = {}
+        self._pack_key = None
+        self._ws: Dict[Tuple, torch.Tensor] = {}
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------------------------------------
+    def _buf(self, name, shape, dtype, device):
+        key = (name, tuple(int(s) for s in shape), dtype, str(device))
+        t = self._ws.get(key)
+        if t is None:
+            for k in [k for k in self._ws if k[0] == name]:
+                del self._ws[k]
+            t = torch.empty(key[1], dtype=dtype, device=device)
+            self._ws[key] = t
+        return t
+
+    def _packed(self, device):
+        """fp16 (hi | lo) MMA-operand copies of the conv weights, rebuilt when a parameter changes."""
+        key = (str(device), self.precise, tuple(p._version for p in self.parameters()), tuple(p.data_ptr() for p in self.parameters()))
+        if key == self._pack_key:
+            return self._pack
+        s = 2 if self.precise else 1
+        pk: Dict[str, torch.Tensor] = {}
+
+        def conv_w(w):  # [Co, Ci, 3,3,3] -> [Co, s*27*Ci_pad]
+            co, ci = w.shape[:2]
+            wp = torch.zeros(co, 27, _pad16(ci), device=device)
+            wp[:, :, :ci] = w.detach().to(device, F32).permute(0, 2, 3, 4, 1).reshape(co, 27, ci)
+            return _split_pack(wp.reshape(co, -1), s)
+
+        def gn(m, cpad):
+            g = torch.zeros(cpad, device=device)
+            b = torch.zeros(cpad, device=device)
+            g[: m.num_channels] = m.weight.detach().to(device, F32)
+            b[: m.num_channels] = m.bias.detach().to(device, F32)
+            return g, b
+
+        def block(prefix, blk: ExtResNetBlock):
+            for j, sc in enumerate((blk.conv1, blk.conv2, blk.conv3), 1):
+                pk[f"{prefix}.w{j}"] = conv_w(sc.conv.weight)
+                pk[f"{prefix}.g{j}"], pk[f"{prefix}.b{j}"] = gn(sc.groupnorm, _pad16(sc.groupnorm.num_channels))
+
+        for i, enc in enumerate(self.encoders):
+            block(f"enc{i}", enc.basic_module)
+        for i, dec in enumerate(self.decoders):
+            block(f"dec{i}", dec.basic_module)
+            w = dec.upsampling.upsample.weight  # [Ci, Co, 3,3,3]
+            ci, co = w.shape[:2]
+            pk[f"dec{i}.up_w"] = _split_pack(w.detach().to(device, F32).permute(1, 2, 3, 4, 0).reshape(co, 27 * ci), s)
+            pk[f"dec{i}.up_b"] = dec.upsampling.upsample.bias.detach().to(device, F32).contiguous()
+        fw = self.final_conv.weight
+        pk["final.w"] = _split_pack(fw.detach().to(device, F32).reshape(fw.shape[0], fw.shape[1]), s)
+        pk["final.b"] = self.final_conv.bias.detach().to(device, F32).contiguous()
+        self._pack, self._pack_key = pk, key
+        return pk
+
+    # ------------------------------------------------------------------------------------------------
+    def _res_block(self, pk, prefix, blk: ExtResNetBlock, x_raw, x_stats, *, N, dims, c_in_pad, c_in_real, lvl, dev,
+                   want32: bool, want16: bool):
+        """ExtResNetBlock.forward (unet3d.py:243-259): o1 = relu(conv(gn(x))); o2 = relu(conv(gn(o1)));
+        out = relu(conv(gn(o2)) + o1). Returns (out32 | None, out16 | None)."""
+        D, H, W = dims
+        S = D * H * W
+        s = 2 if self.precise else 1
+        c_out = blk.conv1.conv.out_channels
+        xn = self._buf(f"l{lvl}_xn", (N, S, s * max(c_in_pad, c_out)), F16, dev)
+        o1 = self._buf(f"l{lvl}_o1", (N, S, c_out), F32, dev)
+        o2 = self._buf(f"l{lvl}_o2", (N, S, c_out), F32, dev)
+        g2, g3 = blk.conv2.num_groups, blk.conv3.num_groups
+        st = self._buf(f"l{lvl}_st", (2, N, 8, 2), F64, dev)
+        st.zero_()
+        common = dict(kind=ops.CONV_3X3X3, N=N, D=D, H=H, W=W, a_splits=s, w_splits=s, precise=self.precise)
+        ops.groupnorm_apply(x_raw, x_stats, pk[prefix + ".g1"], pk[prefix + ".b1"], xn, N=N, S=S, C=c_in_pad,
+                            C_real=c_in_real, groups=blk.conv1.num_groups, splits=s)
+        ops.conv3d(xn, pk[prefix + ".w1"], C_in=c_in_pad, C_out=c_out, relu=True, out32=o1, stats=st[0], groups=g2, **common)
+        ops.groupnorm_apply(o1, st[0], pk[prefix + ".g2"], pk[prefix + ".b2"], xn, N=N, S=S, C=c_out, C_real=c_out,
+                            groups=g2, splits=s)
+        ops.conv3d(xn, pk[prefix + ".w2"], C_in=c_out, C_out=c_out, relu=True, out32=o2, stats=st[1], groups=g3, **common)
+        ops.groupnorm_apply(o2, st[1], pk[prefix + ".g3"], pk[prefix + ".b3"], xn, N=N, S=S, C=c_out, C_real=c_out,
+                            groups=g3, splits=s)
+        out32 = self._buf(f"l{lvl}_out32", (N, S, c_out), F32, dev) if want32 else None
+        out16 = self._buf(f"l{lvl}_out16", (N, S, s * c_out), F16, dev) if want16 else None
+        ops.conv3d(xn, pk[prefix + ".w3"], C_in=c_out, C_out=c_out, residual=o1, relu=True, out32=out32, out16=out16,
+                   o16_splits=s, **common)
+        self.kernel_launches += 6
+        return out32, out16
+
+    def forward_channels_last(self, x_raw, x_stats, N, dims, dev):
+        """Core of Abstract3DUNet.forward (unet3d.py:596-621) on channels-last buffers. x_raw [N,S,Cpad] fp32 with
+        its GroupNorm statistics. Returns the final conv output, channels-last fp32 [N,S,out_channels]."""
+        pk = self._packed(dev)
+        s = 2 if self.precise else 1
+        L = len(self.encoders)
+        feats: List[Tuple[torch.Tensor, Tuple[int, int, int]]] = []
+        cur_raw, cur_stats = x_raw, x_stats
+        c_pad, c_real = _pad16(self.in_channels), self.in_channels
+        cur16 = None
+        for i, enc in enumerate(self.encoders):
+            if i > 0:
+                D, H, W = dims
+                g_next = enc.basic_module.conv1.num_groups
+                pooled = self._buf(f"l{i}_in", (N, (D // 2) * (H // 2) * (W // 2), c_pad), F32, dev)
+                pst = self._buf(f"l{i}_pst", (N, 8, 2), F64, dev)
+                pst.zero_()
+                ops.maxpool3d_2(cur_raw, pooled, N=N, D=D, H=H, W=W, C=c_pad, groups=g_next, stats=pst)
+                self.kernel_launches += 1
+                dims = (D // 2, H // 2, W // 2)
+                cur_raw, cur_stats = pooled, pst
+            last = i == L - 1
+            out32, out16 = self._res_block(pk, f"enc{i}", enc.basic_module, cur_raw, cur_stats, N=N, dims=dims,
+                                           c_in_pad=c_pad, c_in_real=c_real, lvl=i, dev=dev, want32=not last,
+                                           want16=last)
+            c_pad = c_real = self.f_maps[i]
+            if not last:
+                feats.insert(0, (out32, dims))
+                cur_raw = out32
+            else:
+                cur16 = out16
+        for j, (dec, (skip, sdims)) in enumerate(zip(self.decoders, feats)):
+            lvl = L - 2 - j
+            D, H, W = dims  # input grid of the transposed conv
+            c_in, c_out = self.f_maps[lvl + 1], self.f_maps[lvl]
+            S_out = sdims[0] * sdims[1] * sdims[2]
+            up = self._buf(f"l{lvl}_up", (N, S_out, c_out), F32, dev)
+            ust = self._buf(f"l{lvl}_ust", (N, 8, 2), F64, dev)
+            ust.zero_()
+            g1 = dec.basic_module.conv1.num_groups
+            assert sdims == (2 * D, 2 * H, 2 * W), "ConvTranspose3d(output_size) path expects exact 2x up-sampling"
+            for parity in range(8):
+                # Upsampling.forward + summation joining (unet3d.py:385-396, 438-440)
+                ops.conv3d(cur16, pk[f"dec{j}.up_w"], kind=ops.CONV_TRANSPOSE_PARITY, parity=parity, N=N, D=D, H=H, W=W,
+                           C_in=c_in, C_out=c_out, a_splits=s, w_splits=s, precise=self.precise, bias=pk[f"dec{j}.up_b"],
+                           residual=skip, out32=up, stats=ust, groups=g1)
+            self.kernel_launches += 8
+            dims = sdims
+            _, cur16 = self._res_block(pk, f"dec{j}", dec.basic_module, up, ust, N=N, dims=dims, c_in_pad=c_out,
+                                       c_in_real=c_out, lvl=lvl, dev=dev, want32=False, want16=True)
+        D, H, W = dims
+        out = self._buf("final_cl", (N, D * H * W, self.out_channels), F32, dev)
+        ops.conv3d(cur16, pk["final.w"], kind=ops.CONV_1X1X1, N=N, D=D, H=H, W=W, C_in=self.f_maps[0],
+                   C_out=self.out_channels, a_splits=s, w_splits=s, precise=self.precise, bias=pk["final.b"], out32=out)
+        self.kernel_launches += 1
+        return out
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x [N, C, D, H, W] fp32 on a CUDA device -> [N, out_channels, D, H, W] fp32 (NCDHW, like the reference)."""
+        if not x.is_cuda:
+            raise RuntimeError("semabs_b200.ResidualUNet3D runs on CUDA devices only; there is no CPU path")
+        N, C, D, H, W = x.shape
+        assert C == self.in_channels
+        dev = x.device
+        x = x.contiguous().float()
+        S = D * H * W
+        cpad = _pad16(C)
+        g_in = self.encoders[0].basic_module.conv1.num_groups
+        raw = self._buf("l0_in", (N, S, cpad), F32, dev)
+        st = self._buf("l0_pst", (N, 8, 2), F64, dev)
+        st.zero_()
+        ops.ncdhw_to_ndhwc(x, raw, N=N, S=S, C=C, Cpad=cpad, groups=g_in, stats=st)
+        out_cl = self.forward_channels_last(raw, st, N, (D, H, W), dev)
+        y = torch.empty(N, self.out_channels, D, H, W, device=dev)
+        ops.ndhwc_to_ncdhw(out_cl, y, N=N, S=S, C=self.out_channels)
+        self.kernel_launches += 2
+        return y
