@@ -97,20 +97,23 @@ int semabs_layernorm_bwd(const float* dy, const float* dres, const float* x, int
                          void* dx16, int64_t out16_stride, int32_t M, int32_t d, int32_t splits, void* stream);
 
 /* Multi-head self-attention forward, head dim 64 (multi_head_attention_forward, CLIP/clip/auxiliary.py:260-337).
- * qkv [B*T, 3d] fp32 with q pre-scaled (auxiliary.py:207); probs (optional) [B*H, T, T] fp32 = softmax(q k^T)
- * (what the reference stores through its hook, :334); o32 (optional) [B*T, d]; o16 (optional) [B*T, splits*d].
- * causal != 0 applies the text transformer's mask (model_explainability.py:452-458). */
-int semabs_attn_fwd(const float* qkv, float* probs, float* o32, void* o16, int32_t B, int32_t T, int32_t H,
-                    int32_t causal, int32_t splits, void* stream);
+ * qkv [B*T, 3d] fp32 with q pre-scaled (auxiliary.py:207); softmax(q k^T) — what the reference stores through its
+ * hook (:334) — is written to probs [B*H,T,T] fp32 (optional) and/or probs16 [B*H,T,ld_p16] fp16 (optional, rows
+ * zero-padded up to ld_p16; the backward kernels read this one); o32 (optional) [B*T,d]; o16 (optional)
+ * [B*T,splits*d]. causal != 0 applies the text transformer's mask (model_explainability.py:452-458). T <= 416. */
+int semabs_attn_fwd(const float* qkv, float* probs, void* probs16, int32_t ld_p16, float* o32, void* o16, int32_t B,
+                    int32_t T, int32_t H, int32_t causal, int32_t splits, void* stream);
 
 /* Attention backward for P stacked cotangents + the relevance term of ClipGradcam.interpret
- * (clip_gradcam.py:90-126).  dO16 [P*B*T, ld_do] fp16 is the gradient w.r.t. the pre-out-proj attention output.
+ * (clip_gradcam.py:90-126).  qkv16 [B*T,3d] fp16 (q pre-scaled), probs16 [B*H,T,ld_p16] fp16 with
+ * ld_p16 >= 16*ceil(T/16), o32 [B*T,d] forward attention output, dO16 [P*B*T, ld_do] fp16 = gradient w.r.t. the
+ * pre-out-proj attention output.
  *   dA = dO V^T ;  wpart[pb,h,j] = (1/H) sum_i r[pb,i] * relu?(dA ⊙ A)[i,j]   (relu iff positive_only)
  *   dS = A ⊙ (dA - rowsum(dA ⊙ A)) ; dQ = scale dS K ; dK = dS^T Q ; dV = A^T dO -> dqkv16 [P*B*T, splits*3d]
- * delta_ws is a [P*B*H*T] fp32 workspace.  need_dqkv == 0 computes the relevance term only. */
-int semabs_attn_bwd(const float* qkv, const float* probs, const float* o32, const void* dO16, int32_t ld_do,
-                    const float* r, float* delta_ws, float* wpart, void* dqkv16, int32_t P, int32_t B, int32_t T,
-                    int32_t H, int32_t splits, int32_t positive_only, int32_t need_dqkv, void* stream);
+ * delta_ws is a [P*B*H*T] fp32 workspace.  need_dqkv == 0 computes the relevance term only.  T <= 272. */
+int semabs_attn_bwd(const void* qkv16, const void* probs16, int32_t ld_p16, const float* o32, const void* dO16,
+                    int32_t ld_do, const float* r, float* delta_ws, float* wpart, void* dqkv16, int32_t P, int32_t B,
+                    int32_t T, int32_t H, int32_t splits, int32_t positive_only, int32_t need_dqkv, void* stream);
 
 /* logits[b,p] = 100 * f_b/|f_b| . W[:,p] (ClipGradcam.forward, clip_gradcam.py:58-68) and the cotangent seed
  * d logits[b,p] / d f_b -> seed16 [P*B, splits*E] (row p*B + b). Either output may be NULL. W is [E,P] fp32. */

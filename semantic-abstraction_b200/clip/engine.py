@@ -57,19 +57,20 @@ class ClipEngine:
         M = n_seq * T
         ws = self.ws
         h16 = ws.get("h16", (M, s * d), F16)
-        mean1 = rstd1 = mean2 = rstd2 = probs = o32 = u = None
+        mean1 = rstd1 = mean2 = rstd2 = probs16 = qkv16 = o32 = u = None
+        qkv = ws.get("qkv", (M, 3 * d))
         if saved is not None:
             mean1, rstd1 = saved["mean1"], saved["rstd1"]
             mean2, rstd2 = saved["mean2"], saved["rstd2"]
-            probs, o32, u = saved["probs"], saved["o32"], saved["u"]
-            qkv, x_mid = saved["qkv"], saved["x_mid"]
+            probs16, qkv16, o32, u = saved["probs16"], saved["qkv16"], saved["o32"], saved["u"]
+            x_mid = saved["x_mid"]
         else:
-            qkv = ws.get("qkv", (M, 3 * d))
             x_mid = ws.get("x_mid", (M, d))
         ops.layernorm_fwd(x, blk.ln1_g, blk.ln1_b, M=M, d=d, y16=h16, mean=mean1, rstd=rstd1, splits=s)
-        ops.gemm_f16(h16, blk.w_in, a_splits=s, bias=blk.b_in, out_f32=qkv, scale_cols=d, scale=0.125)
+        # fp32 q,k,v feed the exact-softmax forward; the fp16 copy is the MMA operand of the attention backward
+        ops.gemm_f16(h16, blk.w_in, a_splits=s, bias=blk.b_in, out_f32=qkv, out_f16=qkv16, scale_cols=d, scale=0.125)
         o16 = ws.get("o16", (M, s * d), F16)
-        ops.attn_fwd(qkv, B=n_seq, T=T, H=H, probs=probs, o32=o32, o16=o16, causal=causal, splits=s)
+        ops.attn_fwd(qkv, B=n_seq, T=T, H=H, probs16=probs16, o32=o32, o16=o16, causal=causal, splits=s)
         ops.gemm_f16(o16, blk.w_out, a_splits=s, bias=blk.b_out, residual=x, out_f32=x_mid)
         ops.layernorm_fwd(x_mid, blk.ln2_g, blk.ln2_b, M=M, d=d, y16=h16, mean=mean2, rstd=rstd2, splits=s)
         g16 = ws.get("g16", (M, s * 4 * d), F16)
@@ -119,7 +120,8 @@ class ClipEngine:
             "x_in": None,
             "mean1": ws.get(f"s{i}_mean1", (M,)), "rstd1": ws.get(f"s{i}_rstd1", (M,)),
             "mean2": ws.get(f"s{i}_mean2", (M,)), "rstd2": ws.get(f"s{i}_rstd2", (M,)),
-            "qkv": ws.get(f"s{i}_qkv", (M, 3 * d)), "probs": ws.get(f"s{i}_probs", (B * H, T, T)),
+            "qkv16": ws.get(f"s{i}_qkv16", (M, 3 * d), F16),
+            "probs16": ws.get(f"s{i}_probs16", (B * H, T, (T + 15) // 16 * 16), F16),
             "o32": ws.get(f"s{i}_o32", (M, d)), "x_mid": ws.get(f"s{i}_xmid", (M, d)),
             "u": ws.get(f"s{i}_u", (M, 4 * d)),
         }  # fmt: skip
@@ -218,7 +220,7 @@ class ClipEngine:
             # x_mid = x_in + out_proj(attn(ln_1(x_in)))
             ops.gemm_f16(dxm16, blk.w_outT, a_splits=sb, out_f16=dO16)
             need = i > self.start_block
-            ops.attn_bwd(sv["qkv"], sv["probs"], sv["o32"], dO16, d, r, delta, wpart, dqkv16 if need else None, P=P,
+            ops.attn_bwd(sv["qkv16"], sv["probs16"], sv["o32"], dO16, d, r, delta, wpart, dqkv16 if need else None, P=P,
                          B=B, T=T, H=H, splits=sb, positive_only=positive_attn_only, need_dqkv=need)
             ops.rollout_update(r, wpart, PB, H, T)
             self.kernel_launches += 8 if need else 7

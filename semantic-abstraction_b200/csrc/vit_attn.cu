@@ -20,8 +20,8 @@ constexpr int KV_STRIDE = 68;  // floats; float4-aligned rows, conflict-free for
 
 template <int NCHUNK>
 __global__ void __launch_bounds__(256, 1)
-attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ probs, float* __restrict__ o32,
-                __half* __restrict__ o16, int T, int H, int d, int causal, int splits) {
+attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ probs, __half* __restrict__ probs16, int ld_p16,
+                float* __restrict__ o32, __half* __restrict__ o16, int T, int H, int d, int causal, int splits) {
   extern __shared__ float sm[];
   float* Ks = sm;
   float* Vs = Ks + size_t(T) * KV_STRIDE;
@@ -85,6 +85,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ probs, float*
       const float a = s[c] / sum;
       prow[j] = a;
       if (probs && j < T) probs[(size_t(blockIdx.x) * T + i) * T + j] = a;
+      if (probs16 && j < ld_p16) probs16[(size_t(blockIdx.x) * T + i) * ld_p16 + j] = __float2half_rn(a);
     }
     __syncwarp();
     // O[i, :] = sum_j a_j V[j, :]; lane owns columns 2*lane, 2*lane+1
@@ -125,48 +126,51 @@ attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ probs, float*
 // =========================================================================================================
 // backward
 // =========================================================================================================
-// delta[pbh, i] = sum_d dO[pb, i, h, d] * O[b, i, h, d]  ( == sum_j dA_ij A_ij, the softmax-backward row term )
-__global__ void attn_bwd_delta_kernel(const __half* __restrict__ dO16, int ld_do, const float* __restrict__ o32,
-                                      float* __restrict__ delta, int PB, int B, int T, int H, int d) {
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (gw >= PB * T * H) return;
-  const int h = gw % H, i = (gw / H) % T, pb = gw / (H * T);
-  const int b = pb % B;
-  const __half2 g = *reinterpret_cast<const __half2*>(dO16 + (size_t(pb) * T + i) * ld_do + h * HD + 2 * lane);
-  const float2 o = *reinterpret_cast<const float2*>(o32 + (size_t(b) * T + i) * d + h * HD + 2 * lane);
-  const float2 gf = __half22float2(g);
-  float s = gf.x * o.x + gf.y * o.y;
-  s = warp_sum(s);
-  if (lane == 0) delta[(size_t(pb) * H + h) * T + i] = s;
-}
-
+// All MMA operands are fp16 produced upstream: qkv16 [B*T, 3d] (QKV GEMM epilogue), probs16 [B*H, T, ldp]
+// (attention forward, rows zero-padded to ldp >= 272), dO16 (out-proj dgrad GEMM epilogue).  One CTA owns one
+// (label p, tile b, head h); its 6 warps split the 17 16-row MMA tiles of the 257 tokens.  Two passes so that
+// nothing needs atomics (run-to-run deterministic):
+//   row owner    : delta_i = dO_i . O_i, dA = dO V^T, dS = A ⊙ (dA - delta), dQ = scale dS K
+//   column owner : dA^T = V dO^T, relevance_j = sum_i r_i relu(dA ⊙ A)_ij / H, dK = dS^T Q, dV = A^T dO
+// The whole head's K,V (resp. Q,dO) stay in shared memory; A is streamed from L2 (p is the fastest grid index, so
+// the P CTAs that share a (b,h) pair run together).
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_row))));
+}
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
 
-constexpr int TS = 72;   // half stride of 64-wide fp16 smem tiles (conflict-free 32-bit fragment loads)
-constexpr int AS = 68;   // float stride of the fp32 probability tile
+constexpr int TS = 72;        // half stride of [token][64] tiles: 144 B rows, 16B-aligned, conflict-free fragment loads
+constexpr int TR = 272;       // 17 MMA row tiles
+constexpr int BWD_WARPS = 6;
+constexpr int STRIP = 24;     // half stride of the per-warp [64][16] probability strip
 
 struct AttnBwdArgs {
-  const float* qkv;      // [B*T, 3d] fp32 (q already scaled)
-  const float* probs;    // [B*H, T, T] fp32
-  const __half* dO16;    // [P*B*T, ld_do] fp16 (hi part used)
+  const __half* qkv16;   // [B*T, 3d] (q already scaled)
+  const __half* probs16; // [B*H, T, ldp]
+  int ldp;
+  const float* o32;      // [B*T, d] forward attention output (pre out-proj)
+  const __half* dO16;    // [P*B*T, ld_do]
   int ld_do;
-  const float* delta;    // [P*B*H, T]
+  float* delta;          // [P*B*H, T] written by the row pass, read by the column pass
   const float* r;        // [P*B, T] current rollout row vector
   float* wpart;          // [P*B*H, T] out: per-head relevance contribution
   __half* dqkv16;        // [P*B*T, splits*3d] out
   int P, B, T, H, d, splits;
-  float scale;           // hd^-0.5 (chain rule through q *= scale)
+  float scale;
   int positive_only;
-  int need_dqkv;         // 0 for the lowest rollout block (only relevance is needed)
+  int need_dqkv;
 };
 
 __device__ __forceinline__ void store_h2_split(__half* base, size_t row_off, int col, int width, int splits, float x,
@@ -179,255 +183,261 @@ __device__ __forceinline__ void store_h2_split(__half* base, size_t row_off, int
   }
 }
 
-// ---- pass 1: row owner. CTA = 64 query rows (4 warps x 16), loops over key blocks; dQ = (A ⊙ (dA - delta)) K
-__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnBwdArgs a) {
-  __shared__ __align__(16) __half Vs[64 * TS];  // [key][d]
-  __shared__ __align__(16) __half Kt[64 * TS];  // [d][key]
-  const int p = blockIdx.x % a.P, iblk = blockIdx.x / a.P;
-  const int b = blockIdx.y / a.H, h = blockIdx.y % a.H;
-  const int pb = p * a.B + b;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int T = a.T, d = a.d;
-  const int i0 = iblk * 64 + warp * 16;
-  const int ia = i0 + g, ib = i0 + g + 8;
-
-  // dO fragments (A operand, 16 rows x 64)
-  uint32_t fo[4][4];
-  {
-    const __half* ra = a.dO16 + (size_t(pb) * T + ia) * a.ld_do + h * HD;
-    const __half* rb = a.dO16 + (size_t(pb) * T + ib) * a.ld_do + h * HD;
-#pragma unroll
-    for (int kt = 0; kt < 4; ++kt) {
-      fo[kt][0] = ia < T ? *reinterpret_cast<const uint32_t*>(ra + kt * 16 + 2 * t) : 0u;
-      fo[kt][1] = ib < T ? *reinterpret_cast<const uint32_t*>(rb + kt * 16 + 2 * t) : 0u;
-      fo[kt][2] = ia < T ? *reinterpret_cast<const uint32_t*>(ra + kt * 16 + 2 * t + 8) : 0u;
-      fo[kt][3] = ib < T ? *reinterpret_cast<const uint32_t*>(rb + kt * 16 + 2 * t + 8) : 0u;
-    }
-  }
-  const float* dl = a.delta + (size_t(pb) * a.H + h) * T;
-  const float da = ia < T ? dl[ia] : 0.f, db = ib < T ? dl[ib] : 0.f;
-  const float* Arow_a = a.probs + (size_t(blockIdx.y) * T + (ia < T ? ia : 0)) * T;
-  const float* Arow_b = a.probs + (size_t(blockIdx.y) * T + (ib < T ? ib : 0)) * T;
-
-  float dq[8][4];
-#pragma unroll
-  for (int n = 0; n < 8; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
-
-  const float* kvbase = a.qkv + size_t(b) * T * 3 * d + h * HD;
-  for (int j0 = 0; j0 < T; j0 += 64) {
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 64 * 32; idx += blockDim.x) {
-      const int j = idx >> 5, c = (idx & 31) * 2;
-      float2 kk = make_float2(0.f, 0.f), vv = make_float2(0.f, 0.f);
-      if (j0 + j < T) {
-        kk = *reinterpret_cast<const float2*>(kvbase + size_t(j0 + j) * 3 * d + d + c);
-        vv = *reinterpret_cast<const float2*>(kvbase + size_t(j0 + j) * 3 * d + 2 * d + c);
-      }
-      *reinterpret_cast<__half2*>(Vs + j * TS + c) = __floats2half2_rn(vv.x, vv.y);
-      Kt[c * TS + j] = __float2half_rn(kk.x);
-      Kt[(c + 1) * TS + j] = __float2half_rn(kk.y);
-    }
-    __syncthreads();
-
-    float gacc[8][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      gacc[n][0] = gacc[n][1] = gacc[n][2] = gacc[n][3] = 0.f;
-#pragma unroll
-      for (int kt = 0; kt < 4; ++kt) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(Vs + (n * 8 + g) * TS + kt * 16 + 2 * t);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(Vs + (n * 8 + g) * TS + kt * 16 + 2 * t + 8);
-        mma_16816(gacc[n], fo[kt], b0, b1);
-      }
-    }
-    // dS = A ⊙ (G - delta_i)
-    uint32_t fs[4][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const int j = j0 + n * 8 + 2 * t;
-      const float a00 = (ia < T && j < T) ? Arow_a[j] : 0.f;
-      const float a01 = (ia < T && j + 1 < T) ? Arow_a[j + 1] : 0.f;
-      const float a10 = (ib < T && j < T) ? Arow_b[j] : 0.f;
-      const float a11 = (ib < T && j + 1 < T) ? Arow_b[j + 1] : 0.f;
-      const float s00 = a00 * (gacc[n][0] - da), s01 = a01 * (gacc[n][1] - da);
-      const float s10 = a10 * (gacc[n][2] - db), s11 = a11 * (gacc[n][3] - db);
-      fs[n >> 1][(n & 1) * 2 + 0] = pack_h2(s00, s01);
-      fs[n >> 1][(n & 1) * 2 + 1] = pack_h2(s10, s11);
-    }
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-#pragma unroll
-      for (int kt = 0; kt < 4; ++kt) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(Kt + (n * 8 + g) * TS + kt * 16 + 2 * t);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(Kt + (n * 8 + g) * TS + kt * 16 + 2 * t + 8);
-        mma_16816(dq[n], fs[kt], b0, b1);
-      }
-    }
-  }
-  const size_t ld = size_t(a.splits) * 3 * d;
-#pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    const int col = h * HD + n * 8 + 2 * t;
-    if (ia < T) store_h2_split(a.dqkv16, (size_t(pb) * T + ia) * ld, col, 3 * d, a.splits, dq[n][0] * a.scale, dq[n][1] * a.scale);
-    if (ib < T) store_h2_split(a.dqkv16, (size_t(pb) * T + ib) * ld, col, 3 * d, a.splits, dq[n][2] * a.scale, dq[n][3] * a.scale);
+// rows [0,T) of a [T, 64] fp16 slice (row pitch `pitch` halfs) -> smem [TR][TS], rows >= T zeroed
+__device__ __forceinline__ void load_head_tile(__half* dst, const __half* src, size_t pitch, int T) {
+  for (int idx = threadIdx.x; idx < TR * 8; idx += blockDim.x) {
+    const int row = idx >> 3, c = (idx & 7) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row < T) v = *reinterpret_cast<const uint4*>(src + size_t(row) * pitch + c);
+    *reinterpret_cast<uint4*>(dst + row * TS + c) = v;
   }
 }
 
-// ---- pass 2: column owner. CTA = 64 key rows, loops over query blocks; relevance, dK = dSᵀ Q, dV = Aᵀ dO
-__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnBwdArgs a) {
-  __shared__ __align__(16) __half dOs[64 * TS];  // [query][d]
-  __shared__ __align__(16) __half dOt[64 * TS];  // [d][query]
-  __shared__ __align__(16) __half Qt[64 * TS];   // [d][query]
-  __shared__ __align__(16) float As[64 * AS];    // [query][key]
-  __shared__ float Dl[64], Rw[64];
-  const int p = blockIdx.x % a.P, jblk = blockIdx.x / a.P;
-  const int b = blockIdx.y / a.H, h = blockIdx.y % a.H;
+__global__ void __launch_bounds__(BWD_WARPS * 32, 2) attn_bwd_row_kernel(AttnBwdArgs a) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  __half* Ks = reinterpret_cast<__half*>(smraw);
+  __half* Vs = Ks + TR * TS;
+  const int p = blockIdx.x, bh = blockIdx.y;
+  const int b = bh / a.H, h = bh % a.H;
   const int pb = p * a.B + b;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int T = a.T, d = a.d;
-  const int jbase = jblk * 64;
-  const int ja = jbase + warp * 16 + g, jb = ja + 8;
-  const float* kvbase = a.qkv + size_t(b) * T * 3 * d + h * HD;
+  const __half* kv = a.qkv16 + size_t(b) * T * 3 * d + h * HD;
+  load_head_tile(Ks, kv + d, size_t(3) * d, T);
+  load_head_tile(Vs, kv + 2 * d, size_t(3) * d, T);
+  __syncthreads();
+  const int ntiles_total = (T + 7) / 8;  // key n-tiles that contain at least one valid key
 
-  // V_j fragments (A operand of Gᵀ = V dOᵀ)
-  uint32_t fv[4][4];
-  {
-    const float* ra = kvbase + size_t(ja < T ? ja : 0) * 3 * d + 2 * d;
-    const float* rb = kvbase + size_t(jb < T ? jb : 0) * 3 * d + 2 * d;
-#pragma unroll
-    for (int kt = 0; kt < 4; ++kt) {
-      const float2 x0 = *reinterpret_cast<const float2*>(ra + kt * 16 + 2 * t);
-      const float2 x1 = *reinterpret_cast<const float2*>(rb + kt * 16 + 2 * t);
-      const float2 x2 = *reinterpret_cast<const float2*>(ra + kt * 16 + 2 * t + 8);
-      const float2 x3 = *reinterpret_cast<const float2*>(rb + kt * 16 + 2 * t + 8);
-      fv[kt][0] = ja < T ? pack_h2(x0.x, x0.y) : 0u;
-      fv[kt][1] = jb < T ? pack_h2(x1.x, x1.y) : 0u;
-      fv[kt][2] = ja < T ? pack_h2(x2.x, x2.y) : 0u;
-      fv[kt][3] = jb < T ? pack_h2(x3.x, x3.y) : 0u;
-    }
-  }
-  float dk[8][4], dv[8][4];
-#pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
-    dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
-  }
-  float wa = 0.f, wb = 0.f;  // relevance partial sums for rows ja / jb
-
-  const float* dl = a.delta + (size_t(pb) * a.H + h) * T;
-  const float* rr = a.r + size_t(pb) * T;
-  const float* Abase = a.probs + size_t(blockIdx.y) * T * T;
-
-  for (int i0 = 0; i0 < T; i0 += 64) {
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 64 * 32; idx += blockDim.x) {
-      const int i = idx >> 5, c = (idx & 31) * 2;
-      __half2 go = __floats2half2_rn(0.f, 0.f);
-      float2 qq = make_float2(0.f, 0.f);
-      if (i0 + i < T) {
-        go = *reinterpret_cast<const __half2*>(a.dO16 + (size_t(pb) * T + i0 + i) * a.ld_do + h * HD + c);
-        qq = *reinterpret_cast<const float2*>(kvbase + size_t(i0 + i) * 3 * d + c);
-      }
-      *reinterpret_cast<__half2*>(dOs + i * TS + c) = go;
-      dOt[c * TS + i] = __low2half(go);
-      dOt[(c + 1) * TS + i] = __high2half(go);
-      Qt[c * TS + i] = __float2half_rn(qq.x);
-      Qt[(c + 1) * TS + i] = __float2half_rn(qq.y);
-    }
-    for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
-      const int i = idx >> 6, j = idx & 63;
-      As[i * AS + j] = (i0 + i < T && jbase + j < T) ? Abase[size_t(i0 + i) * T + jbase + j] : 0.f;
-    }
-    if (threadIdx.x < 64) {
-      const int i = i0 + threadIdx.x;
-      Dl[threadIdx.x] = i < T ? dl[i] : 0.f;
-      Rw[threadIdx.x] = i < T ? rr[i] : 0.f;
-    }
-    __syncthreads();
-
-    // Gᵀ tile [16 keys x 64 queries]
-    float gacc[8][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      gacc[n][0] = gacc[n][1] = gacc[n][2] = gacc[n][3] = 0.f;
+  for (int mt = warp; mt * 16 < T; mt += BWD_WARPS) {
+    const int ia = mt * 16 + g, ib = ia + 8;
+    const bool va = ia < T, vb = ib < T;
+    uint32_t fo[4][4];
+    float da = 0.f, db = 0.f;
+    {
+      const __half* ra = a.dO16 + (size_t(pb) * T + (va ? ia : 0)) * a.ld_do + h * HD;
+      const __half* rb = a.dO16 + (size_t(pb) * T + (vb ? ib : 0)) * a.ld_do + h * HD;
+      const float* oa = a.o32 + (size_t(b) * T + (va ? ia : 0)) * d + h * HD;
+      const float* ob = a.o32 + (size_t(b) * T + (vb ? ib : 0)) * d + h * HD;
 #pragma unroll
       for (int kt = 0; kt < 4; ++kt) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(dOs + (n * 8 + g) * TS + kt * 16 + 2 * t);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(dOs + (n * 8 + g) * TS + kt * 16 + 2 * t + 8);
-        mma_16816(gacc[n], fv[kt], b0, b1);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int col = kt * 16 + 2 * t + 8 * hf;
+          const uint32_t xa = va ? *reinterpret_cast<const uint32_t*>(ra + col) : 0u;
+          const uint32_t xb = vb ? *reinterpret_cast<const uint32_t*>(rb + col) : 0u;
+          fo[kt][2 * hf] = xa, fo[kt][2 * hf + 1] = xb;
+          const float2 fa = unpack_h2(xa), fb = unpack_h2(xb);
+          const float2 pa = *reinterpret_cast<const float2*>(oa + col), pb2 = *reinterpret_cast<const float2*>(ob + col);
+          da += fa.x * pa.x + fa.y * pa.y;
+          db += fb.x * pb2.x + fb.y * pb2.y;
+        }
+      }
+      da += __shfl_xor_sync(0xffffffffu, da, 1), da += __shfl_xor_sync(0xffffffffu, da, 2);
+      db += __shfl_xor_sync(0xffffffffu, db, 1), db += __shfl_xor_sync(0xffffffffu, db, 2);
+      if (t == 0) {
+        float* dl = a.delta + (size_t(pb) * a.H + h) * T;
+        if (va) dl[ia] = da;
+        if (vb) dl[ib] = db;
       }
     }
-    uint32_t fs[4][4], fa[4][4];
-    const int wj = warp * 16 + g;
+    if (!a.need_dqkv) continue;
+    const __half* Arow_a = a.probs16 + (size_t(bh) * T + (va ? ia : 0)) * a.ldp;
+    const __half* Arow_b = a.probs16 + (size_t(bh) * T + (vb ? ib : 0)) * a.ldp;
+    float dq[8][4];
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const int i = n * 8 + 2 * t;  // local query index of c0 / c2 ; +1 for c1 / c3
-      const float a00 = As[i * AS + wj], a01 = As[(i + 1) * AS + wj];
-      const float a10 = As[i * AS + wj + 8], a11 = As[(i + 1) * AS + wj + 8];
-      const float d0 = Dl[i], d1 = Dl[i + 1], r0 = Rw[i], r1 = Rw[i + 1];
-      float x00 = gacc[n][0] * a00, x01 = gacc[n][1] * a01, x10 = gacc[n][2] * a10, x11 = gacc[n][3] * a11;
-      if (a.positive_only) x00 = fmaxf(x00, 0.f), x01 = fmaxf(x01, 0.f), x10 = fmaxf(x10, 0.f), x11 = fmaxf(x11, 0.f);
-      wa += r0 * x00 + r1 * x01;
-      wb += r0 * x10 + r1 * x11;
-      fs[n >> 1][(n & 1) * 2 + 0] = pack_h2(a00 * (gacc[n][0] - d0), a01 * (gacc[n][1] - d1));
-      fs[n >> 1][(n & 1) * 2 + 1] = pack_h2(a10 * (gacc[n][2] - d0), a11 * (gacc[n][3] - d1));
-      fa[n >> 1][(n & 1) * 2 + 0] = pack_h2(a00, a01);
-      fa[n >> 1][(n & 1) * 2 + 1] = pack_h2(a10, a11);
-    }
-    if (a.need_dqkv) {
+    for (int n = 0; n < 8; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
+
+    for (int jc = 0; jc * 8 < ntiles_total; ++jc) {
+      const int nt = min(8, ntiles_total - jc * 8);
+      uint32_t fs[4][4];
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
+        float gacc[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 aa = make_float2(0.f, 0.f), ab = make_float2(0.f, 0.f);
+        if (n < nt) {
+          const int key = jc * 64 + n * 8;
 #pragma unroll
-        for (int kt = 0; kt < 4; ++kt) {
-          const uint32_t q0 = *reinterpret_cast<const uint32_t*>(Qt + (n * 8 + g) * TS + kt * 16 + 2 * t);
-          const uint32_t q1 = *reinterpret_cast<const uint32_t*>(Qt + (n * 8 + g) * TS + kt * 16 + 2 * t + 8);
-          mma_16816(dk[n], fs[kt], q0, q1);
-          const uint32_t o0 = *reinterpret_cast<const uint32_t*>(dOt + (n * 8 + g) * TS + kt * 16 + 2 * t);
-          const uint32_t o1 = *reinterpret_cast<const uint32_t*>(dOt + (n * 8 + g) * TS + kt * 16 + 2 * t + 8);
-          mma_16816(dv[n], fa[kt], o0, o1);
+          for (int kt = 0; kt < 4; ++kt) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(Vs + (key + g) * TS + kt * 16 + 2 * t);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(Vs + (key + g) * TS + kt * 16 + 2 * t + 8);
+            mma_16816(gacc, fo[kt], b0, b1);
+          }
+          if (va) aa = unpack_h2(*reinterpret_cast<const uint32_t*>(Arow_a + key + 2 * t));
+          if (vb) ab = unpack_h2(*reinterpret_cast<const uint32_t*>(Arow_b + key + 2 * t));
+        }
+        fs[n >> 1][(n & 1) * 2 + 0] = pack_h2(aa.x * (gacc[0] - da), aa.y * (gacc[1] - da));
+        fs[n >> 1][(n & 1) * 2 + 1] = pack_h2(ab.x * (gacc[2] - db), ab.y * (gacc[3] - db));
+      }
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        if (2 * kt < nt) {
+          const int krow = jc * 64 + kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+          for (int nd2 = 0; nd2 < 4; ++nd2) {
+            uint32_t bb[4];
+            ldmatrix_x4_trans(bb, Ks + krow * TS + nd2 * 16 + (lane >> 4) * 8);
+            mma_16816(dq[2 * nd2], fs[kt], bb[0], bb[1]);
+            mma_16816(dq[2 * nd2 + 1], fs[kt], bb[2], bb[3]);
+          }
         }
       }
     }
-  }
-  // relevance: reduce over the 4 lanes of a quad (they hold different query columns of the same key row)
-  wa += __shfl_xor_sync(0xffffffffu, wa, 1);
-  wa += __shfl_xor_sync(0xffffffffu, wa, 2);
-  wb += __shfl_xor_sync(0xffffffffu, wb, 1);
-  wb += __shfl_xor_sync(0xffffffffu, wb, 2);
-  if (t == 0) {
-    float* wp = a.wpart + (size_t(pb) * a.H + h) * T;
-    const float invH = 1.0f / a.H;
-    if (ja < T) wp[ja] = wa * invH;
-    if (jb < T) wp[jb] = wb * invH;
-  }
-  if (a.need_dqkv) {
     const size_t ld = size_t(a.splits) * 3 * d;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       const int col = h * HD + n * 8 + 2 * t;
-      if (ja < T) {
-        store_h2_split(a.dqkv16, (size_t(pb) * T + ja) * ld, d + col, 3 * d, a.splits, dk[n][0], dk[n][1]);
-        store_h2_split(a.dqkv16, (size_t(pb) * T + ja) * ld, 2 * d + col, 3 * d, a.splits, dv[n][0], dv[n][1]);
+      if (va) store_h2_split(a.dqkv16, (size_t(pb) * T + ia) * ld, col, 3 * d, a.splits, dq[n][0] * a.scale, dq[n][1] * a.scale);
+      if (vb) store_h2_split(a.dqkv16, (size_t(pb) * T + ib) * ld, col, 3 * d, a.splits, dq[n][2] * a.scale, dq[n][3] * a.scale);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BWD_WARPS * 32, 2) attn_bwd_col_kernel(AttnBwdArgs a) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  __half* Qs = reinterpret_cast<__half*>(smraw);
+  __half* dOs = Qs + TR * TS;
+  float* Dl = reinterpret_cast<float*>(dOs + TR * TS);
+  float* Rw = Dl + TR;
+  __half* strips = reinterpret_cast<__half*>(Rw + TR);
+  const int p = blockIdx.x, bh = blockIdx.y;
+  const int b = bh / a.H, h = bh % a.H;
+  const int pb = p * a.B + b;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int T = a.T, d = a.d;
+  const __half* qv = a.qkv16 + size_t(b) * T * 3 * d + h * HD;
+  load_head_tile(Qs, qv, size_t(3) * d, T);
+  load_head_tile(dOs, a.dO16 + size_t(pb) * T * a.ld_do + h * HD, size_t(a.ld_do), T);
+  for (int i = threadIdx.x; i < TR; i += blockDim.x) {
+    Dl[i] = (i < T && a.need_dqkv) ? a.delta[(size_t(pb) * a.H + h) * T + i] : 0.f;
+    Rw[i] = i < T ? a.r[size_t(pb) * T + i] : 0.f;
+  }
+  __syncthreads();
+  __half* strip = strips + warp * 64 * STRIP;
+  const int ntiles_total = (T + 7) / 8;
+  const __half* Abase = a.probs16 + size_t(bh) * T * a.ldp;
+
+  for (int mt = warp; mt * 16 < T; mt += BWD_WARPS) {
+    const int j0 = mt * 16, ja = j0 + g, jb = ja + 8;
+    const bool va = ja < T, vb = jb < T;
+    uint32_t fv[4][4];
+    {
+      const __half* ra = qv + size_t(va ? ja : 0) * 3 * d + 2 * d;
+      const __half* rb = qv + size_t(vb ? jb : 0) * 3 * d + 2 * d;
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        fv[kt][0] = va ? *reinterpret_cast<const uint32_t*>(ra + kt * 16 + 2 * t) : 0u;
+        fv[kt][1] = vb ? *reinterpret_cast<const uint32_t*>(rb + kt * 16 + 2 * t) : 0u;
+        fv[kt][2] = va ? *reinterpret_cast<const uint32_t*>(ra + kt * 16 + 2 * t + 8) : 0u;
+        fv[kt][3] = vb ? *reinterpret_cast<const uint32_t*>(rb + kt * 16 + 2 * t + 8) : 0u;
       }
-      if (jb < T) {
-        store_h2_split(a.dqkv16, (size_t(pb) * T + jb) * ld, d + col, 3 * d, a.splits, dk[n][2], dk[n][3]);
-        store_h2_split(a.dqkv16, (size_t(pb) * T + jb) * ld, 2 * d + col, 3 * d, a.splits, dv[n][2], dv[n][3]);
+    }
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
+      dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+    }
+    float wa = 0.f, wb = 0.f;
+
+    for (int ic = 0; ic * 8 < ntiles_total; ++ic) {
+      const int nt = min(8, ntiles_total - ic * 8);
+      const int ibase = ic * 64;
+      // stage the [64 queries][16 keys] strip of A
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = lane + 32 * k, row = c >> 1, hf = c & 1;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (ibase + row < T) v = *reinterpret_cast<const uint4*>(Abase + size_t(ibase + row) * a.ldp + j0 + hf * 8);
+        *reinterpret_cast<uint4*>(strip + row * STRIP + hf * 8) = v;
+      }
+      __syncwarp();
+      uint32_t fs[4][4], fa[4][4];
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        // A^T fragments (rows = keys, k = queries) through a transposed ldmatrix of the [query][key] strip
+        ldmatrix_x4_trans(fa[kt], strip + (kt * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * STRIP + ((lane >> 3) & 1) * 8);
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        float gacc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (n < nt) {
+#pragma unroll
+          for (int kt = 0; kt < 4; ++kt) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(dOs + (ibase + n * 8 + g) * TS + kt * 16 + 2 * t);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(dOs + (ibase + n * 8 + g) * TS + kt * 16 + 2 * t + 8);
+            mma_16816(gacc, fv[kt], b0, b1);
+          }
+        }
+        // C layout of this n-tile: c0,c1 = (key ja; queries i, i+1), c2,c3 = (key jb; queries i, i+1)
+        const int i = ibase + n * 8 + 2 * t;
+        const float2 aa = unpack_h2(fa[n >> 1][(n & 1) * 2 + 0]);  // A[i, ja], A[i+1, ja]
+        const float2 ab = unpack_h2(fa[n >> 1][(n & 1) * 2 + 1]);  // A[i, jb], A[i+1, jb]
+        const float d0 = Dl[i], d1 = Dl[i + 1], r0 = Rw[i], r1 = Rw[i + 1];
+        float x00 = gacc[0] * aa.x, x01 = gacc[1] * aa.y, x10 = gacc[2] * ab.x, x11 = gacc[3] * ab.y;
+        if (a.positive_only) x00 = fmaxf(x00, 0.f), x01 = fmaxf(x01, 0.f), x10 = fmaxf(x10, 0.f), x11 = fmaxf(x11, 0.f);
+        wa += r0 * x00 + r1 * x01;
+        wb += r0 * x10 + r1 * x11;
+        fs[n >> 1][(n & 1) * 2 + 0] = pack_h2(aa.x * (gacc[0] - d0), aa.y * (gacc[1] - d1));
+        fs[n >> 1][(n & 1) * 2 + 1] = pack_h2(ab.x * (gacc[2] - d0), ab.y * (gacc[3] - d1));
+      }
+      if (a.need_dqkv) {
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+          if (2 * kt < nt) {
+            const int krow = ibase + kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+            for (int nd2 = 0; nd2 < 4; ++nd2) {
+              uint32_t bq[4], bo[4];
+              ldmatrix_x4_trans(bq, Qs + krow * TS + nd2 * 16 + (lane >> 4) * 8);
+              ldmatrix_x4_trans(bo, dOs + krow * TS + nd2 * 16 + (lane >> 4) * 8);
+              mma_16816(dk[2 * nd2], fs[kt], bq[0], bq[1]);
+              mma_16816(dk[2 * nd2 + 1], fs[kt], bq[2], bq[3]);
+              mma_16816(dv[2 * nd2], fa[kt], bo[0], bo[1]);
+              mma_16816(dv[2 * nd2 + 1], fa[kt], bo[2], bo[3]);
+            }
+          }
+        }
+      }
+    }
+    wa += __shfl_xor_sync(0xffffffffu, wa, 1), wa += __shfl_xor_sync(0xffffffffu, wa, 2);
+    wb += __shfl_xor_sync(0xffffffffu, wb, 1), wb += __shfl_xor_sync(0xffffffffu, wb, 2);
+    if (t == 0) {
+      float* wp = a.wpart + (size_t(pb) * a.H + h) * T;
+      const float invH = 1.0f / a.H;
+      if (va) wp[ja] = wa * invH;
+      if (vb) wp[jb] = wb * invH;
+    }
+    if (a.need_dqkv) {
+      const size_t ld = size_t(a.splits) * 3 * d;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int col = h * HD + n * 8 + 2 * t;
+        if (va) {
+          store_h2_split(a.dqkv16, (size_t(pb) * T + ja) * ld, d + col, 3 * d, a.splits, dk[n][0], dk[n][1]);
+          store_h2_split(a.dqkv16, (size_t(pb) * T + ja) * ld, 2 * d + col, 3 * d, a.splits, dv[n][0], dv[n][1]);
+        }
+        if (vb) {
+          store_h2_split(a.dqkv16, (size_t(pb) * T + jb) * ld, d + col, 3 * d, a.splits, dk[n][2], dk[n][3]);
+          store_h2_split(a.dqkv16, (size_t(pb) * T + jb) * ld, 2 * d + col, 3 * d, a.splits, dv[n][2], dv[n][3]);
+        }
       }
     }
   }
 }
 
 template <int NCHUNK>
-static int launch_attn_fwd(const float* qkv, float* probs, float* o32, __half* o16, int B, int T, int H, int d,
-                           int causal, int splits, cudaStream_t st) {
+static int launch_attn_fwd(const float* qkv, float* probs, __half* probs16, int ld_p16, float* o32, __half* o16, int B,
+                           int T, int H, int d, int causal, int splits, cudaStream_t st) {
   const size_t smem = (size_t(2) * T * KV_STRIDE + size_t(8) * NCHUNK * 32) * sizeof(float);
   SB_REQUIRE(smem <= 227 * 1024, "attention forward: T=%d does not fit in shared memory", T);
+  SB_REQUIRE(!probs16 || ld_p16 <= NCHUNK * 32, "attention forward: probs16 pitch %d too wide", ld_p16);
   static bool configured = false;
   if (!configured) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NCHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  attn_fwd_kernel<NCHUNK><<<B * H, 256, smem, st>>>(qkv, probs, o32, o16, T, H, d, causal, splits);
+  attn_fwd_kernel<NCHUNK><<<B * H, 256, smem, st>>>(qkv, probs, probs16, ld_p16, o32, o16, T, H, d, causal, splits);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -436,46 +446,51 @@ static int launch_attn_fwd(const float* qkv, float* probs, float* o32, __half* o
 
 using namespace sb;
 
-extern "C" int semabs_attn_fwd(const float* qkv, float* probs, float* o32, void* o16, int32_t B, int32_t T, int32_t H,
-                               int32_t causal, int32_t splits, void* stream) {
+extern "C" int semabs_attn_fwd(const float* qkv, float* probs, void* probs16, int32_t ld_p16, float* o32, void* o16,
+                               int32_t B, int32_t T, int32_t H, int32_t causal, int32_t splits, void* stream) {
   SB_REQUIRE(qkv && (o32 || o16) && B > 0 && T > 0 && H > 0, "semabs_attn_fwd: bad arguments");
+  SB_REQUIRE(!probs16 || (ld_p16 >= T && ld_p16 % 8 == 0), "semabs_attn_fwd: bad probs16 pitch %d", ld_p16);
   const int d = H * HD;
   cudaStream_t st = (cudaStream_t)stream;
+  __half* p16 = (__half*)probs16;
   const int nchunk = (T + 31) / 32;
-  if (nchunk <= 2) return launch_attn_fwd<2>(qkv, probs, o32, (__half*)o16, B, T, H, d, causal, splits, st);
-  if (nchunk <= 3) return launch_attn_fwd<3>(qkv, probs, o32, (__half*)o16, B, T, H, d, causal, splits, st);
-  if (nchunk <= 9) return launch_attn_fwd<9>(qkv, probs, o32, (__half*)o16, B, T, H, d, causal, splits, st);
+  if (nchunk <= 2) return launch_attn_fwd<2>(qkv, probs, p16, ld_p16, o32, (__half*)o16, B, T, H, d, causal, splits, st);
+  if (nchunk <= 3) return launch_attn_fwd<3>(qkv, probs, p16, ld_p16, o32, (__half*)o16, B, T, H, d, causal, splits, st);
+  if (nchunk <= 9) return launch_attn_fwd<9>(qkv, probs, p16, ld_p16, o32, (__half*)o16, B, T, H, d, causal, splits, st);
   SB_REQUIRE(nchunk <= 13, "semabs_attn_fwd: T=%d > 416 tokens is not supported", T);
-  return launch_attn_fwd<13>(qkv, probs, o32, (__half*)o16, B, T, H, d, causal, splits, st);
+  return launch_attn_fwd<13>(qkv, probs, p16, ld_p16, o32, (__half*)o16, B, T, H, d, causal, splits, st);
 }
 
-extern "C" int semabs_attn_bwd(const float* qkv, const float* probs, const float* o32, const void* dO16, int32_t ld_do,
-                               const float* r, float* delta_ws, float* wpart, void* dqkv16, int32_t P, int32_t B,
-                               int32_t T, int32_t H, int32_t splits, int32_t positive_only, int32_t need_dqkv,
-                               void* stream) {
-  SB_REQUIRE(qkv && probs && o32 && dO16 && r && delta_ws && wpart, "semabs_attn_bwd: null pointer");
+extern "C" int semabs_attn_bwd(const void* qkv16, const void* probs16, int32_t ld_p16, const float* o32,
+                               const void* dO16, int32_t ld_do, const float* r, float* delta_ws, float* wpart,
+                               void* dqkv16, int32_t P, int32_t B, int32_t T, int32_t H, int32_t splits,
+                               int32_t positive_only, int32_t need_dqkv, void* stream) {
+  SB_REQUIRE(qkv16 && probs16 && o32 && dO16 && r && delta_ws && wpart, "semabs_attn_bwd: null pointer");
   SB_REQUIRE(!need_dqkv || dqkv16, "semabs_attn_bwd: dqkv16 missing");
   SB_REQUIRE(P > 0 && B > 0 && T > 0 && H > 0 && B * H <= 65535, "semabs_attn_bwd: bad shape");
+  SB_REQUIRE(T <= TR, "semabs_attn_bwd: T=%d > %d tokens is not supported", T, TR);
+  SB_REQUIRE(ld_p16 % 8 == 0 && ld_p16 >= ((T + 15) / 16) * 16, "semabs_attn_bwd: probs16 pitch %d must be a multiple of 8 and >= %d",
+             ld_p16, ((T + 15) / 16) * 16);
   cudaStream_t st = (cudaStream_t)stream;
-  const int d = H * HD;
-  const int PB = P * B;
-  {
-    const long long warps = (long long)PB * T * H;
-    attn_bwd_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>((const __half*)dO16, ld_do, o32, delta_ws, PB, B,
-                                                                       T, H, d);
-    SB_CHECK_CUDA(cudaGetLastError());
-  }
   AttnBwdArgs a{};
-  a.qkv = qkv, a.probs = probs, a.dO16 = (const __half*)dO16, a.ld_do = ld_do, a.delta = delta_ws, a.r = r;
-  a.wpart = wpart, a.dqkv16 = (__half*)dqkv16, a.P = P, a.B = B, a.T = T, a.H = H, a.d = d, a.splits = splits;
+  a.qkv16 = (const __half*)qkv16, a.probs16 = (const __half*)probs16, a.ldp = ld_p16, a.o32 = o32;
+  a.dO16 = (const __half*)dO16, a.ld_do = ld_do, a.delta = delta_ws, a.r = r, a.wpart = wpart;
+  a.dqkv16 = (__half*)dqkv16, a.P = P, a.B = B, a.T = T, a.H = H, a.d = H * HD, a.splits = splits;
   a.scale = 0.125f, a.positive_only = positive_only, a.need_dqkv = need_dqkv;
-  const int nblk = (T + 63) / 64;
-  dim3 grid(P * nblk, B * H);
+  const size_t smem_row = size_t(2) * TR * TS * sizeof(__half);
+  const size_t smem_col = smem_row + size_t(2) * TR * sizeof(float) + size_t(BWD_WARPS) * 64 * STRIP * sizeof(__half);
+  static bool configured = false;
+  if (!configured) {
+    SB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
+    configured = true;
+  }
+  dim3 grid(P, B * H);
   if (need_dqkv) {
-    attn_bwd_dq_kernel<<<grid, 128, 0, st>>>(a);
+    attn_bwd_row_kernel<<<grid, BWD_WARPS * 32, smem_row, st>>>(a);
     SB_CHECK_CUDA(cudaGetLastError());
   }
-  attn_bwd_dkv_kernel<<<grid, 128, 0, st>>>(a);
+  attn_bwd_col_kernel<<<grid, BWD_WARPS * 32, smem_col, st>>>(a);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

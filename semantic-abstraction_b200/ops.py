@@ -135,16 +135,20 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx32, *, M, d, x_rows, x_stride=None
     )
 
 
-def attn_fwd(qkv, *, B, T, H, probs=None, o32=None, o16=None, causal=False, splits=1):
-    check(lib().semabs_attn_fwd(ptr(qkv), ptr(probs), ptr(o32), ptr(o16), i32(B), i32(T), i32(H), i32(int(causal)), i32(splits), stream_ptr()))
+def attn_fwd(qkv, *, B, T, H, probs=None, probs16=None, o32=None, o16=None, causal=False, splits=1):
+    ldp = probs16.shape[-1] if probs16 is not None else 0
+    check(lib().semabs_attn_fwd(ptr(qkv), ptr(probs), ptr(probs16), i32(ldp), ptr(o32), ptr(o16), i32(B), i32(T), i32(H),
+                                i32(int(causal)), i32(splits), stream_ptr()))
 
 
-def attn_bwd(qkv, probs, o32, dO16, ld_do, r, delta_ws, wpart, dqkv16, *, P, B, T, H, splits=1, positive_only=True,
+def attn_bwd(qkv16, probs16, o32, dO16, ld_do, r, delta_ws, wpart, dqkv16, *, P, B, T, H, splits=1, positive_only=True,
              need_dqkv=True):
+    assert qkv16.dtype == torch.float16 and probs16.dtype == torch.float16
     check(
         lib().semabs_attn_bwd(
-            ptr(qkv), ptr(probs), ptr(o32), ptr(dO16), i32(ld_do), ptr(r), ptr(delta_ws), ptr(wpart), ptr(dqkv16),
-            i32(P), i32(B), i32(T), i32(H), i32(splits), i32(int(positive_only)), i32(int(need_dqkv)), stream_ptr(),
+            ptr(qkv16), ptr(probs16), i32(probs16.shape[-1]), ptr(o32), ptr(dO16), i32(ld_do), ptr(r), ptr(delta_ws),
+            ptr(wpart), ptr(dqkv16), i32(P), i32(B), i32(T), i32(H), i32(splits), i32(int(positive_only)),
+            i32(int(need_dqkv)), stream_ptr(),
         )
     )
 

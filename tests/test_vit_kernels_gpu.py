@@ -72,14 +72,18 @@ def test_attn_bwd(T, H):
     qkv = torch.randn(B * T, 3 * d, device=dev, generator=g)
     qkv[:, :d] *= 0.125 * 1.5
     probs = torch.empty(B * H, T, T, device=dev)
+    Tp = (T + 15) // 16 * 16
+    probs16 = torch.full((B * H, T, Tp), float("nan"), device=dev, dtype=torch.float16)
     o32 = torch.empty(B * T, d, device=dev)
-    ops.attn_fwd(qkv, B=B, T=T, H=H, probs=probs, o32=o32)
+    ops.attn_fwd(qkv, B=B, T=T, H=H, probs=probs, probs16=probs16, o32=o32)
+    assert torch.equal(probs16[..., :T], probs.half()) and (probs16[..., T:] == 0).all()
+    qkv16 = qkv.half()
     dO = torch.randn(P * B * T, d, device=dev, generator=g).half()
     r = torch.rand(P * B, T, device=dev, generator=g)
     delta = torch.empty(P * B * H, T, device=dev)
     wpart = torch.full((P * B * H, T), float("nan"), device=dev)
     dqkv16 = torch.full((P * B * T, 2 * 3 * d), float("nan"), device=dev, dtype=torch.float16)
-    ops.attn_bwd(qkv, probs, o32, dO, d, r, delta, wpart, dqkv16, P=P, B=B, T=T, H=H, splits=2, positive_only=True)
+    ops.attn_bwd(qkv16, probs16, o32, dO, d, r, delta, wpart, dqkv16, P=P, B=B, T=T, H=H, splits=2, positive_only=True)
     torch.cuda.synchronize()
 
     # torch reference (fp32, same fp16-rounded dO)
