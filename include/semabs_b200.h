@@ -44,16 +44,19 @@ int semabs_device_sync(void);
  * ---------------------------------------------------------------------------------------------------------- */
 enum {
   SEMABS_ACT_NONE = 0,
-  SEMABS_ACT_QUICKGELU = 1,      /* out_f32 = pre-activation v, out_f16 = v * sigmoid(1.702 v)           */
-  SEMABS_ACT_QUICKGELU_GRAD = 2  /* v *= d/du quickgelu(u), u = aux[(row % aux_rows), col]                */
+  SEMABS_ACT_QUICKGELU = 1,      /* out_f32 = pre-activation v, out_f16 = v * sigmoid(1.702 v),          */
+                                 /* out_aux16 = d/dv quickgelu(v) (fp16, kept for the backward sweep)    */
+  SEMABS_ACT_MUL_AUX16 = 2       /* v *= aux16[(row % aux_rows), col]  (dgrad through QuickGELU)         */
 };
 
 typedef struct semabs_gemm_epilogue {
   const float* bias;      /* [N] or NULL                                                                  */
   const float* residual;  /* [M, ld_out] fp32 added after bias/activation, or NULL                        */
-  const float* aux;       /* [aux_rows, ld_aux] fp32, used by SEMABS_ACT_QUICKGELU_GRAD                   */
+  const void* aux16;      /* [aux_rows, ld_aux] fp16, used by SEMABS_ACT_MUL_AUX16                        */
   int32_t aux_rows;
   int32_t ld_aux;
+  void* out_aux16;        /* [M, ld_out_aux] fp16 or NULL, written by SEMABS_ACT_QUICKGELU                 */
+  int32_t ld_out_aux;
   float* out_f32;         /* [M, ld_out] or NULL                                                          */
   int32_t ld_out;
   void* out_f16;          /* [M, ld_out16] fp16 or NULL; with out_f16_splits == 2 the lo part goes to      */
@@ -176,10 +179,21 @@ int semabs_ncdhw_to_ndhwc(const float* x, float* y, int32_t N, int64_t S, int32_
 int semabs_ndhwc_to_ncdhw(const float* x, float* y, int32_t N, int64_t S, int32_t C, void* stream);
 
 /* nn.GroupNorm apply (unet3d.py:78-83; biased variance, eps 1e-5, affine): x raw fp32 [N,S,C] + stats ->
- * y16 [N,S,splits*C]. gamma/beta are [C] (zero for padded channels >= C_real). */
+ * y16 [N,S,splits*C] (planar == 0) or the chunk-planar layout [N][splits*C/8][S][8] consumed by
+ * semabs_conv3d_halo (planar != 0). gamma/beta are [C] (zero for padded channels >= C_real). */
 int semabs_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* y16,
                            int32_t N, int64_t S, int32_t C, int32_t C_real, int32_t groups, int32_t splits,
-                           void* stream);
+                           int32_t planar, void* stream);
+
+/* Halo-resident 3x3x3 conv (padding 1, no bias) for the full-resolution level: W == 128, C_in, C_out in {16, 32}.
+ * x16_planar: [N][a_splits*C_in/8][D][H][W][8] fp16 (see semabs_groupnorm_apply). w_img: per tap t = (kd*3+kh)*3+kw
+ * and weight split s the UMMA no-swizzle core-matrix image [C_in/16][C_out/8][2][8][8]
+ * (= W[co = g*8 + r][ci = kb*16 + kc*8 + e][tap]), taps outermost. Same epilogue options as semabs_conv3d.
+ * Every activation row is loaded from L2 once per y-neighbour (3x) instead of once per tap and pass (81x). */
+int semabs_conv3d_halo(const void* x16_planar, int32_t a_splits, const void* w_img, int32_t w_splits, int32_t N,
+                       int32_t D, int32_t H, int32_t W, int32_t C_in, int32_t C_out, int32_t precise,
+                       const float* residual, int32_t relu, float* out32, void* out16, int32_t o16_splits,
+                       double* stats, int32_t groups, void* stream);
 
 /* nn.MaxPool3d(2) (Encoder.forward, unet3d.py:298,313-317) + statistics of the pooled tensor. */
 int semabs_maxpool3d_2(const float* x, float* y, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C,

@@ -25,9 +25,11 @@ class GemmEpilogue(C.Structure):
     _fields_ = [
         ("bias", C.c_void_p),
         ("residual", C.c_void_p),
-        ("aux", C.c_void_p),
+        ("aux16", C.c_void_p),
         ("aux_rows", C.c_int32),
         ("ld_aux", C.c_int32),
+        ("out_aux16", C.c_void_p),
+        ("ld_out_aux", C.c_int32),
         ("out_f32", C.c_void_p),
         ("ld_out", C.c_int32),
         ("out_f16", C.c_void_p),
@@ -39,7 +41,7 @@ class GemmEpilogue(C.Structure):
     ]
 
 
-ACT_NONE, ACT_QUICKGELU, ACT_QUICKGELU_GRAD = 0, 1, 2
+ACT_NONE, ACT_QUICKGELU, ACT_MUL_AUX16 = 0, 1, 2
 
 
 def lib() -> C.CDLL:

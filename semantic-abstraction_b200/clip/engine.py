@@ -57,12 +57,12 @@ class ClipEngine:
         M = n_seq * T
         ws = self.ws
         h16 = ws.get("h16", (M, s * d), F16)
-        mean1 = rstd1 = mean2 = rstd2 = probs16 = qkv16 = o32 = u = None
+        mean1 = rstd1 = mean2 = rstd2 = probs16 = qkv16 = o32 = gg16 = None
         qkv = ws.get("qkv", (M, 3 * d))
         if saved is not None:
             mean1, rstd1 = saved["mean1"], saved["rstd1"]
             mean2, rstd2 = saved["mean2"], saved["rstd2"]
-            probs16, qkv16, o32, u = saved["probs16"], saved["qkv16"], saved["o32"], saved["u"]
+            probs16, qkv16, o32, gg16 = saved["probs16"], saved["qkv16"], saved["o32"], saved["gelu_grad16"]
             x_mid = saved["x_mid"]
         else:
             x_mid = ws.get("x_mid", (M, d))
@@ -74,8 +74,9 @@ class ClipEngine:
         ops.gemm_f16(o16, blk.w_out, a_splits=s, bias=blk.b_out, residual=x, out_f32=x_mid)
         ops.layernorm_fwd(x_mid, blk.ln2_g, blk.ln2_b, M=M, d=d, y16=h16, mean=mean2, rstd=rstd2, splits=s)
         g16 = ws.get("g16", (M, s * 4 * d), F16)
-        ops.gemm_f16(h16, blk.w_fc, a_splits=s, bias=blk.b_fc, act=ops.ACT_QUICKGELU, out_f32=u, out_f16=g16,
-                     out_f16_splits=s)
+        # the backward sweep needs d quickgelu / du only: keep it as fp16 instead of the fp32 pre-activation
+        ops.gemm_f16(h16, blk.w_fc, a_splits=s, bias=blk.b_fc, act=ops.ACT_QUICKGELU, out_f16=g16, out_f16_splits=s,
+                     out_aux16=gg16)
         ops.gemm_f16(g16, blk.w_proj, a_splits=s, bias=blk.b_proj, residual=x_mid, out_f32=x_next)
         self.kernel_launches += 7
 
@@ -123,7 +124,7 @@ class ClipEngine:
             "qkv16": ws.get(f"s{i}_qkv16", (M, 3 * d), F16),
             "probs16": ws.get(f"s{i}_probs16", (B * H, T, (T + 15) // 16 * 16), F16),
             "o32": ws.get(f"s{i}_o32", (M, d)), "x_mid": ws.get(f"s{i}_xmid", (M, d)),
-            "u": ws.get(f"s{i}_u", (M, 4 * d)),
+            "gelu_grad16": ws.get(f"s{i}_gg16", (M, 4 * d), F16),
         }  # fmt: skip
 
     def encode_image(self, tiles: torch.Tensor, keep_for_backward: bool = False):
@@ -212,7 +213,7 @@ class ClipEngine:
         for i in range(L - 1, self.start_block - 1, -1):
             blk, sv = vt.blocks[i], st["saved"][i]
             # x_out = x_mid + c_proj(quickgelu(c_fc(ln_2(x_mid))))
-            ops.gemm_f16(dx16, blk.w_projT, a_splits=sb, aux=sv["u"], act=ops.ACT_QUICKGELU_GRAD, out_f16=du16,
+            ops.gemm_f16(dx16, blk.w_projT, a_splits=sb, aux16=sv["gelu_grad16"], act=ops.ACT_MUL_AUX16, out_f16=du16,
                          out_f16_splits=sb)
             ops.gemm_f16(du16, blk.w_fcT, a_splits=sb, out_f32=dh)
             ops.layernorm_bwd(dh, sv["x_mid"], sv["mean2"], sv["rstd2"], blk.ln2_g, dxm, M=Mb, d=d, x_rows=B * T,

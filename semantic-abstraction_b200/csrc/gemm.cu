@@ -23,15 +23,20 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int BAR_BYTES = 256;
+  // NOTE: the epilogue deliberately does NOT stage through shared memory: with SS-mode 128x128x16 MMAs the tensor
+  // core already consumes the full 128 B/clk of shared-memory bandwidth, and an smem-transposed epilogue (tried in
+  // round 1: -40 % on K=1024 shapes) steals it. Each thread owns one accumulator row and moves whole 32 B sectors.
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KiB alignment
 };
 
 struct EpiParams {
   const float* bias;
   const float* residual;
-  const float* aux;
+  const __half* aux16;
   int aux_rows;
   int ld_aux;
+  __half* out_aux16;
+  int ld_out_aux;
   float* out_f32;
   int ld_out;
   __half* out_f16;
@@ -152,8 +157,8 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       const int row = m_blk * GEMM_BM + q * 32 + lane;
       const bool row_ok = row < M;
-      const float* aux_row = nullptr;
-      if (ep.act == SEMABS_ACT_QUICKGELU_GRAD && row_ok) aux_row = ep.aux + size_t(row % ep.aux_rows) * ep.ld_aux;
+      const __half* aux_row = nullptr;
+      if (ep.act == SEMABS_ACT_MUL_AUX16 && row_ok) aux_row = ep.aux16 + size_t(row % ep.aux_rows) * ep.ld_aux;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -176,12 +181,16 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int j = 0; j < 32; ++j)
               if (col0 + j < ep.scale_cols) v[j] *= ep.scale;
           }
-          if (ep.act == SEMABS_ACT_QUICKGELU_GRAD) {
+          if (ep.act == SEMABS_ACT_MUL_AUX16) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 u = *reinterpret_cast<const float4*>(aux_row + col0 + j);
-              v[j] *= quick_gelu_grad(u.x), v[j + 1] *= quick_gelu_grad(u.y);
-              v[j + 2] *= quick_gelu_grad(u.z), v[j + 3] *= quick_gelu_grad(u.w);
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(aux_row + col0 + j);
+              const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(hp[k]);
+                v[j + 2 * k] *= f.x, v[j + 2 * k + 1] *= f.y;
+              }
             }
           }
           if (ep.residual) {
@@ -199,12 +208,22 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
           if (ep.out_f16) {
+            __align__(16) __half2 h[16];
             if (ep.act == SEMABS_ACT_QUICKGELU) {
+              // one sigmoid gives both the activation and (for the backward sweep) its derivative
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+              for (int j = 0; j < 32; j += 2) {
+                const float s0 = sigmoidf_precise(1.702f * v[j]), s1 = sigmoidf_precise(1.702f * v[j + 1]);
+                h[j >> 1] = __floats2half2_rn(s0 + 1.702f * v[j] * s0 * (1.0f - s0), s1 + 1.702f * v[j + 1] * s1 * (1.0f - s1));
+                v[j] *= s0, v[j + 1] *= s1;
+              }
+              if (ep.out_aux16) {
+                __half* ga = ep.out_aux16 + size_t(row) * ep.ld_out_aux + col0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(ga)[j] = reinterpret_cast<const uint4*>(h)[j];
+              }
             }
             __half* o = ep.out_f16 + size_t(row) * ep.ld_out16 + col0;
-            __align__(16) __half2 h[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
 #pragma unroll
@@ -265,8 +284,9 @@ extern "C" int semabs_gemm_f16(const void* A, int32_t lda, const void* B, int32_
   SB_REQUIRE(N % 32 == 0, "semabs_gemm_f16: N must be a multiple of 32 (got %d)", N);
   SB_REQUIRE(a_splits == 1 || K % GEMM_BK == 0, "semabs_gemm_f16: split-A needs K %% 64 == 0");
   SB_REQUIRE(e->out_f32 || e->out_f16, "semabs_gemm_f16: no output buffer");
-  SB_REQUIRE(e->act != SEMABS_ACT_QUICKGELU_GRAD || (e->aux && e->aux_rows > 0), "semabs_gemm_f16: aux missing");
-  SB_REQUIRE(e->ld_out % 4 == 0 && e->ld_out16 % 8 == 0 && e->ld_aux % 4 == 0, "semabs_gemm_f16: bad output pitch");
+  SB_REQUIRE(e->act != SEMABS_ACT_MUL_AUX16 || (e->aux16 && e->aux_rows > 0), "semabs_gemm_f16: aux16 missing");
+  SB_REQUIRE(e->ld_out % 4 == 0 && e->ld_out16 % 8 == 0 && e->ld_aux % 8 == 0 && e->ld_out_aux % 8 == 0,
+             "semabs_gemm_f16: bad output pitch");
 
   const int kblocks = (K + GEMM_BK - 1) / GEMM_BK;
   const int BN = (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
@@ -287,9 +307,11 @@ extern "C" int semabs_gemm_f16(const void* A, int32_t lda, const void* B, int32_
   EpiParams ep;
   ep.bias = e->bias;
   ep.residual = e->residual;
-  ep.aux = e->aux;
+  ep.aux16 = reinterpret_cast<const __half*>(e->aux16);
   ep.aux_rows = e->aux_rows;
   ep.ld_aux = e->ld_aux;
+  ep.out_aux16 = reinterpret_cast<__half*>(e->out_aux16);
+  ep.ld_out_aux = e->ld_out_aux;
   ep.out_f32 = e->out_f32;
   ep.ld_out = e->ld_out;
   ep.out_f16 = reinterpret_cast<__half*>(e->out_f16);

@@ -86,7 +86,7 @@ ndhwc_to_ncdhw_kernel(const float* __restrict__ x, float* __restrict__ y, long l
 __global__ void __launch_bounds__(EW_THREADS)
 gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, __half* __restrict__ y, long long S, int C, int groups, int cpg,
-                double inv_count, int splits) {
+                double inv_count, int splits, int planar) {
   __shared__ float s_scale[1024], s_shift[1024];
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -110,12 +110,15 @@ gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats, c
     const float4 a = *reinterpret_cast<const float4*>(xn + size_t(v) * C + c);
     const float o0 = fmaf(a.x, sc.x, sh.x), o1 = fmaf(a.y, sc.y, sh.y), o2 = fmaf(a.z, sc.z, sh.z), o3 = fmaf(a.w, sc.w, sh.w);
     const __half2 h0 = __floats2half2_rn(o0, o1), h1 = __floats2half2_rn(o2, o3);
-    __half* dst = yn + size_t(v) * splits * C + c;
+    // channels-last [v][splits*C], or chunk-planar [chunk][v][8] (chunk = 8 channels; hi chunks then lo chunks) for
+    // the halo-resident level-0 convolution (conv3d_halo.cu)
+    __half* dst = planar ? yn + (size_t(c >> 3) * S + v) * 8 + (c & 7) : yn + size_t(v) * splits * C + c;
     *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
     if (splits == 2) {
       const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
       const __half2 l0 = __floats2half2_rn(o0 - f0.x, o1 - f0.y), l1 = __floats2half2_rn(o2 - f1.x, o3 - f1.y);
-      *reinterpret_cast<uint2*>(dst + C) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      __half* dlo = planar ? dst + size_t(C >> 3) * S * 8 : dst + C;
+      *reinterpret_cast<uint2*>(dlo) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
     }
   }
 }
@@ -184,7 +187,7 @@ extern "C" int semabs_ndhwc_to_ncdhw(const float* x, float* y, int32_t N, int64_
 
 extern "C" int semabs_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta,
                                       void* y16, int32_t N, int64_t S, int32_t C, int32_t C_real, int32_t groups,
-                                      int32_t splits, void* stream) {
+                                      int32_t splits, int32_t planar, void* stream) {
   SB_REQUIRE(x && stats && gamma && beta && y16 && N > 0 && S > 0, "semabs_groupnorm_apply: null pointer");
   SB_REQUIRE(C % 4 == 0 && C <= 1024 && (EW_THREADS % (C / 4)) == 0 && groups >= 1 && groups <= 8 && C_real <= C,
              "semabs_groupnorm_apply: unsupported channel count %d", C);
@@ -192,8 +195,9 @@ extern "C" int semabs_groupnorm_apply(const float* x, const double* stats, const
   const double inv_count = 1.0 / (double(S) * double(groups == 1 ? C_real : cpg));
   const int vpb = EW_THREADS / (C / 4);
   dim3 grid(ew_grid(S, vpb), N);
+  SB_REQUIRE(!planar || C % 8 == 0, "semabs_groupnorm_apply: planar output needs C %% 8 == 0");
   gn_apply_kernel<<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, stats, gamma, beta, (__half*)y16, S, C, groups, cpg,
-                                                                 inv_count, splits);
+                                                                 inv_count, splits, planar);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

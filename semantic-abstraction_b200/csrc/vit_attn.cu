@@ -426,6 +426,182 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2) attn_bwd_col_kernel(AttnBwd
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// forward on mma.sync with 3-term fp16 splits (hi*hi + hi*lo + lo*hi, fp32 accumulate ≈ fp32 accuracy):
+// one CTA per (tile, head); K and V of the head live in shared memory as hi/lo fp16 pairs; each warp owns 16-row
+// query tiles, keeps the whole score strip [16 x T] in registers, does an exact two-pass softmax and multiplies
+// by V.  Used for T <= 272 (every CLIP ViT-B/32, ViT-L/14 and text case); the SIMT kernel above is the fallback.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int FWD_WARPS = 6;
+constexpr int NT_MAX = TR / 8;  // 34 key n-tiles
+
+struct AttnFwdArgs {
+  const float* qkv;
+  float* probs;
+  __half* probs16;
+  int ldp;
+  float* o32;
+  __half* o16;
+  int T, H, d, causal, splits;
+};
+
+__device__ __forceinline__ void split_h2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x - f.x, y - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__global__ void __launch_bounds__(FWD_WARPS * 32, 1) attn_fwd_mma_kernel(AttnFwdArgs a) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  __half* Kh = reinterpret_cast<__half*>(smraw);
+  __half* Kl = Kh + TR * TS;
+  __half* Vh = Kl + TR * TS;
+  __half* Vl = Vh + TR * TS;
+  const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int T = a.T, d = a.d;
+  const float* base = a.qkv + size_t(b) * T * 3 * d + h * HD;
+  for (int idx = threadIdx.x; idx < TR * 32; idx += blockDim.x) {
+    const int row = idx >> 5, c = (idx & 31) * 2;
+    float2 kk = make_float2(0.f, 0.f), vv = make_float2(0.f, 0.f);
+    if (row < T) {
+      kk = *reinterpret_cast<const float2*>(base + size_t(row) * 3 * d + d + c);
+      vv = *reinterpret_cast<const float2*>(base + size_t(row) * 3 * d + 2 * d + c);
+    }
+    uint32_t hi, lo;
+    split_h2(kk.x, kk.y, hi, lo);
+    *reinterpret_cast<uint32_t*>(Kh + row * TS + c) = hi, *reinterpret_cast<uint32_t*>(Kl + row * TS + c) = lo;
+    split_h2(vv.x, vv.y, hi, lo);
+    *reinterpret_cast<uint32_t*>(Vh + row * TS + c) = hi, *reinterpret_cast<uint32_t*>(Vl + row * TS + c) = lo;
+  }
+  __syncthreads();
+  const int ntiles = (T + 7) / 8;
+
+  for (int mt = warp; mt * 16 < T; mt += FWD_WARPS) {
+    const int ia = mt * 16 + g, ib = ia + 8;
+    const bool va = ia < T, vb = ib < T;
+    float s[NT_MAX][4];
+    {
+      uint32_t qh[4][4], ql[4][4];
+      const float* ra = base + size_t(va ? ia : 0) * 3 * d;
+      const float* rb = base + size_t(vb ? ib : 0) * 3 * d;
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int col = kt * 16 + 2 * t + 8 * hf;
+          const float2 xa = va ? *reinterpret_cast<const float2*>(ra + col) : make_float2(0.f, 0.f);
+          const float2 xb = vb ? *reinterpret_cast<const float2*>(rb + col) : make_float2(0.f, 0.f);
+          split_h2(xa.x, xa.y, qh[kt][2 * hf], ql[kt][2 * hf]);
+          split_h2(xb.x, xb.y, qh[kt][2 * hf + 1], ql[kt][2 * hf + 1]);
+        }
+#pragma unroll
+      for (int n = 0; n < NT_MAX; ++n) {
+        s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+        if (n < ntiles) {
+#pragma unroll
+          for (int kt = 0; kt < 4; ++kt) {
+            const int off = (n * 8 + g) * TS + kt * 16 + 2 * t;
+            const uint32_t h0 = *reinterpret_cast<const uint32_t*>(Kh + off), h1 = *reinterpret_cast<const uint32_t*>(Kh + off + 8);
+            const uint32_t l0 = *reinterpret_cast<const uint32_t*>(Kl + off), l1 = *reinterpret_cast<const uint32_t*>(Kl + off + 8);
+            mma_16816(s[n], qh[kt], h0, h1);
+            mma_16816(s[n], qh[kt], l0, l1);
+            mma_16816(s[n], ql[kt], h0, h1);
+          }
+        }
+      }
+    }
+    // mask + exact softmax over the row (rows ia: c0,c1 ; ib: c2,c3)
+    float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NT_MAX; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = n * 8 + 2 * t + e;
+        const bool dead = j >= T;
+        if (dead || (a.causal && j > ia)) s[n][e] = -INFINITY;
+        if (dead || (a.causal && j > ib)) s[n][2 + e] = -INFINITY;
+      }
+      ma = fmaxf(ma, fmaxf(s[n][0], s[n][1]));
+      mb = fmaxf(mb, fmaxf(s[n][2], s[n][3]));
+    }
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1)), ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1)), mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+    float sa = 0.f, sb2 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT_MAX; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[n][e] = (s[n][e] == -INFINITY) ? 0.f : expf(s[n][e] - ma);
+        s[n][2 + e] = (s[n][2 + e] == -INFINITY) ? 0.f : expf(s[n][2 + e] - mb);
+      }
+      sa += s[n][0] + s[n][1];
+      sb2 += s[n][2] + s[n][3];
+    }
+    sa += __shfl_xor_sync(0xffffffffu, sa, 1), sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+    sb2 += __shfl_xor_sync(0xffffffffu, sb2, 1), sb2 += __shfl_xor_sync(0xffffffffu, sb2, 2);
+#pragma unroll
+    for (int n = 0; n < NT_MAX; ++n) {
+      s[n][0] /= sa, s[n][1] /= sa, s[n][2] /= sb2, s[n][3] /= sb2;
+      const int j = n * 8 + 2 * t;
+      if (a.probs16 && j < a.ldp) {
+        if (va) *reinterpret_cast<__half2*>(a.probs16 + (size_t(bh) * T + ia) * a.ldp + j) = __floats2half2_rn(s[n][0], s[n][1]);
+        if (vb) *reinterpret_cast<__half2*>(a.probs16 + (size_t(bh) * T + ib) * a.ldp + j) = __floats2half2_rn(s[n][2], s[n][3]);
+      }
+      if (a.probs) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (va && j + e < T) a.probs[(size_t(bh) * T + ia) * T + j + e] = s[n][e];
+          if (vb && j + e < T) a.probs[(size_t(bh) * T + ib) * T + j + e] = s[n][2 + e];
+        }
+      }
+    }
+    // O = A V
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < NT_MAX / 2; ++kt) {
+      if (2 * kt < ntiles) {
+        uint32_t ah[4], al[4];
+        split_h2(s[2 * kt][0], s[2 * kt][1], ah[0], al[0]);
+        split_h2(s[2 * kt][2], s[2 * kt][3], ah[1], al[1]);
+        split_h2(s[2 * kt + 1][0], s[2 * kt + 1][1], ah[2], al[2]);
+        split_h2(s[2 * kt + 1][2], s[2 * kt + 1][3], ah[3], al[3]);
+        const int krow = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int nd2 = 0; nd2 < 4; ++nd2) {
+          uint32_t bhv[4], blv[4];
+          ldmatrix_x4_trans(bhv, Vh + krow * TS + nd2 * 16 + (lane >> 4) * 8);
+          ldmatrix_x4_trans(blv, Vl + krow * TS + nd2 * 16 + (lane >> 4) * 8);
+          mma_16816(o[2 * nd2], ah, bhv[0], bhv[1]);
+          mma_16816(o[2 * nd2], ah, blv[0], blv[1]);
+          mma_16816(o[2 * nd2], al, bhv[0], bhv[1]);
+          mma_16816(o[2 * nd2 + 1], ah, bhv[2], bhv[3]);
+          mma_16816(o[2 * nd2 + 1], ah, blv[2], blv[3]);
+          mma_16816(o[2 * nd2 + 1], al, bhv[2], bhv[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int col = h * HD + n * 8 + 2 * t;
+      if (va) {
+        const size_t row = size_t(b) * T + ia;
+        if (a.o32) *reinterpret_cast<float2*>(a.o32 + row * d + col) = make_float2(o[n][0], o[n][1]);
+        if (a.o16) store_h2_split(a.o16, row * size_t(a.splits) * d, col, d, a.splits, o[n][0], o[n][1]);
+      }
+      if (vb) {
+        const size_t row = size_t(b) * T + ib;
+        if (a.o32) *reinterpret_cast<float2*>(a.o32 + row * d + col) = make_float2(o[n][2], o[n][3]);
+        if (a.o16) store_h2_split(a.o16, row * size_t(a.splits) * d, col, d, a.splits, o[n][2], o[n][3]);
+      }
+    }
+  }
+}
+
 template <int NCHUNK>
 static int launch_attn_fwd(const float* qkv, float* probs, __half* probs16, int ld_p16, float* o32, __half* o16, int B,
                            int T, int H, int d, int causal, int splits, cudaStream_t st) {
@@ -453,6 +629,18 @@ extern "C" int semabs_attn_fwd(const float* qkv, float* probs, void* probs16, in
   const int d = H * HD;
   cudaStream_t st = (cudaStream_t)stream;
   __half* p16 = (__half*)probs16;
+  if (T <= TR && (!probs16 || ld_p16 <= TR)) {
+    AttnFwdArgs a{qkv, probs, p16, ld_p16, o32, (__half*)o16, T, H, d, causal, splits};
+    const size_t smem = size_t(4) * TR * TS * sizeof(__half);
+    static bool configured = false;
+    if (!configured) {
+      SB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    attn_fwd_mma_kernel<<<B * H, FWD_WARPS * 32, smem, st>>>(a);
+    SB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int nchunk = (T + 31) / 32;
   if (nchunk <= 2) return launch_attn_fwd<2>(qkv, probs, p16, ld_p16, o32, (__half*)o16, B, T, H, d, causal, splits, st);
   if (nchunk <= 3) return launch_attn_fwd<3>(qkv, probs, p16, ld_p16, o32, (__half*)o16, B, T, H, d, causal, splits, st);

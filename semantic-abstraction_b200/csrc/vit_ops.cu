@@ -153,6 +153,103 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(LnBwdArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-per-row LayerNorm forward / backward for d = 128 * NV (512, 768, 1024): float4 per lane, the row lives in
+// registers, reductions are pure warp shuffles (no block barrier).  Same math as the generic kernels above.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_split4(__half* row16, int col, int width, int splits, const float4& v) {
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(row16 + col) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  if (splits == 2) {
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    *reinterpret_cast<uint2*>(row16 + width + col) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_fwd_warp_kernel(LnFwdArgs a) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= a.M) return;
+  const float* src = a.x + size_t(row) * a.x_stride;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    v[k] = *reinterpret_cast<const float4*>(src + (k * 32 + lane) * 4);
+    s += v[k].x + v[k].y + v[k].z + v[k].w;
+  }
+  const float mean = warp_sum(s) / a.d;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const float c0 = v[k].x - mean, c1 = v[k].y - mean, c2 = v[k].z - mean, c3 = v[k].w - mean;
+    q += c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / a.d + 1e-5f);
+  if (lane == 0) {
+    if (a.mean) a.mean[row] = mean;
+    if (a.rstd) a.rstd[row] = rstd;
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int col = (k * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(a.gamma + col), b = *reinterpret_cast<const float4*>(a.beta + col);
+    float4 y;
+    y.x = (v[k].x - mean) * rstd * g.x + b.x, y.y = (v[k].y - mean) * rstd * g.y + b.y;
+    y.z = (v[k].z - mean) * rstd * g.z + b.z, y.w = (v[k].w - mean) * rstd * g.w + b.w;
+    if (a.y32) *reinterpret_cast<float4*>(a.y32 + size_t(row) * a.d + col) = y;
+    if (a.y16) store_split4(a.y16 + size_t(row) * a.splits * a.d, col, a.d, a.splits, y);
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_warp_kernel(LnBwdArgs a) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= a.M) return;
+  const int fr = row % a.x_rows;
+  const float mean = a.mean[fr], rstd = a.rstd[fr];
+  const float* x = a.x + size_t(fr) * a.x_stride;
+  const float* dy = a.dy + size_t(row) * a.d;
+  float4 g[NV], xh[NV];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int col = (k * 32 + lane) * 4;
+    const float4 d4 = *reinterpret_cast<const float4*>(dy + col), w4 = *reinterpret_cast<const float4*>(a.gamma + col);
+    const float4 x4 = *reinterpret_cast<const float4*>(x + col);
+    g[k] = make_float4(d4.x * w4.x, d4.y * w4.y, d4.z * w4.z, d4.w * w4.w);
+    xh[k] = make_float4((x4.x - mean) * rstd, (x4.y - mean) * rstd, (x4.z - mean) * rstd, (x4.w - mean) * rstd);
+    s1 += g[k].x + g[k].y + g[k].z + g[k].w;
+    s2 += g[k].x * xh[k].x + g[k].y * xh[k].y + g[k].z * xh[k].z + g[k].w * xh[k].w;
+  }
+  const float m1 = warp_sum(s1) / a.d, m2 = warp_sum(s2) / a.d;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int col = (k * 32 + lane) * 4;
+    float4 v;
+    v.x = rstd * (g[k].x - m1 - xh[k].x * m2), v.y = rstd * (g[k].y - m1 - xh[k].y * m2);
+    v.z = rstd * (g[k].z - m1 - xh[k].z * m2), v.w = rstd * (g[k].w - m1 - xh[k].w * m2);
+    if (a.dres) {
+      const float4 r4 = *reinterpret_cast<const float4*>(a.dres + size_t(row) * a.out_stride + col);
+      v.x += r4.x, v.y += r4.y, v.z += r4.z, v.w += r4.w;
+    }
+    *reinterpret_cast<float4*>(a.dx32 + size_t(row) * a.out_stride + col) = v;
+    if (a.dx16) store_split4(a.dx16 + size_t(row) * a.out16_stride, col, a.d, a.splits, v);
+  }
+}
+
+template <typename Args, typename K4, typename K6, typename K8>
+static bool launch_warp_ln(const Args& a, int d, cudaStream_t st, K4 k4, K6 k6, K8 k8) {
+  const int grid = (a.M + 7) / 8;
+  if (d == 512) k4<<<grid, 256, 0, st>>>(a);
+  else if (d == 768) k6<<<grid, 256, 0, st>>>(a);
+  else if (d == 1024) k8<<<grid, 256, 0, st>>>(a);
+  else return false;
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // CLIP logits and the backward seed (ClipGradcam.forward, clip_gradcam.py:58-68):
 //   fhat = f / |f| ; logit[b,p] = 100 * fhat . W[:,p]
@@ -259,7 +356,10 @@ extern "C" int semabs_layernorm_fwd(const float* x, int64_t x_stride, const floa
   LnFwdArgs a{};
   a.x = x, a.x_stride = x_stride, a.gamma = gamma, a.beta = beta, a.y32 = y32, a.y16 = (__half*)y16;
   a.mean = mean, a.rstd = rstd, a.M = M, a.d = d, a.splits = splits;
-  layernorm_fwd_kernel<<<M, 256, d * sizeof(float), (cudaStream_t)stream>>>(a);
+  const bool aligned = (x_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (!(aligned && launch_warp_ln(a, d, (cudaStream_t)stream, layernorm_fwd_warp_kernel<4>, layernorm_fwd_warp_kernel<6>,
+                                  layernorm_fwd_warp_kernel<8>)))
+    layernorm_fwd_kernel<<<M, 256, d * sizeof(float), (cudaStream_t)stream>>>(a);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -284,7 +384,10 @@ extern "C" int semabs_layernorm_bwd(const float* dy, const float* dres, const fl
   a.dy = dy, a.dres = dres, a.x = x, a.x_stride = x_stride, a.x_rows = x_rows, a.mean = mean, a.rstd = rstd;
   a.gamma = gamma, a.dx32 = dx32, a.out_stride = out_stride, a.dx16 = (__half*)dx16, a.out16_stride = out16_stride;
   a.M = M, a.d = d, a.splits = splits;
-  layernorm_bwd_kernel<<<M, 256, 2 * d * sizeof(float), (cudaStream_t)stream>>>(a);
+  const bool aligned = (x_stride % 4 == 0) && (out_stride % 4 == 0) && (out16_stride % 4 == 0);
+  if (!(aligned && launch_warp_ln(a, d, (cudaStream_t)stream, layernorm_bwd_warp_kernel<4>, layernorm_bwd_warp_kernel<6>,
+                                  layernorm_bwd_warp_kernel<8>)))
+    layernorm_bwd_kernel<<<M, 256, 2 * d * sizeof(float), (cudaStream_t)stream>>>(a);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -6,7 +6,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_QUICKGELU, ACT_QUICKGELU_GRAD, GemmEpilogue, check, f32, i32, lib, ptr, stream_ptr
+from ._lib import ACT_MUL_AUX16, ACT_NONE, ACT_QUICKGELU, GemmEpilogue, check, f32, i32, lib, ptr, stream_ptr
 
 
 class _GemmProfile:
@@ -38,7 +38,8 @@ def gemm_f16(
     a_splits: int = 1,
     bias: torch.Tensor | None = None,
     residual: torch.Tensor | None = None,
-    aux: torch.Tensor | None = None,
+    aux16: torch.Tensor | None = None,
+    out_aux16: torch.Tensor | None = None,
     act: int = ACT_NONE,
     out_f32: torch.Tensor | None = None,
     out_f16: torch.Tensor | None = None,
@@ -55,9 +56,13 @@ def gemm_f16(
     ep = GemmEpilogue()
     ep.bias = bias.data_ptr() if bias is not None else None
     ep.residual = residual.data_ptr() if residual is not None else None
-    ep.aux = aux.data_ptr() if aux is not None else None
-    ep.aux_rows = aux.shape[0] if aux is not None else 0
-    ep.ld_aux = aux.stride(0) if aux is not None else 0
+    ep.aux16 = aux16.data_ptr() if aux16 is not None else None
+    ep.aux_rows = aux16.shape[0] if aux16 is not None else 0
+    ep.ld_aux = aux16.stride(0) if aux16 is not None else 0
+    ep.out_aux16 = out_aux16.data_ptr() if out_aux16 is not None else None
+    ep.ld_out_aux = out_aux16.stride(0) if out_aux16 is not None else 0
+    assert aux16 is None or aux16.dtype == torch.float16
+    assert out_aux16 is None or (out_aux16.dtype == torch.float16 and out_aux16.shape == (M, N))
     ep.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
     ep.ld_out = out_f32.stride(0) if out_f32 is not None else (residual.stride(0) if residual is not None else 0)
     ep.out_f16 = out_f16.data_ptr() if out_f16 is not None else None
@@ -214,9 +219,35 @@ def ndhwc_to_ncdhw(x, y, *, N, S, C):
     check(lib().semabs_ndhwc_to_ncdhw(ptr(x), ptr(y), i32(N), _i64(S), i32(C), stream_ptr()))
 
 
-def groupnorm_apply(x, stats, gamma, beta, y16, *, N, S, C, C_real, groups, splits=1):
+def groupnorm_apply(x, stats, gamma, beta, y16, *, N, S, C, C_real, groups, splits=1, planar=False):
     check(lib().semabs_groupnorm_apply(ptr(x), ptr(stats), ptr(gamma), ptr(beta), ptr(y16), i32(N), _i64(S), i32(C),
-                                       i32(C_real), i32(groups), i32(splits), stream_ptr()))
+                                       i32(C_real), i32(groups), i32(splits), i32(int(planar)), stream_ptr()))
+
+
+def conv3d_halo(x16_planar, w_img, *, N, D, H, W, C_in, C_out, a_splits=1, w_splits=1, precise=False, residual=None,
+                relu=False, out32=None, out16=None, o16_splits=1, stats=None, groups=0):
+    check(
+        lib().semabs_conv3d_halo(
+            ptr(x16_planar), i32(a_splits), ptr(w_img), i32(w_splits), i32(N), i32(D), i32(H), i32(W), i32(C_in),
+            i32(C_out), i32(int(precise)), ptr(residual), i32(int(relu)), ptr(out32), ptr(out16), i32(o16_splits),
+            ptr(stats), i32(groups), stream_ptr(),
+        )
+    )
+
+
+def pack_halo_weights(w: torch.Tensor, splits: int) -> torch.Tensor:
+    """conv.weight [Co, Ci, 3,3,3] fp32 -> per-tap UMMA no-swizzle core-matrix images, fp16:
+    [27 taps][splits][Ci/16][Co/8][2][8 rows][8 elems] with value W[co = g*8 + r][ci = kb*16 + kc*8 + e][tap]."""
+    co, ci = w.shape[:2]
+    w = w.detach().float().reshape(co, ci, 27)
+    hi = w.half()
+    parts = [hi] if splits == 1 else [hi, (w - hi.float()).half()]
+    imgs = []
+    for part in parts:
+        # [co, ci, tap] -> [tap, kb, g, kc, r, e]
+        t = part.permute(2, 0, 1).reshape(27, co // 8, 8, ci // 16, 2, 8)  # tap, g, r, kb, kc, e
+        imgs.append(t.permute(0, 3, 1, 4, 2, 5).contiguous())  # tap, kb, g, kc, r, e
+    return torch.stack(imgs, dim=1).contiguous()  # tap, split, kb, g, kc, r, e
 
 
 def maxpool3d_2(x, y, *, N, D, H, W, C, groups=1, stats=None):

@@ -93,6 +93,7 @@ class ResidualUNet3D(nn.Module):
         self.f_maps = list(f_maps)
         self.in_channels, self.out_channels, self.num_groups = in_channels, out_channels, num_groups
         self.precise = precise
+        self.use_halo = True  # halo-resident conv kernel at the 128-wide level (conv3d_halo.cu)
         encoders = []
         for i, out_f in enumerate(f_maps):
             encoders.append(Encoder(in_channels if i == 0 else f_maps[i - 1], out_f, apply_pooling=i > 0,
@@ -141,9 +142,18 @@ class ResidualUNet3D(nn.Module):
             b[: m.num_channels] = m.bias.detach().to(device, F32)
             return g, b
 
+        def halo_w(w):  # [Co, Ci, 3,3,3] -> per-tap core-matrix images for the halo-resident kernel (W == 128 level)
+            co, ci = w.shape[:2]
+            wp = torch.zeros(co, _pad16(ci), 3, 3, 3, device=device)
+            wp[:, :ci] = w.detach().to(device, F32)
+            return ops.pack_halo_weights(wp, s)
+
         def block(prefix, blk: ExtResNetBlock):
             for j, sc in enumerate((blk.conv1, blk.conv2, blk.conv3), 1):
                 pk[f"{prefix}.w{j}"] = conv_w(sc.conv.weight)
+                co, ci = sc.conv.weight.shape[:2]
+                if co in (16, 32) and _pad16(ci) in (16, 32):
+                    pk[f"{prefix}.wh{j}"] = halo_w(sc.conv.weight)
                 pk[f"{prefix}.g{j}"], pk[f"{prefix}.b{j}"] = gn(sc.groupnorm, _pad16(sc.groupnorm.num_channels))
 
         for i, enc in enumerate(self.encoders):
@@ -175,19 +185,23 @@ class ResidualUNet3D(nn.Module):
         g2, g3 = blk.conv2.num_groups, blk.conv3.num_groups
         st = self._buf(f"l{lvl}_st", (2, N, 8, 2), F64, dev)
         st.zero_()
-        common = dict(kind=ops.CONV_3X3X3, N=N, D=D, H=H, W=W, a_splits=s, w_splits=s, precise=self.precise)
-        ops.groupnorm_apply(x_raw, x_stats, pk[prefix + ".g1"], pk[prefix + ".b1"], xn, N=N, S=S, C=c_in_pad,
-                            C_real=c_in_real, groups=blk.conv1.num_groups, splits=s)
-        ops.conv3d(xn, pk[prefix + ".w1"], C_in=c_in_pad, C_out=c_out, relu=True, out32=o1, stats=st[0], groups=g2, **common)
-        ops.groupnorm_apply(o1, st[0], pk[prefix + ".g2"], pk[prefix + ".b2"], xn, N=N, S=S, C=c_out, C_real=c_out,
-                            groups=g2, splits=s)
-        ops.conv3d(xn, pk[prefix + ".w2"], C_in=c_out, C_out=c_out, relu=True, out32=o2, stats=st[1], groups=g3, **common)
-        ops.groupnorm_apply(o2, st[1], pk[prefix + ".g3"], pk[prefix + ".b3"], xn, N=N, S=S, C=c_out, C_real=c_out,
-                            groups=g3, splits=s)
+        halo = W == 128 and c_in_pad in (16, 32) and c_out in (16, 32) and self.use_halo
+        common = dict(N=N, D=D, H=H, W=W, a_splits=s, w_splits=s, precise=self.precise)
+
+        def gcr(j, src, src_stats, c_src_pad, c_src_real, groups, **epi):
+            """one 'gc[r]' unit: GroupNorm-apply then the implicit-GEMM conv (halo-resident kernel at full resolution)"""
+            ops.groupnorm_apply(src, src_stats, pk[f"{prefix}.g{j}"], pk[f"{prefix}.b{j}"], xn, N=N, S=S, C=c_src_pad,
+                                C_real=c_src_real, groups=groups, splits=s, planar=halo)
+            if halo:
+                ops.conv3d_halo(xn, pk[f"{prefix}.wh{j}"], C_in=c_src_pad, C_out=c_out, **common, **epi)
+            else:
+                ops.conv3d(xn, pk[f"{prefix}.w{j}"], kind=ops.CONV_3X3X3, C_in=c_src_pad, C_out=c_out, **common, **epi)
+
+        gcr(1, x_raw, x_stats, c_in_pad, c_in_real, blk.conv1.num_groups, relu=True, out32=o1, stats=st[0], groups=g2)
+        gcr(2, o1, st[0], c_out, c_out, g2, relu=True, out32=o2, stats=st[1], groups=g3)
         out32 = self._buf(f"l{lvl}_out32", (N, S, c_out), F32, dev) if want32 else None
         out16 = self._buf(f"l{lvl}_out16", (N, S, s * c_out), F16, dev) if want16 else None
-        ops.conv3d(xn, pk[prefix + ".w3"], C_in=c_out, C_out=c_out, residual=o1, relu=True, out32=out32, out16=out16,
-                   o16_splits=s, **common)
+        gcr(3, o2, st[1], c_out, c_out, g3, residual=o1, relu=True, out32=out32, out16=out16, o16_splits=s)
         self.kernel_launches += 6
         return out32, out16
 

@@ -65,18 +65,19 @@ def test_gemm_epilogues():
     recon = o16[:, :N].float() + o16[:, N:].float()
     assert torch.allclose(recon, o32, atol=1e-5, rtol=1e-5)
 
-    # quickgelu: fp32 = pre-activation, fp16 = activation
+    # quickgelu: fp32 = pre-activation, fp16 = activation, aux16 = derivative
     u = torch.empty(M, N, device="cuda")
     gq = torch.empty(M, N, device="cuda", dtype=torch.float16)
-    ops.gemm_f16(a, b, bias=bias, act=ops.ACT_QUICKGELU, out_f32=u, out_f16=gq)
+    gg = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    ops.gemm_f16(a, b, bias=bias, act=ops.ACT_QUICKGELU, out_f32=u, out_f16=gq, out_aux16=gg)
     pre = base + bias
+    sg = torch.sigmoid(1.702 * pre)
     assert torch.allclose(u, pre, atol=1e-4, rtol=1e-5)
-    assert torch.allclose(gq.float(), pre * torch.sigmoid(1.702 * pre), atol=2e-3, rtol=2e-3)
+    assert torch.allclose(gq.float(), pre * sg, atol=2e-3, rtol=2e-3)
+    assert torch.allclose(gg.float(), sg + 1.702 * pre * sg * (1 - sg), atol=2e-3, rtol=2e-3)
 
-    # quickgelu grad with row-broadcast aux (aux_rows divides M)
-    aux = torch.randn(M // 2, N, device="cuda", generator=g)
+    # dgrad through quickgelu: multiply by a row-broadcast fp16 aux (aux_rows divides M)
+    aux = torch.randn(M // 2, N, device="cuda", generator=g).half()
     d = torch.empty(M, N, device="cuda")
-    ops.gemm_f16(a, b, aux=aux, act=ops.ACT_QUICKGELU_GRAD, out_f32=d)
-    s = torch.sigmoid(1.702 * aux)
-    gr = (s + 1.702 * aux * s * (1 - s)).repeat(2, 1)
-    assert torch.allclose(d, base * gr, atol=1e-4, rtol=1e-4)
+    ops.gemm_f16(a, b, aux16=aux, act=ops.ACT_MUL_AUX16, out_f32=d)
+    assert torch.allclose(d, base * aux.float().repeat(2, 1), atol=1e-4, rtol=1e-4)

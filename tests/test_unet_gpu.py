@@ -202,3 +202,61 @@ def test_semabsvool_matches_reference(gold):
     err = _maxrel(out, ref)
     print(f"SemAbsVOOL logits: {err:.2e}")
     assert out.shape == ref.shape and err < TOL
+
+
+@pytest.mark.parametrize("N,D,H,Ci,Co,precise", [(1, 4, 6, 16, 16, True), (2, 8, 8, 32, 32, True), (1, 16, 5, 32, 16, False),
+                                                  (1, 32, 4, 16, 32, True)])
+def test_conv_halo_resident(N, D, H, Ci, Co, precise):
+    """semabs_conv3d_halo (W = 128 level): chunk-planar input via groupnorm_apply(planar), per-tap weight images."""
+    from semabs_b200 import ops
+
+    W = 128
+    g = torch.Generator(device=dev).manual_seed(D * 10 + Ci + Co)
+    s = 2 if precise else 1
+    S = D * H * W
+    x = torch.randn(N, Ci, D, H, W, device=dev, generator=g) * 1.5 + 0.3
+    w = torch.randn(Co, Ci, 3, 3, 3, device=dev, generator=g) / (27 * Ci) ** 0.5
+    gamma, beta = 1 + 0.2 * torch.randn(Ci, device=dev, generator=g), 0.2 * torch.randn(Ci, device=dev, generator=g)
+    G = 8
+    raw = torch.empty(N, S, Ci, device=dev)
+    st = torch.zeros(N, G, 2, device=dev, dtype=torch.float64)
+    ops.ncdhw_to_ndhwc(x, raw, N=N, S=S, C=Ci, Cpad=Ci, groups=G, stats=st)
+    xn = torch.empty(N * s * Ci * S, device=dev, dtype=torch.float16)
+    ops.groupnorm_apply(raw, st, gamma, beta, xn, N=N, S=S, C=Ci, C_real=Ci, groups=G, splits=s, planar=True)
+    res = torch.randn(N, D, H, W, Co, device=dev, generator=g)
+    out = torch.full((N, D, H, W, Co), float("nan"), device=dev)
+    out16 = torch.empty(N, D, H, W, s * Co, device=dev, dtype=torch.float16)
+    stats = torch.zeros(N, G, 2, device=dev, dtype=torch.float64)
+    ops.conv3d_halo(xn, ops.pack_halo_weights(w, s), N=N, D=D, H=H, W=W, C_in=Ci, C_out=Co, a_splits=s, w_splits=s,
+                    precise=precise, residual=res, relu=True, out32=out, out16=out16, o16_splits=s, stats=stats, groups=G)
+    torch.cuda.synchronize()
+    xg = F.group_norm(x, G, gamma, beta, 1e-5)
+    if not precise:
+        xg, w = xg.half().float(), w.half().float()
+    ref = F.relu(F.conv3d(xg, w, padding=1).permute(0, 2, 3, 4, 1) + res)
+    err = _maxrel(out, ref)
+    assert err < (5e-5 if precise else 2e-4), err
+    got16 = out16[..., :Co].float() + (out16[..., Co:].float() if s == 2 else 0)
+    assert _maxrel(got16, out) < (1e-5 if s == 2 else 2e-3)
+    r = out.view(N, -1, G, Co // G)
+    st_ref = torch.stack([r.double().sum(dim=(1, 3)), (r.double() ** 2).sum(dim=(1, 3))], dim=-1)
+    assert torch.allclose(stats, st_ref, rtol=1e-5, atol=1e-6)
+
+
+def test_unet_full_resolution_row_path():
+    """A UNet whose first level is 128 voxels wide goes through the halo-resident kernel; compare with the oracle."""
+    from oracle import unet_oracle
+    from semabs_b200.unet3d import ResidualUNet3D
+
+    torch.manual_seed(11)
+    m = ResidualUNet3D(in_channels=16, out_channels=16, f_maps=16, num_groups=8, num_levels=3).to(dev)
+    x = torch.randn(1, 16, 16, 16, 128, generator=torch.Generator().manual_seed(12))
+    y = m(x.to(dev)).cpu()
+    with torch.no_grad():
+        ref = unet_oracle.residual_unet3d({k: v.cpu() for k, v in m.state_dict().items()}, x)
+    err = _maxrel(y, ref)
+    print(f"UNet 16x16x128 (halo path): {err:.2e}")
+    assert err < TOL
+    m.use_halo = False
+    y2 = m(x.to(dev)).cpu()
+    assert _maxrel(y2, ref) < TOL
