@@ -46,7 +46,31 @@ _MEAN = torch.tensor((0.48145466, 0.4578275, 0.40821073)).view(1, 3, 1, 1)
 _STD = torch.tensor((0.26862954, 0.26130258, 0.27577711)).view(1, 3, 1, 1)
 
 
+_POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
+        _POOL = ThreadPoolExecutor(max_workers=max(1, min(32, (os.cpu_count() or 2))))
+    return _POOL
+
+
 def preprocess_tiles(tiles_u8: Sequence[np.ndarray], n_px: int) -> torch.Tensor:
+    """Host tile preprocessing, fanned out over a thread pool (PIL's resize releases the GIL); the per-tile
+    arithmetic is `_preprocess_tiles_serial`'s."""
+    n = len(tiles_u8)
+    if n < 32:
+        return _preprocess_tiles_serial(tiles_u8, n_px)
+    step = max(8, (n + 63) // 64)
+    chunks = [tiles_u8[i : i + step] for i in range(0, n, step)]
+    return torch.cat(list(_pool().map(lambda c: _preprocess_tiles_serial(c, n_px), chunks)), dim=0)
+
+
+def _preprocess_tiles_serial(tiles_u8: Sequence[np.ndarray], n_px: int) -> torch.Tensor:
     """The reference's `_transform` (clip_explainability.py:98-108) on a list of uint8 crops: PIL bicubic resize of
     the shorter side to 224 (hard-coded there), centre crop/pad to n_px, /255, normalise. Host side, like the
     reference (it is the reference's declared bottleneck, __init__.py:275; a device version is a 'next' row)."""
@@ -161,50 +185,79 @@ class ClipWrapper:
     @classmethod
     def get_clip_saliency_device(cls, tile_imgs, tile_desc, size_order, text_labels, H, W, horizontal_flipping=False,
                                  positive_attn_only=False, tile_batch_size=32, prompt_batch_size=32):
-        """Device half of get_clip_saliency_convolve: preprocessed tiles [n,3,R,R] (host or device) -> maps
-        [P,H,W] on the device."""
+        """Device half of get_clip_saliency_convolve: preprocessed tiles -> maps [P,H,W] on the device.
+        `tile_imgs` is a tensor [n,3,R,R] (host or device) or an iterable of such batches (e.g. produced by worker
+        threads while earlier batches are already on the GPU)."""
         gc = cls.clip_gradcam
         gc.positive_attn_only = positive_attn_only
         dev = cls.device
-        tile_imgs = tile_imgs.to(dev, non_blocking=True)
         labels = list(text_labels)
+        if torch.is_tensor(tile_imgs):
+            tile_imgs = [tile_imgs[t : t + tile_batch_size] for t in range(0, len(tile_imgs), tile_batch_size)]
 
-        def run(tiles):
-            return torch.cat(
-                [
-                    torch.cat(
-                        [gc(x=tiles[t : t + tile_batch_size], o=labels[p : p + prompt_batch_size]).clone()
-                         for t in range(0, len(tiles), tile_batch_size)],
-                        dim=1,
-                    )
-                    for p in range(0, len(labels), prompt_batch_size)
-                ],
-                dim=0,
-            ).contiguous()  # fmt: skip
+        def relevancy(tiles):  # [b,3,R,R] on device -> [P, b, g, g]
+            return torch.cat([gc(x=tiles, o=labels[p : p + prompt_batch_size]).clone()
+                              for p in range(0, len(labels), prompt_batch_size)], dim=0)  # fmt: skip
 
-        rel = run(tile_imgs)
+        rel_parts, kept = [], []
+        for batch in tile_imgs:
+            batch = cls._to_device(batch)
+            rel_parts.append(relevancy(batch))
+            if horizontal_flipping:
+                kept.append(batch)
+        rel = torch.cat(rel_parts, dim=1).contiguous()
         if horizontal_flipping:
             # flipping the tile is pure data movement (__init__.py:170-173)
-            rel = ops.flip_average(rel, run(tile_imgs.flip(-1).contiguous()))
+            flipped = torch.cat([relevancy(b.flip(-1).contiguous()) for b in kept], dim=1).contiguous()
+            rel = ops.flip_average(rel, flipped)
         out = torch.empty(len(labels), H, W, device=dev)
         desc = torch.as_tensor(np.ascontiguousarray(tile_desc), dtype=torch.int32).to(dev)
         order = torch.as_tensor(list(size_order), dtype=torch.int32).to(dev)
         return ops.tile_assemble(rel, desc, order, H, W, out)
 
+    _staging = None
+
+    @classmethod
+    def _to_device(cls, batch):
+        """Host batch -> device through a small ring of pinned staging buffers (async H2D on the current stream)."""
+        if batch.is_cuda:
+            return batch
+        if batch.is_pinned():
+            return batch.to(cls.device, non_blocking=True)
+        if cls._staging is None or cls._staging["buf"][0].shape[1:] != batch.shape[1:] or cls._staging["buf"][0].shape[0] < batch.shape[0]:
+            cls._staging = {"buf": [torch.empty((max(32, batch.shape[0]),) + tuple(batch.shape[1:])).pin_memory() for _ in range(3)],
+                            "ev": [None] * 3, "i": 0}
+        st = cls._staging
+        i = st["i"]
+        st["i"] = (i + 1) % 3
+        if st["ev"][i] is not None:
+            st["ev"][i].synchronize()
+        pinned = st["buf"][i][: batch.shape[0]]
+        pinned.copy_(batch)
+        out = pinned.to(cls.device, non_blocking=True)
+        st["ev"][i] = torch.cuda.Event()
+        st["ev"][i].record()
+        return out
+
     @classmethod
     def get_clip_saliency_convolve(cls, text_labels, horizontal_flipping=False, positive_attn_only: bool = False,
                                    tile_batch_size=32, prompt_batch_size=32, tile_interpolate_batch_size=32, **kwargs):
-        tile_desc, tile_imgs, size_order = cls.create_tiles(**kwargs)
+        """Reference: CLIP/clip/__init__.py:135-236. Host tile preprocessing runs in worker threads, one future per
+        tile batch, and overlaps with the GPU work of the batches already submitted."""
+        tile_desc, crops, size_order = cls.enumerate_crops(**kwargs)
+        n_px = cls.clip_gradcam.n_px
+        futs = [_pool().submit(_preprocess_tiles_serial, crops[i : i + tile_batch_size], n_px)
+                for i in range(0, len(crops), tile_batch_size)]
         H, W = kwargs["img"].shape[:2]
-        out = cls.get_clip_saliency_device(tile_imgs, tile_desc, size_order, text_labels, H, W, horizontal_flipping,
-                                           positive_attn_only, tile_batch_size, prompt_batch_size)
+        out = cls.get_clip_saliency_device((f.result() for f in futs), tile_desc, size_order, text_labels, H, W,
+                                           horizontal_flipping, positive_attn_only, tile_batch_size, prompt_batch_size)
         return out.cpu()
 
     @classmethod
-    def create_tiles(cls, img, augmentations, cropping_augmentations, **kwargs):
+    def enumerate_crops(cls, img, augmentations, cropping_augmentations, **kwargs):
         """Tile enumeration in the reference's order (__init__.py:238-282): image copies (original + ColorJitter
         draws) -> crop sizes -> column offset -> row offset. Returns (tile_desc int32 [n,3] = (row0,col0,size),
-        preprocessed tiles [n,3,R,R] fp32 (pinned host memory), size order)."""
+        list of uint8 crops (views), size order)."""
         assert type(img) == np.ndarray
         cls.check_initialized()
         img_pil = Image.fromarray(img)
@@ -223,8 +276,15 @@ class ClipWrapper:
                             continue
                         desc.append((int(x), int(y), int(ts)))
                         crops.append(im[x : x + ts, y : y + ts])
+        size_order = list(dict.fromkeys(a["tile_size"] for a in cropping_augmentations))
+        return np.array(desc, dtype=np.int32).reshape(-1, 3), crops, size_order
+
+    @classmethod
+    def create_tiles(cls, img, augmentations, cropping_augmentations, **kwargs):
+        """Eager variant of the reference's create_tiles: (tile_desc, preprocessed tiles [n,3,R,R] fp32 in pinned host
+        memory, size order)."""
+        desc, crops, size_order = cls.enumerate_crops(img, augmentations, cropping_augmentations)
         tiles = preprocess_tiles(crops, cls.clip_gradcam.n_px)
         if torch.cuda.is_available():
             tiles = tiles.pin_memory()
-        size_order = list(dict.fromkeys(a["tile_size"] for a in cropping_augmentations))
-        return np.array(desc, dtype=np.int32).reshape(-1, 3), tiles, size_order
+        return desc, tiles, size_order

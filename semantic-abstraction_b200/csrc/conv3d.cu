@@ -148,8 +148,11 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // whole warp runs the loop, the elected lane issues (see umma_f16_elect in ptx.cuh)
+    {
+      const uint32_t leader = elect_one() ? 1u : 0u;
       constexpr uint32_t idesc = make_idesc_f16(128, BN);
+      const uint64_t desc0 = make_smem_desc(0, 16, Cfg::SBO, Cfg::SWZ) + (smem_u32(smem) >> 4);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -161,20 +164,18 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
-          const uint64_t da = make_smem_desc(a_addr, 16, Cfg::SBO, Cfg::SWZ);
-          const uint64_t db = make_smem_desc(b_addr, 16, Cfg::SBO, Cfg::SWZ);
+          const uint64_t da = desc0 + uint32_t(stage) * uint32_t(Cfg::STAGE_BYTES >> 4);
+          const uint64_t db = da + uint32_t(Cfg::A_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < KB / 16; ++k)
-            umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (ks | k) != 0);
-          umma_commit(&empty_bar[stage]);
+            umma_f16_elect(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (ks | k) != 0, leader);
+          umma_commit_elect(&empty_bar[stage], leader);
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);
+        umma_commit_elect(&tmem_full[acc], leader);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

@@ -13,7 +13,12 @@
 //     tap (dy, dx) is therefore just a different descriptor START ADDRESS into the same plane — no data movement;
 //   * a CTA walks a column of output rows along z for fixed (n, y): ring of 4 planes (z-1, z, z+1 + one in flight),
 //     one new plane per output row => each activation byte crosses L2->SM 3x (once per y neighbour) instead of 81x;
-//   * weights stream per tap through a small ring as pre-packed core-matrix images (cp.async.bulk).
+//   * weights are RESIDENT in shared memory (pre-packed UMMA core-matrix images, loaded once per CTA).  A first
+//     version streamed them per tap through a 6 x 4 KB ring and was latency-bound (bytes in flight / L2 latency
+//     = ~14 GB/s per SM, 7.5 ms per conv).  To make them fit, a CTA owns 16 output channels (C_out = 32 is split
+//     over two work items), and the two weight halves of the precise mode are stacked along N:
+//     B = [W_hi ; W_lo] (N = 32) is multiplied with x_hi in ONE MMA (D columns 0-15 and 16-31), x_lo only with W_hi
+//     (N = 16, columns 0-15); the epilogue adds the two column halves.  A is thus read twice, not three times.
 // Warp roles / TMEM double buffering / epilogue are those of conv3d.cu.
 #include "../../include/semabs_b200.h"
 #include "common.cuh"
@@ -21,24 +26,25 @@
 
 namespace sb {
 
-constexpr int HALO_THREADS = 256;
+constexpr int HALO_THREADS = 384;                   // 8 role warps + 4 plane-producer warps
+constexpr int HALO_PRODUCERS = 128;
 constexpr int HALO_W = 128;
 constexpr int HALO_XP = HALO_W + 2;                 // voxels per row incl. halo
 constexpr int HALO_CHUNK_DATA = 3 * HALO_XP * 16;   // one chunk of one plane: 3 rows x 130 voxels x 16 B = 6240
 constexpr int HALO_CHUNK_BYTES = (HALO_CHUNK_DATA + 127) / 128 * 128;  // smem pitch (TMA destinations 128 B aligned)
-constexpr int HALO_PLANES = 4;
-constexpr int HALO_WSTAGES = 6;
+constexpr int HALO_CO = 16;                         // output channels per work item
 
 struct HaloParams {
   int N, D, H;
   int C_in, C_out;
   int nchunks;            // a_splits * C_in / 8
-  int npass;
-  int8_t pass_a[3], pass_w[3];
-  int w_splits;
+  int precise;
+  int co_halves;          // C_out / 16
+  int nplanes;            // ring depth (3 or 4)
   int zseg, nseg;         // output rows per work item along z, segments per column
   int plane_bytes;        // nchunks * HALO_CHUNK_BYTES
-  int wtap_bytes;         // w_splits * C_in * C_out * 2
+  int wres_bytes;         // resident weight image per 16-channel half: 27 * (C_in/16) * wk_bytes
+  int wk_bytes;           // one (tap, K=16 block): [N/8 groups][2 k-chunks][8 rows x 16 B], N = 32 (precise) or 16
   const float* residual;
   int relu;
   float* out32;
@@ -55,34 +61,44 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                : "memory");
 }
 
-template <int BN>
+template <int KSTEPS, bool PRECISE>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
-conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __half* __restrict__ wimg,
+conv3d_halo_kernel(const __half* __restrict__ xplanar, const __half* __restrict__ wimg,
                    const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  uint8_t* planes = smem;                                         // HALO_PLANES x plane_bytes
-  uint8_t* wring = planes + HALO_PLANES * p.plane_bytes;          // HALO_WSTAGES x wtap_bytes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + HALO_WSTAGES * p.wtap_bytes);
-  uint64_t* plane_full = bars;
-  uint64_t* plane_empty = plane_full + HALO_PLANES;
-  uint64_t* w_full = plane_empty + HALO_PLANES;
-  uint64_t* w_empty = w_full + HALO_WSTAGES;
-  uint64_t* tmem_full = w_empty + HALO_WSTAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* planes = smem;                              // nplanes x plane_bytes
+  uint8_t* wres = planes + p.nplanes * p.plane_bytes;  // resident weights of the current 16-channel half
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wres + p.wres_bytes);
+  uint64_t* plane_full = bars;        // [4]
+  uint64_t* plane_empty = bars + 4;   // [4]
+  uint64_t* w_full = bars + 8;        // [1]
+  uint64_t* tmem_full = bars + 9;     // [2]
+  uint64_t* tmem_empty = bars + 11;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_items = p.N * p.H * p.nseg;
+  const int NP = p.nplanes;
+  // work item = (co half, n, y, z segment); a CTA keeps one co half for its whole life (weights stay resident):
+  // CTAs [0, g0) take half 0, the rest half 1
+  const int items_per_half = p.N * p.H * p.nseg;
+  const int ctas_per_half = gridDim.x / p.co_halves;
+  const int half = blockIdx.x / ctas_per_half;
+  const int cta_in_half = blockIdx.x % ctas_per_half;
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmA);
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < HALO_PLANES; ++s) mbar_init(&plane_full[s], 1), mbar_init(&plane_empty[s], 1);
-    for (int s = 0; s < HALO_WSTAGES; ++s) mbar_init(&w_full[s], 1), mbar_init(&w_empty[s], 1);
+    for (int s = 0; s < 4; ++s) mbar_init(&plane_full[s], HALO_PRODUCERS), mbar_init(&plane_empty[s], 1);
+    mbar_init(w_full, 1);
     for (int a = 0; a < 2; ++a) mbar_init(&tmem_full[a], 1), mbar_init(&tmem_empty[a], 4);
     fence_barrier_init();
   }
-  constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  // Dependent tcgen05.mma's into ONE accumulator serialise on the accumulate latency (~150 cycles measured with
+  // N = 16/32, where the throughput floor is only 8-16 cycles), so the taps are spread round-robin over NPART
+  // independent partial accumulators that the epilogue adds up: hi partials are 32 columns wide
+  // ([x_hi W_hi | x_hi W_lo]), lo partials 16 (x_lo W_hi).
+  constexpr int NPART = 4;
+  constexpr int ACC_COLS = NPART * 32 + NPART * 16;  // 192
+  constexpr int TMEM_COLS = 512;                     // 2 x 192 rounded up to a power of two
   if (warp == 2) {
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
@@ -100,100 +116,127 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __half* __rest
   };
 
   if (warp == 0) {
-    // ===== producer: activation planes =====
+    // ===== resident weights, once =====
     if (lane == 0) {
-      uint32_t pc = 0;  // running plane counter -> ring slot / phase
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int n, y, z0;
-        decode(item, n, y, z0);
-        for (int k = 0; k < p.zseg + 2; ++k, ++pc) {
-          const int slot = pc % HALO_PLANES;
-          const uint32_t phase = (pc / HALO_PLANES) & 1;
-          mbar_wait(&plane_empty[slot], phase ^ 1);
-          mbar_arrive_expect_tx(&plane_full[slot], p.nchunks * HALO_CHUNK_DATA);
-          uint8_t* dst = planes + slot * p.plane_bytes;
-          for (int c = 0; c < p.nchunks; ++c)
-            tma_load_5d(dst + c * HALO_CHUNK_BYTES, &tmA, &plane_full[slot], 0, -1, y - 1, z0 - 1 + k, n * p.nchunks + c);
-        }
+      mbar_arrive_expect_tx(w_full, p.wres_bytes);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(wimg) + size_t(half) * p.wres_bytes;
+      for (int off = 0; off < p.wres_bytes; off += 16384) {
+        const int n = min(16384, p.wres_bytes - off);
+        bulk_load(wres + off, src + off, n, w_full);
       }
     }
-  } else if (warp == 3) {
-    // ===== producer: weight taps =====
-    if (lane == 0) {
-      uint32_t wc = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        for (int i = 0; i < p.zseg; ++i) {
-          for (int tp = 0; tp < 27; ++tp, ++wc) {
-            const int st = wc % HALO_WSTAGES;
-            const uint32_t phase = (wc / HALO_WSTAGES) & 1;
-            mbar_wait(&w_empty[st], phase ^ 1);
-            mbar_arrive_expect_tx(&w_full[st], p.wtap_bytes);
-            bulk_load(wring + st * p.wtap_bytes, reinterpret_cast<const uint8_t*>(wimg) + size_t(tp) * p.wtap_bytes,
-                      p.wtap_bytes, &w_full[st]);
-          }
+  } else if (warp >= 8) {
+    // ===== producers: activation planes with 16-byte cp.async (zero-fill outside the grid = conv padding) =====
+    // (A 5-D TMA box with a 16-byte inner extent was tried first: TMA throughput turned out to be bound by the number
+    //  of box rows — ~5 cycles per 16 B row, 15k cycles per plane — not by bytes.  LDGSTS moves 512 B per warp
+    //  instruction.)  Two planes are kept in flight per thread with cp.async groups.
+    const int tid = threadIdx.x - 8 * 32;
+    const int per_plane = p.nchunks * 3 * HALO_XP;  // 16-byte copies per plane
+    uint32_t pc = 0;
+    int prev_slot = -1;
+    for (int item = cta_in_half; item < items_per_half; item += ctas_per_half) {
+      int n, y, z0;
+      decode(item, n, y, z0);
+      for (int k = 0; k < p.zseg + 2; ++k, ++pc) {
+        const int slot = pc % NP;
+        const uint32_t phase = (pc / NP) & 1;
+        const int z = z0 - 1 + k;
+        mbar_wait(&plane_empty[slot], phase ^ 1);
+        const uint32_t dst0 = smem_u32(planes + slot * p.plane_bytes);
+        const bool z_ok = z >= 0 && z < p.D;
+        for (int id = tid; id < per_plane; id += HALO_PRODUCERS) {
+          const int xx = id % HALO_XP, rem = id / HALO_XP, yy = rem % 3, c = rem / 3;
+          const int gx = xx - 1, gy = y - 1 + yy;
+          const bool ok = z_ok && gx >= 0 && gx < HALO_W && gy >= 0 && gy < p.H;
+          const __half* src = xplanar;
+          if (ok) src += ((((size_t(n) * p.nchunks + c) * p.D + z) * p.H + gy) * HALO_W + gx) * 8;
+          const uint32_t dst = dst0 + uint32_t(c) * HALO_CHUNK_BYTES + uint32_t(yy * HALO_XP + xx) * 16u;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (prev_slot >= 0) {
+          asm volatile("cp.async.wait_group 1;" ::: "memory");  // the previous plane of this thread has landed
+          fence_proxy_async_smem();
+          mbar_arrive(&plane_full[prev_slot]);
+        }
+        prev_slot = slot;
       }
+    }
+    if (prev_slot >= 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      fence_proxy_async_smem();
+      mbar_arrive(&plane_full[prev_slot]);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, BN);
-      const int ksteps = p.C_in / 16;
-      const uint32_t wsplit_bytes = uint32_t(p.C_in) * p.C_out * 2;
-      const uint32_t wk_bytes = uint32_t(p.C_out / 8) * 256;  // one K=16 block of B: [C_out/8 groups][2 k-chunks][128 B]
-      uint32_t pc = 0, wc = 0;
+    // One thread issues ~100-160 MMAs per output row, each only 8-32 tensor-core cycles long, so the ISSUE LOOP is
+    // the critical path (a first version rebuilt both 64-bit descriptors with ~40 dependent integer instructions per
+    // MMA and ran at ~150 cycles/MMA regardless of how operands were staged).  Everything loop-invariant is hoisted:
+    // a descriptor is `constant high word | (smem address >> 4)`, so taps / k-steps / splits are plain adds; and the
+    // whole warp runs the loop convergently with only the elected lane's MMA taking effect (umma_f16_elect).
+    {
+      const uint32_t leader = elect_one() ? 1u : 0u;
+      const uint32_t idesc_hi = make_idesc_f16(128, PRECISE ? 32 : 16);  // x_hi * [W_hi ; W_lo]
+      const uint32_t idesc_lo = make_idesc_f16(128, 16);                 // x_lo * W_hi
+      // A: rows = voxels at 16 B pitch (8-row core matrices of 128 B, SBO), K halves one chunk pitch apart (LBO)
+      const uint64_t a_desc0 = make_smem_desc(0, HALO_CHUNK_BYTES, 128, SW_NONE);
+      // B: [N/8 groups (256 B, SBO)][2 k-chunks (128 B, LBO)][8 rows x 16 B]
+      const uint64_t b_desc0 = make_smem_desc(0, 128, 256, SW_NONE) + (smem_u32(wres) >> 4);
+      constexpr uint32_t KS_STEP = 2 * HALO_CHUNK_BYTES / 16;            // next 16 channels of A
+      const uint32_t lo_off = uint32_t(p.C_in / 8) * HALO_CHUNK_BYTES / 16;
+      const uint32_t wk16 = uint32_t(p.wk_bytes) >> 4;
+      uint32_t pc = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      mbar_wait(w_full, 0);
+      for (int item = cta_in_half; item < items_per_half; item += ctas_per_half) {
         // planes pc+0 (z0-1) and pc+1 (z0) must have landed before the first row; plane pc+i+2 before dz=+1 of row i
-        for (int k = 0; k < 2; ++k) mbar_wait(&plane_full[(pc + k) % HALO_PLANES], ((pc + k) / HALO_PLANES) & 1);
+        for (int k = 0; k < 2; ++k) mbar_wait(&plane_full[(pc + k) % NP], ((pc + k) / NP) & 1);
         for (int i = 0; i < p.zseg; ++i) {
           mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BN;
-          bool first = true;
+          const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+          uint64_t bd = b_desc0;
+#pragma unroll
           for (int dz = 0; dz < 3; ++dz) {
             const uint32_t pidx = pc + i + dz;
-            if (dz == 2) mbar_wait(&plane_full[pidx % HALO_PLANES], (pidx / HALO_PLANES) & 1);
+            if (dz == 2) mbar_wait(&plane_full[pidx % NP], (pidx / NP) & 1);
             tc_fence_after();
-            const uint32_t plane_addr = smem_u32(planes + (pidx % HALO_PLANES) * p.plane_bytes);
+            const uint64_t ad = a_desc0 + (smem_u32(planes + (pidx % NP) * p.plane_bytes) >> 4);
+#pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
-              for (int dx = 0; dx < 3; ++dx, ++wc) {
-                const int st = wc % HALO_WSTAGES;
-                mbar_wait(&w_full[st], (wc / HALO_WSTAGES) & 1);
-                tc_fence_after();
-                const uint32_t w_addr = smem_u32(wring + st * p.wtap_bytes);
-                const uint32_t tap_off = uint32_t(dy * HALO_XP + dx) * 16u;
-                for (int ps = 0; ps < p.npass; ++ps) {
-                  const uint32_t a_chunk0 = uint32_t(p.pass_a[ps]) * (p.C_in / 8);
-                  const uint32_t wb = w_addr + uint32_t(p.pass_w[ps]) * wsplit_bytes;
-                  for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint32_t a_addr = plane_addr + (a_chunk0 + 2 * ks) * HALO_CHUNK_BYTES + tap_off;
-                    // A: rows = voxels at 16 B pitch (8-row core matrices of 128 B), K halves HALO_CHUNK_BYTES apart
-                    const uint64_t da = make_smem_desc(a_addr, HALO_CHUNK_BYTES, 128, SW_NONE);
-                    // B: [C_out/8 groups (256 B)][2 k-chunks (128 B)][8 rows x 16 B]
-                    const uint64_t db = make_smem_desc(wb + ks * wk_bytes, 128, 256, SW_NONE);
-                    umma_f16(d_tmem, da, db, idesc, first ? 0u : 1u);
-                    first = false;
-                  }
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                  constexpr int dummy = 0;
+                  (void)dummy;
+                  const int mi = ((dz * 3 + dy) * 3 + dx) * KSTEPS + ks;  // compile-time
+                  const int part = mi % NPART;
+                  const uint32_t accum = mi >= NPART ? 1u : 0u;
+                  const uint64_t a_hi = ad + uint32_t(dy * HALO_XP + dx) + uint32_t(ks) * KS_STEP;
+                  umma_f16_elect(d_tmem + part * 32, a_hi, bd, idesc_hi, accum, leader);
+                  if (PRECISE) umma_f16_elect(d_tmem + NPART * 32 + part * 16, a_hi + lo_off, bd, idesc_lo, accum, leader);
+                  bd += wk16;
                 }
-                umma_commit(&w_empty[st]);
               }
             }
+            // plane z-1 is dead after the dz = 0 taps: release it now so the producers refill the slot while the
+            // remaining 18 taps run (this is what lets a 3-slot ring overlap loads with MMAs)
+            if (dz == 0) umma_commit_elect(&plane_empty[(pc + i) % NP], leader);
           }
-          umma_commit(&tmem_full[acc]);
-          umma_commit(&plane_empty[(pc + i) % HALO_PLANES]);  // plane z-1 is not needed by later rows
+          umma_commit_elect(&tmem_full[acc], leader);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
         // the last two planes of the column are not reused by this CTA
-        umma_commit(&plane_empty[(pc + p.zseg) % HALO_PLANES]);
-        umma_commit(&plane_empty[(pc + p.zseg + 1) % HALO_PLANES]);
+        umma_commit_elect(&plane_empty[(pc + p.zseg) % NP], leader);
+        umma_commit_elect(&plane_empty[(pc + p.zseg + 1) % NP], leader);
         pc += p.zseg + 2;
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: thread = voxel x of the output row =====
+    // ===== epilogue: thread = voxel x of the output row; 16 output channels [half*16, +16) =====
     const int q = warp & 3;
     const int x = q * 32 + lane;
     constexpr int MAXG = 8;
@@ -201,16 +244,18 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __half* __rest
 #pragma unroll
     for (int i = 0; i < MAXG; ++i) gs[i] = gq[i] = 0.f;
     int stat_n = -1;
-    const int cpg = p.stats ? p.C_out / p.groups : 1;
-    const int ngroups = p.stats ? p.groups : 0;
+    const int cpg = p.stats ? p.C_out / p.groups : 16;
+    const int col0 = half * HALO_CO;
+    const int gfirst = col0 / cpg;                               // first group this CTA's channels touch
+    const int per = cpg >= 16 ? 1 : 16 / cpg;                    // groups inside the 16 channels
     auto flush = [&]() {
       if (stat_n < 0) return;
 #pragma unroll
       for (int i = 0; i < MAXG; ++i) {
-        if (i < ngroups) {
+        if (i < per) {
           const float s = warp_sum(gs[i]), s2 = warp_sum(gq[i]);
           if (lane == 0) {
-            double* dst = p.stats + (size_t(stat_n) * p.groups + i) * 2;
+            double* dst = p.stats + (size_t(stat_n) * p.groups + gfirst + i) * 2;
             atomicAdd(dst, double(s));
             atomicAdd(dst + 1, double(s2));
           }
@@ -220,7 +265,7 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __half* __rest
     };
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (int item = cta_in_half; item < items_per_half; item += ctas_per_half) {
       int n, y, z0;
       decode(item, n, y, z0);
       if (p.stats && n != stat_n) {
@@ -232,71 +277,79 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __half* __rest
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const size_t ovox = ((size_t(n) * p.D + z) * p.H + y) * HALO_W + x;
-#pragma unroll 1
-        for (int c = 0; c < BN / 16; ++c) {
-          uint32_t rr[16];
-          tmem_ld_32x32b_x16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 16), rr);
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * ACC_COLS);
+#pragma unroll
+        for (int part = 0; part < NPART; ++part) {
+          uint32_t rh[16];
+          tmem_ld_32x32b_x16(trow + part * 32, rh);
           tc_wait_ld();
-          const int col0 = c * 16;
-          float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
-          if (p.residual) {
-            const float* rs = p.residual + ovox * p.C_out + col0;
+          for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(rh[j]);
+          if (PRECISE) {
+            uint32_t r2[16], r3[16];
+            tmem_ld_32x32b_x16(trow + part * 32 + 16, r2);
+            tmem_ld_32x32b_x16(trow + NPART * 32 + part * 16, r3);
+            tc_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(rs + j);
-              v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.out32) {
-            float* o = p.out32 + ovox * p.C_out + col0;
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-          if (p.out16) {
-            __half* o = p.out16 + ovox * size_t(p.o16_splits) * p.C_out + col0;
-            __align__(16) __half2 hh[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) hh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-            reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(hh)[0];
-            reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(hh)[1];
-            if (p.o16_splits == 2) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 f = __half22float2(hh[j]);
-                hh[j] = __floats2half2_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y);
-              }
-              reinterpret_cast<uint4*>(o + p.C_out)[0] = reinterpret_cast<const uint4*>(hh)[0];
-              reinterpret_cast<uint4*>(o + p.C_out)[1] = reinterpret_cast<const uint4*>(hh)[1];
-            }
-          }
-          if (p.stats) {
-            // channels per group is a power of two in {2,4,8,16,32}: groups inside this 16-channel chunk
-            const int per = cpg >= 16 ? 1 : 16 / cpg;
-#pragma unroll
-            for (int i = 0; i < MAXG; ++i) {
-              const int gfirst = (c * 16) / cpg;  // first group touched by this chunk
-              const int lg = i - gfirst;
-              if (lg >= 0 && lg < per) {
-                float s = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (cpg >= 16 || j / cpg == lg) s += v[j], s2 += v[j] * v[j];
-                gs[i] += s, gq[i] += s2;
-              }
-            }
+            for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r2[j]) + __uint_as_float(r3[j]);
           }
         }
+        // accumulator drained: hand it back before the (long) global-memory part of the epilogue
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+
+        if (p.residual) {
+          const float* rs = p.residual + ovox * p.C_out + col0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(rs + j);
+            v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.out32) {
+          float* o = p.out32 + ovox * p.C_out + col0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (p.out16) {
+          __half* o = p.out16 + ovox * size_t(p.o16_splits) * p.C_out + col0;
+          __align__(16) __half2 hh[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) hh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+          reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(hh)[0];
+          reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(hh)[1];
+          if (p.o16_splits == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 f = __half22float2(hh[j]);
+              hh[j] = __floats2half2_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+            }
+            reinterpret_cast<uint4*>(o + p.C_out)[0] = reinterpret_cast<const uint4*>(hh)[0];
+            reinterpret_cast<uint4*>(o + p.C_out)[1] = reinterpret_cast<const uint4*>(hh)[1];
+          }
+        }
+        if (p.stats) {
+#pragma unroll
+          for (int i = 0; i < MAXG; ++i) {
+            if (i < per) {
+              float s = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cpg >= 16 || j / cpg == i) s += v[j], s2 += v[j] * v[j];
+              gs[i] += s, gq[i] += s2;
+            }
+          }
+        }
       }
     }
     if (p.stats) flush();
@@ -321,58 +374,53 @@ extern "C" int semabs_conv3d_halo(const void* x16_planar, int32_t a_splits, cons
   SB_REQUIRE(x16_planar && w_img && (out32 || out16), "semabs_conv3d_halo: null pointer");
   SB_REQUIRE(W == HALO_W, "semabs_conv3d_halo: W must be %d (got %d)", HALO_W, W);
   SB_REQUIRE((C_in == 16 || C_in == 32) && (C_out == 16 || C_out == 32), "semabs_conv3d_halo: C_in/C_out must be 16 or 32");
-  SB_REQUIRE(!precise || (a_splits == 2 && w_splits == 2), "semabs_conv3d_halo: precise mode needs hi/lo operands");
+  SB_REQUIRE(precise ? (a_splits == 2 && w_splits == 2) : (w_splits == 1),
+             "semabs_conv3d_halo: precise mode needs hi/lo operands; fast mode a single-split weight image");
   SB_REQUIRE(!stats || (groups >= 1 && groups <= 8 && C_out % groups == 0 && (C_out / groups) >= 2),
              "semabs_conv3d_halo: bad GroupNorm groups");
   SB_REQUIRE(N > 0 && D > 0 && H > 0, "semabs_conv3d_halo: bad grid");
   HaloParams p{};
   p.N = N, p.D = D, p.H = H, p.C_in = C_in, p.C_out = C_out;
   p.nchunks = a_splits * C_in / 8;
-  p.w_splits = w_splits;
-  if (precise) {
-    p.npass = 3;
-    p.pass_a[0] = 0, p.pass_w[0] = 0, p.pass_a[1] = 1, p.pass_w[1] = 0, p.pass_a[2] = 0, p.pass_w[2] = 1;
-  } else {
-    p.npass = 1, p.pass_a[0] = 0, p.pass_w[0] = 0;
-  }
-  // work item = (n, y, z segment); enough items for ~7 rounds over the SMs, segments not shorter than 16 rows
+  p.precise = precise;
+  p.co_halves = C_out / HALO_CO;
+  p.wk_bytes = (precise ? 4 : 2) * 256;
+  p.wres_bytes = 27 * (C_in / 16) * p.wk_bytes;
+  p.plane_bytes = p.nchunks * HALO_CHUNK_BYTES;
+  p.nplanes = (size_t(4) * p.plane_bytes + p.wres_bytes + 1024 <= size_t(227) * 1024) ? 4 : 3;
+  const size_t smem = size_t(p.nplanes) * p.plane_bytes + p.wres_bytes + 256 + 128;
+  SB_REQUIRE(smem <= 227 * 1024, "semabs_conv3d_halo: %zu bytes of shared memory needed", smem);
+  // CTAs are split evenly between the 16-channel halves and keep their half's weights resident
+  const int ctas_per_half = num_sms() / p.co_halves;
+  // work item = (n, y, z segment); enough items for ~6 rounds over the CTAs of a half, segments >= 16 rows
   int zseg = D;
-  while (zseg > 16 && (long long)N * H * (D / zseg) < 6LL * num_sms() && zseg % 2 == 0) zseg /= 2;
+  while (zseg > 16 && (long long)N * H * (D / zseg) < 6LL * ctas_per_half && zseg % 2 == 0) zseg /= 2;
   p.zseg = zseg, p.nseg = D / zseg;
   SB_REQUIRE(p.zseg * p.nseg == D, "semabs_conv3d_halo: D=%d not divisible into z segments", D);
-  p.plane_bytes = p.nchunks * HALO_CHUNK_BYTES;
-  p.wtap_bytes = w_splits * C_in * C_out * 2;
   p.residual = residual, p.relu = relu, p.out32 = out32, p.out16 = (__half*)out16, p.o16_splits = o16_splits;
   p.stats = stats, p.groups = groups;
-  const size_t smem = size_t(HALO_PLANES) * p.plane_bytes + size_t(HALO_WSTAGES) * p.wtap_bytes + 512 + 128;
-  SB_REQUIRE(smem <= 227 * 1024, "semabs_conv3d_halo: %zu bytes of shared memory needed", smem);
 
-  CUtensorMap tmA;
-  {
-    // [n*nchunks][z][y][x][8] fp16
-    uint64_t dims[5] = {8, uint64_t(W), uint64_t(H), uint64_t(D), uint64_t(N) * p.nchunks};
-    uint64_t str[4] = {16, 16ull * W, 16ull * W * H, 16ull * W * H * D};
-    uint32_t box[5] = {8, uint32_t(HALO_XP), 3, 1, 1};
-    if (int rc = make_tmap_f16(&tmA, x16_planar, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
-  }
   cudaStream_t st = (cudaStream_t)stream;
   const int items = N * H * p.nseg;
-  const int grid = items < num_sms() ? items : num_sms();
-  if (C_out == 32) {
-    static bool cfg = false;
-    if (!cfg) {
-      SB_CHECK_CUDA(cudaFuncSetAttribute(conv3d_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      cfg = true;
-    }
-    conv3d_halo_kernel<32><<<grid, HALO_THREADS, smem, st>>>(tmA, (const __half*)w_img, p);
-  } else {
-    static bool cfg = false;
-    if (!cfg) {
-      SB_CHECK_CUDA(cudaFuncSetAttribute(conv3d_halo_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      cfg = true;
-    }
-    conv3d_halo_kernel<16><<<grid, HALO_THREADS, smem, st>>>(tmA, (const __half*)w_img, p);
-  }
+  const int per_half = items < ctas_per_half ? items : ctas_per_half;
+  const int grid = per_half * p.co_halves;
+  const __half* xp = (const __half*)x16_planar;
+  const __half* wp = (const __half*)w_img;
+#define SB_HALO_LAUNCH(KS, PR)                                                                                        \
+  do {                                                                                                                \
+    static bool cfg = false;                                                                                          \
+    if (!cfg) {                                                                                                       \
+      SB_CHECK_CUDA(cudaFuncSetAttribute(conv3d_halo_kernel<KS, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                         227 * 1024));                                                                \
+      cfg = true;                                                                                                     \
+    }                                                                                                                 \
+    conv3d_halo_kernel<KS, PR><<<grid, HALO_THREADS, smem, st>>>(xp, wp, p);                                          \
+  } while (0)
+  if (C_in == 32 && precise) SB_HALO_LAUNCH(2, true);
+  else if (C_in == 32) SB_HALO_LAUNCH(2, false);
+  else if (precise) SB_HALO_LAUNCH(1, true);
+  else SB_HALO_LAUNCH(1, false);
+#undef SB_HALO_LAUNCH
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

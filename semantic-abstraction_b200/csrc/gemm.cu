@@ -112,9 +112,12 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: whole warp runs the loop, the elected lane issues (see umma_f16_elect) =====
+    {
+      const uint32_t leader = elect_one() ? 1u : 0u;
       constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
+      // descriptor = loop-invariant high word | (smem address >> 4)
+      const uint64_t desc0 = make_smem_desc(0, 16, 1024, SW_128B) + (smem_u32(smem) >> 4);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -126,22 +129,20 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int kb = 0; kb < kblocks_total; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + S::A_BYTES;
-          const uint64_t da = make_smem_desc(a_addr, 16, 1024, SW_128B);
-          const uint64_t db = make_smem_desc(b_addr, 16, 1024, SW_128B);
+          const uint64_t da = desc0 + uint32_t(stage) * uint32_t(S::STAGE_BYTES >> 4);
+          const uint64_t db = da + uint32_t(S::A_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128B swizzle row: +2 in the 16-byte address field
-            umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+            umma_f16_elect(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0, leader);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          umma_commit_elect(&empty_bar[stage], leader);  // smem slot reusable once these MMAs retire
           if (++stage == S::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
+        umma_commit_elect(&tmem_full[acc], leader);  // accumulator complete
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

@@ -128,6 +128,32 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-convergent issue: every lane of the MMA warp executes the (warp-uniform) address arithmetic and this call, only
+// the elected lane's instruction takes effect.  Issuing from inside a divergent `if (lane == 0)` block instead makes the
+// compiler move every descriptor into uniform registers through an ELECT / R2UR.BROADCAST / BRA.U.ANY loop — measured
+// ~100 cycles of issue overhead per MMA, i.e. more than a 128x128x16 MMA takes to execute.
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %1, 0;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(leader)
+      : "memory");
+}
 // mbarrier arrives when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

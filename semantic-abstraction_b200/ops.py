@@ -236,18 +236,22 @@ def conv3d_halo(x16_planar, w_img, *, N, D, H, W, C_in, C_out, a_splits=1, w_spl
 
 
 def pack_halo_weights(w: torch.Tensor, splits: int) -> torch.Tensor:
-    """conv.weight [Co, Ci, 3,3,3] fp32 -> per-tap UMMA no-swizzle core-matrix images, fp16:
-    [27 taps][splits][Ci/16][Co/8][2][8 rows][8 elems] with value W[co = g*8 + r][ci = kb*16 + kc*8 + e][tap]."""
+    """conv.weight [Co, Ci, 3,3,3] fp32 -> resident UMMA no-swizzle core-matrix images for semabs_conv3d_halo, fp16:
+    [Co/16 halves][27 taps][Ci/16 k-blocks][N/8 groups][2 k-chunks][8 rows][8 elems], where the N rows of a half are
+    its 16 output channels of W_hi followed (splits == 2) by the same 16 channels of W_lo = fp16(W - W_hi)."""
     co, ci = w.shape[:2]
     w = w.detach().float().reshape(co, ci, 27)
     hi = w.half()
-    parts = [hi] if splits == 1 else [hi, (w - hi.float()).half()]
-    imgs = []
-    for part in parts:
-        # [co, ci, tap] -> [tap, kb, g, kc, r, e]
-        t = part.permute(2, 0, 1).reshape(27, co // 8, 8, ci // 16, 2, 8)  # tap, g, r, kb, kc, e
-        imgs.append(t.permute(0, 3, 1, 4, 2, 5).contiguous())  # tap, kb, g, kc, r, e
-    return torch.stack(imgs, dim=1).contiguous()  # tap, split, kb, g, kc, r, e
+    halves = []
+    for h in range(co // 16):
+        rows = [hi[h * 16 : (h + 1) * 16]]
+        if splits == 2:
+            rows.append((w - hi.float()).half()[h * 16 : (h + 1) * 16])
+        b = torch.cat(rows, dim=0)  # [N, ci, 27]
+        n = b.shape[0]
+        t = b.permute(2, 0, 1).reshape(27, n // 8, 8, ci // 16, 2, 8)  # tap, g, r, kb, kc, e
+        halves.append(t.permute(0, 3, 1, 4, 2, 5).contiguous())  # tap, kb, g, kc, r, e
+    return torch.stack(halves, dim=0).contiguous()
 
 
 def maxpool3d_2(x, y, *, N, D, H, W, C, groups=1, stats=None):

@@ -188,10 +188,10 @@ class ResidualUNet3D(nn.Module):
         halo = W == 128 and c_in_pad in (16, 32) and c_out in (16, 32) and self.use_halo
         common = dict(N=N, D=D, H=H, W=W, a_splits=s, w_splits=s, precise=self.precise)
 
-        def gcr(j, src, src_stats, c_src_pad, c_src_real, groups, **epi):
+        def gcr(j, src, src_stats, c_src_pad, c_src_real, gn_groups, **epi):
             """one 'gc[r]' unit: GroupNorm-apply then the implicit-GEMM conv (halo-resident kernel at full resolution)"""
             ops.groupnorm_apply(src, src_stats, pk[f"{prefix}.g{j}"], pk[f"{prefix}.b{j}"], xn, N=N, S=S, C=c_src_pad,
-                                C_real=c_src_real, groups=groups, splits=s, planar=halo)
+                                C_real=c_src_real, groups=gn_groups, splits=s, planar=halo)
             if halo:
                 ops.conv3d_halo(xn, pk[f"{prefix}.wh{j}"], C_in=c_src_pad, C_out=c_out, **common, **epi)
             else:

@@ -1,0 +1,50 @@
+"""CPU suite: the N>1 plumbing (unit sharding, max-over-ranks timing) under gloo with world_size 2."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from semabs_b200 import dist as sd
+
+    r, w = sd.rank_world()
+    units = list(range(17))
+    mine = sd.shard_units(units, r, w)
+    step_ms = 10.0 + 5.0 * rank  # rank 1 is the slow one
+    out.put((rank, mine, sd.max_over_ranks(step_ms), sd.sum_over_ranks(len(mine))))
+    dist.destroy_process_group()
+
+
+def test_sharding_and_timing_reduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    (r0, u0, t0, n0), (r1, u1, t1, n1) = res
+    assert u0 + u1 == list(range(17)) and abs(len(u0) - len(u1)) <= 1  # every unit exactly once, balanced
+    assert t0 == t1 == 15.0  # max over ranks
+    assert n0 == n1 == 17.0
+
+
+def test_shard_units_properties():
+    from semabs_b200.dist import shard_units
+
+    for n in (0, 1, 7, 8, 64):
+        for world in (1, 2, 3, 8):
+            parts = [shard_units(list(range(n)), r, world) for r in range(world)]
+            assert sum(parts, []) == list(range(n))
+            assert max(map(len, parts)) - min(map(len, parts)) <= 1
