@@ -130,8 +130,10 @@ conv3d_halo_kernel(const __half* __restrict__ xplanar, const __half* __restrict_
     // (A 5-D TMA box with a 16-byte inner extent was tried first: TMA throughput turned out to be bound by the number
     //  of box rows — ~5 cycles per 16 B row, 15k cycles per plane — not by bytes.  LDGSTS moves 512 B per warp
     //  instruction.)  Two planes are kept in flight per thread with cp.async groups.
-    const int tid = threadIdx.x - 8 * 32;
-    const int per_plane = p.nchunks * 3 * HALO_XP;  // 16-byte copies per plane
+    // warp pw owns the (chunk, row) segments pw, pw+4, ...; a lane walks x with stride 32: per copy only a few
+    // integer instructions (the first version recomputed div/mod per 16-byte copy and spent ~5k cycles per plane).
+    const int pw = warp - 8;
+    const int nseg = p.nchunks * 3;
     uint32_t pc = 0;
     int prev_slot = -1;
     for (int item = cta_in_half; item < items_per_half; item += ctas_per_half) {
@@ -144,14 +146,20 @@ conv3d_halo_kernel(const __half* __restrict__ xplanar, const __half* __restrict_
         mbar_wait(&plane_empty[slot], phase ^ 1);
         const uint32_t dst0 = smem_u32(planes + slot * p.plane_bytes);
         const bool z_ok = z >= 0 && z < p.D;
-        for (int id = tid; id < per_plane; id += HALO_PRODUCERS) {
-          const int xx = id % HALO_XP, rem = id / HALO_XP, yy = rem % 3, c = rem / 3;
-          const int gx = xx - 1, gy = y - 1 + yy;
-          const bool ok = z_ok && gx >= 0 && gx < HALO_W && gy >= 0 && gy < p.H;
-          const __half* src = xplanar;
-          if (ok) src += ((((size_t(n) * p.nchunks + c) * p.D + z) * p.H + gy) * HALO_W + gx) * 8;
-          const uint32_t dst = dst0 + uint32_t(c) * HALO_CHUNK_BYTES + uint32_t(yy * HALO_XP + xx) * 16u;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+        for (int sg = pw; sg < nseg; sg += 4) {
+          const int c = sg / 3, yy = sg - 3 * c;
+          const int gy = y - 1 + yy;
+          const bool row_ok = z_ok && gy >= 0 && gy < p.H;
+          // element (x = -1) of the row: the halo copy at xx = 0 reads nothing (src-size 0), so the pointer is never used
+          const __half* srow = xplanar + ((((size_t(n) * p.nchunks + c) * p.D + (z_ok ? z : 0)) * p.H + (row_ok ? gy : 0)) * HALO_W) * 8 - 8;
+          const uint32_t drow = dst0 + uint32_t(c) * HALO_CHUNK_BYTES + uint32_t(yy * HALO_XP) * 16u;
+#pragma unroll
+          for (int xx = lane; xx < HALO_XP; xx += 32) {
+            const bool ok = row_ok && xx >= 1 && xx <= HALO_W;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(drow + uint32_t(xx) * 16u),
+                         "l"(ok ? srow + xx * 8 : xplanar), "r"(ok ? 16u : 0u)
+                         : "memory");
+          }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (prev_slot >= 0) {

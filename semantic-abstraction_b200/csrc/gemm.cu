@@ -290,7 +290,10 @@ extern "C" int semabs_gemm_f16(const void* A, int32_t lda, const void* B, int32_
              "semabs_gemm_f16: bad output pitch");
 
   const int kblocks = (K + GEMM_BK - 1) / GEMM_BK;
-  const int BN = (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
+  // 128x256 tiles when the problem is big enough to fill the SMs: one MMA then reads A (4 KB) + B (8 KB) per 128
+  // tensor cycles = 96 B/clk of shared-memory bandwidth instead of the 128 B/clk (the full SMEM rate) of 128x128
+  const long long tiles256 = (long long)((M + GEMM_BM - 1) / GEMM_BM) * (N / 256);
+  const int BN = (N % 256 == 0 && tiles256 >= 2LL * num_sms()) ? 256 : (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
 
   CUtensorMap tmA, tmB;
   {
@@ -323,6 +326,7 @@ extern "C" int semabs_gemm_f16(const void* A, int32_t lda, const void* B, int32_
   ep.scale = e->scale;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int kb_total = kblocks * a_splits;
+  if (BN == 256) return launch_gemm<256>(tmA, tmB, M, N, kb_total, kblocks, ep, st);
   if (BN == 128) return launch_gemm<128>(tmA, tmB, M, N, kb_total, kblocks, ep, st);
   if (BN == 64) return launch_gemm<64>(tmA, tmB, M, N, kb_total, kblocks, ep, st);
   return launch_gemm<32>(tmA, tmB, M, N, kb_total, kblocks, ep, st);
