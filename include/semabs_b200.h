@@ -118,6 +118,13 @@ int semabs_attn_bwd(const void* qkv16, const void* probs16, int32_t ld_p16, cons
                     int32_t ld_do, const float* r, float* delta_ws, float* wpart, void* dqkv16, int32_t P, int32_t B,
                     int32_t T, int32_t H, int32_t splits, int32_t positive_only, int32_t need_dqkv, void* stream);
 
+/* Attention backward of the LAST transformer block, where only the class-token row of dO is non-zero (the logits
+ * read x[:,0] only, model_explainability.py:349): same outputs as semabs_attn_bwd (wpart, dqkv16 for all T rows)
+ * from dO16_cls [P*B, ld_do] = class-token rows of the cotangent. */
+int semabs_attn_bwd_cls(const void* qkv16, const void* probs16, int32_t ld_p16, const void* dO16_cls, int32_t ld_do,
+                        const float* r, float* wpart, void* dqkv16, int32_t P, int32_t B, int32_t T, int32_t H,
+                        int32_t splits, int32_t positive_only, int32_t need_dqkv, void* stream);
+
 /* logits[b,p] = 100 * f_b/|f_b| . W[:,p] (ClipGradcam.forward, clip_gradcam.py:58-68) and the cotangent seed
  * d logits[b,p] / d f_b -> seed16 [P*B, splits*E] (row p*B + b). Either output may be NULL. W is [E,P] fp32. */
 int semabs_clip_logit_seed(const float* f, const float* W, float* logits, void* seed16, int32_t B, int32_t P,

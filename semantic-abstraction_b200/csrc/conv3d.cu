@@ -277,28 +277,18 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if (p.stats) {
-            // 16 consecutive channels: they belong to group (col0 / cpg) ... ((col0 + 15) / cpg)
-            if (cpg >= 16) {
-              const int gi = (BN >= cpg) ? (c * 16) / cpg : 0;
-              float s = 0.f, s2 = 0.f;
+            // 16 consecutive channels -> 16/cpg partial group sums, added to the accumulators of the groups
+            // [first, first + per) of this BN-wide tile (static register indices, compare instead of divide)
+            float ps[8], pq[8];
+            group_sums16(v, cpg, ps, pq);
+            const int per = cpg >= 16 ? 1 : 16 / cpg;
+            const int first = (BN >= cpg) ? (c * 16) / cpg : 0;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) s += v[j], s2 += v[j] * v[j];
+            for (int k = 0; k < 8; ++k) {
+              if (k < per) {
 #pragma unroll
-              for (int i = 0; i < MAXG; ++i)
-                if (i == gi) gs[i] += s, gq[i] += s2;
-            } else {
-              // cpg in {2, 4, 8}: several groups inside this 16-channel chunk
-              const int per = 16 / cpg;
-#pragma unroll
-              for (int i = 0; i < MAXG; ++i) {
-                const int lg = i - c * per;  // group index local to this chunk
-                if (lg >= 0 && lg < per) {
-                  float s = 0.f, s2 = 0.f;
-#pragma unroll
-                  for (int j = 0; j < 16; ++j)
-                    if (j / cpg == lg) s += v[j], s2 += v[j] * v[j];
-                  gs[i] += s, gq[i] += s2;
-                }
+                for (int i = 0; i < MAXG; ++i)
+                  if (i == first + k) gs[i] += ps[k], gq[i] += pq[k];
               }
             }
           }

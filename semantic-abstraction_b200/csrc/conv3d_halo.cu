@@ -347,16 +347,11 @@ conv3d_halo_kernel(const __half* __restrict__ xplanar, const __half* __restrict_
           }
         }
         if (p.stats) {
+          float ps[8], pq[8];
+          group_sums16(v, cpg, ps, pq);
 #pragma unroll
-          for (int i = 0; i < MAXG; ++i) {
-            if (i < per) {
-              float s = 0.f, s2 = 0.f;
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (cpg >= 16 || j / cpg == i) s += v[j], s2 += v[j] * v[j];
-              gs[i] += s, gq[i] += s2;
-            }
-          }
+          for (int i = 0; i < MAXG; ++i)
+            if (i < per) gs[i] += ps[i], gq[i] += pq[i];
         }
       }
     }

@@ -154,7 +154,8 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(
 constexpr int TS = 72;        // half stride of [token][64] tiles: 144 B rows, 16B-aligned, conflict-free fragment loads
 constexpr int TR = 272;       // 17 MMA row tiles
 constexpr int BWD_WARPS = 6;
-constexpr int STRIP = 24;     // half stride of the per-warp [64][16] probability strip
+constexpr int STRIP = 16;     // half stride of the per-warp [64][16] probability strip (two buffers per warp); the two
+                              // 16-byte halves of a row are XOR-swizzled with bit 2 of the row => conflict-free ldmatrix
 
 struct AttnBwdArgs {
   const __half* qkv16;   // [B*T, 3d] (q already scaled)
@@ -247,8 +248,23 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2) attn_bwd_row_kernel(AttnBwd
 #pragma unroll
     for (int n = 0; n < 8; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
 
+    // probabilities of this warp's two rows are streamed from L2 one 64-key chunk AHEAD of their use (the loads
+    // were the top stall of the first version: a dependent L2 round trip per 8-key tile)
+    uint32_t cur_a[8], cur_b[8];
+    auto load_probs = [&](int jc, uint32_t (&xa)[8], uint32_t (&xb)[8]) {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int key = jc * 64 + n * 8 + 2 * t;
+        const bool in = key < a.ldp;  // rows are zero-padded up to ldp
+        xa[n] = (va && in) ? *reinterpret_cast<const uint32_t*>(Arow_a + key) : 0u;
+        xb[n] = (vb && in) ? *reinterpret_cast<const uint32_t*>(Arow_b + key) : 0u;
+      }
+    };
+    load_probs(0, cur_a, cur_b);
     for (int jc = 0; jc * 8 < ntiles_total; ++jc) {
       const int nt = min(8, ntiles_total - jc * 8);
+      uint32_t na[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, nb[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      if ((jc + 1) * 8 < ntiles_total) load_probs(jc + 1, na, nb);
       uint32_t fs[4][4];
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
@@ -262,12 +278,14 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2) attn_bwd_row_kernel(AttnBwd
             const uint32_t b1 = *reinterpret_cast<const uint32_t*>(Vs + (key + g) * TS + kt * 16 + 2 * t + 8);
             mma_16816(gacc, fo[kt], b0, b1);
           }
-          if (va) aa = unpack_h2(*reinterpret_cast<const uint32_t*>(Arow_a + key + 2 * t));
-          if (vb) ab = unpack_h2(*reinterpret_cast<const uint32_t*>(Arow_b + key + 2 * t));
+          aa = unpack_h2(cur_a[n]);
+          ab = unpack_h2(cur_b[n]);
         }
         fs[n >> 1][(n & 1) * 2 + 0] = pack_h2(aa.x * (gacc[0] - da), aa.y * (gacc[1] - da));
         fs[n >> 1][(n & 1) * 2 + 1] = pack_h2(ab.x * (gacc[2] - db), ab.y * (gacc[3] - db));
       }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) cur_a[n] = na[n], cur_b[n] = nb[n];
 #pragma unroll
       for (int kt = 0; kt < 4; ++kt) {
         if (2 * kt < nt) {
@@ -312,7 +330,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2) attn_bwd_col_kernel(AttnBwd
     Rw[i] = i < T ? a.r[size_t(pb) * T + i] : 0.f;
   }
   __syncthreads();
-  __half* strip = strips + warp * 64 * STRIP;
+  __half* strip_buf = strips + warp * 2 * 64 * STRIP;
   const int ntiles_total = (T + 7) / 8;
   const __half* Abase = a.probs16 + size_t(bh) * T * a.ldp;
 
@@ -339,24 +357,40 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2) attn_bwd_col_kernel(AttnBwd
     }
     float wa = 0.f, wb = 0.f;
 
-    for (int ic = 0; ic * 8 < ntiles_total; ++ic) {
-      const int nt = min(8, ntiles_total - ic * 8);
-      const int ibase = ic * 64;
-      // stage the [64 queries][16 keys] strip of A
-      __syncwarp();
+    // [64 queries][16 keys] strips of A are double-buffered with cp.async: chunk ic+1 streams from L2 while chunk ic
+    // is multiplied (zero-fill for query rows >= T)
+    auto stage_strip = [&](int ic, __half* dstbuf) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int c = lane + 32 * k, row = c >> 1, hf = c & 1;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (ibase + row < T) v = *reinterpret_cast<const uint4*>(Abase + size_t(ibase + row) * a.ldp + j0 + hf * 8);
-        *reinterpret_cast<uint4*>(strip + row * STRIP + hf * 8) = v;
+        const bool ok = ic * 64 + row < T;
+        const __half* src = ok ? Abase + size_t(ic * 64 + row) * a.ldp + j0 + hf * 8 : Abase;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                         static_cast<uint32_t>(__cvta_generic_to_shared(dstbuf + row * STRIP + (hf ^ ((row >> 2) & 1)) * 8))),
+                     "l"(src), "r"(ok ? 16u : 0u)
+                     : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    __syncwarp();
+    stage_strip(0, strip_buf);
+    for (int ic = 0; ic * 8 < ntiles_total; ++ic) {
+      const int nt = min(8, ntiles_total - ic * 8);
+      const int ibase = ic * 64;
+      __half* strip = strip_buf + (ic & 1) * 64 * STRIP;
+      if ((ic + 1) * 8 < ntiles_total) {
+        stage_strip(ic + 1, strip_buf + ((ic + 1) & 1) * 64 * STRIP);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
       __syncwarp();
       uint32_t fs[4][4], fa[4][4];
 #pragma unroll
       for (int kt = 0; kt < 4; ++kt) {
         // A^T fragments (rows = keys, k = queries) through a transposed ldmatrix of the [query][key] strip
-        ldmatrix_x4_trans(fa[kt], strip + (kt * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * STRIP + ((lane >> 3) & 1) * 8);
+        const int srow = kt * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
+        ldmatrix_x4_trans(fa[kt], strip + srow * STRIP + ((((lane >> 3) & 1)) ^ ((srow >> 2) & 1)) * 8);
       }
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
@@ -602,6 +636,110 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, 1) attn_fwd_mma_kernel(AttnFwd
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Backward of the LAST block: the cotangent of the block output is non-zero at the class token only
+// (logits depend on x[:, 0] alone, model_explainability.py:349), so dO has a single non-zero query row and the whole
+// attention backward collapses to vector work: one warp per (label, tile, head), lanes over keys.
+//   dA_0j = dO_0 . V_j ; w_j = r_0 relu(dA_0j A_0j) / H ; dS_0j = A_0j (dA_0j - sum_j dA_0j A_0j)
+//   dQ_0 = scale sum_j dS_0j K_j ; dK_j = dS_0j Q_0 ; dV_j = A_0j dO_0 ; dQ_i = 0 for i > 0
+// ---------------------------------------------------------------------------------------------------------
+struct AttnClsArgs {
+  const __half* qkv16;   // [B*T, 3d]
+  const __half* probs16; // [B*H, T, ldp]
+  int ldp;
+  const __half* dO16;    // [P*B, ld_do]  (class-token rows only)
+  int ld_do;
+  const float* r;        // [P*B, T]
+  float* wpart;          // [P*B*H, T]
+  __half* dqkv16;        // [P*B*T, splits*3d]
+  int P, B, T, H, d, splits;
+  float scale;
+  int positive_only, need_dqkv;
+};
+
+__global__ void __launch_bounds__(256) attn_bwd_cls_kernel(AttnClsArgs a) {
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (gw >= a.P * a.B * a.H) return;
+  const int h = gw % a.H, pb = gw / a.H, b = pb % a.B;
+  const int T = a.T, d = a.d;
+  const __half* base = a.qkv16 + size_t(b) * T * 3 * d + h * HD;
+  // dO_0 and Q_0 (64 values each) replicated in registers
+  float dO[HD], q0[HD];
+  {
+    const __half2* g2 = reinterpret_cast<const __half2*>(a.dO16 + size_t(pb) * a.ld_do + h * HD);
+    const __half2* q2 = reinterpret_cast<const __half2*>(base);
+#pragma unroll
+    for (int e = 0; e < HD / 2; ++e) {
+      const float2 x = __half22float2(g2[e]), y = __half22float2(q2[e]);
+      dO[2 * e] = x.x, dO[2 * e + 1] = x.y, q0[2 * e] = y.x, q0[2 * e + 1] = y.y;
+    }
+  }
+  const __half* Arow = a.probs16 + size_t(b * a.H + h) * T * a.ldp;  // query row 0
+  const float r0 = a.r[size_t(pb) * T];
+  constexpr int JMAX = (TR + 31) / 32;  // 9 keys per lane
+  float G[JMAX], A[JMAX];
+  float dsum = 0.f;
+#pragma unroll
+  for (int c = 0; c < JMAX; ++c) {
+    const int j = c * 32 + lane;
+    G[c] = 0.f, A[c] = 0.f;
+    if (j < T) {
+      const __half2* v2 = reinterpret_cast<const __half2*>(base + size_t(j) * 3 * d + 2 * d);
+      float acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < HD / 2; ++e) {
+        const float2 v = __half22float2(v2[e]);
+        acc = fmaf(dO[2 * e], v.x, acc), acc = fmaf(dO[2 * e + 1], v.y, acc);
+      }
+      G[c] = acc;
+      A[c] = __half2float(Arow[j]);
+      dsum += acc * A[c];
+    }
+  }
+  dsum = warp_sum(dsum);
+  float* wp = a.wpart + size_t(gw) * T;
+  float dq[HD];
+#pragma unroll
+  for (int e = 0; e < HD; ++e) dq[e] = 0.f;
+  const size_t ld = size_t(a.splits) * 3 * d;
+  const float invH = 1.0f / a.H;
+#pragma unroll
+  for (int c = 0; c < JMAX; ++c) {
+    const int j = c * 32 + lane;
+    if (j < T) {
+      float x = G[c] * A[c];
+      if (a.positive_only) x = fmaxf(x, 0.f);
+      wp[j] = r0 * x * invH;
+      if (a.need_dqkv) {
+        const float ds = A[c] * (G[c] - dsum);
+        const __half2* k2 = reinterpret_cast<const __half2*>(base + size_t(j) * 3 * d + d);
+        __half* orow = a.dqkv16 + (size_t(pb) * T + j) * ld + h * HD;
+#pragma unroll
+        for (int e = 0; e < HD / 2; ++e) {
+          const float2 k = __half22float2(k2[e]);
+          dq[2 * e] = fmaf(ds, k.x, dq[2 * e]), dq[2 * e + 1] = fmaf(ds, k.y, dq[2 * e + 1]);
+          store_h2_split(orow, 0, d + 2 * e, 3 * d, a.splits, ds * q0[2 * e], ds * q0[2 * e + 1]);
+          store_h2_split(orow, 0, 2 * d + 2 * e, 3 * d, a.splits, A[c] * dO[2 * e], A[c] * dO[2 * e + 1]);
+          if (j > 0) store_h2_split(orow, 0, 2 * e, 3 * d, a.splits, 0.f, 0.f);
+        }
+      }
+    }
+  }
+  if (a.need_dqkv) {
+    // dQ_0: reduce the per-lane partial sums over the warp, lane e ends up with elements 2e, 2e+1
+    float mine0 = 0.f, mine1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < HD; ++e) {
+      const float s = warp_sum(dq[e]);
+      if ((e >> 1) == lane) {
+        if (e & 1) mine1 = s; else mine0 = s;
+      }
+    }
+    __half* orow = a.dqkv16 + (size_t(pb) * T) * ld + h * HD;
+    store_h2_split(orow, 0, 2 * lane, 3 * d, a.splits, mine0 * a.scale, mine1 * a.scale);
+  }
+}
+
 template <int NCHUNK>
 static int launch_attn_fwd(const float* qkv, float* probs, __half* probs16, int ld_p16, float* o32, __half* o16, int B,
                            int T, int H, int d, int causal, int splits, cudaStream_t st) {
@@ -666,7 +804,7 @@ extern "C" int semabs_attn_bwd(const void* qkv16, const void* probs16, int32_t l
   a.dqkv16 = (__half*)dqkv16, a.P = P, a.B = B, a.T = T, a.H = H, a.d = H * HD, a.splits = splits;
   a.scale = 0.125f, a.positive_only = positive_only, a.need_dqkv = need_dqkv;
   const size_t smem_row = size_t(2) * TR * TS * sizeof(__half);
-  const size_t smem_col = smem_row + size_t(2) * TR * sizeof(float) + size_t(BWD_WARPS) * 64 * STRIP * sizeof(__half);
+  const size_t smem_col = smem_row + size_t(2) * TR * sizeof(float) + size_t(BWD_WARPS) * 2 * 64 * STRIP * sizeof(__half);
   static bool configured = false;
   if (!configured) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
@@ -679,6 +817,23 @@ extern "C" int semabs_attn_bwd(const void* qkv16, const void* probs16, int32_t l
     SB_CHECK_CUDA(cudaGetLastError());
   }
   attn_bwd_col_kernel<<<grid, BWD_WARPS * 32, smem_col, st>>>(a);
+  SB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int semabs_attn_bwd_cls(const void* qkv16, const void* probs16, int32_t ld_p16, const void* dO16_cls,
+                                   int32_t ld_do, const float* r, float* wpart, void* dqkv16, int32_t P, int32_t B,
+                                   int32_t T, int32_t H, int32_t splits, int32_t positive_only, int32_t need_dqkv,
+                                   void* stream) {
+  SB_REQUIRE(qkv16 && probs16 && dO16_cls && r && wpart, "semabs_attn_bwd_cls: null pointer");
+  SB_REQUIRE(!need_dqkv || dqkv16, "semabs_attn_bwd_cls: dqkv16 missing");
+  SB_REQUIRE(P > 0 && B > 0 && T > 0 && T <= TR && H > 0, "semabs_attn_bwd_cls: bad shape");
+  AttnClsArgs a{};
+  a.qkv16 = (const __half*)qkv16, a.probs16 = (const __half*)probs16, a.ldp = ld_p16, a.dO16 = (const __half*)dO16_cls;
+  a.ld_do = ld_do, a.r = r, a.wpart = wpart, a.dqkv16 = (__half*)dqkv16, a.P = P, a.B = B, a.T = T, a.H = H;
+  a.d = H * HD, a.splits = splits, a.scale = 0.125f, a.positive_only = positive_only, a.need_dqkv = need_dqkv;
+  const int warps = P * B * H;
+  attn_bwd_cls_kernel<<<(warps + 7) / 8, 256, 0, (cudaStream_t)stream>>>(a);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

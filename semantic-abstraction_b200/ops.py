@@ -158,6 +158,16 @@ def attn_bwd(qkv16, probs16, o32, dO16, ld_do, r, delta_ws, wpart, dqkv16, *, P,
     )
 
 
+def attn_bwd_cls(qkv16, probs16, dO16_cls, ld_do, r, wpart, dqkv16, *, P, B, T, H, splits=1, positive_only=True,
+                 need_dqkv=True):
+    check(
+        lib().semabs_attn_bwd_cls(
+            ptr(qkv16), ptr(probs16), i32(probs16.shape[-1]), ptr(dO16_cls), i32(ld_do), ptr(r), ptr(wpart), ptr(dqkv16),
+            i32(P), i32(B), i32(T), i32(H), i32(splits), i32(int(positive_only)), i32(int(need_dqkv)), stream_ptr(),
+        )
+    )
+
+
 def clip_logit_seed(f, W, *, B, P, E, logits=None, seed16=None, splits=1):
     check(lib().semabs_clip_logit_seed(ptr(f), ptr(W), ptr(logits), ptr(seed16), i32(B), i32(P), i32(E), i32(splits), stream_ptr()))
 

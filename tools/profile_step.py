@@ -10,7 +10,8 @@ if what == "vit":
     sd = synthetic_clip_state_dict("ViT-L/14", seed=0)
     eng = ClipEngine(pack_clip_weights("ViT-L/14", sd, "cuda"), "cuda")
     g = torch.Generator().manual_seed(0)
-    tiles = torch.randn(32, 3, 224, 224, generator=g).cuda()
+    NB = int(os.environ.get("VIT_B", "32"))
+    tiles = torch.randn(NB, 3, 224, 224, generator=g).cuda()
     W = torch.randn(768, 16, generator=g); W = (W / W.norm(dim=0, keepdim=True)).contiguous().cuda()
     for _ in range(1 + reps):
         eng.relevancy(tiles, W)
