@@ -33,6 +33,9 @@ PROMPT = "a photograph of a {} in a home."
 PYRAMID = [{"tile_size": s, "stride": s // 4} for s in (336, 224, 168, 112, 84)]  # 1+9+25+81+169 = 285 tiles
 IMG = 336
 IMAGES_PER_STEP = 8
+# tiles per engine call: the reference's `tile_batch_size` kwarg (a memory knob there, default 32, no effect on results);
+# 95 = 285 / 3 keeps every GEMM's M dimension large and leaves no ragged last batch
+TILE_BATCH = 95
 MODEL = "ViT-L/14"
 # algorithmic work (SURVEY.md §8d / BASELINE.md §3): per tile 162.0 GF forward + 89.1 GF backward per label
 GF_FWD_TILE, GF_BWD_TILE_LABEL = 162.0, 89.1
@@ -192,13 +195,15 @@ def main():
     def step_device():
         out = None
         for (desc, _, order), tl in zip(pre, dev_tiles):
-            out = ClipWrapper.get_clip_saliency_device(tl, desc, order, LABELS16, IMG, IMG, positive_attn_only=True)
+            out = ClipWrapper.get_clip_saliency_device(tl, desc, order, LABELS16, IMG, IMG, positive_attn_only=True,
+                                                       tile_batch_size=TILE_BATCH)
         return out
 
     def step_e2e():
         last = None
         for im in imgs:
-            maps = ClipWrapper.get_clip_saliency_convolve(img=im, text_labels=LABELS16, positive_attn_only=True, **cfg)
+            maps = ClipWrapper.get_clip_saliency_convolve(img=im, text_labels=LABELS16, positive_attn_only=True,
+                                                          tile_batch_size=TILE_BATCH, **cfg)
             last = maps
         return last
 
@@ -268,7 +273,7 @@ def main():
                 "config": {"workload": f"configs[1]: {MODEL} (seeded random init), {args.images} images 336x336 per GPU per step, "
                                        f"{n_tiles} tiles/image (5 crop sizes), {P} labels, no jitter/flip",
                            "l2_policy": "inputs larger than L2: per-step working set ~6 GB of saved activations + 1.4 GB tiles",
-                           "fwd_splits": eng.fwd_splits, "bwd_splits": eng.bwd_splits},
+                           "tile_batch_size": TILE_BATCH, "fwd_splits": eng.fwd_splits, "bwd_splits": eng.bwd_splits},
                 "e2e": {"value": e2e_value, "unit": "relevancy-maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": "ClipWrapper.get_clip_saliency_convolve: host PIL tile preprocessing inside the timed region"},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "voxel": voxel}

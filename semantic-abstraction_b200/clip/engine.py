@@ -50,6 +50,7 @@ class ClipEngine:
         self.bwd_splits = bwd_splits
         self.ws = _Workspace(self.device)
         self.kernel_launches = 0
+        self.sparse_last_block = True
 
     # ------------------------------------------------------------------------------------------------
     def _block_forward(self, blk: BlockWeights, x, x_next, *, n_seq, T, H, d, causal, saved: Optional[dict]):
@@ -193,10 +194,6 @@ class ClipEngine:
         ops.gemm_f16(seed16, w.proj, a_splits=sb, out_f32=dy)
         dx = ws.get("dx_a", (Mb, d))
         dx16 = ws.get("dx16_a", (Mb, sb * d), F16)
-        dx.zero_()
-        dx16.zero_()
-        ops.layernorm_bwd(dy, st["x_final"], st["mean_p"], st["rstd_p"], w.ln_post_g, dx, M=PB, d=d, x_rows=B,
-                          x_stride=T * d, out_stride=T * d, dx16=dx16, out16_stride=T * sb * d, splits=sb)
         r = ws.get("rollout_r", (PB, T))
         ops.rollout_init(r, PB, T)
         self.kernel_launches += 6
@@ -210,7 +207,50 @@ class ClipEngine:
         wpart = ws.get("attn_wpart", (PB * H, T))
         dqkv16 = ws.get("dqkv16", (Mb, sb * 3 * d), F16) if L - 1 > self.start_block else None
 
-        for i in range(L - 1, self.start_block - 1, -1):
+        # ---- last block: its output cotangent is non-zero at the class token only (the logits read x[:,0]), so the
+        # MLP / out-proj dgrads and both LayerNorm backwards run on P*B rows instead of P*B*T, and the attention
+        # backward is vector work (semabs_attn_bwd_cls). From the block below everything is dense.
+        first = L - 1
+        if self.sparse_last_block:
+            blk, sv = vt.blocks[first], st["saved"][first]
+            need = first > self.start_block
+            dxc = ws.get("cls_dx", (PB, d))
+            dxc16 = ws.get("cls_dx16", (PB, sb * d), F16)
+            ops.layernorm_bwd(dy, st["x_final"], st["mean_p"], st["rstd_p"], w.ln_post_g, dxc, M=PB, d=d, x_rows=B,
+                              x_stride=T * d, dx16=dxc16, splits=sb)
+            gg_cls = sv["gelu_grad16"].view(B, T, 4 * d)[:, 0, :]  # strided view: class-token rows
+            duc16 = ws.get("cls_du16", (PB, sb * 4 * d), F16)
+            ops.gemm_f16(dxc16, blk.w_projT, a_splits=sb, aux16=gg_cls, act=ops.ACT_MUL_AUX16, out_f16=duc16,
+                         out_f16_splits=sb)
+            dhc = ws.get("cls_dh", (PB, d))
+            ops.gemm_f16(duc16, blk.w_fcT, a_splits=sb, out_f32=dhc)
+            mean2c = sv["mean2"].view(B, T)[:, 0].contiguous()
+            rstd2c = sv["rstd2"].view(B, T)[:, 0].contiguous()
+            dxmc = ws.get("cls_dxm", (PB, d))
+            dxmc16 = ws.get("cls_dxm16", (PB, sb * d), F16)
+            ops.layernorm_bwd(dhc, sv["x_mid"], mean2c, rstd2c, blk.ln2_g, dxmc, M=PB, d=d, x_rows=B, x_stride=T * d,
+                              dres=dxc, dx16=dxmc16, splits=sb)
+            dOc16 = ws.get("cls_dO16", (PB, d), F16)
+            ops.gemm_f16(dxmc16, blk.w_outT, a_splits=sb, out_f16=dOc16)
+            ops.attn_bwd_cls(sv["qkv16"], sv["probs16"], dOc16, d, r, wpart, dqkv16 if need else None, P=P, B=B, T=T, H=H,
+                             splits=sb, positive_only=positive_attn_only, need_dqkv=need)
+            ops.rollout_update(r, wpart, PB, H, T)
+            self.kernel_launches += 8
+            if need:
+                dxm.zero_()
+                dxm.view(PB, T, d)[:, 0, :].copy_(dxmc)  # scatter of the class-token rows (data movement)
+                ops.gemm_f16(dqkv16, blk.w_inT, a_splits=sb, out_f32=dh)
+                ops.layernorm_bwd(dh, sv["x_in"], sv["mean1"], sv["rstd1"], blk.ln1_g, dx, M=Mb, d=d, x_rows=B * T,
+                                  dres=dxm, dx16=dx16, splits=sb)
+                self.kernel_launches += 2
+            first -= 1
+        else:
+            dx.zero_()
+            dx16.zero_()
+            ops.layernorm_bwd(dy, st["x_final"], st["mean_p"], st["rstd_p"], w.ln_post_g, dx, M=PB, d=d, x_rows=B,
+                              x_stride=T * d, out_stride=T * d, dx16=dx16, out16_stride=T * sb * d, splits=sb)
+
+        for i in range(first, self.start_block - 1, -1):
             blk, sv = vt.blocks[i], st["saved"][i]
             # x_out = x_mid + c_proj(quickgelu(c_fc(ln_2(x_mid))))
             ops.gemm_f16(dx16, blk.w_projT, a_splits=sb, aux16=sv["gelu_grad16"], act=ops.ACT_MUL_AUX16, out_f16=du16,

@@ -122,3 +122,36 @@ def test_logit_seed():
         (gr,) = torch.autograd.grad(lg[:, p].sum(), fr, retain_graph=True)
         got = _recon(seed16[p * B : (p + 1) * B], E, 2)
         assert torch.allclose(got, gr, atol=1e-5, rtol=1e-3)
+
+
+@pytest.mark.parametrize("T,H", [(50, 12), (257, 16)])
+def test_attn_bwd_class_token_only_matches_dense(T, H):
+    """Last-block shortcut: dO non-zero at the class-token row only -> semabs_attn_bwd_cls == semabs_attn_bwd."""
+    from semabs_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(T + 7)
+    B, P, d = 2, 3, H * 64
+    qkv = torch.randn(B * T, 3 * d, device=dev, generator=g)
+    qkv[:, :d] *= 0.125 * 1.5
+    Tp = (T + 15) // 16 * 16
+    probs16 = torch.empty(B * H, T, Tp, device=dev, dtype=torch.float16)
+    o32 = torch.empty(B * T, d, device=dev)
+    ops.attn_fwd(qkv, B=B, T=T, H=H, probs16=probs16, o32=o32)
+    qkv16 = qkv.half()
+    dO_cls = torch.randn(P * B, d, device=dev, generator=g).half()
+    dO = torch.zeros(P * B, T, d, device=dev, dtype=torch.float16)
+    dO[:, 0] = dO_cls
+    r = torch.rand(P * B, T, device=dev, generator=g)
+    delta = torch.empty(P * B * H, T, device=dev)
+    w_ref = torch.empty(P * B * H, T, device=dev)
+    dq_ref = torch.empty(P * B * T, 2 * 3 * d, device=dev, dtype=torch.float16)
+    ops.attn_bwd(qkv16, probs16, o32, dO.view(-1, d), d, r, delta, w_ref, dq_ref, P=P, B=B, T=T, H=H, splits=2)
+    w = torch.full_like(w_ref, float("nan"))
+    dq = torch.full_like(dq_ref, float("nan"))
+    ops.attn_bwd_cls(qkv16, probs16, dO_cls, d, r, w, dq, P=P, B=B, T=T, H=H, splits=2)
+    torch.cuda.synchronize()
+    assert torch.allclose(w, w_ref, atol=2e-3 * w_ref.abs().max().item(), rtol=2e-3)
+    a = dq[:, : 3 * d].float() + dq[:, 3 * d :].float()
+    b = dq_ref[:, : 3 * d].float() + dq_ref[:, 3 * d :].float()
+    assert not torch.isnan(a).any()
+    assert (a - b).abs().max().item() < 4e-3 * b.abs().max().item()
