@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2) attn_bwd_col_kernel(AttnBwd
 // query tiles, keeps the whole score strip [16 x T] in registers, does an exact two-pass softmax and multiplies
 // by V.  Used for T <= 272 (every CLIP ViT-B/32, ViT-L/14 and text case); the SIMT kernel above is the fallback.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int FWD_WARPS = 6;
+constexpr int FWD_WARPS = 6;   // (9 warps would cap registers at 224/thread and spill the score strip)
 constexpr int NT_MAX = TR / 8;  // 34 key n-tiles
 
 struct AttnFwdArgs {
