@@ -235,6 +235,37 @@ int semabs_sample_decode(const float* vol0, const float* vol1, int32_t C0, const
                          const float* w1t, const float* b1, const float* w2t, const float* b2, int32_t Hs,
                          int32_t out_dim, const float* emb, float temperature, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimiser side of the training step (train.cu) — reference utils.loop (utils.py:404-422).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Masked, weighted binary_cross_entropy_with_logits with mean reduction over the kept points + its gradient +
+ * accuracy (train_ovssc.get_losses, train_ovssc.py:133-150; train_vool.py:163-185): kept = !ignore[i];
+ * loss_acc[0] = sum_kept w*bce / #kept, loss_acc[1] = mean_kept((logit > 0) == label);
+ * dlogits (optional) = w*(sigmoid(x) - y)/#kept on kept points, 0 elsewhere. weight / ignore may be NULL.
+ * acc_ws: 3 doubles of workspace. */
+int semabs_bce_with_logits(const float* logits, const float* labels, const float* weight, const uint8_t* ignore,
+                           int64_t n, double* acc_ws, float* loss_acc, float* dlogits, void* stream);
+
+/* Chunk table shared by the three calls below: a device array of n_chunks records
+ *   { float* p; const float* g; float* m; float* v; int32_t n; int32_t tensor; }   (semabs_lamb_chunk_bytes() bytes)
+ * covering every parameter tensor that has a gradient (<= 65536 elements per chunk, tensor = its index). */
+int32_t semabs_lamb_chunk_bytes(void);
+
+/* out[0] = sum over all chunks of |g|^2 (the squared total_norm of torch.nn.utils.clip_grad_norm_, utils.py:415). */
+int semabs_grad_sumsq(const void* chunks, int32_t n_chunks, double* out, void* stream);
+/* g *= min(1, max_grad_norm / (sqrt(grad_sumsq) + 1e-6)) in place (clip_grad_norm_). */
+int semabs_clip_grads(const void* chunks, int32_t n_chunks, const double* grad_sumsq, float max_grad_norm,
+                      void* stream);
+
+/* One LAMB step for the whole model (arm/optim/lamb.py:59-127): m,v moments without bias correction,
+ * adam_step = m/(sqrt(v)+eps) + wd*p, trust = clamp(|p|,0,10)/|adam_step| (1 if either is 0, or adam_mode),
+ * p -= lr*trust*adam_step. If grad_sumsq != NULL the clip coefficient above is applied to g on the fly
+ * (gradients are left untouched). norms_ws: 2*n_tensors doubles. */
+int semabs_lamb_step(const void* chunks, int32_t n_chunks, int32_t n_tensors, double* norms_ws,
+                     const double* grad_sumsq, float max_grad_norm, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, int32_t adam_mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,5 +115,33 @@ def main():
     print("wrote unet_golden.npz")
 
 
+def check_train_oracle():
+    """Pins oracle/train_oracle.py against the reference's own Lamb (arm/optim/lamb.py) and torch's clip / BCE."""
+    from oracle import train_oracle
+
+    lamb_mod = ref_import.import_reference_module("arm.optim.lamb")
+    g = torch.Generator().manual_seed(0)
+    shapes = [(70000,), (33, 17), (5,), (8, 8)]
+    ps = [torch.nn.Parameter(torch.randn(*s, generator=g)) for s in shapes]
+    ps[2].data.zero_()  # weight_norm == 0 branch
+    mine = [p.detach().clone() for p in ps]
+    state = [dict() for _ in ps]
+    opt = lamb_mod.Lamb(ps, lr=1e-2, betas=(0.9, 0.999), weight_decay=0.01)
+    for step in range(3):
+        grads = [torch.randn(*s, generator=g) * (10 if step == 1 else 1) for s in shapes]
+        grads[3] = None  # a parameter without gradient is skipped
+        for p, gr in zip(ps, grads):
+            p.grad = None if gr is None else gr.clone()
+        total_ref = torch.nn.utils.clip_grad_norm_(ps, 2.0)
+        total, coef = train_oracle.clip_coefficient(grads, 2.0)
+        assert torch.allclose(total, total_ref)
+        opt.step()
+        train_oracle.lamb_step(mine, [None if gr is None else gr * coef for gr in grads], state, lr=1e-2, weight_decay=0.01)
+        for a, b in zip(mine, ps):
+            assert torch.allclose(a, b.data, rtol=1e-6, atol=1e-7), (step, (a - b.data).abs().max())
+    print("LAMB + clip oracle-vs-reference ok")
+
+
 if __name__ == "__main__":
     main()
+    check_train_oracle()
