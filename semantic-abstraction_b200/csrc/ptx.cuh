@@ -204,4 +204,42 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
          (uint64_t((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | (layout << 61);
 }
 
+// ---- 256-bit global accesses (PTX 8.8, sm_100+): one full 32-byte sector per thread per instruction ----------------
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t* v) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p)
+               : "memory");
+}
+// store / load NW 32-bit words per thread: 256-bit accesses when the row is 32-byte aligned, 128-bit otherwise
+template <int NW>
+__device__ __forceinline__ void st_row_words(void* p, const uint32_t* w, bool wide) {
+  if (wide) {
+#pragma unroll
+    for (int j = 0; j < NW; j += 8) st_global_256(reinterpret_cast<uint32_t*>(p) + j, w + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < NW; j += 4)
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(p) + j) = make_uint4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+  }
+}
+template <int NW>
+__device__ __forceinline__ void ld_row_words(const void* p, uint32_t* w, bool wide) {
+  if (wide) {
+#pragma unroll
+    for (int j = 0; j < NW; j += 8) ld_global_256(reinterpret_cast<const uint32_t*>(p) + j, w + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < NW; j += 4) {
+      const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(p) + j);
+      w[j] = u.x, w[j + 1] = u.y, w[j + 2] = u.z, w[j + 3] = u.w;
+    }
+  }
+}
+
 }  // namespace sb

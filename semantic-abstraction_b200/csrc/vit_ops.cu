@@ -205,8 +205,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_warp_kernel(LnFwdArgs a) {
 }
 
 template <int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_warp_kernel(LnBwdArgs a) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(128, 4) layernorm_bwd_warp_kernel(LnBwdArgs a) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= a.M) return;
   const int fr = row % a.x_rows;
   const float mean = a.mean[fr], rstd = a.rstd[fr];
@@ -224,6 +224,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_warp_kernel(LnBwdArgs a) {
     s1 += g[k].x + g[k].y + g[k].z + g[k].w;
     s2 += g[k].x * xh[k].x + g[k].y * xh[k].y + g[k].z * xh[k].z + g[k].w * xh[k].w;
   }
+  // the residual-stream gradient is fetched here, with the other loads still in flight: read inside the store loop
+  // below, each of its NV loads waited behind the previous store (possible aliasing) = NV serial DRAM round trips
+  float4 rs[NV];
+  if (a.dres) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      rs[k] = *reinterpret_cast<const float4*>(a.dres + size_t(row) * a.out_stride + (k * 32 + lane) * 4);
+  }
   const float m1 = warp_sum(s1) / a.d, m2 = warp_sum(s2) / a.d;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -231,21 +239,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_warp_kernel(LnBwdArgs a) {
     float4 v;
     v.x = rstd * (g[k].x - m1 - xh[k].x * m2), v.y = rstd * (g[k].y - m1 - xh[k].y * m2);
     v.z = rstd * (g[k].z - m1 - xh[k].z * m2), v.w = rstd * (g[k].w - m1 - xh[k].w * m2);
-    if (a.dres) {
-      const float4 r4 = *reinterpret_cast<const float4*>(a.dres + size_t(row) * a.out_stride + col);
-      v.x += r4.x, v.y += r4.y, v.z += r4.z, v.w += r4.w;
-    }
+    if (a.dres) v.x += rs[k].x, v.y += rs[k].y, v.z += rs[k].z, v.w += rs[k].w;
     *reinterpret_cast<float4*>(a.dx32 + size_t(row) * a.out_stride + col) = v;
     if (a.dx16) store_split4(a.dx16 + size_t(row) * a.out16_stride, col, a.d, a.splits, v);
   }
 }
 
 template <typename Args, typename K4, typename K6, typename K8>
-static bool launch_warp_ln(const Args& a, int d, cudaStream_t st, K4 k4, K6 k6, K8 k8) {
-  const int grid = (a.M + 7) / 8;
-  if (d == 512) k4<<<grid, 256, 0, st>>>(a);
-  else if (d == 768) k6<<<grid, 256, 0, st>>>(a);
-  else if (d == 1024) k8<<<grid, 256, 0, st>>>(a);
+static bool launch_warp_ln(const Args& a, int d, cudaStream_t st, K4 k4, K6 k6, K8 k8, int rows_per_cta = 8) {
+  const int grid = (a.M + rows_per_cta - 1) / rows_per_cta, threads = rows_per_cta * 32;
+  if (d == 512) k4<<<grid, threads, 0, st>>>(a);
+  else if (d == 768) k6<<<grid, threads, 0, st>>>(a);
+  else if (d == 1024) k8<<<grid, threads, 0, st>>>(a);
   else return false;
   return true;
 }
@@ -386,7 +391,7 @@ extern "C" int semabs_layernorm_bwd(const float* dy, const float* dres, const fl
   a.M = M, a.d = d, a.splits = splits;
   const bool aligned = (x_stride % 4 == 0) && (out_stride % 4 == 0) && (out16_stride % 4 == 0);
   if (!(aligned && launch_warp_ln(a, d, (cudaStream_t)stream, layernorm_bwd_warp_kernel<4>, layernorm_bwd_warp_kernel<6>,
-                                  layernorm_bwd_warp_kernel<8>)))
+                                  layernorm_bwd_warp_kernel<8>, 4)))
     layernorm_bwd_kernel<<<M, 256, 2 * d * sizeof(float), (cudaStream_t)stream>>>(a);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;

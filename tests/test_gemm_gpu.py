@@ -81,3 +81,40 @@ def test_gemm_epilogues():
     d = torch.empty(M, N, device="cuda")
     ops.gemm_f16(a, b, aux16=aux, act=ops.ACT_MUL_AUX16, out_f32=d)
     assert torch.allclose(d, base * aux.float().repeat(2, 1), atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("S,P,N", [(257, 16, 256), (4 * 257, 5, 512), (1024, 3, 128), (200, 7, 256)])
+def test_gemm_aux_rasterised_tile_order(S, P, N):
+    """MUL_AUX16 with aux_rows < M visits the P repeats of an aux row block back to back (gemm.cu tile_coords); the
+    repeat stride is not a multiple of the 128-row tile, so row blocks straddle repeats — every row must still be
+    written exactly once."""
+    from semabs_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(S + P)
+    M, K = S * P, 192
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).half()
+    aux = torch.randn(S, N, device="cuda", generator=g).half()
+    d32 = torch.full((M, N), float("nan"), device="cuda")
+    d16 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+    ops.gemm_f16(a, b, aux16=aux, act=ops.ACT_MUL_AUX16, out_f32=d32, out_f16=d16)
+    ref = _ref(a, b) * aux.float().repeat(P, 1)
+    assert torch.allclose(d32, ref, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(d16.float(), ref, atol=2e-3, rtol=2e-3)
+
+
+def test_gemm_unaligned_rows_use_narrow_accesses():
+    """Output / residual rows that are only 16-byte aligned (a column slice of a wider buffer) take the 128-bit path."""
+    from semabs_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, N, K = 300, 64, 128
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).half()
+    wide32 = torch.zeros(M, N + 4, device="cuda")
+    res = torch.randn(M, N + 4, device="cuda", generator=g)
+    out = wide32[:, 4:]
+    assert out.data_ptr() % 32 != 0
+    ops.gemm_f16(a, b, residual=res[:, 4:], out_f32=out)
+    assert torch.allclose(out, _ref(a, b) + res[:, 4:], atol=1e-4, rtol=1e-4)
+    assert wide32[:, :4].abs().max().item() == 0.0
