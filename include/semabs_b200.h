@@ -107,21 +107,32 @@ int semabs_layernorm_bwd(const float* dy, const float* dres, const float* x, int
 int semabs_attn_fwd(const float* qkv, float* probs, void* probs16, int32_t ld_p16, float* o32, void* o16, int32_t B,
                     int32_t T, int32_t H, int32_t causal, int32_t splits, void* stream);
 
+/* Same operator on tcgen05 / TMEM (vit_attn_tc.cu) for T <= 272: qkv16 [B*T, in_splits*3d] fp16 — the QKV GEMM's
+ * out_f16 with out_f16_splits = in_splits, i.e. rows [hi(3d) | lo(3d)], q pre-scaled — instead of fp32 qkv.  With
+ * in_splits = 2 both products run as hi*hi + lo*hi + hi*lo (fp32-grade).  probs16 pitch must be a multiple of 16. */
+int semabs_attn_fwd_tc(const void* qkv16, int32_t in_splits, void* probs16, int32_t ld_p16, float* o32, void* o16,
+                       int32_t o_splits, int32_t B, int32_t T, int32_t H, int32_t causal, void* stream);
+
+/* Known-answer hook for the two tcgen05 operand forms the attention kernels add to the GEMM's (A operand in TMEM,
+ * MN-major B in shared memory): D[128,64] = A16[128,Kd] * B16[Kd,64], Kd % 16 == 0, Kd <= 256; lbo / sbo are the
+ * descriptor byte offsets under test.  Test infrastructure for tests/test_vit_kernels_gpu.py. */
+int semabs_selftest_ts_mma(const void* A16, const void* B16, float* D, int32_t Kd, int32_t lbo, int32_t sbo, void* stream);
+
 /* Attention backward for P stacked cotangents + the relevance term of ClipGradcam.interpret
- * (clip_gradcam.py:90-126).  qkv16 [B*T,3d] fp16 (q pre-scaled), probs16 [B*H,T,ld_p16] fp16 with
+ * (clip_gradcam.py:90-126).  qkv16 [B*T,ld_qkv >= 3d] fp16 (q pre-scaled; the first 3d columns of each row), probs16 [B*H,T,ld_p16] fp16 with
  * ld_p16 >= 16*ceil(T/16), o32 [B*T,d] forward attention output, dO16 [P*B*T, ld_do] fp16 = gradient w.r.t. the
  * pre-out-proj attention output.
  *   dA = dO V^T ;  wpart[pb,h,j] = (1/H) sum_i r[pb,i] * relu?(dA ⊙ A)[i,j]   (relu iff positive_only)
  *   dS = A ⊙ (dA - rowsum(dA ⊙ A)) ; dQ = scale dS K ; dK = dS^T Q ; dV = A^T dO -> dqkv16 [P*B*T, splits*3d]
  * delta_ws is a [P*B*H*T] fp32 workspace.  need_dqkv == 0 computes the relevance term only.  T <= 272. */
-int semabs_attn_bwd(const void* qkv16, const void* probs16, int32_t ld_p16, const float* o32, const void* dO16,
+int semabs_attn_bwd(const void* qkv16, int32_t ld_qkv, const void* probs16, int32_t ld_p16, const float* o32, const void* dO16,
                     int32_t ld_do, const float* r, float* delta_ws, float* wpart, void* dqkv16, int32_t P, int32_t B,
                     int32_t T, int32_t H, int32_t splits, int32_t positive_only, int32_t need_dqkv, void* stream);
 
 /* Attention backward of the LAST transformer block, where only the class-token row of dO is non-zero (the logits
  * read x[:,0] only, model_explainability.py:349): same outputs as semabs_attn_bwd (wpart, dqkv16 for all T rows)
  * from dO16_cls [P*B, ld_do] = class-token rows of the cotangent. */
-int semabs_attn_bwd_cls(const void* qkv16, const void* probs16, int32_t ld_p16, const void* dO16_cls, int32_t ld_do,
+int semabs_attn_bwd_cls(const void* qkv16, int32_t ld_qkv, const void* probs16, int32_t ld_p16, const void* dO16_cls, int32_t ld_do,
                         const float* r, float* wpart, void* dqkv16, int32_t P, int32_t B, int32_t T, int32_t H,
                         int32_t splits, int32_t positive_only, int32_t need_dqkv, void* stream);
 

@@ -51,6 +51,7 @@ class ClipEngine:
         self.ws = _Workspace(self.device)
         self.kernel_launches = 0
         self.sparse_last_block = True
+        self.tc_attention = True  # tcgen05 attention kernels (T <= 272); False = the mma.sync kernels of vit_attn.cu
 
     # ------------------------------------------------------------------------------------------------
     def _block_forward(self, blk: BlockWeights, x, x_next, *, n_seq, T, H, d, causal, saved: Optional[dict]):
@@ -59,7 +60,6 @@ class ClipEngine:
         ws = self.ws
         h16 = ws.get("h16", (M, s * d), F16)
         mean1 = rstd1 = mean2 = rstd2 = probs16 = qkv16 = o32 = gg16 = None
-        qkv = ws.get("qkv", (M, 3 * d))
         if saved is not None:
             mean1, rstd1 = saved["mean1"], saved["rstd1"]
             mean2, rstd2 = saved["mean2"], saved["rstd2"]
@@ -68,10 +68,21 @@ class ClipEngine:
         else:
             x_mid = ws.get("x_mid", (M, d))
         ops.layernorm_fwd(x, blk.ln1_g, blk.ln1_b, M=M, d=d, y16=h16, mean=mean1, rstd=rstd1, splits=s)
-        # fp32 q,k,v feed the exact-softmax forward; the fp16 copy is the MMA operand of the attention backward
-        ops.gemm_f16(h16, blk.w_in, a_splits=s, bias=blk.b_in, out_f32=qkv, out_f16=qkv16, scale_cols=d, scale=0.125)
         o16 = ws.get("o16", (M, s * d), F16)
-        ops.attn_fwd(qkv, B=n_seq, T=T, H=H, probs16=probs16, o32=o32, o16=o16, causal=causal, splits=s)
+        if qkv16 is None:
+            qkv16 = ws.get("qkv16_scratch", (M, s * 3 * d), F16)
+        if self.tc_attention and T <= 272:
+            # tcgen05 attention: q,k,v leave the GEMM as fp16 hi|lo rows (hi*hi + lo*hi + hi*lo = fp32-grade products);
+            # the hi part doubles as the MMA operand of the attention backward
+            ops.gemm_f16(h16, blk.w_in, a_splits=s, bias=blk.b_in, out_f16=qkv16, out_f16_splits=s, scale_cols=d, scale=0.125)
+            ops.attn_fwd_tc(qkv16, in_splits=s, B=n_seq, T=T, H=H, probs16=probs16, o32=o32, o16=o16, o_splits=s,
+                            causal=causal)
+        else:
+            # fp32 q,k,v feed the mma.sync forward; the fp16 copy is the MMA operand of the attention backward
+            qkv = ws.get("qkv", (M, 3 * d))
+            ops.gemm_f16(h16, blk.w_in, a_splits=s, bias=blk.b_in, out_f32=qkv, out_f16=qkv16[:, : 3 * d], scale_cols=d,
+                         scale=0.125)
+            ops.attn_fwd(qkv, B=n_seq, T=T, H=H, probs16=probs16, o32=o32, o16=o16, causal=causal, splits=s)
         ops.gemm_f16(o16, blk.w_out, a_splits=s, bias=blk.b_out, residual=x, out_f32=x_mid)
         ops.layernorm_fwd(x_mid, blk.ln2_g, blk.ln2_b, M=M, d=d, y16=h16, mean=mean2, rstd=rstd2, splits=s)
         g16 = ws.get("g16", (M, s * 4 * d), F16)
@@ -122,7 +133,7 @@ class ClipEngine:
             "x_in": None,
             "mean1": ws.get(f"s{i}_mean1", (M,)), "rstd1": ws.get(f"s{i}_rstd1", (M,)),
             "mean2": ws.get(f"s{i}_mean2", (M,)), "rstd2": ws.get(f"s{i}_rstd2", (M,)),
-            "qkv16": ws.get(f"s{i}_qkv16", (M, 3 * d), F16),
+            "qkv16": ws.get(f"s{i}_qkv16", (M, self.fwd_splits * 3 * d), F16),
             "probs16": ws.get(f"s{i}_probs16", (B * H, T, (T + 15) // 16 * 16), F16),
             "o32": ws.get(f"s{i}_o32", (M, d)), "x_mid": ws.get(f"s{i}_xmid", (M, d)),
             "gelu_grad16": ws.get(f"s{i}_gg16", (M, 4 * d), F16),

@@ -158,7 +158,8 @@ constexpr int STRIP = 16;     // half stride of the per-warp [64][16] probabilit
                               // 16-byte halves of a row are XOR-swizzled with bit 2 of the row => conflict-free ldmatrix
 
 struct AttnBwdArgs {
-  const __half* qkv16;   // [B*T, 3d] (q already scaled)
+  const __half* qkv16;   // [B*T, ldq >= 3d] (q already scaled)
+  int ldq;
   const __half* probs16; // [B*H, T, ldp]
   int ldp;
   const float* o32;      // [B*T, d] forward attention output (pre out-proj)
@@ -203,9 +204,9 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2) attn_bwd_row_kernel(AttnBwd
   const int pb = p * a.B + b;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int T = a.T, d = a.d;
-  const __half* kv = a.qkv16 + size_t(b) * T * 3 * d + h * HD;
-  load_head_tile(Ks, kv + d, size_t(3) * d, T);
-  load_head_tile(Vs, kv + 2 * d, size_t(3) * d, T);
+  const __half* kv = a.qkv16 + size_t(b) * T * a.ldq + h * HD;
+  load_head_tile(Ks, kv + d, size_t(a.ldq), T);
+  load_head_tile(Vs, kv + 2 * d, size_t(a.ldq), T);
   __syncthreads();
   const int ntiles_total = (T + 7) / 8;  // key n-tiles that contain at least one valid key
 
@@ -322,8 +323,8 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2) attn_bwd_col_kernel(AttnBwd
   const int pb = p * a.B + b;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int T = a.T, d = a.d;
-  const __half* qv = a.qkv16 + size_t(b) * T * 3 * d + h * HD;
-  load_head_tile(Qs, qv, size_t(3) * d, T);
+  const __half* qv = a.qkv16 + size_t(b) * T * a.ldq + h * HD;
+  load_head_tile(Qs, qv, size_t(a.ldq), T);
   load_head_tile(dOs, a.dO16 + size_t(pb) * T * a.ld_do + h * HD, size_t(a.ld_do), T);
   for (int i = threadIdx.x; i < TR; i += blockDim.x) {
     Dl[i] = (i < T && a.need_dqkv) ? a.delta[(size_t(pb) * a.H + h) * T + i] : 0.f;
@@ -339,8 +340,8 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2) attn_bwd_col_kernel(AttnBwd
     const bool va = ja < T, vb = jb < T;
     uint32_t fv[4][4];
     {
-      const __half* ra = qv + size_t(va ? ja : 0) * 3 * d + 2 * d;
-      const __half* rb = qv + size_t(vb ? jb : 0) * 3 * d + 2 * d;
+      const __half* ra = qv + size_t(va ? ja : 0) * a.ldq + 2 * d;
+      const __half* rb = qv + size_t(vb ? jb : 0) * a.ldq + 2 * d;
 #pragma unroll
       for (int kt = 0; kt < 4; ++kt) {
         fv[kt][0] = va ? *reinterpret_cast<const uint32_t*>(ra + kt * 16 + 2 * t) : 0u;
@@ -644,7 +645,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, 1) attn_fwd_mma_kernel(AttnFwd
 //   dQ_0 = scale sum_j dS_0j K_j ; dK_j = dS_0j Q_0 ; dV_j = A_0j dO_0 ; dQ_i = 0 for i > 0
 // ---------------------------------------------------------------------------------------------------------
 struct AttnClsArgs {
-  const __half* qkv16;   // [B*T, 3d]
+  const __half* qkv16;   // [B*T, ldq >= 3d]
+  int ldq;
   const __half* probs16; // [B*H, T, ldp]
   int ldp;
   const __half* dO16;    // [P*B, ld_do]  (class-token rows only)
@@ -662,7 +664,7 @@ __global__ void __launch_bounds__(256) attn_bwd_cls_kernel(AttnClsArgs a) {
   if (gw >= a.P * a.B * a.H) return;
   const int h = gw % a.H, pb = gw / a.H, b = pb % a.B;
   const int T = a.T, d = a.d;
-  const __half* base = a.qkv16 + size_t(b) * T * 3 * d + h * HD;
+  const __half* base = a.qkv16 + size_t(b) * T * a.ldq + h * HD;
   // dO_0 and Q_0 (64 values each) replicated in registers
   float dO[HD], q0[HD];
   {
@@ -684,7 +686,7 @@ __global__ void __launch_bounds__(256) attn_bwd_cls_kernel(AttnClsArgs a) {
     const int j = c * 32 + lane;
     G[c] = 0.f, A[c] = 0.f;
     if (j < T) {
-      const __half2* v2 = reinterpret_cast<const __half2*>(base + size_t(j) * 3 * d + 2 * d);
+      const __half2* v2 = reinterpret_cast<const __half2*>(base + size_t(j) * a.ldq + 2 * d);
       float acc = 0.f;
 #pragma unroll
       for (int e = 0; e < HD / 2; ++e) {
@@ -712,7 +714,7 @@ __global__ void __launch_bounds__(256) attn_bwd_cls_kernel(AttnClsArgs a) {
       wp[j] = r0 * x * invH;
       if (a.need_dqkv) {
         const float ds = A[c] * (G[c] - dsum);
-        const __half2* k2 = reinterpret_cast<const __half2*>(base + size_t(j) * 3 * d + d);
+        const __half2* k2 = reinterpret_cast<const __half2*>(base + size_t(j) * a.ldq + d);
         __half* orow = a.dqkv16 + (size_t(pb) * T + j) * ld + h * HD;
 #pragma unroll
         for (int e = 0; e < HD / 2; ++e) {
@@ -787,7 +789,7 @@ extern "C" int semabs_attn_fwd(const float* qkv, float* probs, void* probs16, in
   return launch_attn_fwd<13>(qkv, probs, p16, ld_p16, o32, (__half*)o16, B, T, H, d, causal, splits, st);
 }
 
-extern "C" int semabs_attn_bwd(const void* qkv16, const void* probs16, int32_t ld_p16, const float* o32,
+extern "C" int semabs_attn_bwd(const void* qkv16, int32_t ld_qkv, const void* probs16, int32_t ld_p16, const float* o32,
                                const void* dO16, int32_t ld_do, const float* r, float* delta_ws, float* wpart,
                                void* dqkv16, int32_t P, int32_t B, int32_t T, int32_t H, int32_t splits,
                                int32_t positive_only, int32_t need_dqkv, void* stream) {
@@ -798,7 +800,9 @@ extern "C" int semabs_attn_bwd(const void* qkv16, const void* probs16, int32_t l
   SB_REQUIRE(ld_p16 % 8 == 0 && ld_p16 >= ((T + 15) / 16) * 16, "semabs_attn_bwd: probs16 pitch %d must be a multiple of 8 and >= %d",
              ld_p16, ((T + 15) / 16) * 16);
   cudaStream_t st = (cudaStream_t)stream;
+  SB_REQUIRE(ld_qkv >= 3 * H * HD && ld_qkv % 8 == 0, "semabs_attn_bwd: bad qkv16 pitch %d", ld_qkv);
   AttnBwdArgs a{};
+  a.ldq = ld_qkv;
   a.qkv16 = (const __half*)qkv16, a.probs16 = (const __half*)probs16, a.ldp = ld_p16, a.o32 = o32;
   a.dO16 = (const __half*)dO16, a.ld_do = ld_do, a.delta = delta_ws, a.r = r, a.wpart = wpart;
   a.dqkv16 = (__half*)dqkv16, a.P = P, a.B = B, a.T = T, a.H = H, a.d = H * HD, a.splits = splits;
@@ -821,14 +825,16 @@ extern "C" int semabs_attn_bwd(const void* qkv16, const void* probs16, int32_t l
   return 0;
 }
 
-extern "C" int semabs_attn_bwd_cls(const void* qkv16, const void* probs16, int32_t ld_p16, const void* dO16_cls,
+extern "C" int semabs_attn_bwd_cls(const void* qkv16, int32_t ld_qkv, const void* probs16, int32_t ld_p16, const void* dO16_cls,
                                    int32_t ld_do, const float* r, float* wpart, void* dqkv16, int32_t P, int32_t B,
                                    int32_t T, int32_t H, int32_t splits, int32_t positive_only, int32_t need_dqkv,
                                    void* stream) {
   SB_REQUIRE(qkv16 && probs16 && dO16_cls && r && wpart, "semabs_attn_bwd_cls: null pointer");
   SB_REQUIRE(!need_dqkv || dqkv16, "semabs_attn_bwd_cls: dqkv16 missing");
   SB_REQUIRE(P > 0 && B > 0 && T > 0 && T <= TR && H > 0, "semabs_attn_bwd_cls: bad shape");
+  SB_REQUIRE(ld_qkv >= 3 * H * HD && ld_qkv % 8 == 0, "semabs_attn_bwd_cls: bad qkv16 pitch %d", ld_qkv);
   AttnClsArgs a{};
+  a.ldq = ld_qkv;
   a.qkv16 = (const __half*)qkv16, a.probs16 = (const __half*)probs16, a.ldp = ld_p16, a.dO16 = (const __half*)dO16_cls;
   a.ld_do = ld_do, a.r = r, a.wpart = wpart, a.dqkv16 = (__half*)dqkv16, a.P = P, a.B = B, a.T = T, a.H = H;
   a.d = H * HD, a.splits = splits, a.scale = 0.125f, a.positive_only = positive_only, a.need_dqkv = need_dqkv;

@@ -146,12 +146,24 @@ def attn_fwd(qkv, *, B, T, H, probs=None, probs16=None, o32=None, o16=None, caus
                                 i32(int(causal)), i32(splits), stream_ptr()))
 
 
+def attn_fwd_tc(qkv16, *, in_splits, B, T, H, probs16=None, o32=None, o16=None, o_splits=1, causal=False):
+    """tcgen05 attention forward; qkv16 [B*T, in_splits*3d] fp16 rows [hi | lo]."""
+    assert qkv16.dtype == torch.float16 and qkv16.is_contiguous()
+    ldp = probs16.shape[-1] if probs16 is not None else 0
+    check(lib().semabs_attn_fwd_tc(ptr(qkv16), i32(in_splits), ptr(probs16), i32(ldp), ptr(o32), ptr(o16), i32(o_splits),
+                                   i32(B), i32(T), i32(H), i32(int(causal)), stream_ptr()))
+
+
+def selftest_ts_mma(A16, B16, D, lbo=16, sbo=1024):
+    check(lib().semabs_selftest_ts_mma(ptr(A16), ptr(B16), ptr(D), i32(A16.shape[1]), i32(lbo), i32(sbo), stream_ptr()))
+
+
 def attn_bwd(qkv16, probs16, o32, dO16, ld_do, r, delta_ws, wpart, dqkv16, *, P, B, T, H, splits=1, positive_only=True,
              need_dqkv=True):
     assert qkv16.dtype == torch.float16 and probs16.dtype == torch.float16
     check(
         lib().semabs_attn_bwd(
-            ptr(qkv16), ptr(probs16), i32(probs16.shape[-1]), ptr(o32), ptr(dO16), i32(ld_do), ptr(r), ptr(delta_ws),
+            ptr(qkv16), i32(qkv16.stride(0)), ptr(probs16), i32(probs16.shape[-1]), ptr(o32), ptr(dO16), i32(ld_do), ptr(r), ptr(delta_ws),
             ptr(wpart), ptr(dqkv16), i32(P), i32(B), i32(T), i32(H), i32(splits), i32(int(positive_only)),
             i32(int(need_dqkv)), stream_ptr(),
         )
@@ -162,7 +174,7 @@ def attn_bwd_cls(qkv16, probs16, dO16_cls, ld_do, r, wpart, dqkv16, *, P, B, T, 
                  need_dqkv=True):
     check(
         lib().semabs_attn_bwd_cls(
-            ptr(qkv16), ptr(probs16), i32(probs16.shape[-1]), ptr(dO16_cls), i32(ld_do), ptr(r), ptr(wpart), ptr(dqkv16),
+            ptr(qkv16), i32(qkv16.stride(0)), ptr(probs16), i32(probs16.shape[-1]), ptr(dO16_cls), i32(ld_do), ptr(r), ptr(wpart), ptr(dqkv16),
             i32(P), i32(B), i32(T), i32(H), i32(splits), i32(int(positive_only)), i32(int(need_dqkv)), stream_ptr(),
         )
     )

@@ -155,3 +155,48 @@ def test_attn_bwd_class_token_only_matches_dense(T, H):
     b = dq_ref[:, : 3 * d].float() + dq_ref[:, 3 * d :].float()
     assert not torch.isnan(a).any()
     assert (a - b).abs().max().item() < 4e-3 * b.abs().max().item()
+
+
+def test_tcgen05_tmem_a_operand_and_mn_major_b():
+    """Known-answer test of the two operand forms vit_attn_tc.cu adds to the GEMM's: A read from TMEM (packed fp16
+    pairs stored with tcgen05.st) and an MN-major 128B-swizzled B tile."""
+    from semabs_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(5)
+    for Kd in (16, 64, 256):
+        A = torch.randn(128, Kd, device=dev, generator=g).half()
+        Bm = torch.randn(Kd, 64, device=dev, generator=g).half()
+        D = torch.full((128, 64), float("nan"), device=dev)
+        ops.selftest_ts_mma(A, Bm, D)
+        ref = (A.double() @ Bm.double()).float()
+        assert torch.allclose(D, ref, atol=1e-3, rtol=1e-4), (Kd, (D - ref).abs().max().item())
+
+
+@pytest.mark.parametrize("T,H,causal,splits", [(50, 12, False, 2), (257, 16, False, 2), (77, 8, True, 2), (257, 16, False, 1),
+                                               (197, 12, False, 2), (128, 4, False, 2), (129, 4, True, 2)])
+def test_attn_fwd_tc(T, H, causal, splits):
+    from semabs_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(T)
+    B, d = 3, H * 64
+    qkv = torch.randn(B * T, 3 * d, device=dev, generator=g)
+    qkv[:, :d] *= 0.125 * 2.0
+    if splits == 1:
+        qkv = qkv.half().float()
+    qkv16 = ops.split_f16(qkv) if splits == 2 else qkv.half()
+    ldp = (T + 15) // 16 * 16
+    probs16 = torch.full((B * H, T, ldp), float("nan"), device=dev, dtype=torch.float16)
+    o32 = torch.full((B * T, d), float("nan"), device=dev)
+    o16 = torch.full((B * T, 2 * d), float("nan"), device=dev, dtype=torch.float16)
+    ops.attn_fwd_tc(qkv16, in_splits=splits, B=B, T=T, H=H, probs16=probs16, o32=o32, o16=o16, o_splits=2, causal=causal)
+    q, k, v = (t.reshape(B, T, H, 64).permute(0, 2, 1, 3) for t in qkv.view(B, T, 3 * d).chunk(3, -1))
+    s = q @ k.transpose(-1, -2)
+    if causal:
+        s = s + torch.full((T, T), float("-inf"), device=dev).triu_(1)
+    a = s.softmax(-1)
+    o = (a @ v).permute(0, 2, 1, 3).reshape(B * T, d)
+    tol = 1e-5 if splits == 2 else 2e-3
+    assert torch.allclose(probs16[:, :, :T].float().view(B, H, T, T), a, atol=1e-3, rtol=1e-3)
+    assert probs16[:, :, T:].abs().max().item() == 0.0 if ldp > T else True
+    assert torch.allclose(o32, o, atol=tol, rtol=1e-4), (o32 - o).abs().max().item()
+    assert torch.allclose(_recon(o16, d, 2), o, atol=tol, rtol=1e-4)
