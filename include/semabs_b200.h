@@ -113,6 +113,14 @@ int semabs_attn_fwd(const float* qkv, float* probs, void* probs16, int32_t ld_p1
 int semabs_attn_fwd_tc(const void* qkv16, int32_t in_splits, void* probs16, int32_t ld_p16, float* o32, void* o16,
                        int32_t o_splits, int32_t B, int32_t T, int32_t H, int32_t causal, void* stream);
 
+/* semabs_attn_bwd on tcgen05 / TMEM for T <= 272 (same arguments and results; ld_p16 and ld_do multiples of 16):
+ * row pass G = dO V^T -> dS in TMEM -> dQ = dS K ; column pass G^T = V dO^T -> relevance column sums, dS^T and A^T in
+ * TMEM -> dK = dS^T Q, dV = A^T dO.  With need_dqkv == 0 only wpart is produced (one launch). */
+int semabs_attn_bwd_tc(const void* qkv16, int32_t ld_qkv, const void* probs16, int32_t ld_p16, const float* o32,
+                       const void* dO16, int32_t ld_do, const float* r, float* delta_ws, float* wpart, void* dqkv16,
+                       int32_t P, int32_t B, int32_t T, int32_t H, int32_t splits, int32_t positive_only,
+                       int32_t need_dqkv, void* stream);
+
 /* Known-answer hook for the two tcgen05 operand forms the attention kernels add to the GEMM's (A operand in TMEM,
  * MN-major B in shared memory): D[128,64] = A16[128,Kd] * B16[Kd,64], Kd % 16 == 0, Kd <= 256; lbo / sbo are the
  * descriptor byte offsets under test.  Test infrastructure for tests/test_vit_kernels_gpu.py. */

@@ -51,7 +51,8 @@ class ClipEngine:
         self.ws = _Workspace(self.device)
         self.kernel_launches = 0
         self.sparse_last_block = True
-        self.tc_attention = True  # tcgen05 attention kernels (T <= 272); False = the mma.sync kernels of vit_attn.cu
+        self.tc_attention = True  # tcgen05 attention forward (T <= 272); False = the mma.sync kernel of vit_attn.cu
+        self.tc_attention_bwd = False  # tcgen05 attention backward (first version: correct, slower than mma.sync)
 
     # ------------------------------------------------------------------------------------------------
     def _block_forward(self, blk: BlockWeights, x, x_next, *, n_seq, T, H, d, causal, saved: Optional[dict]):
@@ -272,8 +273,9 @@ class ClipEngine:
             # x_mid = x_in + out_proj(attn(ln_1(x_in)))
             ops.gemm_f16(dxm16, blk.w_outT, a_splits=sb, out_f16=dO16)
             need = i > self.start_block
-            ops.attn_bwd(sv["qkv16"], sv["probs16"], sv["o32"], dO16, d, r, delta, wpart, dqkv16 if need else None, P=P,
-                         B=B, T=T, H=H, splits=sb, positive_only=positive_attn_only, need_dqkv=need)
+            attn_bwd = ops.attn_bwd_tc if (self.tc_attention_bwd and T <= 272) else ops.attn_bwd
+            attn_bwd(sv["qkv16"], sv["probs16"], sv["o32"], dO16, d, r, delta, wpart, dqkv16 if need else None, P=P,
+                     B=B, T=T, H=H, splits=sb, positive_only=positive_attn_only, need_dqkv=need)
             ops.rollout_update(r, wpart, PB, H, T)
             self.kernel_launches += 8 if need else 7
             if need:

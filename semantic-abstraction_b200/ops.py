@@ -170,6 +170,19 @@ def attn_bwd(qkv16, probs16, o32, dO16, ld_do, r, delta_ws, wpart, dqkv16, *, P,
     )
 
 
+def attn_bwd_tc(qkv16, probs16, o32, dO16, ld_do, r, delta_ws, wpart, dqkv16, *, P, B, T, H, splits=1, positive_only=True,
+                need_dqkv=True):
+    """tcgen05 version of attn_bwd (T <= 272)."""
+    assert qkv16.dtype == torch.float16 and probs16.dtype == torch.float16
+    check(
+        lib().semabs_attn_bwd_tc(
+            ptr(qkv16), i32(qkv16.stride(0)), ptr(probs16), i32(probs16.shape[-1]), ptr(o32), ptr(dO16), i32(ld_do), ptr(r),
+            ptr(delta_ws), ptr(wpart), ptr(dqkv16), i32(P), i32(B), i32(T), i32(H), i32(splits), i32(int(positive_only)),
+            i32(int(need_dqkv)), stream_ptr(),
+        )
+    )
+
+
 def attn_bwd_cls(qkv16, probs16, dO16_cls, ld_do, r, wpart, dqkv16, *, P, B, T, H, splits=1, positive_only=True,
                  need_dqkv=True):
     check(

@@ -63,8 +63,9 @@ def test_attn_fwd(T, H, causal):
     assert torch.allclose(_recon(o16, d, 2), o, atol=1e-5, rtol=1e-4)
 
 
-@pytest.mark.parametrize("T,H", [(50, 12), (257, 16)])
-def test_attn_bwd(T, H):
+@pytest.mark.parametrize("T,H,impl", [(50, 12, "mma"), (257, 16, "mma"), (50, 12, "tc"), (257, 16, "tc"), (197, 12, "tc"),
+                                      (128, 4, "tc"), (130, 4, "tc")])
+def test_attn_bwd(T, H, impl):
     from semabs_b200 import ops
 
     g = torch.Generator(device=dev).manual_seed(T + 1)
@@ -83,8 +84,14 @@ def test_attn_bwd(T, H):
     delta = torch.empty(P * B * H, T, device=dev)
     wpart = torch.full((P * B * H, T), float("nan"), device=dev)
     dqkv16 = torch.full((P * B * T, 2 * 3 * d), float("nan"), device=dev, dtype=torch.float16)
-    ops.attn_bwd(qkv16, probs16, o32, dO, d, r, delta, wpart, dqkv16, P=P, B=B, T=T, H=H, splits=2, positive_only=True)
+    bwd = ops.attn_bwd_tc if impl == "tc" else ops.attn_bwd
+    bwd(qkv16, probs16, o32, dO, d, r, delta, wpart, dqkv16, P=P, B=B, T=T, H=H, splits=2, positive_only=True)
     torch.cuda.synchronize()
+    if impl == "tc":  # relevance-only call (last dense block): same wpart, nothing else touched
+        w2 = torch.full_like(wpart, float("nan"))
+        ops.attn_bwd_tc(qkv16, probs16, o32, dO, d, r, delta, w2, None, P=P, B=B, T=T, H=H, splits=2, positive_only=True,
+                        need_dqkv=False)
+        assert torch.equal(w2, wpart)
 
     # torch reference (fp32, same fp16-rounded dO)
     dOf = dO.float().view(P, B, T, H, 64).permute(0, 1, 3, 2, 4)  # P,B,H,T,hd
