@@ -52,7 +52,7 @@ class ClipEngine:
         self.kernel_launches = 0
         self.sparse_last_block = True
         self.tc_attention = True  # tcgen05 attention forward (T <= 272); False = the mma.sync kernel of vit_attn.cu
-        self.tc_attention_bwd = False  # tcgen05 attention backward (first version: correct, slower than mma.sync)
+        self.tc_attention_bwd = True  # tcgen05 attention backward (T <= 272); False = the mma.sync kernels
 
     # ------------------------------------------------------------------------------------------------
     def _block_forward(self, blk: BlockWeights, x, x_next, *, n_seq, T, H, d, causal, saved: Optional[dict]):

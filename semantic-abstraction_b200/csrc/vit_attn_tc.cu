@@ -346,14 +346,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_fwd_tc_kernel(const __grid
 
 // ---------------------------------------------------------------------------------------------------------
 // backward + relevance (ClipGradcam.interpret, CLIP/clip/clip_gradcam.py:90-126; the autograd graph of
-// auxiliary.multi_head_attention_forward), one CTA per (label, sequence, head):
+// auxiliary.multi_head_attention_forward):
 //   G = dO V^T ; delta_i = dO_i . O_i ; dS = A o (G - delta) ; w_j = (1/H) sum_i r_i relu?(G o A)_ij
 //   dQ = scale dS K ; dK = dS^T Q ; dV = A^T dO
 // Row pass (thread = query row i):  MMA G[128 x 272] -> dS packed in place -> TS MMA dQ = dS K (K as MN-major B).
 // Column pass (thread = key j):     MMA G^T = V dO^T -> relevance column sums are thread-local -> dS^T and A^T packed
 //                                   in place -> TS MMAs dK = dS^T Q, dV = A^T dO (Q, dO as MN-major B).
+// Both are persistent: a CTA owns (sequence, head, 128-row tile) units and walks the P label cotangents of each unit,
+// so K / V / Q / the probability tile (and, in the row pass, each thread's probability row, in registers) are fetched
+// once per unit while the per-label dO tiles stream through a 2-stage TMA ring.  All 8 warps share the elementwise
+// phase (warp w and w+4 split the strip columns of TMEM lane quadrant w%4); warp 0 also issues TMA and MMAs.
+// T = 128 k + t with t <= 8 (ViT-L/14: 257 = 2*128 + 1) leaves t rows / keys to attn_bwd_tail_kernel (SIMT) instead of
+// paying a whole 128-row tile for them.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int TC_TAIL_MAX = 8;
+
 struct AttnBwdTcArgs {
+  const __half* qkv16;    // [B*T, ldq]
+  int ldq;
   const __half* probs16;  // [B*H, T, ldp]
   int ldp;
   const float* o32;       // [B*T, d]
@@ -366,49 +376,56 @@ struct AttnBwdTcArgs {
   int P, B, T, H, d, splits;
   float scale;
   int positive_only, need_dqkv;
+  int n_full;             // 128-row MMA tiles per (sequence, head)
+  int n_tail;             // rows / keys left to the SIMT tail kernel
 };
 
-struct RowSmem {
-  static constexpr int DO = 0;
-  static constexpr int V = DO + TC_BOX_BYTES;
-  static constexpr int K = V + TC_KV_BYTES;
-  static constexpr int BARS = K + TC_KV_BYTES;
-  static constexpr int TOTAL = BARS + 128 + 1024;
-};
-
-__device__ __forceinline__ void store_row64_f16(__half* dst, int lo_off, int splits, const uint32_t (&o)[64], float scale) {
-  uint32_t hi[32], lo[32];
+__device__ __forceinline__ void store_row_f16(__half* dst, int lo_off, int splits, const uint32_t* o, int n, float scale) {
+  // n fp32 values (multiple of 16) -> fp16 hi (and lo at +lo_off elements)
+  for (int e0 = 0; e0 < n; e0 += 16) {
+    uint32_t hi[8], lo[8];
 #pragma unroll
-  for (int e = 0; e < 32; ++e) split_pack(__uint_as_float(o[2 * e]) * scale, __uint_as_float(o[2 * e + 1]) * scale, hi[e], lo[e]);
-#pragma unroll
-  for (int e = 0; e < 32; e += 8) st_global_256(dst + 2 * e, hi + e);
-  if (splits == 2) {
-#pragma unroll
-    for (int e = 0; e < 32; e += 8) st_global_256(dst + lo_off + 2 * e, lo + e);
+    for (int e = 0; e < 8; ++e)
+      split_pack(__uint_as_float(o[e0 + 2 * e]) * scale, __uint_as_float(o[e0 + 2 * e + 1]) * scale, hi[e], lo[e]);
+    st_global_256(dst + e0, hi);
+    if (splits == 2) st_global_256(dst + lo_off + e0, lo);
   }
 }
+
+struct RowSmem {
+  static constexpr int K = 0;
+  static constexpr int V = K + TC_KV_BYTES;
+  static constexpr int DO = V + TC_KV_BYTES;            // 2 stages
+  static constexpr int DPART = DO + 2 * TC_BOX_BYTES;   // float [2][128] delta partial sums
+  static constexpr int BARS = DPART + 1024;
+  static constexpr int TOTAL = BARS + 128 + 1024;
+};
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_bwd_row_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, AttnBwdTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RowSmem::BARS);
-  uint64_t *bar_kv = bars, *bar_q = bars + 1, *bar_s = bars + 2, *bar_p = bars + 3, *bar_o = bars + 4, *bar_free = bars + 5;
+  uint64_t *bar_kv = bars, *bar_do = bars + 1 /* [2] */, *bar_s = bars + 3, *bar_p = bars + 4, *bar_o = bars + 5;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* s_dpart = reinterpret_cast<float*>(smem + RowSmem::DPART);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.x % a.P, bh = blockIdx.x / a.P, b = bh / a.H, h = bh % a.H;
-  const int pb = p * a.B + b;
-  const int T = a.T, d = a.d;
-  const int n_mt = (T + 127) / 128;
+  const int q = warp & 3, half = warp >> 2, rr = q * 32 + lane;
+  const int T = a.T, d = a.d, P = a.P;
   const int ncol = (T + 15) & ~15;
   const int n1 = ncol < 256 ? ncol : 256, n2 = ncol - n1;
+  const int nch = ncol / 16, c_split = (nch + 1) / 2;
+  const int c0 = half ? c_split : 0, c1 = half ? nch : c_split;
+  const int n_units = a.B * a.H * a.n_full;
+  const int n_my = (n_units - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int N = n_my * P;  // items of this CTA: unit-major, label fastest
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
-    mbar_init(bar_kv, 1), mbar_init(bar_q, 1), mbar_init(bar_s, 1), mbar_init(bar_o, 1);
-    mbar_init(bar_p, 128), mbar_init(bar_free, 128);
+    mbar_init(bar_kv, 1), mbar_init(&bar_do[0], 1), mbar_init(&bar_do[1], 1), mbar_init(bar_s, 1), mbar_init(bar_o, 1);
+    mbar_init(bar_p, TC_THREADS);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -419,118 +436,160 @@ attn_bwd_row_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16);
+  const uint32_t tS = tmem_base + TC_COL_S, tO = tmem_base + TC_COL_O;
 
-  if (warp == 0) {
-    const uint32_t leader = elect_one() ? 1u : 0u;
-    if (leader) {
-      mbar_arrive_expect_tx(bar_kv, 2u * TC_KV_BYTES);
-      for (int bx = 0; bx < 2; ++bx) {
-        tma_load_2d(smem + RowSmem::V + bx * TC_BOX_BYTES, &tm_qkv, bar_kv, 2 * d + h * TC_HD, b * T + bx * TC_BOX_ROWS);
-        tma_load_2d(smem + RowSmem::K + bx * TC_BOX_BYTES, &tm_qkv, bar_kv, d + h * TC_HD, b * T + bx * TC_BOX_ROWS);
-      }
+  auto item = [&](int n, int& bh, int& mt, int& p) {
+    const int u = int(blockIdx.x) + (n / P) * int(gridDim.x);
+    p = n % P, bh = u / a.n_full, mt = u % a.n_full;
+  };
+  uint32_t leader = 0;
+  if (warp == 0) leader = elect_one() ? 1u : 0u;
+  const uint32_t sbase = smem_u32(smem);
+  const uint64_t dV = desc_kmajor(sbase + RowSmem::V), dK = desc_mnmajor(sbase + RowSmem::K, 16);
+  const uint32_t idesc_s1 = make_idesc_f16(128, n1), idesc_s2 = make_idesc_f16(128, n2 ? n2 : 16);
+  constexpr uint32_t idesc_o = make_idesc_f16(128, TC_HD, false, true);
+
+  auto load_do = [&](int n) {  // elected lane of warp 0
+    int bh, mt, p;
+    item(n, bh, mt, p);
+    const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+    mbar_arrive_expect_tx(&bar_do[n & 1], TC_BOX_BYTES);
+    tma_load_2d(smem + RowSmem::DO + (n & 1) * TC_BOX_BYTES, &tm_do, &bar_do[n & 1], h * TC_HD, pb * T + mt * 128);
+  };
+  auto load_kv = [&](int n) {  // elected lane of warp 0; n = first item of a unit
+    int bh, mt, p;
+    item(n, bh, mt, p);
+    const int b = bh / a.H, h = bh % a.H;
+    mbar_arrive_expect_tx(bar_kv, 2u * TC_KV_BYTES);
+    for (int bx = 0; bx < 2; ++bx) {
+      tma_load_2d(smem + RowSmem::V + bx * TC_BOX_BYTES, &tm_qkv, bar_kv, 2 * d + h * TC_HD, b * T + bx * TC_BOX_ROWS);
+      tma_load_2d(smem + RowSmem::K + bx * TC_BOX_BYTES, &tm_qkv, bar_kv, d + h * TC_HD, b * T + bx * TC_BOX_ROWS);
     }
-    const uint32_t sbase = smem_u32(smem);
-    const uint64_t dDO = desc_kmajor(sbase + RowSmem::DO), dV = desc_kmajor(sbase + RowSmem::V);
-    const uint64_t dK = desc_mnmajor(sbase + RowSmem::K, 16);
-    const uint32_t idesc_s1 = make_idesc_f16(128, n1), idesc_s2 = make_idesc_f16(128, n2 ? n2 : 16);
-    constexpr uint32_t idesc_o = make_idesc_f16(128, TC_HD, false, true);
-    const uint32_t tS = tmem_base + TC_COL_S, tO = tmem_base + TC_COL_O;
-    for (int mt = 0; mt < n_mt; ++mt) {
-      if (leader) {
-        mbar_arrive_expect_tx(bar_q, TC_BOX_BYTES);
-        tma_load_2d(smem + RowSmem::DO, &tm_do, bar_q, h * TC_HD, pb * T + mt * 128);
-      }
-      mbar_wait(bar_q, mt & 1);
-      if (mt == 0) mbar_wait(bar_kv, 0);
-      if (mt > 0) mbar_wait(bar_free, (mt - 1) & 1);
-      tc_fence_after();
+  };
+  auto issue_g = [&](int n) {  // warp 0, convergent
+    if (n % P == 0) mbar_wait(bar_kv, (n / P) & 1);
+    mbar_wait(&bar_do[n & 1], (n >> 1) & 1);
+    tc_fence_after();
+    const uint64_t dDO = desc_kmajor(sbase + RowSmem::DO + (n & 1) * TC_BOX_BYTES);
 #pragma unroll
-      for (int k = 0; k < TC_HD / 16; ++k) {
-        umma_f16_elect(tS, dDO + uint64_t(2 * k), dV + uint64_t(2 * k), idesc_s1, k != 0, leader);
-        if (n2) umma_f16_elect(tS + 256, dDO + uint64_t(2 * k), dV + uint64_t(2 * k) + uint64_t((256 * 128) >> 4), idesc_s2, k != 0, leader);
-      }
-      umma_commit_elect(bar_s, leader);
-      mbar_wait(bar_p, mt & 1);
-      tc_fence_after();
-      if (a.need_dqkv) {
-        for (int s = 0; s < ncol / 16; ++s)
-          umma_f16_ts_elect(tO, tS + uint32_t(16 * s), dK + uint64_t(s) * (2048 >> 4), idesc_o, s > 0, leader);
-      }
-      umma_commit_elect(bar_o, leader);
+    for (int k = 0; k < TC_HD / 16; ++k) {
+      umma_f16_elect(tS, dDO + uint64_t(2 * k), dV + uint64_t(2 * k), idesc_s1, k != 0, leader);
+      if (n2) umma_f16_elect(tS + 256, dDO + uint64_t(2 * k), dV + uint64_t(2 * k) + uint64_t((256 * 128) >> 4), idesc_s2, k != 0, leader);
     }
-  } else if (warp >= 4) {
-    const int q = warp & 3;
-    const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16);
-    for (int mt = 0; mt < n_mt; ++mt) {
-      const int i = mt * 128 + q * 32 + lane;
-      const bool valid = i < T;
-      // probability row and delta_i = dO_i . O_i, fetched while the G MMA runs
-      uint32_t arow[TC_MAX_T / 16][8];
+    umma_commit_elect(bar_s, leader);
+  };
+
+  if (warp == 0 && N > 0) {
+    if (leader) {
+      load_kv(0);
+      load_do(0);
+      if (N > 1) load_do(1);
+    }
+    __syncwarp();
+    issue_g(0);
+  }
+
+  uint32_t arow[(TC_MAX_T / 16 + 1) / 2][8];  // this thread's half of its probability row (kept across the P labels)
+  for (int n = 0; n < N; ++n) {
+    int bh, mt, p;
+    item(n, bh, mt, p);
+    const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+    const int i = mt * 128 + rr;
+    const bool valid = i < T;
+    if (p == 0) {
       const __half* prow = a.probs16 + (size_t(bh) * T + (valid ? i : 0)) * a.ldp;
 #pragma unroll
-      for (int c = 0; c < TC_MAX_T / 16; ++c) {
-        if (c * 16 < ncol) {
+      for (int cc = 0; cc < (TC_MAX_T / 16 + 1) / 2; ++cc) {
+        if (c0 + cc < c1) {
           if (valid) {
-            ld_global_256(prow + c * 16, arow[c]);
+            ld_global_256(prow + (c0 + cc) * 16, arow[cc]);
           } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) arow[c][e] = 0u;
+            for (int e = 0; e < 8; ++e) arow[cc][e] = 0u;
           }
         }
-      }
-      float delta = 0.f;
-      if (valid) {
-        const float* orow = a.o32 + (size_t(b) * T + i) * d + h * TC_HD;
-        const __half* grow = a.dO16 + (size_t(pb) * T + i) * a.ld_do + h * TC_HD;
-#pragma unroll
-        for (int e = 0; e < 64; e += 16) {
-          uint32_t ov[16], gv[8];
-          ld_global_256(orow + e, ov);
-          ld_global_256(orow + e + 8, ov + 8);
-          ld_global_256(grow + e, gv);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&gv[k]));
-            delta = fmaf(g2.x, __uint_as_float(ov[2 * k]), delta);
-            delta = fmaf(g2.y, __uint_as_float(ov[2 * k + 1]), delta);
-          }
-        }
-        a.delta[(size_t(pb) * a.H + h) * T + i] = delta;
-      }
-      mbar_wait(bar_s, mt & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < TC_MAX_T / 16; ++c) {
-        if (c * 16 < ncol) {
-          uint32_t g[16], w[8];
-          tmem_ld_32x32b_x16(t_row + uint32_t(TC_COL_S + c * 16), g);
-          tc_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&arow[c][e]));
-            w[e] = pack_h2(a2.x * (__uint_as_float(g[2 * e]) - delta), a2.y * (__uint_as_float(g[2 * e + 1]) - delta));
-          }
-          tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + c * 16), w);
-        }
-      }
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(bar_p);
-      mbar_wait(bar_o, mt & 1);
-      tc_fence_after();
-      if (a.need_dqkv) {
-        uint32_t o[64];
-        tmem_ld_32x32b_x32(t_row + uint32_t(TC_COL_O), *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
-        tmem_ld_32x32b_x32(t_row + uint32_t(TC_COL_O + 32), *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
-        tc_wait_ld();
-        tc_fence_before();
-        mbar_arrive(bar_free);
-        if (valid) store_row64_f16(a.dqkv16 + (size_t(pb) * T + i) * size_t(a.splits) * 3 * d + h * TC_HD, 3 * d, a.splits, o, a.scale);
-      } else {
-        tc_fence_before();
-        mbar_arrive(bar_free);
       }
     }
+    // delta_i = dO_i . O_i : each half sums 32 of the 64 head channels
+    {
+      float part = 0.f;
+      if (valid) {
+        const float* orow = a.o32 + (size_t(b) * T + i) * d + h * TC_HD + 32 * half;
+        const __half* grow = a.dO16 + (size_t(pb) * T + i) * a.ld_do + h * TC_HD + 32 * half;
+        uint32_t ov[32], gv[16];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ld_global_256(orow + 8 * e, ov + 8 * e);
+        ld_global_256(grow, gv);
+        ld_global_256(grow + 16, gv + 8);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&gv[k]));
+          part = fmaf(g2.x, __uint_as_float(ov[2 * k]), part);
+          part = fmaf(g2.y, __uint_as_float(ov[2 * k + 1]), part);
+        }
+      }
+      s_dpart[half * 128 + rr] = part;
+      // rows left to the tail kernel: their delta is needed by the column pass too
+      if (mt == 0 && int(threadIdx.x) < a.n_tail) {
+        const int it = a.n_full * 128 + int(threadIdx.x);
+        const float* orow = a.o32 + (size_t(b) * T + it) * d + h * TC_HD;
+        const __half2* grow = reinterpret_cast<const __half2*>(a.dO16 + (size_t(pb) * T + it) * a.ld_do + h * TC_HD);
+        float dl = 0.f;
+        for (int k = 0; k < 32; ++k) {
+          const float2 g2 = __half22float2(grow[k]);
+          dl = fmaf(g2.x, orow[2 * k], dl), dl = fmaf(g2.y, orow[2 * k + 1], dl);
+        }
+        a.delta[(size_t(pb) * a.H + h) * T + it] = dl;
+      }
+    }
+    __syncthreads();
+    const float delta = s_dpart[rr] + s_dpart[128 + rr];
+    if (half == 0 && valid) a.delta[(size_t(pb) * a.H + h) * T + i] = delta;
+
+    mbar_wait(bar_s, n & 1);
+    tc_fence_after();
+    if (leader && n + 2 < N) load_do(n + 2);  // G(n) has consumed stage n&1
+    __syncwarp();
+#pragma unroll
+    for (int cc = 0; cc < (TC_MAX_T / 16 + 1) / 2; ++cc) {
+      if (c0 + cc < c1) {
+        uint32_t g[16], w[8];
+        tmem_ld_32x32b_x16(t_row + uint32_t(TC_COL_S + (c0 + cc) * 16), g);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&arow[cc][e]));
+          w[e] = pack_h2(a2.x * (__uint_as_float(g[2 * e]) - delta), a2.y * (__uint_as_float(g[2 * e + 1]) - delta));
+        }
+        tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + (c0 + cc) * 16), w);
+      }
+    }
+    tc_wait_st();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+    if (warp == 0) {
+      mbar_wait(bar_p, n & 1);
+      tc_fence_after();
+      for (int s = 0; s < nch; ++s)
+        umma_f16_ts_elect(tO, tS + uint32_t(16 * s), dK + uint64_t(s) * (2048 >> 4), idesc_o, s > 0, leader);
+      umma_commit_elect(bar_o, leader);
+    }
+    mbar_wait(bar_o, n & 1);
+    tc_fence_after();
+    if (warp == 0 && n + 1 < N) {
+      if ((n + 1) % P == 0 && leader) load_kv(n + 1);  // dQ(n) was the last reader of this unit's K / V
+      __syncwarp();
+      issue_g(n + 1);  // overlaps the epilogue below (different TMEM columns)
+    }
+    {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(t_row + uint32_t(TC_COL_O + 32 * half), o);
+      tc_wait_ld();
+      if (valid)
+        store_row_f16(a.dqkv16 + (size_t(pb) * T + i) * size_t(a.splits) * 3 * d + h * TC_HD + 32 * half, 3 * d, a.splits, o, 32, a.scale);
+    }
+    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
@@ -541,12 +600,13 @@ attn_bwd_row_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 }
 
 struct ColSmem {
-  static constexpr int V = 0;                          // key tile (A operand of G^T)
-  static constexpr int DO = V + TC_BOX_BYTES;          // all query rows: B of G^T (K-major) and of dV (MN-major)
-  static constexpr int Q = DO + TC_KV_BYTES;           // all query rows: B of dK (MN-major)
-  static constexpr int PR = Q + TC_KV_BYTES;           // probabilities [272 i][128 j]: 2 column blocks x 2 row boxes
-  static constexpr int DR = PR + 4 * TC_BOX_BYTES;     // float2 {delta_i, r_i}
-  static constexpr int BARS = DR + TC_MAX_T * 8;
+  static constexpr int Q = 0;                           // all query rows: B of dK (MN-major)
+  static constexpr int V = Q + TC_KV_BYTES;             // key tile (A operand of G^T)
+  static constexpr int PR = V + TC_BOX_BYTES;           // probabilities [272 i][128 j]: 2 column blocks x 2 row boxes
+  static constexpr int DO = PR + 4 * TC_BOX_BYTES;      // 2 stages of all query rows: B of G^T (K-major) / dV (MN-major)
+  static constexpr int DR = DO + 2 * TC_KV_BYTES;       // float2 {delta_i, r_i} [2][272]
+  static constexpr int W = DR + 2 * TC_MAX_T * 8;       // float [2 buffers][2 halves][128] relevance partial sums
+  static constexpr int BARS = W + 2048;
   static constexpr int TOTAL = BARS + 128 + 1024;
 };
 
@@ -556,80 +616,169 @@ attn_bwd_col_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ColSmem::BARS);
-  uint64_t *bar_kv = bars, *bar_q = bars + 1, *bar_s = bars + 2, *bar_p = bars + 3, *bar_o = bars + 4, *bar_free = bars + 5;
+  uint64_t *bar_kv = bars, *bar_do = bars + 1 /* [2] */, *bar_s = bars + 3, *bar_p = bars + 4, *bar_o = bars + 5;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   float2* s_dr = reinterpret_cast<float2*>(smem + ColSmem::DR);
+  float* s_w = reinterpret_cast<float*>(smem + ColSmem::W);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.x % a.P, bh = blockIdx.x / a.P, b = bh / a.H, h = bh % a.H;
-  const int pb = p * a.B + b;
-  const int T = a.T, d = a.d;
-  const int n_mt = (T + 127) / 128;
+  const int q = warp & 3, half = warp >> 2, jj = q * 32 + lane;
+  const int T = a.T, d = a.d, P = a.P;
   const int ncol = (T + 15) & ~15;  // query columns of G^T
   const int n1 = ncol < 256 ? ncol : 256, n2 = ncol - n1;
+  const int nch = ncol / 16, c_split = (nch + 1) / 2;
+  const int c0 = half ? c_split : 0, c1 = half ? nch : c_split;
+  const int n_units = a.B * a.H * a.n_full;
+  const int n_my = (n_units - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int N = n_my * P;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_pr);
-    mbar_init(bar_kv, 1), mbar_init(bar_q, 1), mbar_init(bar_s, 1), mbar_init(bar_o, 1);
-    mbar_init(bar_p, 128), mbar_init(bar_free, 128);
+    mbar_init(bar_kv, 1), mbar_init(&bar_do[0], 1), mbar_init(&bar_do[1], 1), mbar_init(bar_s, 1), mbar_init(bar_o, 1);
+    mbar_init(bar_p, TC_THREADS);
     fence_barrier_init();
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < TC_MAX_T; i += blockDim.x) {
-    float2 v = make_float2(0.f, 0.f);
-    if (i < T) {
-      v.x = a.need_dqkv ? a.delta[(size_t(pb) * a.H + h) * T + i] : 0.f;
-      v.y = a.r[size_t(pb) * T + i];
+  auto item = [&](int n, int& bh, int& mt, int& p) {
+    const int u = int(blockIdx.x) + (n / P) * int(gridDim.x);
+    p = n % P, bh = u / a.n_full, mt = u % a.n_full;
+  };
+  auto load_dr = [&](int n) {  // all threads: {delta_i, r_i} of item n into buffer n&1
+    int bh, mt, p;
+    item(n, bh, mt, p);
+    const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+    for (int i = threadIdx.x; i < TC_MAX_T; i += TC_THREADS) {
+      float2 v = make_float2(0.f, 0.f);
+      if (i < T) {
+        v.x = a.need_dqkv ? a.delta[(size_t(pb) * a.H + h) * T + i] : 0.f;
+        v.y = a.r[size_t(pb) * T + i];
+      }
+      s_dr[(n & 1) * TC_MAX_T + i] = v;
     }
-    s_dr[i] = v;
-  }
+  };
+  if (N > 0) load_dr(0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16);
+  const uint32_t tS = tmem_base + TC_COL_S, tK = tmem_base + TC_COL_O, tV = tmem_base + TC_COL_O2;
 
-  if (warp == 0) {
-    const uint32_t leader = elect_one() ? 1u : 0u;
-    if (leader) {
-      mbar_arrive_expect_tx(bar_kv, 2u * TC_KV_BYTES);
-      for (int bx = 0; bx < 2; ++bx) {
-        tma_load_2d(smem + ColSmem::DO + bx * TC_BOX_BYTES, &tm_do, bar_kv, h * TC_HD, pb * T + bx * TC_BOX_ROWS);
-        tma_load_2d(smem + ColSmem::Q + bx * TC_BOX_BYTES, &tm_qkv, bar_kv, h * TC_HD, b * T + bx * TC_BOX_ROWS);
-      }
-    }
-    const uint32_t sbase = smem_u32(smem);
-    const uint64_t dVt = desc_kmajor(sbase + ColSmem::V), dDOk = desc_kmajor(sbase + ColSmem::DO);
-    const uint64_t dDOm = desc_mnmajor(sbase + ColSmem::DO, 16), dQm = desc_mnmajor(sbase + ColSmem::Q, 16);
-    const uint32_t idesc_s1 = make_idesc_f16(128, n1), idesc_s2 = make_idesc_f16(128, n2 ? n2 : 16);
-    constexpr uint32_t idesc_o = make_idesc_f16(128, TC_HD, false, true);
-    const uint32_t tS = tmem_base + TC_COL_S, tK = tmem_base + TC_COL_O, tV = tmem_base + TC_COL_O2;
-    for (int mt = 0; mt < n_mt; ++mt) {
-      if (mt > 0) mbar_wait(bar_free, (mt - 1) & 1);  // previous tile's threads are done with the probability tile
-      if (leader) {
-        mbar_arrive_expect_tx(bar_q, 5u * TC_BOX_BYTES);
-        tma_load_2d(smem + ColSmem::V, &tm_qkv, bar_q, 2 * d + h * TC_HD, b * T + mt * 128);
-        for (int cb = 0; cb < 2; ++cb)
-          for (int bx = 0; bx < 2; ++bx)
-            tma_load_2d(smem + ColSmem::PR + (cb * 2 + bx) * TC_BOX_BYTES, &tm_pr, bar_q, mt * 128 + cb * 64, bh * T + bx * TC_BOX_ROWS);
-      }
-      mbar_wait(bar_q, mt & 1);
-      if (mt == 0) mbar_wait(bar_kv, 0);
-      tc_fence_after();
+  uint32_t leader = 0;
+  if (warp == 0) leader = elect_one() ? 1u : 0u;
+  const uint32_t sbase = smem_u32(smem);
+  const uint64_t dVt = desc_kmajor(sbase + ColSmem::V), dQm = desc_mnmajor(sbase + ColSmem::Q, 16);
+  const uint32_t idesc_s1 = make_idesc_f16(128, n1), idesc_s2 = make_idesc_f16(128, n2 ? n2 : 16);
+  constexpr uint32_t idesc_o = make_idesc_f16(128, TC_HD, false, true);
+
+  auto load_do = [&](int n) {
+    int bh, mt, p;
+    item(n, bh, mt, p);
+    const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+    mbar_arrive_expect_tx(&bar_do[n & 1], TC_KV_BYTES);
+    for (int bx = 0; bx < 2; ++bx)
+      tma_load_2d(smem + ColSmem::DO + (n & 1) * TC_KV_BYTES + bx * TC_BOX_BYTES, &tm_do, &bar_do[n & 1], h * TC_HD,
+                  pb * T + bx * TC_BOX_ROWS);
+  };
+  auto load_unit = [&](int n) {
+    int bh, mt, p;
+    item(n, bh, mt, p);
+    const int b = bh / a.H, h = bh % a.H;
+    mbar_arrive_expect_tx(bar_kv, 7u * TC_BOX_BYTES);
+    for (int bx = 0; bx < 2; ++bx)
+      tma_load_2d(smem + ColSmem::Q + bx * TC_BOX_BYTES, &tm_qkv, bar_kv, h * TC_HD, b * T + bx * TC_BOX_ROWS);
+    tma_load_2d(smem + ColSmem::V, &tm_qkv, bar_kv, 2 * d + h * TC_HD, b * T + mt * 128);
+    for (int cb = 0; cb < 2; ++cb)
+      for (int bx = 0; bx < 2; ++bx)
+        tma_load_2d(smem + ColSmem::PR + (cb * 2 + bx) * TC_BOX_BYTES, &tm_pr, bar_kv, mt * 128 + cb * 64, bh * T + bx * TC_BOX_ROWS);
+  };
+  auto issue_g = [&](int n) {
+    if (n % P == 0) mbar_wait(bar_kv, (n / P) & 1);
+    mbar_wait(&bar_do[n & 1], (n >> 1) & 1);
+    tc_fence_after();
+    const uint64_t dDOk = desc_kmajor(sbase + ColSmem::DO + (n & 1) * TC_KV_BYTES);
 #pragma unroll
-      for (int k = 0; k < TC_HD / 16; ++k) {
-        umma_f16_elect(tS, dVt + uint64_t(2 * k), dDOk + uint64_t(2 * k), idesc_s1, k != 0, leader);
-        if (n2) umma_f16_elect(tS + 256, dVt + uint64_t(2 * k), dDOk + uint64_t(2 * k) + uint64_t((256 * 128) >> 4), idesc_s2, k != 0, leader);
+    for (int k = 0; k < TC_HD / 16; ++k) {
+      umma_f16_elect(tS, dVt + uint64_t(2 * k), dDOk + uint64_t(2 * k), idesc_s1, k != 0, leader);
+      if (n2) umma_f16_elect(tS + 256, dVt + uint64_t(2 * k), dDOk + uint64_t(2 * k) + uint64_t((256 * 128) >> 4), idesc_s2, k != 0, leader);
+    }
+    umma_commit_elect(bar_s, leader);
+  };
+
+  if (warp == 0 && N > 0) {
+    if (leader) {
+      load_unit(0);
+      load_do(0);
+      if (N > 1) load_do(1);
+    }
+    __syncwarp();
+    issue_g(0);
+  }
+
+  // probability tile addressing: element (i, jj) sits at  i*128 + (((jj%64)/8 ^ (i%8)) << 4) + (jj%8)*2  inside column block
+  // jj/64 (the two 136-row TMA boxes of a column block are contiguous and 136 % 8 == 0, so i needs no box arithmetic)
+  const uint8_t* pcol = smem + ColSmem::PR + (jj >> 6) * (2 * TC_BOX_BYTES) + (jj & 7) * 2;
+  uint32_t poff[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) poff[k] = uint32_t(k * 128 + (((((jj & 63) >> 3) ^ k)) << 4));
+  const float invH = 1.0f / a.H;
+
+  for (int n = 0; n < N; ++n) {
+    int bh, mt, p;
+    item(n, bh, mt, p);
+    const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+    const int j = mt * 128 + jj;
+    const bool valid = j < T;
+    if (n + 1 < N) load_dr(n + 1);
+    if (p == 0) mbar_wait(bar_kv, (n / P) & 1);  // the probability tile is read with ordinary loads: every thread acquires it
+    mbar_wait(bar_s, n & 1);
+    tc_fence_after();
+    const float2* dr = s_dr + (n & 1) * TC_MAX_T;
+    float w = 0.f;
+    for (int c = c0; c < c1; ++c) {
+      uint32_t g[16], ds[8], aw[8];
+      tmem_ld_32x32b_x16(t_row + uint32_t(TC_COL_S + c * 16), g);
+      const uint8_t* prow = pcol + c * 2048;
+      const float4* dr4 = reinterpret_cast<const float4*>(dr + c * 16);
+      const bool full = c * 16 + 16 <= T;
+      uint32_t raw[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        raw[e] = *reinterpret_cast<const uint16_t*>(prow + (e >> 3) * 1024 + poff[e & 7]);
+        if (!full && c * 16 + e >= T) raw[e] = 0u;  // rows past T belong to the next head
       }
-      umma_commit_elect(bar_s, leader);
-      mbar_wait(bar_p, mt & 1);
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) {
+        const uint32_t word = raw[e] | (raw[e + 1] << 16);
+        const float2 av = __half22float2(*reinterpret_cast<const __half2*>(&word));
+        const float4 d4 = dr4[e >> 1];  // {delta_i, r_i, delta_i+1, r_i+1}
+        const float g0 = __uint_as_float(g[e]), g1 = __uint_as_float(g[e + 1]);
+        float x0 = g0 * av.x, x1 = g1 * av.y;
+        if (a.positive_only) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f);
+        w = fmaf(d4.y, x0, w);
+        w = fmaf(d4.w, x1, w);
+        ds[e >> 1] = pack_h2(av.x * (g0 - d4.x), av.y * (g1 - d4.z));
+        aw[e >> 1] = word;
+      }
+      tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + c * 16), ds);
+      tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + c * 16 + 8), aw);
+    }
+    s_w[(n & 1) * 256 + half * 128 + jj] = w;
+    tc_wait_st();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+    mbar_wait(bar_p, n & 1);
+    if (warp == 0) {
       tc_fence_after();
       if (a.need_dqkv) {
-        for (int s = 0; s < ncol / 16; ++s) {
+        const uint64_t dDOm = desc_mnmajor(sbase + ColSmem::DO + (n & 1) * TC_KV_BYTES, 16);
+        for (int s = 0; s < nch; ++s) {
           const uint64_t kadv = uint64_t(s) * (2048 >> 4);
           umma_f16_ts_elect(tK, tS + uint32_t(16 * s), dQm + kadv, idesc_o, s > 0, leader);
           umma_f16_ts_elect(tV, tS + uint32_t(16 * s + 8), dDOm + kadv, idesc_o, s > 0, leader);
@@ -637,76 +786,161 @@ attn_bwd_col_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       }
       umma_commit_elect(bar_o, leader);
     }
-  } else if (warp >= 4) {
-    const int q = warp & 3;
-    const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16);
-    const int jj = q * 32 + lane;  // key inside the tile
-    // probability tile: column block jj/64, 16-byte chunk (jj%64)/8 (xor-swizzled with the row), element jj%8
-    const uint8_t* ptile = smem + ColSmem::PR + (jj >> 6) * (2 * TC_BOX_BYTES) + (jj & 7) * 2;
-    const int chunk = (jj & 63) >> 3;
-    const float invH = 1.0f / a.H;
-    for (int mt = 0; mt < n_mt; ++mt) {
-      const int j = mt * 128 + jj;
-      const bool valid = j < T;
-      mbar_wait(bar_q, mt & 1);  // probability tile landed
-      mbar_wait(bar_s, mt & 1);
-      tc_fence_after();
-      float w = 0.f;
-      for (int c = 0; c < ncol; c += 16) {
-        uint32_t g[16], ds[8], aw[8];
-        tmem_ld_32x32b_x16(t_row + uint32_t(TC_COL_S + c), g);
-        tc_wait_ld();
-#pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-          float av[2], dv[2];
-          uint32_t araw[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int i = c + e + u;
-            const int bx = i >= TC_BOX_ROWS, ii = i - bx * TC_BOX_ROWS;
-            const uint16_t raw = (i < T) ? *reinterpret_cast<const uint16_t*>(ptile + bx * TC_BOX_BYTES + ii * 128 + ((chunk ^ (ii & 7)) << 4)) : uint16_t(0);
-            araw[u] = raw;
-            av[u] = __half2float(__ushort_as_half(raw));
-            const float2 dr = s_dr[i];
-            const float gv = __uint_as_float(g[e + u]);
-            float x = gv * av[u];
-            if (a.positive_only) x = fmaxf(x, 0.f);
-            w = fmaf(dr.y, x, w);
-            dv[u] = av[u] * (gv - dr.x);
-          }
-          ds[e >> 1] = pack_h2(dv[0], dv[1]);
-          aw[e >> 1] = araw[0] | (araw[1] << 16);
-        }
-        tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + c), ds);
-        tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + c + 8), aw);
+    mbar_wait(bar_o, n & 1);
+    tc_fence_after();
+    if (warp == 0) {
+      if (leader && n + 2 < N) load_do(n + 2);  // stage n&1 was last read by dV(n)
+      if (n + 1 < N) {
+        if ((n + 1) % P == 0 && leader) load_unit(n + 1);
+        __syncwarp();
+        issue_g(n + 1);
       }
-      if (valid) a.wpart[(size_t(pb) * a.H + h) * T + j] = w * invH;
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(bar_p);
-      mbar_wait(bar_o, mt & 1);
-      tc_fence_after();
-      if (a.need_dqkv) {
-        uint32_t o[64];
-        __half* drow = a.dqkv16 + (size_t(pb) * T + (valid ? j : 0)) * size_t(a.splits) * 3 * d + h * TC_HD;
-        tmem_ld_32x32b_x32(t_row + uint32_t(TC_COL_O), *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
-        tmem_ld_32x32b_x32(t_row + uint32_t(TC_COL_O + 32), *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
-        tc_wait_ld();
-        if (valid) store_row64_f16(drow + d, 3 * d, a.splits, o, 1.0f);
-        tmem_ld_32x32b_x32(t_row + uint32_t(TC_COL_O2), *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
-        tmem_ld_32x32b_x32(t_row + uint32_t(TC_COL_O2 + 32), *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
-        tc_wait_ld();
-        if (valid) store_row64_f16(drow + 2 * d, 3 * d, a.splits, o, 1.0f);
-      }
-      tc_fence_before();
-      mbar_arrive(bar_free);
     }
+    if (half == 0 && valid)
+      a.wpart[(size_t(pb) * a.H + h) * T + j] = (s_w[(n & 1) * 256 + jj] + s_w[(n & 1) * 256 + 128 + jj]) * invH;
+    if (a.need_dqkv) {
+      uint32_t o[64];
+      const uint32_t col = half ? TC_COL_O2 : TC_COL_O;
+      tmem_ld_32x32b_x32(t_row + col, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+      tmem_ld_32x32b_x32(t_row + col + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+      tc_wait_ld();
+      if (valid)
+        store_row_f16(a.dqkv16 + (size_t(pb) * T + j) * size_t(a.splits) * 3 * d + (half ? 2 * d : d) + h * TC_HD, 3 * d, a.splits,
+                      o, 64, 1.0f);
+    }
+    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SIMT tail: the n_tail (<= 8) query rows / keys past the last full 128-row tile.  One warp per (label, sequence, head,
+// tail index): the column part (key j0: relevance, dK_j0, dV_j0) runs with lanes over queries, the row part (query i0:
+// dQ_i0) with lanes over keys.  delta was written by the row pass.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_row64(const __half* p, __half2 (&v)[32]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p + 8 * e * 2);
+    *reinterpret_cast<uint4*>(&v[8 * e]) = u;
+    const uint4 u2 = *reinterpret_cast<const uint4*>(p + 8 * e * 2 + 8);
+    *reinterpret_cast<uint4*>(&v[8 * e + 4]) = u2;
+  }
+}
+__device__ __forceinline__ float dot64(const __half2 (&x)[32], const __half2 (&y)[32]) {
+  float acc = 0.f;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    const float2 fx = __half22float2(x[e]), fy = __half22float2(y[e]);
+    acc = fmaf(fx.x, fy.x, acc), acc = fmaf(fx.y, fy.y, acc);
+  }
+  return acc;
+}
+// sums acc[0..63] over the warp; lane l returns elements 2l, 2l+1
+__device__ __forceinline__ float2 warp_reduce64(float (&acc)[64], int lane) {
+  float2 mine = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < 64; ++e) {
+    const float s = warp_sum(acc[e]);
+    if ((e >> 1) == lane) {
+      if (e & 1) mine.y = s; else mine.x = s;
+    }
+  }
+  return mine;
+}
+__device__ __forceinline__ void store_pair_split(__half* row, int col, int lo_off, int splits, float x, float y) {
+  uint32_t hi, lo;
+  split_pack(x, y, hi, lo);
+  *reinterpret_cast<uint32_t*>(row + col) = hi;
+  if (splits == 2) *reinterpret_cast<uint32_t*>(row + lo_off + col) = lo;
+}
+
+__global__ void __launch_bounds__(128) attn_bwd_tail_kernel(AttnBwdTcArgs a) {
+  const int gw = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (gw >= a.P * a.B * a.H * a.n_tail) return;
+  const int t = gw % a.n_tail, rest = gw / a.n_tail, p = rest % a.P, bh = rest / a.P;
+  const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+  const int T = a.T, d = a.d;
+  const int x0 = a.n_full * 128 + t;  // the tail row / key
+  const __half* qkv = a.qkv16 + size_t(b) * T * a.ldq + h * TC_HD;
+  const __half* dOb = a.dO16 + size_t(pb) * T * a.ld_do + h * TC_HD;
+  const __half* Ab = a.probs16 + size_t(bh) * T * a.ldp;
+  const float* dl = a.delta + (size_t(pb) * a.H + h) * T;
+  const size_t ld = size_t(a.splits) * 3 * d;
+  constexpr int JMAX = (TC_MAX_T + 31) / 32;
+  // ---- column part: key x0, lanes over queries i
+  {
+    __half2 v0[32];
+    load_row64(qkv + size_t(x0) * a.ldq + 2 * d, v0);
+    float dk[64], dv[64];
+#pragma unroll
+    for (int e = 0; e < 64; ++e) dk[e] = 0.f, dv[e] = 0.f;
+    float wsum = 0.f;
+    for (int c = 0; c < JMAX; ++c) {
+      const int i = c * 32 + lane;
+      if (i < T) {
+        __half2 gi[32];
+        load_row64(dOb + size_t(i) * a.ld_do, gi);
+        const float g = dot64(gi, v0);
+        const float av = __half2float(Ab[size_t(i) * a.ldp + x0]);
+        float x = g * av;
+        if (a.positive_only) x = fmaxf(x, 0.f);
+        wsum = fmaf(a.r[size_t(pb) * T + i], x, wsum);
+        if (a.need_dqkv) {
+          const float ds = av * (g - dl[i]);
+          __half2 qi[32];
+          load_row64(qkv + size_t(i) * a.ldq, qi);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float2 fq = __half22float2(qi[e]), fg = __half22float2(gi[e]);
+            dk[2 * e] = fmaf(ds, fq.x, dk[2 * e]), dk[2 * e + 1] = fmaf(ds, fq.y, dk[2 * e + 1]);
+            dv[2 * e] = fmaf(av, fg.x, dv[2 * e]), dv[2 * e + 1] = fmaf(av, fg.y, dv[2 * e + 1]);
+          }
+        }
+      }
+    }
+    wsum = warp_sum(wsum);
+    if (lane == 0) a.wpart[(size_t(pb) * a.H + h) * T + x0] = wsum / a.H;
+    if (a.need_dqkv) {
+      __half* orow = a.dqkv16 + (size_t(pb) * T + x0) * ld + h * TC_HD;
+      const float2 k2 = warp_reduce64(dk, lane);
+      store_pair_split(orow, d + 2 * lane, 3 * d, a.splits, k2.x, k2.y);
+      const float2 v2 = warp_reduce64(dv, lane);
+      store_pair_split(orow, 2 * d + 2 * lane, 3 * d, a.splits, v2.x, v2.y);
+    }
+  }
+  // ---- row part: query x0, lanes over keys j
+  if (a.need_dqkv) {
+    __half2 g0[32];
+    load_row64(dOb + size_t(x0) * a.ld_do, g0);
+    const float delta0 = dl[x0];
+    float dq[64];
+#pragma unroll
+    for (int e = 0; e < 64; ++e) dq[e] = 0.f;
+    for (int c = 0; c < JMAX; ++c) {
+      const int j = c * 32 + lane;
+      if (j < T) {
+        __half2 vj[32], kj[32];
+        load_row64(qkv + size_t(j) * a.ldq + 2 * d, vj);
+        const float g = dot64(g0, vj);
+        const float av = __half2float(Ab[size_t(x0) * a.ldp + j]);
+        const float ds = av * (g - delta0);
+        load_row64(qkv + size_t(j) * a.ldq + d, kj);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float2 fk = __half22float2(kj[e]);
+          dq[2 * e] = fmaf(ds, fk.x, dq[2 * e]), dq[2 * e + 1] = fmaf(ds, fk.y, dq[2 * e + 1]);
+        }
+      }
+    }
+    const float2 q2 = warp_reduce64(dq, lane);
+    __half* orow = a.dqkv16 + (size_t(pb) * T + x0) * ld + h * TC_HD;
+    store_pair_split(orow, 2 * lane, 3 * d, a.splits, q2.x * a.scale, q2.y * a.scale);
   }
 }
 
@@ -779,22 +1013,32 @@ extern "C" int semabs_attn_bwd_tc(const void* qkv16, int32_t ld_qkv, const void*
   if (int rc = make_tile_tmap(&tm_do, dO16, (long long)P * B * T, d, ld_do)) return rc;
   if (int rc = make_tile_tmap(&tm_pr, probs16, (long long)B * H * T, ld_p16, ld_p16)) return rc;
   AttnBwdTcArgs a{};
+  a.qkv16 = (const __half*)qkv16, a.ldq = ld_qkv;
   a.probs16 = (const __half*)probs16, a.ldp = ld_p16, a.o32 = o32, a.dO16 = (const __half*)dO16, a.ld_do = ld_do;
   a.delta = delta_ws, a.r = r, a.wpart = wpart, a.dqkv16 = (__half*)dqkv16;
   a.P = P, a.B = B, a.T = T, a.H = H, a.d = d, a.splits = splits, a.scale = 0.125f;
   a.positive_only = positive_only, a.need_dqkv = need_dqkv;
+  const int rem = T % 128;
+  a.n_tail = (T > 128 && rem >= 1 && rem <= TC_TAIL_MAX) ? rem : 0;
+  a.n_full = a.n_tail ? T / 128 : (T + 127) / 128;
   static bool configured = false;
   if (!configured) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_row_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RowSmem::TOTAL));
     SB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_col_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ColSmem::TOTAL));
     configured = true;
   }
-  const int grid = P * B * H;
+  const int n_units = B * H * a.n_full;
+  const int grid = n_units < num_sms() ? n_units : num_sms();
   if (need_dqkv) {  // the row pass produces dQ and delta; the relevance-only last step needs neither
     attn_bwd_row_tc_kernel<<<grid, TC_THREADS, RowSmem::TOTAL, st>>>(tm_qkv, tm_do, a);
     SB_CHECK_CUDA(cudaGetLastError());
   }
   attn_bwd_col_tc_kernel<<<grid, TC_THREADS, ColSmem::TOTAL, st>>>(tm_qkv, tm_do, tm_pr, a);
   SB_CHECK_CUDA(cudaGetLastError());
+  if (a.n_tail) {
+    const int warps = P * B * H * a.n_tail;
+    attn_bwd_tail_kernel<<<(warps + 3) / 4, 128, 0, st>>>(a);
+    SB_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
