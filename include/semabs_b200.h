@@ -187,6 +187,9 @@ int semabs_flip_average(float* rel, const float* rel_flipped, int64_t n_maps, in
  *   kind 2: nn.ConvTranspose3d k3 s2 p1 with output_size = 2x input (Upsampling, unet3d.py:428-440), one output
  *           parity class per call (parity bit2 = z, bit1 = y, bit0 = x; 8 calls cover the output);
  *           w16 [C_out, w_splits*27*C_in] = upsample.weight.permute(1,2,3,4,0)
+ *   kind 3: adjoint of kind 2 = 3x3x3 conv, stride 2, padding 1 over x16 [N,2D,2H,2W,C_in] -> (D,H,W) (data gradient
+ *           of the transposed conv); one INPUT parity class per call, the 8 calls are chained through
+ *           residual == out32; w16 [C_out, w_splits*27*C_in] = upsample.weight.permute(0,2,3,4,1)
  * precise != 0 (needs a_splits == w_splits == 2) accumulates x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (≈ fp32 accuracy).
  * Epilogue: + bias[C_out] (opt) + residual (opt, fp32, same layout as out32), ReLU (opt); writes out32
  * [N,Do,Ho,Wo,C_out] and/or out16 [.., o16_splits*C_out]; accumulates `stats` of what it wrote for a GroupNorm
@@ -224,6 +227,70 @@ int semabs_conv3d_halo(const void* x16_planar, int32_t a_splits, const void* w_i
 /* nn.MaxPool3d(2) (Encoder.forward, unet3d.py:298,313-317) + statistics of the pooled tensor. */
 int semabs_maxpool3d_2(const float* x, float* y, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C,
                        int32_t groups, double* stats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Backward of the UNet stages (unet_bwd.cu) — what `loss.backward()` (utils.py:404-411) does through
+ * unet3d.py's 'gcr' units (GroupNorm -> Conv3d -> ReLU, :20-95), ExtResNetBlock (:243-259), MaxPool3d (:298),
+ * ConvTranspose3d + skip sum (:385-396,428-440) and final_conv (:578).
+ * Scaling protocol: an fp32 gradient tensor is true scale unless it is the raw output of a data-gradient conv run
+ * on scaled fp16 operands; then a device float `scale` accompanies it (true = stored / scale). `amax` slots are
+ * device uint32 holding the bit pattern of a non-negative float, zeroed by the caller, updated with atomicMax.
+ * Data gradients: semabs_conv3d / semabs_conv3d_halo with adjoint weight packs (kind 0 with flipped taps and
+ * swapped channel roles, kind 1 transposed, kind 3 for the transposed conv).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* amax = max(amax, max|x|), n % 4 == 0. */
+int semabs_absmax_f32(const float* x, int64_t n, void* amax_slot, void* stream);
+
+/* fp32 [N,D,H,W,C] -> fp16 MMA operands, value * f * [mask > 0], f = 2^(12 - ilogb(*amax)) (1 if amax == NULL);
+ * *scale_out = (*g_scale or 1) * f.  pad16 (optional): zero-padded channels-last [N, D+2, H+2, W+2, Cp], interior
+ * only is written (ring and guard rows must already be zero); parity != 0: the 8 parity sub-grids as 8 consecutive
+ * padded volumes [8][N, D/2+2, H/2+2, W/2+2, Cp] (sub-grid q = (z&1)<<2 | (y&1)<<1 | (x&1)).  op16 (optional):
+ * op_layout 1 = channels-last [N,S,C], 2 = chunk-planar [N][C/8][S][8] (semabs_conv3d_halo operand). */
+int semabs_unet_bwd_pack(const float* g, const float* g_scale, const void* amax, const float* mask, int32_t N, int32_t D,
+                         int32_t H, int32_t W, int32_t C, void* pad16, int32_t Cp, int32_t parity, void* op16,
+                         int32_t op_layout, float* scale_out, void* stream);
+
+/* semabs_groupnorm_apply into the padded operand layout [N, D+2, H+2, W+2, Cp] (single fp16 split). */
+int semabs_groupnorm_apply_padded(const float* x, const double* stats, const float* gamma, const float* beta, void* pad16,
+                                  int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t C_real, int32_t groups,
+                                  int32_t Cp, void* stream);
+
+/* Weight gradient as a split-K reduction over flat padded voxels (mma.sync m16n8k16, fp32 accumulation):
+ *   grad[(a*Cb_real + b)*KT + slot_k[slot]] (+)= (1 / *scale) * sum_p A16[p][a] * B16[p + off(slot)][b]
+ * A16 / B16: padded channels-last fp16 with channel strides lda / ldb; p runs over [0, nvox) (multiple of 64; rows of
+ * A outside the interior must be zero, B must be finite wherever A is non-zero... and readable for every offset).
+ * Taps are grouped in <= 9 segments of <= 3 taps: tap j of segment s has off = seg_off[s] + seg_sh[3s+j]
+ * (seg_sh in {0,1,2}) and output slot seg_slot[3s+j] < nslots.  seg_* are HOST arrays, slot_k a DEVICE int32 array.
+ * workspace holds the per-split partial sums ([nsplit][nslots][Ca][Cb] fp32; nsplit is fitted to workspace_bytes).
+ * Conv3d weight [Co,Ci,27]: A = scaled output gradient, B = normalised input, off = tap offset; ConvTranspose3d
+ * weight [Ci,Co,27]: A = input, B = parity-split output gradient. */
+int semabs_conv3d_wgrad(const void* A16, int32_t lda, int32_t Ca, int32_t Ca_real, const void* B16, int32_t ldb,
+                        int32_t Cb, int32_t Cb_real, int64_t nvox, int32_t nseg, const int64_t* seg_off,
+                        const int32_t* seg_ntaps, const int32_t* seg_sh, const int32_t* seg_slot, int32_t nslots,
+                        const int32_t* slot_k_dev, int32_t KT, void* workspace, int64_t workspace_bytes,
+                        const float* scale, float* grad, int32_t accumulate, void* stream);
+
+/* GroupNorm backward (torch.nn.GroupNorm semantics). reduce: sums[N,C,2] += (sum_v dy, sum_v dy*x) (x may be NULL:
+ * column sums only, for bias gradients); sums zeroed by the caller.  apply:
+ *   dx = rstd*(gamma*dy - mean_g(gamma*dy) - xhat*mean_g(gamma*dy*xhat)) / *dy_scale
+ *        + add * [add_mask > 0] / *add_scale  (+ dx when accumulate),   amax slot updated with max|dx|.
+ * param_grads: dgamma[c] (+)= sum_n rstd*(sum dy x - mean sum dy) / *scale, dbeta[c] (+)= sum_n sum dy / *scale
+ * (stats == NULL, dgamma == NULL: bias gradient of a convolution). */
+int semabs_groupnorm_bwd_reduce(const float* dy, const float* x, int32_t N, int64_t S, int32_t C, double* sums,
+                                void* stream);
+int semabs_groupnorm_bwd_apply(const float* dy, const float* dy_scale, const float* x, const double* stats,
+                               const float* gamma, const double* sums, int32_t N, int64_t S, int32_t C, int32_t C_real,
+                               int32_t groups, const float* add, const float* add_scale, const float* add_mask,
+                               float* dx, int32_t accumulate, void* amax_slot, void* stream);
+int semabs_groupnorm_param_grads(const double* sums, const double* stats, const float* scale, int32_t N, int64_t S,
+                                 int32_t C, int32_t C_real, int32_t groups, float* dgamma, float* dbeta,
+                                 int32_t accumulate, void* stream);
+
+/* MaxPool3d(2) backward: g [N,D/2,H/2,W/2,C] (/ *g_scale) routed to the first maximum (z,y,x scan order) of each
+ * 2x2x2 cell of x [N,D,H,W,C]; dx written (or added to, accumulate != 0); amax slot updated with max|dx|. */
+int semabs_maxpool3d_2_bwd(const float* g, const float* g_scale, const float* x, int32_t N, int32_t D, int32_t H,
+                           int32_t W, int32_t C, float* dx, int32_t accumulate, void* amax_slot, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Point <-> voxel stages of SemAbs3D / SemAbsVOOL (points.cu) — reference net.py.

@@ -340,7 +340,8 @@ static int dispatch_bn(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, c
 
 using namespace sb;
 
-// kind: 0 = 3x3x3 pad 1 (27 taps), 1 = 1x1x1, 2 = transposed k3 s2 p1 output-parity class `parity` (bit2=z,bit1=y,bit0=x)
+// kind: 0 = 3x3x3 pad 1 (27 taps), 1 = 1x1x1, 2 = transposed k3 s2 p1 output-parity class `parity` (bit2=z,bit1=y,bit0=x),
+// 3 = stride-2 3x3x3 pad 1 over the 2x grid (adjoint of kind 2), input-parity class `parity` per call
 extern "C" int semabs_conv3d(const void* x16, int32_t a_splits, const void* w16, int32_t w_splits, int32_t kind,
                              int32_t parity, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C_in, int32_t C_out,
                              int32_t precise, const float* bias, const float* residual, int32_t relu, float* out32,
@@ -381,6 +382,22 @@ extern "C" int semabs_conv3d(const void* x16, int32_t a_splits, const void* w16,
         }
     p.ntaps = t;
     p.os = 2, p.oz = pz, p.oy = py, p.ox = px, p.Do = 2 * D, p.Ho = 2 * H, p.Wo = 2 * W;
+  } else if (kind == 3) {
+    // adjoint of kind 2 (data gradient of the transposed conv = 3x3x3 conv, stride 2, padding 1, over the 2x grid):
+    // out[i] = sum_k in[2i - 1 + k] W[k].  Input parity class `parity` of the (2D,2H,2W) grid per call:
+    // parity 0 -> (k=1, j=i); parity 1 -> (k=0, j=i-1), (k=2, j=i) with in[2j + parity]
+    p.w_slices = 27;
+    const int pz = (parity >> 2) & 1, py = (parity >> 1) & 1, px = parity & 1;
+    const int kk[2][2] = {{1, -1}, {0, 2}}, dl[2][2] = {{0, 0}, {-1, 0}};
+    int t = 0;
+    for (int a = 0; a < (pz ? 2 : 1); ++a)
+      for (int b = 0; b < (py ? 2 : 1); ++b)
+        for (int c = 0; c < (px ? 2 : 1); ++c) {
+          p.tap[t][0] = dl[pz][a], p.tap[t][1] = dl[py][b], p.tap[t][2] = dl[px][c];
+          p.tap_w[t] = (kk[pz][a] * 3 + kk[py][b]) * 3 + kk[px][c];
+          ++t;
+        }
+    p.ntaps = t;
   } else {
     SB_REQUIRE(false, "semabs_conv3d: unknown kind %d", kind);
   }
@@ -424,8 +441,15 @@ extern "C" int semabs_conv3d(const void* x16, int32_t a_splits, const void* w16,
     const uint64_t C = uint64_t(a_splits) * C_in;
     uint64_t dims[5] = {C, uint64_t(W), uint64_t(H), uint64_t(D), uint64_t(N)};
     uint64_t str[4] = {C * 2, C * 2 * W, C * 2 * W * H, C * 2 * W * H * D};
+    const uint8_t* base = static_cast<const uint8_t*>(x16);
+    if (kind == 3) {
+      // strided view of one parity class of the [N, 2D, 2H, 2W, C] tensor
+      const uint64_t W2 = 2 * uint64_t(W), H2 = 2 * uint64_t(H), D2 = 2 * uint64_t(D);
+      str[0] = 2 * C * 2, str[1] = 2 * W2 * C * 2, str[2] = 2 * H2 * W2 * C * 2, str[3] = D2 * H2 * W2 * C * 2;
+      base += ((uint64_t((parity >> 2) & 1) * H2 + uint64_t((parity >> 1) & 1)) * W2 + uint64_t(parity & 1)) * C * 2;
+    }
     uint32_t box[5] = {uint32_t(KB), uint32_t(p.bw), uint32_t(p.bh), uint32_t(p.bd), uint32_t(p.bn)};
-    if (int rc = make_tmap_f16(&tmA, x16, 5, dims, str, box, swz)) return rc;
+    if (int rc = make_tmap_f16(&tmA, base, 5, dims, str, box, swz)) return rc;
   }
   {
     const uint64_t K = uint64_t(w_splits) * p.w_slices * C_in;

@@ -327,3 +327,63 @@ def sample_decode(vol0, vol1, C0, query, grid, *, N, nq, concat_xyz, w1t, b1, w2
             ptr(emb), f32(temperature), ptr(out), stream_ptr(),
         )
     )
+
+
+# ---------------------------------------------------------------------------------------------------------
+# UNet backward stages (unet_bwd.cu)
+# ---------------------------------------------------------------------------------------------------------
+CONV_TRANSPOSE_ADJOINT = 3
+WGRAD_KB = 64  # voxels per pipeline stage of the weight-gradient kernel: padded volumes are sized in multiples of it
+
+
+def absmax_f32(x, amax_slot):
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() % 4 == 0
+    check(lib().semabs_absmax_f32(ptr(x), _i64(x.numel()), ptr(amax_slot), stream_ptr()))
+
+
+def unet_bwd_pack(g, *, N, D, H, W, C, g_scale=None, amax=None, mask=None, pad16=None, Cp=0, parity=False, op16=None,
+                  op_layout=1, scale_out=None):
+    check(lib().semabs_unet_bwd_pack(ptr(g), ptr(g_scale), ptr(amax), ptr(mask), i32(N), i32(D), i32(H), i32(W), i32(C),
+                                     ptr(pad16), i32(Cp), i32(int(parity)), ptr(op16), i32(op_layout), ptr(scale_out),
+                                     stream_ptr()))
+
+
+def groupnorm_apply_padded(x, stats, gamma, beta, pad16, *, N, D, H, W, C, C_real, groups, Cp):
+    check(lib().semabs_groupnorm_apply_padded(ptr(x), ptr(stats), ptr(gamma), ptr(beta), ptr(pad16), i32(N), i32(D), i32(H),
+                                              i32(W), i32(C), i32(C_real), i32(groups), i32(Cp), stream_ptr()))
+
+
+def conv3d_wgrad(A16, B16, *, lda, Ca, Ca_real, ldb, Cb, Cb_real, nvox, seg_off, seg_ntaps, seg_sh, seg_slot, nslots,
+                 slot_k, KT, workspace, scale, grad, accumulate=False):
+    """seg_off / seg_ntaps: python lists (one entry per segment); seg_sh / seg_slot: lists of 3-lists; slot_k: device int32."""
+    nseg = len(seg_off)
+    off = (C.c_int64 * nseg)(*[int(v) for v in seg_off])
+    nt = (C.c_int32 * nseg)(*[int(v) for v in seg_ntaps])
+    sh = (C.c_int32 * (3 * nseg))(*[int(v) for row in seg_sh for v in row])
+    sl = (C.c_int32 * (3 * nseg))(*[int(v) for row in seg_slot for v in row])
+    assert slot_k.dtype == torch.int32 and slot_k.numel() >= nslots and grad.dtype == torch.float32 and grad.is_contiguous()
+    check(lib().semabs_conv3d_wgrad(ptr(A16), i32(lda), i32(Ca), i32(Ca_real), ptr(B16), i32(ldb), i32(Cb), i32(Cb_real),
+                                    _i64(nvox), i32(nseg), off, nt, sh, sl, i32(nslots), ptr(slot_k), i32(KT), ptr(workspace),
+                                    _i64(workspace.numel() * workspace.element_size()), ptr(scale), ptr(grad),
+                                    i32(int(accumulate)), stream_ptr()))
+
+
+def groupnorm_bwd_reduce(dy, x, sums, *, N, S, C):
+    check(lib().semabs_groupnorm_bwd_reduce(ptr(dy), ptr(x), i32(N), _i64(S), i32(C), ptr(sums), stream_ptr()))
+
+
+def groupnorm_bwd_apply(dy, x, stats, gamma, sums, dx, *, N, S, C, C_real, groups, dy_scale=None, add=None, add_scale=None,
+                        add_mask=None, accumulate=False, amax=None):
+    check(lib().semabs_groupnorm_bwd_apply(ptr(dy), ptr(dy_scale), ptr(x), ptr(stats), ptr(gamma), ptr(sums), i32(N), _i64(S),
+                                           i32(C), i32(C_real), i32(groups), ptr(add), ptr(add_scale), ptr(add_mask), ptr(dx),
+                                           i32(int(accumulate)), ptr(amax), stream_ptr()))
+
+
+def groupnorm_param_grads(sums, *, N, S, C, C_real, groups=1, stats=None, scale=None, dgamma=None, dbeta=None, accumulate=False):
+    check(lib().semabs_groupnorm_param_grads(ptr(sums), ptr(stats), ptr(scale), i32(N), _i64(S), i32(C), i32(C_real),
+                                             i32(groups), ptr(dgamma), ptr(dbeta), i32(int(accumulate)), stream_ptr()))
+
+
+def maxpool3d_2_bwd(g, x, dx, *, N, D, H, W, C, g_scale=None, accumulate=False, amax=None):
+    check(lib().semabs_maxpool3d_2_bwd(ptr(g), ptr(g_scale), ptr(x), i32(N), i32(D), i32(H), i32(W), i32(C), ptr(dx),
+                                       i32(int(accumulate)), ptr(amax), stream_ptr()))

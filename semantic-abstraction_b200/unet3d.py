@@ -108,6 +108,7 @@ class ResidualUNet3D(nn.Module):
         self._pack: Dict[str, torch.Tensor] = {}
         self._pack_key = None
         self._ws: Dict[Tuple, torch.Tensor] = {}
+        self._bwd_engine = None
         self.kernel_launches = 0
 
     # ------------------------------------------------------------------------------------------------
@@ -120,6 +121,19 @@ class ResidualUNet3D(nn.Module):
             t = torch.empty(key[1], dtype=dtype, device=device)
             self._ws[key] = t
         return t
+
+    def _bwd(self):
+        if getattr(self, "_bwd_engine", None) is None:
+            from .unet3d_bwd import UNetBackward
+
+            self._bwd_engine = UNetBackward(self)
+        return self._bwd_engine
+
+    def _alloc(self, tape, ws_name, tape_name, shape, dtype, dev):
+        """inference: a reusable workspace buffer; training (tape given): a buffer that survives until backward"""
+        if tape is None:
+            return self._buf(ws_name, shape, dtype, dev)
+        return tape.alloc(tape_name, shape, dtype, dev)
 
     def _packed(self, device):
         """fp16 (hi | lo) MMA-operand copies of the conv weights, rebuilt when a parameter changes."""
@@ -172,7 +186,7 @@ class ResidualUNet3D(nn.Module):
 
     # ------------------------------------------------------------------------------------------------
     def _res_block(self, pk, prefix, blk: ExtResNetBlock, x_raw, x_stats, *, N, dims, c_in_pad, c_in_real, lvl, dev,
-                   want32: bool, want16: bool):
+                   want32: bool, want16: bool, tape=None):
         """ExtResNetBlock.forward (unet3d.py:243-259): o1 = relu(conv(gn(x))); o2 = relu(conv(gn(o1)));
         out = relu(conv(gn(o2)) + o1). Returns (out32 | None, out16 | None)."""
         D, H, W = dims
@@ -180,11 +194,12 @@ class ResidualUNet3D(nn.Module):
         s = 2 if self.precise else 1
         c_out = blk.conv1.conv.out_channels
         xn = self._buf(f"l{lvl}_xn", (N, S, s * max(c_in_pad, c_out)), F16, dev)
-        o1 = self._buf(f"l{lvl}_o1", (N, S, c_out), F32, dev)
-        o2 = self._buf(f"l{lvl}_o2", (N, S, c_out), F32, dev)
+        o1 = self._alloc(tape, f"l{lvl}_o1", f"{prefix}.o1", (N, S, c_out), F32, dev)
+        o2 = self._alloc(tape, f"l{lvl}_o2", f"{prefix}.o2", (N, S, c_out), F32, dev)
         g2, g3 = blk.conv2.num_groups, blk.conv3.num_groups
-        st = self._buf(f"l{lvl}_st", (2, N, 8, 2), F64, dev)
+        st = self._alloc(tape, f"l{lvl}_st", f"{prefix}.st", (2, N, 8, 2), F64, dev)
         st.zero_()
+        want32 = want32 or tape is not None  # the backward needs every block output (ReLU mask, next block's input)
         halo = W == 128 and c_in_pad in (16, 32) and c_out in (16, 32) and self.use_halo
         common = dict(N=N, D=D, H=H, W=W, a_splits=s, w_splits=s, precise=self.precise)
 
@@ -199,13 +214,16 @@ class ResidualUNet3D(nn.Module):
 
         gcr(1, x_raw, x_stats, c_in_pad, c_in_real, blk.conv1.num_groups, relu=True, out32=o1, stats=st[0], groups=g2)
         gcr(2, o1, st[0], c_out, c_out, g2, relu=True, out32=o2, stats=st[1], groups=g3)
-        out32 = self._buf(f"l{lvl}_out32", (N, S, c_out), F32, dev) if want32 else None
+        out32 = self._alloc(tape, f"l{lvl}_out32", f"{prefix}.out", (N, S, c_out), F32, dev) if want32 else None
         out16 = self._buf(f"l{lvl}_out16", (N, S, s * c_out), F16, dev) if want16 else None
         gcr(3, o2, st[1], c_out, c_out, g3, residual=o1, relu=True, out32=out32, out16=out16, o16_splits=s)
         self.kernel_launches += 6
+        if tape is not None:
+            tape.blocks[prefix] = dict(x=x_raw, x_stats=x_stats, o1=o1, o2=o2, st=st, out=out32, dims=dims,
+                                       c_in_pad=c_in_pad, c_in_real=c_in_real, c_out=c_out)
         return out32, out16
 
-    def forward_channels_last(self, x_raw, x_stats, N, dims, dev):
+    def forward_channels_last(self, x_raw, x_stats, N, dims, dev, tape=None):
         """Core of Abstract3DUNet.forward (unet3d.py:596-621) on channels-last buffers. x_raw [N,S,Cpad] fp32 with
         its GroupNorm statistics. Returns the final conv output, channels-last fp32 [N,S,out_channels]."""
         pk = self._packed(dev)
@@ -219,8 +237,8 @@ class ResidualUNet3D(nn.Module):
             if i > 0:
                 D, H, W = dims
                 g_next = enc.basic_module.conv1.num_groups
-                pooled = self._buf(f"l{i}_in", (N, (D // 2) * (H // 2) * (W // 2), c_pad), F32, dev)
-                pst = self._buf(f"l{i}_pst", (N, 8, 2), F64, dev)
+                pooled = self._alloc(tape, f"l{i}_in", f"enc{i}.in", (N, (D // 2) * (H // 2) * (W // 2), c_pad), F32, dev)
+                pst = self._alloc(tape, f"l{i}_pst", f"enc{i}.pst", (N, 8, 2), F64, dev)
                 pst.zero_()
                 ops.maxpool3d_2(cur_raw, pooled, N=N, D=D, H=H, W=W, C=c_pad, groups=g_next, stats=pst)
                 self.kernel_launches += 1
@@ -229,7 +247,7 @@ class ResidualUNet3D(nn.Module):
             last = i == L - 1
             out32, out16 = self._res_block(pk, f"enc{i}", enc.basic_module, cur_raw, cur_stats, N=N, dims=dims,
                                            c_in_pad=c_pad, c_in_real=c_real, lvl=i, dev=dev, want32=not last,
-                                           want16=last)
+                                           want16=last, tape=tape)
             c_pad = c_real = self.f_maps[i]
             if not last:
                 feats.insert(0, (out32, dims))
@@ -241,8 +259,8 @@ class ResidualUNet3D(nn.Module):
             D, H, W = dims  # input grid of the transposed conv
             c_in, c_out = self.f_maps[lvl + 1], self.f_maps[lvl]
             S_out = sdims[0] * sdims[1] * sdims[2]
-            up = self._buf(f"l{lvl}_up", (N, S_out, c_out), F32, dev)
-            ust = self._buf(f"l{lvl}_ust", (N, 8, 2), F64, dev)
+            up = self._alloc(tape, f"l{lvl}_up", f"dec{j}.up", (N, S_out, c_out), F32, dev)
+            ust = self._alloc(tape, f"l{lvl}_ust", f"dec{j}.ust", (N, 8, 2), F64, dev)
             ust.zero_()
             g1 = dec.basic_module.conv1.num_groups
             assert sdims == (2 * D, 2 * H, 2 * W), "ConvTranspose3d(output_size) path expects exact 2x up-sampling"
@@ -254,9 +272,11 @@ class ResidualUNet3D(nn.Module):
             self.kernel_launches += 8
             dims = sdims
             _, cur16 = self._res_block(pk, f"dec{j}", dec.basic_module, up, ust, N=N, dims=dims, c_in_pad=c_out,
-                                       c_in_real=c_out, lvl=lvl, dev=dev, want32=False, want16=True)
+                                       c_in_real=c_out, lvl=lvl, dev=dev, want32=False, want16=True, tape=tape)
         D, H, W = dims
-        out = self._buf("final_cl", (N, D * H * W, self.out_channels), F32, dev)
+        out = self._alloc(tape, "final_cl", "final.out", (N, D * H * W, self.out_channels), F32, dev)
+        if tape is not None:
+            tape.meta = dict(N=N, dims0=dims, dev=dev)
         ops.conv3d(cur16, pk["final.w"], kind=ops.CONV_1X1X1, N=N, D=D, H=H, W=W, C_in=self.f_maps[0],
                    C_out=self.out_channels, a_splits=s, w_splits=s, precise=self.precise, bias=pk["final.b"], out32=out)
         self.kernel_launches += 1
@@ -266,6 +286,10 @@ class ResidualUNet3D(nn.Module):
         """x [N, C, D, H, W] fp32 on a CUDA device -> [N, out_channels, D, H, W] fp32 (NCDHW, like the reference)."""
         if not x.is_cuda:
             raise RuntimeError("semabs_b200.ResidualUNet3D runs on CUDA devices only; there is no CPU path")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .unet3d_bwd import _UNetFn  # training: the same kernels + a tape, backward in unet3d_bwd.py
+
+            return _UNetFn.apply(x, self, *self.parameters())
         N, C, D, H, W = x.shape
         assert C == self.in_channels
         dev = x.device
