@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--images", type=int, default=IMAGES_PER_STEP)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-voxel", action="store_true")
+    ap.add_argument("--skip-train", action="store_true")
+    ap.add_argument("--train-descs", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -264,6 +266,11 @@ def main():
     if not args.skip_voxel:
         voxel = bench_voxel(dev, world, dist if world > 1 else None, pk)
 
+    train = None
+    if not args.skip_train:
+        torch.cuda.empty_cache()
+        train = bench_train(dev, rank, world, pk, num_descs=args.train_descs)
+
     if rank == 0:
         cpu = None if args.skip_cpu else cpu_relevancy_sample(2, 16)
         line = {"metric": "relevancy-maps/sec/GPU (336^2, 5 scales, 16 labels)", "value": value, "unit": "relevancy-maps/s",
@@ -276,12 +283,13 @@ def main():
                            "tile_batch_size": TILE_BATCH, "fwd_splits": eng.fwd_splits, "bwd_splits": eng.bwd_splits},
                 "e2e": {"value": e2e_value, "unit": "relevancy-maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": "ClipWrapper.get_clip_saliency_convolve: host PIL tile preprocessing inside the timed region"},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "voxel": voxel}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "voxel": voxel, "train": train}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+@torch.no_grad()
 def bench_voxel(dev, world, dist, pk, C=32, N=4, steps=5, warmup=3):
     """configs[2]: ResidualUNet3D inference, 128^3 x 32 channels, batch 4 (6 levels, 8 groups)."""
     from semabs_b200.unet3d import ResidualUNet3D
@@ -324,6 +332,66 @@ def bench_voxel(dev, world, dist, pk, C=32, N=4, steps=5, warmup=3):
                          "frac": per_gpu * UNET_GB_PER_GRID_FP32[C] / pk["hbm_gbs"], "traffic": None,
                          "tensor_tflops": per_gpu * UNET_GF_PER_GRID[C] / 1e3, "tensor_frac": per_gpu * UNET_GF_PER_GRID[C] / 1e3 / pk["tflops"],
                          "note": "whole-forward algorithmic bytes (BASELINE.md byte rule, fp32 I/O) / time"}}
+
+
+def bench_train(dev, rank, world, pk, C=16, num_descs=16, steps=2, warmup=2):
+    """configs[3]: SemAbsVOOL train step with the reference's defaults (utils.py:38-77: 128^3 grid, 16 channels, 6 levels,
+    80k input / 400k output points, pointing_dim 64, decoder_concat_xyz_pts, LAMB lr 1e-3 wd 1e-5, grad_max_norm 2.0),
+    batch 1 scene x `num_descs` descriptions per GPU = 2 x num_descs voxel grids through the UNet forward + backward,
+    gradient all-reduce over NCCL when world > 1."""
+    import torch.distributed as dist
+
+    from semabs_b200 import train
+    from semabs_b200.net import SemAbsVOOL
+
+    bounds = ((-1.0, -1.0, -0.1), (1.0, 1.0, 1.9))
+    torch.manual_seed(0)  # same initial weights on every rank (what DDP's broadcast would give)
+    net = SemAbsVOOL(pointing_method="cosine_sim", pointing_dim=64, device=str(dev), decoder_concat_xyz_pts=True,
+                     voxel_shape=(128, 128, 128), scene_bounds=bounds, unet_num_channels=C, unet_f_maps=C, unet_num_groups=8,
+                     unet_num_levels=6, network_inputs=["saliency"], use_pts_feat_extractor=True,
+                     pts_feat_extractor_hidden_dim=128, reduce_method="max", batch_size=1).to(dev)
+    opt = train.Lamb(net.parameters(), lr=1e-3, weight_decay=1e-5)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    lo, hi = torch.tensor(bounds[0], device=dev), torch.tensor(bounds[1], device=dev)
+    n_in, n_out, B = 80000, 400000, 1
+    rels = SemAbsVOOL.RELATIONS[:6]
+    batch = dict(
+        input_xyz_pts=lo + (hi - lo) * torch.rand(B, n_in, 3, device=dev, generator=g),
+        input_target_saliency_pts=torch.randn(B, num_descs, n_in, 1, device=dev, generator=g),
+        input_reference_saliency_pts=torch.randn(B, num_descs, n_in, 1, device=dev, generator=g),
+        tsdf_vol=torch.ones(B, 1, device=dev),
+        output_xyz_pts=lo + (hi - lo) * torch.rand(B, num_descs, n_out, 3, device=dev, generator=g),
+        output_label_pts=(torch.rand(B, num_descs, n_out, device=dev, generator=g) < 0.1).float(),
+        out_of_bounds_pts=torch.zeros(B, num_descs, n_out, dtype=torch.bool, device=dev),
+        spatial_relation_name=[[rels[d % 6]] * B for d in range(num_descs)],
+    )
+    unet = net.completion_net.vol_feature_extractor
+    losses = []
+    for _ in range(warmup):
+        losses.append(train.train_step(net, batch, train.get_losses_vool, opt, grad_max_norm=2.0)["loss"])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = unet.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        losses.append(train.train_step(net, batch, train.get_losses_vool, opt, grad_max_norm=2.0)["loss"])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item() / steps
+    grids = 2 * num_descs * B  # target + reference volume per description
+    # forward + backward (data + weight gradients) = 3x the forward convolution FLOPs
+    tf = world * grids * 3 * UNET_GF_PER_GRID[C] / 1e3 / (ms / 1e3)
+    return {"metric": "VOOL train steps/s (128^3, 16 ch, 16 descriptions/GPU)", "value": world * 1e3 / ms, "unit": "steps/s (sum over GPUs)",
+            "ms_per_step": ms, "voxel_grids_trained_per_s": world * grids / (ms / 1e3), "descs_per_gpu": num_descs,
+            "unet_kernel_launches_per_step": (unet.kernel_launches - l0) // steps,
+            "loss_trajectory": [float(x) for x in losses], "unet_algorithmic_tflops": tf, "tensor_frac": tf / world / pk["tflops"],
+            "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2**30,
+            "note": "gradient all-reduce: one flat NCCL all-reduce after backward" if world > 1 else "single GPU: no collective"}
 
 
 if __name__ == "__main__":

@@ -246,10 +246,11 @@ int semabs_absmax_f32(const float* x, int64_t n, void* amax_slot, void* stream);
  * *scale_out = (*g_scale or 1) * f.  pad16 (optional): zero-padded channels-last [N, D+2, H+2, W+2, Cp], interior
  * only is written (ring and guard rows must already be zero); parity != 0: the 8 parity sub-grids as 8 consecutive
  * padded volumes [8][N, D/2+2, H/2+2, W/2+2, Cp] (sub-grid q = (z&1)<<2 | (y&1)<<1 | (x&1)).  op16 (optional):
- * op_layout 1 = channels-last [N,S,C], 2 = chunk-planar [N][C/8][S][8] (semabs_conv3d_halo operand). */
+ * op_layout 1 = channels-last [N,S,op_splits*C], 2 = chunk-planar [N][op_splits*C/8][S][8] (semabs_conv3d_halo
+ * operand); op_splits == 2 stores hi | lo (lo = fp16 of the rounding remainder) for the 3-pass precise convolutions. */
 int semabs_unet_bwd_pack(const float* g, const float* g_scale, const void* amax, const float* mask, int32_t N, int32_t D,
                          int32_t H, int32_t W, int32_t C, void* pad16, int32_t Cp, int32_t parity, void* op16,
-                         int32_t op_layout, float* scale_out, void* stream);
+                         int32_t op_layout, int32_t op_splits, float* scale_out, void* stream);
 
 /* semabs_groupnorm_apply into the padded operand layout [N, D+2, H+2, W+2, Cp] (single fp16 split). */
 int semabs_groupnorm_apply_padded(const float* x, const double* stats, const float* gamma, const float* beta, void* pad16,
@@ -320,6 +321,42 @@ int semabs_sample_decode(const float* vol0, const float* vol1, int32_t C0, const
                          const float* neg_lc, const float* scale, const int32_t* shape, int32_t concat_xyz,
                          const float* w1t, const float* b1, const float* w2t, const float* b2, int32_t Hs,
                          int32_t out_dim, const float* emb, float temperature, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Backward of the point <-> voxel stages (points_bwd.cu) — net.py:204-256, :300-309, :185-201, :358-367 under
+ * loss.backward().  Stage 1 kernels recompute the forward, route feature gradients and write one scratch row per item;
+ * weight gradients are semabs_outer_reduce_f32 over those rows, bias gradients column sums.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* out[r*ld_out + c] += scale * sum_p A[p*lda + r] * B[p*ldb + c]   (r < R, c < Cc, p < P; fp32; out is accumulated
+ * into with atomics, so the caller zero-initialises it). nn.Linear weight gradient: A = output deltas, B = inputs. */
+int semabs_outer_reduce_f32(const float* A, int32_t lda, int32_t R, const float* B, int32_t ldb, int32_t Cc, int64_t P,
+                            float scale, float* out, int32_t ld_out, void* stream);
+
+/* Backward of semabs_sample_decode. dout: gradient of its output ([N,nq,out_dim], or [N,nq] with emb).
+ * w1 / w2 are the nn.Linear weights in their own layout ([Hs][Cin], [out_dim][Hs]), w1t / w2t their transposes.
+ * dvol0 / dvol1 (zero-initialised by the caller, may be NULL): trilinear scatter-add of the feature gradient;
+ * demb [N,out_dim] (zero-initialised, optional): gradient of the cosine head's query embedding.
+ * scratch [N*nq][ld] receives per query: inputs (features | normalised xyz) at 0, hidden activations at off_h,
+ * output deltas at off_do, hidden deltas at off_dp. */
+int semabs_sample_decode_bwd(const float* vol0, const float* vol1, int32_t C0, const float* query, int32_t N, int32_t nq,
+                             const float* neg_lc, const float* scale, const int32_t* shape, int32_t concat_xyz,
+                             const float* w1t, const float* w1, const float* b1, const float* w2t, const float* w2,
+                             const float* b2, int32_t Hs, int32_t out_dim, const float* emb, float temperature,
+                             const float* dout, float* dvol0, float* dvol1, float* demb, float* scratch, int32_t ld,
+                             int32_t off_h, int32_t off_do, int32_t off_dp, void* stream);
+
+/* Backward of semabs_points_to_voxels (use_mlp != 0): dvol [N,S,Cpad] is the gradient of the voxelised volume, cnt the
+ * per-voxel point counts the forward produced (scatter-MEAN: every point receives dvol[voxel] / cnt[voxel]).
+ * w2t [hidden][hidden] is in-major (as in the forward), w2 / w3 are the nn.Linear weights ([out][in]).
+ * scratch [N*npts][ld] receives per point: inputs (xyz | features, 8 floats) at 0, h1 at 8, h2 at 8+hidden, the three
+ * layer deltas at off_d3 (C values), off_d2, off_d1 (hidden values each). */
+int semabs_points_to_voxels_bwd(const float* xyz, int32_t xyz_div, const float* feat, int32_t N, int32_t npts, int32_t F,
+                                int32_t hidden, int32_t C, const float* w1t, const float* b1, const float* w2t,
+                                const float* w2, const float* b2, const float* w3, const float* neg_lc,
+                                const float* scale, const int32_t* shape, const float* dvol, const float* cnt,
+                                int32_t Cpad, float* scratch, int32_t ld, int32_t off_d3, int32_t off_d2, int32_t off_d1,
+                                void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Optimiser side of the training step (train.cu) — reference utils.loop (utils.py:404-422).

@@ -135,7 +135,8 @@ def semabsvool_forward(sd, input_xyz_pts, target_saliency, reference_saliency, o
     place = torch.zeros_like(input_xyz_pts)[..., None, 0:1, :].repeat(1, num_descs, 1, 1)
     vols = []
     for sal in (target_saliency, reference_saliency):
-        _, v = semabs3d_forward(sd, input_xyz_pts, sal, place, bounds, grid_shape, num_groups, concat_xyz,
+        # the completion net is built without decoder_concat_xyz_pts (net.py:481: SemAbs3D(device=device, **kwargs))
+        _, v = semabs3d_forward(sd, input_xyz_pts, sal, place, bounds, grid_shape, num_groups, False,
                                 prefix="completion_net.", return_volume=True)
         vols.append(v)
     fv = torch.cat(vols, dim=1)

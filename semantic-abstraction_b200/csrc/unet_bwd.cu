@@ -58,12 +58,12 @@ __global__ void __launch_bounds__(BW_THREADS) absmax_kernel(const float4* __rest
 // g [N,S,C] fp32; optional ReLU mask (mask > 0); f = scale_from_amax(*amax) (1 when amax == null).
 //   pad : zero-padded channels-last [N, D+2, H+2, W+2, Cp] (interior written only); with parity != 0 the grid (D,H,W)
 //         is split into its 8 parity sub-grids, stored as 8 consecutive padded volumes [8][N, D/2+2, H/2+2, W/2+2, Cp]
-//   op  : unpadded operand of the forward conv kernels: channels-last [N,S,C] (op_layout 1) or chunk-planar
-//         [N][C/8][S][8] (op_layout 2, conv3d_halo.cu)
+//   op  : unpadded operand of the forward conv kernels: channels-last [N,S,splits*C] (op_layout 1) or chunk-planar
+//         [N][splits*C/8][S][8] (op_layout 2, conv3d_halo.cu); splits == 2 appends the fp16 remainder (hi | lo)
 __global__ void __launch_bounds__(BW_THREADS)
 bwd_pack_kernel(const float* __restrict__ g, const float* __restrict__ g_scale, const unsigned int* __restrict__ amax,
                 const float* __restrict__ mask, int D, int H, int W, int C, __half* __restrict__ pad, int Cp, int parity,
-                __half* __restrict__ op, int op_layout, float* __restrict__ scale_out, int N) {
+                __half* __restrict__ op, int op_layout, int op_splits, float* __restrict__ scale_out, int N) {
   const int n = blockIdx.y;
   const long long S = (long long)D * H * W;
   const float f = amax ? scale_from_amax(__uint_as_float(*amax)) : 1.f;
@@ -95,9 +95,16 @@ bwd_pack_kernel(const float* __restrict__ g, const float* __restrict__ g_scale, 
       *reinterpret_cast<uint2*>(pad + p * Cp + c) = packed;
     }
     if (op) {
-      __half* dst = op_layout == 2 ? op + size_t(n) * S * C + (size_t(c >> 3) * S + v) * 8 + (c & 7)
-                                   : op + (size_t(n) * S + v) * C + c;
+      // same layouts as gn_apply_kernel (unet_ops.cu): [v][splits*C] or chunk-planar, hi chunks then lo chunks
+      __half* on = op + size_t(n) * S * op_splits * C;
+      __half* dst = op_layout == 2 ? on + (size_t(c >> 3) * S + v) * 8 + (c & 7) : on + size_t(v) * op_splits * C + c;
       *reinterpret_cast<uint2*>(dst) = packed;
+      if (op_splits == 2) {
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(a.x - f0.x, a.y - f0.y), l1 = __floats2half2_rn(a.z - f1.x, a.w - f1.y);
+        __half* dlo = op_layout == 2 ? dst + size_t(C >> 3) * S * 8 : dst + C;
+        *reinterpret_cast<uint2*>(dlo) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      }
     }
   }
 }
@@ -532,16 +539,17 @@ static bool quad_ok(int C) { return C % 4 == 0 && C >= 4 && C <= 1024 && (BW_THR
 
 extern "C" int semabs_unet_bwd_pack(const float* g, const float* g_scale, const void* amax, const float* mask, int32_t N,
                                     int32_t D, int32_t H, int32_t W, int32_t C, void* pad16, int32_t Cp, int32_t parity,
-                                    void* op16, int32_t op_layout, float* scale_out, void* stream) {
+                                    void* op16, int32_t op_layout, int32_t op_splits, float* scale_out, void* stream) {
   SB_REQUIRE(g && (pad16 || op16) && N > 0 && D > 0 && H > 0 && W > 0, "semabs_unet_bwd_pack: bad arguments");
   SB_REQUIRE(quad_ok(C) && (!pad16 || Cp >= C), "semabs_unet_bwd_pack: unsupported channel count %d", C);
   SB_REQUIRE(!parity || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "semabs_unet_bwd_pack: parity split needs even extents");
-  SB_REQUIRE(!op16 || op_layout == 1 || (op_layout == 2 && C % 8 == 0), "semabs_unet_bwd_pack: bad operand layout");
+  SB_REQUIRE(!op16 || ((op_layout == 1 || (op_layout == 2 && C % 8 == 0)) && (op_splits == 1 || op_splits == 2)),
+             "semabs_unet_bwd_pack: bad operand layout");
   const int vpb = BW_THREADS / (C / 4);
   dim3 grid(bw_grid((long long)D * H * W, vpb), N);
   bwd_pack_kernel<<<grid, BW_THREADS, 0, (cudaStream_t)stream>>>(g, g_scale, (const unsigned int*)amax, mask, D, H, W, C,
                                                                  (__half*)pad16, Cp, parity, (__half*)op16, op_layout,
-                                                                 scale_out, N);
+                                                                 op_splits, scale_out, N);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

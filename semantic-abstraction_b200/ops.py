@@ -342,10 +342,10 @@ def absmax_f32(x, amax_slot):
 
 
 def unet_bwd_pack(g, *, N, D, H, W, C, g_scale=None, amax=None, mask=None, pad16=None, Cp=0, parity=False, op16=None,
-                  op_layout=1, scale_out=None):
+                  op_layout=1, op_splits=1, scale_out=None):
     check(lib().semabs_unet_bwd_pack(ptr(g), ptr(g_scale), ptr(amax), ptr(mask), i32(N), i32(D), i32(H), i32(W), i32(C),
-                                     ptr(pad16), i32(Cp), i32(int(parity)), ptr(op16), i32(op_layout), ptr(scale_out),
-                                     stream_ptr()))
+                                     ptr(pad16), i32(Cp), i32(int(parity)), ptr(op16), i32(op_layout), i32(op_splits),
+                                     ptr(scale_out), stream_ptr()))
 
 
 def groupnorm_apply_padded(x, stats, gamma, beta, pad16, *, N, D, H, W, C, C_real, groups, Cp):
@@ -387,3 +387,39 @@ def groupnorm_param_grads(sums, *, N, S, C, C_real, groups=1, stats=None, scale=
 def maxpool3d_2_bwd(g, x, dx, *, N, D, H, W, C, g_scale=None, accumulate=False, amax=None):
     check(lib().semabs_maxpool3d_2_bwd(ptr(g), ptr(g_scale), ptr(x), i32(N), i32(D), i32(H), i32(W), i32(C), ptr(dx),
                                        i32(int(accumulate)), ptr(amax), stream_ptr()))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# point <-> voxel backward (points_bwd.cu)
+# ---------------------------------------------------------------------------------------------------------
+def outer_reduce_f32(A, B, out, *, R, Cc, P, scale=1.0):
+    """out[r, c] += scale * sum_p A[p, r] * B[p, c]; A / B are 2-D fp32 views with unit column stride."""
+    assert A.dtype == torch.float32 and B.dtype == torch.float32 and A.stride(1) == 1 and B.stride(1) == 1
+    assert out.dtype == torch.float32 and out.stride(-1) == 1
+    check(lib().semabs_outer_reduce_f32(ptr(A), i32(A.stride(0)), i32(R), ptr(B), i32(B.stride(0)), i32(Cc), _i64(P),
+                                        f32(scale), ptr(out), i32(out.stride(0)), stream_ptr()))
+
+
+def sample_decode_bwd(vol0, vol1, C0, query, grid, *, N, nq, concat_xyz, w1t, w1, b1, w2t, w2, b2, Hs, out_dim, dout, dvol0,
+                      dvol1, scratch, off_h, off_do, off_dp, emb=None, temperature=1.0, demb=None):
+    neg_lc, scale, shape = grid
+    check(
+        lib().semabs_sample_decode_bwd(
+            ptr(vol0), ptr(vol1), i32(C0), ptr(query), i32(N), i32(nq), _host3(neg_lc, _cf), _host3(scale, _cf),
+            _host3(shape, _ci), i32(int(concat_xyz)), ptr(w1t), ptr(w1), ptr(b1), ptr(w2t), ptr(w2), ptr(b2), i32(Hs),
+            i32(out_dim), ptr(emb), f32(temperature), ptr(dout), ptr(dvol0), ptr(dvol1), ptr(demb), ptr(scratch),
+            i32(scratch.stride(0)), i32(off_h), i32(off_do), i32(off_dp), stream_ptr(),
+        )
+    )
+
+
+def points_to_voxels_bwd(xyz, feat, grid, *, N, npts, F, xyz_div, hidden, C, w1t, b1, w2t, w2, b2, w3, dvol, cnt, Cpad,
+                         scratch, off_d3, off_d2, off_d1):
+    neg_lc, scale, shape = grid
+    check(
+        lib().semabs_points_to_voxels_bwd(
+            ptr(xyz), i32(xyz_div), ptr(feat), i32(N), i32(npts), i32(F), i32(hidden), i32(C), ptr(w1t), ptr(b1), ptr(w2t),
+            ptr(w2), ptr(b2), ptr(w3), _host3(neg_lc, _cf), _host3(scale, _cf), _host3(shape, _ci), ptr(dvol), ptr(cnt),
+            i32(Cpad), ptr(scratch), i32(scratch.stride(0)), i32(off_d3), i32(off_d2), i32(off_d1), stream_ptr(),
+        )
+    )

@@ -3,7 +3,10 @@ gradient-norm clipping and LAMB — mirrors of `train_ovssc.get_losses`' loss (t
 `torch.nn.utils.clip_grad_norm_` as used at utils.py:415 and `arm.optim.lamb.Lamb` (arm/optim/lamb.py:25-127),
 plus the data-parallel gradient all-reduce (the one real exchange step of the path, utils.py:255-258).
 
-NOT here yet: the backward kernels of SemAbs3D / ResidualUNet3D that produce the gradients.
+The gradients themselves come from the hand-written backward of SemAbs3D / SemAbsVOOL / ResidualUNet3D (net.py
+autograd nodes -> unet3d_bwd.py, csrc/unet_bwd.cu, csrc/points_bwd.cu).  `get_losses_ovssc` / `get_losses_vool` mirror the
+loss part of the reference's `get_losses` (train_ovssc.py:81-150, train_vool.py:118-185; the IoU tables are evaluation,
+SURVEY.md §8f), `train_step` mirrors the train branch of `utils.loop` (utils.py:404-422).
 """
 from __future__ import annotations
 
@@ -34,6 +37,85 @@ def bce_with_logits_masked(logits: torch.Tensor, labels: torch.Tensor, weight: O
     check(lib().semabs_bce_with_logits(ptr(x), ptr(y), ptr(w), ptr(ig), C.c_int64(x.numel()), ptr(acc), ptr(out), ptr(dx),
                                        stream_ptr()))
     return out[0], out[1], dx
+
+
+class _BceFn(torch.autograd.Function):
+    """binary_cross_entropy_with_logits(outputs[keep], labels[keep], weight[keep]) (mean) as one kernel; the same launch
+    produces the gradient, backward only scales it."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, weight, ignore):
+        loss, acc, dx = bce_with_logits_masked(logits, labels, weight, ignore, need_grad=True)
+        ctx.save_for_backward(dx)
+        ctx.mark_non_differentiable(acc)
+        return loss.clone(), acc.clone()
+
+    @staticmethod
+    def backward(ctx, g_loss, g_acc):
+        (dx,) = ctx.saved_tensors
+        return dx * g_loss, None, None, None
+
+
+def get_bce_weight(output_label_pts: torch.Tensor, balance_positive_negative: bool) -> Optional[torch.Tensor]:
+    """utils.get_bce_weight (utils.py:726-749), vectorised; None stands for the all-ones weight."""
+    if not balance_positive_negative:
+        return None
+    pos = output_label_pts.bool()
+    pp = pos.float().mean(dim=2, keepdim=True)
+    w = torch.where(pos, 1.0 / (pp + 1e-10), 1.0 / ((1 - pp) + 1e-10))
+    return w * (float(w.numel()) / w.sum())
+
+
+def get_losses_ovssc(net, batch: dict, balance_positive_negative: bool = False, **kwargs):
+    """Loss / accuracy of train_ovssc.get_losses (train_ovssc.py:81-150): padding patches (label ""), out-of-bounds and
+    out-of-frustum points are ignored; BCE-with-logits, mean over the kept points."""
+    import numpy as np
+
+    outputs = net(**batch)
+    labels = batch["output_label_pts"]
+    ignore = torch.zeros_like(outputs, dtype=torch.bool)
+    if "patch_labels" in batch:
+        pad = torch.from_numpy(np.array(batch["patch_labels"]).T == "").to(outputs.device)
+        ignore[pad] = True
+    ignore |= batch["out_of_bounds_pts"].view(outputs.shape).bool()
+    ignore |= batch["out_of_frustum_pts_mask"].view(outputs.shape).bool()
+    w = get_bce_weight(labels, balance_positive_negative)
+    loss, acc = _BceFn.apply(outputs.contiguous(), labels, w, ignore)
+    return {"loss": loss, "accuracy": acc}, None
+
+
+def get_losses_vool(net, batch: dict, balance_positive_negative: bool = False, **kwargs):
+    """train_vool.get_losses (train_vool.py:118-185): the loss runs over ALL points, only the accuracy honours the
+    padding ("[pad]" relations) / out-of-bounds mask."""
+    import numpy as np
+
+    outputs = net(**batch)
+    labels = batch["output_label_pts"]
+    w = get_bce_weight(labels, balance_positive_negative)
+    loss, _ = _BceFn.apply(outputs.contiguous(), labels, w, None)
+    ignore = torch.zeros_like(outputs, dtype=torch.bool)
+    pad = torch.from_numpy(np.array(batch["spatial_relation_name"]).T == "[pad]").to(outputs.device)
+    ignore[pad] = True
+    ignore |= batch["out_of_bounds_pts"].view(outputs.shape).bool()
+    _, acc, _ = bce_with_logits_masked(outputs.detach().contiguous(), labels, None, ignore, need_grad=False)
+    return {"loss": loss, "accuracy": acc}, None
+
+
+def train_step(net, batch: dict, get_losses_fn, optimizer, grad_max_norm: float = 1e5, **kwargs):
+    """One iteration of utils.loop's train branch (utils.py:404-422): losses -> zero_grad -> backward ->
+    [DDP gradient averaging] -> clip_grad_norm_ -> optimizer.step -> steps += 1.  With this module's Lamb the clip is
+    folded into the optimiser sweep."""
+    stats, _ = get_losses_fn(net=net, batch=batch, **kwargs)
+    optimizer.zero_grad(set_to_none=True)
+    stats["loss"].backward()
+    all_reduce_gradients(net.parameters())
+    if isinstance(optimizer, Lamb):
+        optimizer.step(max_grad_norm=grad_max_norm)
+    else:
+        clip_grad_norm_(net.parameters(), grad_max_norm)
+        optimizer.step()
+    net.steps += 1
+    return stats
 
 
 class _ChunkTable:

@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import ops
-from .unet3d import F16, F32, F64, ExtResNetBlock, ResidualUNet3D, _pad16
+from .unet3d import F16, F32, F64, ExtResNetBlock, ResidualUNet3D, _pad16, _split_pack
 
 I32 = torch.int32
 WGRAD_WS_BYTES = 256 << 20
@@ -55,6 +55,11 @@ class UNetBackward:
         self._bpk: Dict[str, torch.Tensor] = {}
         self._bpk_key = None
         self._slot_i = 0
+        # data-gradient convolutions as dz_hi*w_hi + dz_lo*w_hi + dz_hi*w_lo (like the forward's precise mode): fp16
+        # rounding of the adjoint WEIGHTS is a coherent error over all voxels, which single-pass operands turn into ~1e-2
+        # relative errors of the (strongly cancelling) GroupNorm parameter gradients; the weight-gradient reduction only
+        # sees per-voxel (incoherent) rounding and stays single pass
+        self.precise = True
 
     # ---- tapes ------------------------------------------------------------------------------------------
     def new_tape(self) -> Tape:
@@ -67,10 +72,11 @@ class UNetBackward:
     # ---- adjoint weight packs -----------------------------------------------------------------------------
     def _packed(self, dev):
         u = self.unet
-        key = (str(dev), tuple(p._version for p in u.parameters()), tuple(p.data_ptr() for p in u.parameters()))
+        key = (str(dev), self.precise, tuple(p._version for p in u.parameters()), tuple(p.data_ptr() for p in u.parameters()))
         if key == self._bpk_key:
             return self._bpk
         pk: Dict[str, torch.Tensor] = {}
+        s = 2 if self.precise else 1
 
         def adj(w):  # conv.weight [Co,Ci,3,3,3] -> weight of the adjoint conv [Ci_pad, Co, 3,3,3] (taps flipped)
             co, ci = w.shape[:2]
@@ -81,18 +87,18 @@ class UNetBackward:
         def block(prefix, blk: ExtResNetBlock):
             for j, sc in enumerate((blk.conv1, blk.conv2, blk.conv3), 1):
                 wa = adj(sc.conv.weight)
-                pk[f"{prefix}.wa{j}"] = wa.permute(0, 2, 3, 4, 1).reshape(wa.shape[0], -1).half().contiguous()
+                pk[f"{prefix}.wa{j}"] = _split_pack(wa.permute(0, 2, 3, 4, 1).reshape(wa.shape[0], -1), s)
                 if wa.shape[0] in (16, 32) and wa.shape[1] in (16, 32):
-                    pk[f"{prefix}.wah{j}"] = ops.pack_halo_weights(wa, 1)
+                    pk[f"{prefix}.wah{j}"] = ops.pack_halo_weights(wa, s)
 
         for i, enc in enumerate(u.encoders):
             block(f"enc{i}", enc.basic_module)
         for i, dec in enumerate(u.decoders):
             block(f"dec{i}", dec.basic_module)
             w = dec.upsampling.upsample.weight  # [Ci, Co, 3,3,3]
-            pk[f"dec{i}.up_wa"] = w.detach().to(dev, F32).permute(0, 2, 3, 4, 1).reshape(w.shape[0], -1).half().contiguous()
+            pk[f"dec{i}.up_wa"] = _split_pack(w.detach().to(dev, F32).permute(0, 2, 3, 4, 1).reshape(w.shape[0], -1), s)
         fw = u.final_conv.weight  # [Co, Ci, 1,1,1]
-        pk["final.wa"] = fw.detach().to(dev, F32).reshape(fw.shape[0], fw.shape[1]).t().half().contiguous()
+        pk["final.wa"] = _split_pack(fw.detach().to(dev, F32).reshape(fw.shape[0], fw.shape[1]).t().contiguous(), s)
         pk["slot_k27"] = torch.arange(27, dtype=I32, device=dev)
         # transposed conv: launch A = taps with kx in {0,2} (x-parity 1 volume), launch B = taps with kx == 1
         pk["slot_kA"] = torch.tensor([(kz * 3 + ky) * 3 + kx for kz in range(3) for ky in range(3) for kx in (0, 2)], dtype=I32, device=dev)
@@ -137,10 +143,11 @@ class UNetBackward:
         halo = W == 128 and c_in_pad in (16, 32) and c_out in (16, 32) and u.use_halo
         dz_pad, nvox, (PD, PH, PW) = self._padded("dzp", N, dims, c_out, dev)
         xn_pad, _, _ = self._padded("xnp", N, dims, c_in_pad, dev)
-        dz_op = self._buf("dz_op", (N * S * c_out,), F16, dev)
+        sp = 2 if self.precise else 1
+        dz_op = self._buf("dz_op", (N * S * sp * c_out,), F16, dev)
         _, s_dz = self._slot()
         ops.unet_bwd_pack(g.t, N=N, D=D, H=H, W=W, C=c_out, g_scale=g.scale, amax=g.amax, mask=mask, pad16=dz_pad, Cp=c_out,
-                          op16=dz_op, op_layout=2 if halo else 1, scale_out=s_dz)
+                          op16=dz_op, op_layout=2 if halo else 1, op_splits=sp, scale_out=s_dz)
         gam, bet = fpk[f"{prefix}.g{j}"], fpk[f"{prefix}.b{j}"]
         groups = sc.num_groups
         ops.groupnorm_apply_padded(x_raw, x_stats, gam, bet, xn_pad, N=N, D=D, H=H, W=W, C=c_in_pad, C_real=c_in_real,
@@ -159,7 +166,7 @@ class UNetBackward:
         grads[sc.conv.weight] = gw
         # data gradient through the conv: the forward kernels with the adjoint weights (single fp16 pass)
         dxn = self._buf("dxn", (N * S * c_in_pad,), F32, dev)
-        common = dict(N=N, D=D, H=H, W=W, C_in=c_out, C_out=c_in_pad, a_splits=1, w_splits=1, precise=False, out32=dxn)
+        common = dict(N=N, D=D, H=H, W=W, C_in=c_out, C_out=c_in_pad, a_splits=sp, w_splits=sp, precise=self.precise, out32=dxn)
         if halo:
             ops.conv3d_halo(dz_op, pk[f"{prefix}.wah{j}"], **common)
         else:
@@ -230,8 +237,10 @@ class UNetBackward:
         ops.absmax_f32(d_out_cl, a_y)
         dy_pad, nvox, _ = self._padded("dzp", N, dims0, cop, dev)
         x_pad, _, _ = self._padded("xnp", N, dims0, ci, dev)
-        dy_op = self._buf("dz_op", (N * S * co,), F16, dev)
-        ops.unet_bwd_pack(d_out_cl, N=N, D=D, H=H, W=W, C=co, amax=a_y, pad16=dy_pad, Cp=cop, op16=dy_op, op_layout=1, scale_out=s_y)
+        sp = 2 if self.precise else 1
+        dy_op = self._buf("dz_op", (N * S * sp * co,), F16, dev)
+        ops.unet_bwd_pack(d_out_cl, N=N, D=D, H=H, W=W, C=co, amax=a_y, pad16=dy_pad, Cp=cop, op16=dy_op, op_layout=1,
+                          op_splits=sp, scale_out=s_y)
         ops.unet_bwd_pack(rec["out"], N=N, D=D, H=H, W=W, C=ci, pad16=x_pad, Cp=ci)
         gw = torch.empty_like(u.final_conv.weight, device=dev, dtype=F32)
         ops.conv3d_wgrad(dy_pad, x_pad, lda=cop, Ca=cop, Ca_real=co, ldb=ci, Cb=ci, Cb_real=ci, nvox=nvox, seg_off=[0],
@@ -245,8 +254,8 @@ class UNetBackward:
         ops.groupnorm_param_grads(sums, N=N, S=S, C=co, C_real=co, dbeta=gb)
         grads[u.final_conv.bias] = gb
         d_cur = self._buf("d_top", (N * S * ci,), F32, dev)
-        ops.conv3d(dy_op, pk["final.wa"], kind=ops.CONV_1X1X1, N=N, D=D, H=H, W=W, C_in=co, C_out=ci, a_splits=1, w_splits=1,
-                   precise=False, out32=d_cur)
+        ops.conv3d(dy_op, pk["final.wa"], kind=ops.CONV_1X1X1, N=N, D=D, H=H, W=W, C_in=co, C_out=ci, a_splits=sp, w_splits=sp,
+                   precise=self.precise, out32=d_cur)
         a_c, _ = self._slot()
         ops.absmax_f32(d_cur, a_c)
         g_cur = _Grad(d_cur, s_y, a_c)
@@ -274,9 +283,9 @@ class UNetBackward:
             x_low = tape.blocks[low_prefix]["out"]
             dy_par, nvox_l, (PD, PH, PW) = self._padded("dyp", N, (Dl, Hl, Wl), c_out, dev, volumes=8)
             xl_pad, nvox_x, _ = self._padded("xlp", N, (Dl, Hl, Wl), c_in, dev)
-            dy_op = self._buf("dz_op", (N * S * c_out,), F16, dev)
+            dy_op = self._buf("dz_op", (N * S * sp * c_out,), F16, dev)
             ops.unet_bwd_pack(d_up, N=N, D=dims[0], H=dims[1], W=dims[2], C=c_out, amax=a_up, pad16=dy_par, Cp=c_out, parity=True,
-                              op16=dy_op, op_layout=1, scale_out=s_up)
+                              op16=dy_op, op_layout=1, op_splits=sp, scale_out=s_up)
             ops.unet_bwd_pack(x_low, N=N, D=Dl, H=Hl, W=Wl, C=c_in, pad16=xl_pad, Cp=c_in)
             sums = self._buf("gn_sums", (N, c_out, 2), F64, dev)
             sums.zero_()
@@ -308,7 +317,7 @@ class UNetBackward:
             d_low = self._buf(f"d_low{lvl + 1}", (N * Sl * c_in,), F32, dev)
             for q in range(8):
                 ops.conv3d(dy_op, pk[f"dec{j}.up_wa"], kind=ops.CONV_TRANSPOSE_ADJOINT, parity=q, N=N, D=Dl, H=Hl, W=Wl,
-                           C_in=c_out, C_out=c_in, a_splits=1, w_splits=1, precise=False, out32=d_low,
+                           C_in=c_out, C_out=c_in, a_splits=sp, w_splits=sp, precise=self.precise, out32=d_low,
                            residual=d_low if q > 0 else None)
             a_l, _ = self._slot()
             ops.absmax_f32(d_low, a_l)

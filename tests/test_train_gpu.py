@@ -58,3 +58,124 @@ def test_lamb_with_clipping_matches_reference_semantics():
     ref_total = (sum(p.numel() for p in params if p.grad is not None) * 0.25) ** 0.5
     assert abs(tn.item() - ref_total) < 1e-3 * ref_total
     assert abs(params[0].grad[0].item() - 0.5 / (ref_total + 1e-6)) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole training step: SemAbs3D / SemAbsVOOL gradients vs autograd through the CPU oracle (oracle/unet_oracle.py)
+# ---------------------------------------------------------------------------------------------------------------------
+BOUNDS = ((-1.0, -1.0, -0.1), (1.0, 1.0, 1.9))
+GRAD_TOL = 2e-3  # per tensor ||Δ|| / ||ref||: single fp16 operands in the weight-gradient reductions (tests/test_unet_bwd_gpu.py)
+KINK_TOL = 3e-2
+
+
+def _rel2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def _semabs_args(**over):
+    a = dict(voxel_shape=(16, 16, 16), scene_bounds=BOUNDS, unet_num_channels=16, unet_f_maps=16, unet_num_groups=8,
+             unet_num_levels=3, network_inputs=["saliency"], use_pts_feat_extractor=True,
+             pts_feat_extractor_hidden_dim=128, reduce_method="max", device="cuda", batch_size=1)
+    a.update(over)
+    return a
+
+
+def _points(seed, B, P, n_in, n_out):
+    g = torch.Generator().manual_seed(seed)
+    lo, hi = torch.tensor(BOUNDS[0]), torch.tensor(BOUNDS[1])
+    xyz = lo + (hi - lo) * torch.rand(B, n_in, 3, generator=g)
+    feat = torch.randn(B, P, n_in, 1, generator=g)
+    out_xyz = lo + (hi - lo) * (torch.rand(B, P, n_out, 3, generator=g) * 1.1 - 0.05)
+    return xyz, feat, out_xyz
+
+
+def _check_grads(module, sd):
+    errs = {}
+    for name, p in module.named_parameters():
+        ref = sd[name].grad
+        if ref is None:
+            assert p.grad is None, f"{name}: the reference leaves this gradient None (unused parameter)"
+            continue
+        assert p.grad is not None, name
+        if ref.norm() == 0:
+            continue
+        errs[name] = _rel2(p.grad.cpu(), ref)
+    ranked = sorted(errs.items(), key=lambda kv: -kv[1])
+    print("gradient errors, worst first:", [(k, f"{v:.1e}") for k, v in ranked[:6]], "median", f"{ranked[len(ranked) // 2][1]:.1e}")
+    # ReLU kinks: a pre-activation within fp32 rounding of zero can take the other branch than the oracle (the forward
+    # outputs still agree to 1e-6); that flips ONE element of one unit's gradient by O(1) and shows up in that unit's
+    # (<= 4) strongly cancelling sums (tools/debug_unet_bwd.py: every other intermediate agrees to 5e-6)
+    over = [kv for kv in ranked if kv[1] >= GRAD_TOL]
+    assert len(over) <= 4 and ranked[0][1] < KINK_TOL, ranked[:6]
+    assert ranked[len(ranked) // 2][1] < GRAD_TOL / 2
+    return ranked[0]
+
+
+def test_semabs3d_training_step_matches_oracle():
+    from oracle import train_oracle, unet_oracle
+    from semabs_b200 import train
+    from semabs_b200.net import SemAbs3D
+
+    torch.manual_seed(21)
+    m = SemAbs3D(**_semabs_args()).to(dev)
+    B, P, n_in, n_out = 1, 2, 3000, 5000
+    xyz, feat, oxyz = _points(22, B, P, n_in, n_out)
+    g = torch.Generator().manual_seed(23)
+    labels = (torch.rand(B, P, n_out, generator=g) < 0.15).float()
+    oob = torch.rand(B, P, n_out, generator=g) < 0.1
+    frustum = torch.rand(B, P, n_out, generator=g) < 0.1
+    # oracle: reference forward restated on CPU + torch autograd + reference loss
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.dtype.is_floating_point and k != "steps") for k, v in m.state_dict().items()}
+    out_ref = unet_oracle.semabs3d_forward(sd, xyz, feat, oxyz, BOUNDS, (16, 16, 16))
+    loss_ref, acc_ref = train_oracle.masked_bce(out_ref, labels, None, oob | frustum)
+    loss_ref.backward()
+    batch = dict(input_xyz_pts=xyz.to(dev), input_feature_pts=feat.to(dev), tsdf_vol=torch.ones(B, 1, device=dev),
+                 output_xyz_pts=oxyz.to(dev), output_label_pts=labels.to(dev), out_of_bounds_pts=oob.to(dev),
+                 out_of_frustum_pts_mask=frustum.to(dev), patch_labels=[("a",), ("b",)])
+    stats, _ = train.get_losses_ovssc(m, batch)
+    assert abs(stats["loss"].item() - loss_ref.item()) < 1e-3 * abs(loss_ref.item())
+    assert abs(stats["accuracy"].item() - acc_ref.item()) < 1e-3
+    stats["loss"].backward()
+    print("SemAbs3D worst gradient error", _check_grads(m, sd))
+    # optimiser: one LAMB step with clipping on both sides
+    names = [n for n, p in m.named_parameters()]
+    cpu = [sd[n].detach().clone() for n in names]
+    grads = [sd[n].grad for n in names]
+    total, coef = train_oracle.clip_coefficient(grads, 1e5)
+    train_oracle.lamb_step(cpu, [None if gr is None else gr * coef for gr in grads], [dict() for _ in cpu], lr=1e-3)
+    opt = train.Lamb(m.parameters(), lr=1e-3)
+    opt.step(max_grad_norm=1e5)
+    for n_, a, p in zip(names, cpu, m.parameters()):
+        assert torch.allclose(a, p.data.cpu(), rtol=1e-3, atol=2e-5), (n_, (a - p.data.cpu()).abs().max())
+
+
+def test_semabsvool_training_step_matches_oracle():
+    from oracle import unet_oracle
+    from semabs_b200 import train
+    from semabs_b200.net import SemAbsVOOL
+
+    torch.manual_seed(31)
+    v = SemAbsVOOL(pointing_method="cosine_sim", pointing_dim=64, decoder_concat_xyz_pts=True, **_semabs_args()).to(dev)
+    B, D, n_in, n_out = 1, 3, 2000, 4000
+    xyz, _, oxyz = _points(32, B, D, n_in, n_out)
+    g = torch.Generator().manual_seed(33)
+    tgt, refsal = torch.randn(B, D, n_in, 1, generator=g), torch.randn(B, D, n_in, 1, generator=g)
+    labels = (torch.rand(B, D, n_out, generator=g) < 0.1).float()
+    oob = torch.rand(B, D, n_out, generator=g) < 0.1
+    rel = [["behind"], ["on the left of"], ["behind"]]
+    sd = {k: t.detach().cpu().clone().requires_grad_(t.dtype.is_floating_point and not k.endswith("steps"))
+          for k, t in v.state_dict().items()}
+    out_ref = unet_oracle.semabsvool_forward(sd, xyz, tgt, refsal, oxyz, rel, BOUNDS, (16, 16, 16), concat_xyz=True)
+    loss_ref = torch.nn.functional.binary_cross_entropy_with_logits(out_ref, labels)
+    loss_ref.backward()
+    batch = dict(output_xyz_pts=oxyz.to(dev), spatial_relation_name=rel, input_xyz_pts=xyz.to(dev),
+                 input_target_saliency_pts=tgt.to(dev), input_reference_saliency_pts=refsal.to(dev),
+                 tsdf_vol=torch.ones(B, 1, device=dev), output_label_pts=labels.to(dev), out_of_bounds_pts=oob.to(dev))
+    opt = train.Lamb(v.parameters(), lr=1e-3)
+    stats = train.train_step(v, batch, train.get_losses_vool, opt)
+    assert abs(stats["loss"].item() - loss_ref.item()) < 1e-3 * abs(loss_ref.item())
+    print("SemAbsVOOL worst gradient error", _check_grads(v, sd))
+    # unused parameters (visual_sampler of the completion net, relations not named in the batch) stay untouched
+    assert v.completion_net.visual_sampler.mlp[0].weight.grad is None
+    assert v.relation_embeddings["on"].grad is None and v.relation_embeddings["behind"].grad is not None
+    assert float(v.steps) == 1.0

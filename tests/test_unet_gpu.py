@@ -19,6 +19,14 @@ BOUNDS = ((-1.0, -1.0, -0.1), (1.0, 1.0, 1.9))
 TOL = 1e-3
 
 
+@pytest.fixture(autouse=True)
+def _inference_mode():
+    # forward parity tests: under torch.no_grad() the modules take the inference path (workspace reuse, no tape);
+    # the training path is covered by tests/test_unet_bwd_gpu.py and tests/test_train_gpu.py
+    with torch.no_grad():
+        yield
+
+
 def _maxrel(a, b):
     return ((a - b).abs().max() / b.abs().max()).item()
 
