@@ -251,7 +251,7 @@ class ClipWrapper:
         H, W = kwargs["img"].shape[:2]
         out = cls.get_clip_saliency_device((f.result() for f in futs), tile_desc, size_order, text_labels, H, W,
                                            horizontal_flipping, positive_attn_only, tile_batch_size, prompt_batch_size)
-        return out.cpu()
+        return out if kwargs.get("keep_on_device", False) else out.cpu()
 
     @classmethod
     def enumerate_crops(cls, img, augmentations, cropping_augmentations, **kwargs):

@@ -1,0 +1,103 @@
+"""RGB-D -> relevancy -> OVSSC voxel logits, device resident (BASELINE.json configs[4]).
+
+Mirror of the inference glue the reference spreads over visualize.py: `prep_data` (:60-152: relevancy maps x50, minus the
+mean over labels, back-projected depth, in-bounds mask, per-class point features) and `process_batch_ovssc` (:157-211:
+sub-sample `num_input_pts` points per class, query lattice from `get_sample_points` :283-298, SemAbs3D logits) with
+the class arg-max of :236-238.  Differences, on purpose: the relevancy maps never leave the GPU; the UNet runs ONCE per
+image for all classes (the reference re-runs it for every 2^20-point chunk of the lattice, :182-211) and only the implicit
+decoder is chunked; the point sub-sample is drawn once per class instead of once per chunk.  TSDF / frustum masking
+(:212-247) is evaluation-side and not part of the hot path.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .clip import ClipWrapper
+from .net import SemAbs3D
+
+PROMPT = "a photograph of a {} in a home."
+
+
+def back_project(depth: torch.Tensor, cam_intr, cam_pose=None) -> torch.Tensor:
+    """point_cloud.get_pointcloud (point_cloud.py:34-67) on the device: depth [H,W] fp32 -> xyz [H*W,3] in camera (or
+    world, with a 3x4 / 4x4 `cam_pose`) coordinates, pixel order row-major like the reference's reshape(-1,3)."""
+    dev = depth.device
+    H, W = depth.shape
+    K = torch.as_tensor(np.asarray(cam_intr), dtype=torch.float32, device=dev)
+    px = torch.linspace(0, W - 1, W, device=dev).view(1, W).expand(H, W)
+    py = torch.linspace(0, H - 1, H, device=dev).view(H, 1).expand(H, W)
+    x = (px - K[0, 2]) * (depth / K[0, 0])
+    y = (py - K[1, 2]) * (depth / K[1, 1])
+    pts = torch.stack([x, y, depth], dim=-1).reshape(-1, 3)
+    if cam_pose is not None:
+        T = torch.as_tensor(np.asarray(cam_pose), dtype=torch.float32, device=dev)
+        pts = pts @ T[:3, :3].T + T[:3, 3]
+    return pts
+
+
+def filter_pts_bounds(xyz: torch.Tensor, bounds) -> torch.Tensor:
+    """point_cloud.filter_pts_bounds (point_cloud.py:24-31)."""
+    lo = torch.as_tensor(np.asarray(bounds[0]), dtype=xyz.dtype, device=xyz.device)
+    hi = torch.as_tensor(np.asarray(bounds[1]), dtype=xyz.dtype, device=xyz.device)
+    return ((xyz >= lo) & (xyz <= hi)).all(dim=-1)
+
+
+def get_sample_points(sampling_shape: Sequence[int], scene_bounds, device) -> torch.Tensor:
+    """visualize.get_sample_points (visualize.py:283-298): lattice of query points, [prod(shape), 3]."""
+    axes = [torch.arange(0, n, device=device) for n in sampling_shape]
+    idx = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).to(torch.float32)
+    lc = torch.tensor(scene_bounds[0], device=device, dtype=torch.float32)
+    uc = torch.tensor(scene_bounds[1], device=device, dtype=torch.float32)
+    scales = (uc - lc) / (torch.tensor(list(sampling_shape), device=device, dtype=torch.float32) - 1)
+    return (idx * scales + lc).view(-1, 3)
+
+
+@torch.no_grad()
+def relevancy_point_features(rgb: np.ndarray, labels: Sequence[str], saliency_config: dict, subtract_mean: bool = True,
+                             prompts=(PROMPT,)) -> torch.Tensor:
+    """prep_data's relevancy half (visualize.py:93-110): maps [P,H,W] on the device, x50, minus the mean over labels."""
+    ClipWrapper.check_initialized()
+    gc = ClipWrapper.clip_gradcam
+    gc.templates = list(prompts)
+    gc.set_classes(list(labels))
+    rel = ClipWrapper.get_clip_saliency_convolve(img=rgb, text_labels=list(labels), keep_on_device=True, **saliency_config) * 50
+    if subtract_mean:
+        rel = rel - rel.mean(dim=0, keepdim=True)
+    return rel
+
+
+@torch.no_grad()
+def rgbd_to_ovssc_logits(net: SemAbs3D, rgb: np.ndarray, depth, cam_intr, cam_extr, labels: Sequence[str],
+                         scene_bounds, saliency_config: dict, sampling_shape: Tuple[int, int, int] = (128, 128, 128),
+                         num_input_pts: int = 80000, num_pts_per_pass: int = 2**20, subtract_mean: bool = True,
+                         generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
+    """One image through the whole path. Returns {"relevancies" [P,H,W], "logits" [P, *sampling_shape],
+    "prediction" int64 [*sampling_shape] (arg-max class, visualize.py:236)} — all on the device."""
+    dev = next(net.parameters()).device
+    P = len(labels)
+    rel = relevancy_point_features(rgb, labels, saliency_config, subtract_mean)
+    depth_t = torch.as_tensor(depth, dtype=torch.float32, device=dev)
+    xyz = back_project(depth_t, cam_intr, cam_extr)
+    idx_in = filter_pts_bounds(xyz, scene_bounds).nonzero().squeeze(1)
+    if idx_in.numel() == 0:
+        raise ValueError("no depth point falls inside scene_bounds")
+    # np.random.choice(n, size=num_input_pts) (with replacement) per class, visualize.py:189
+    pick = torch.randint(0, idx_in.numel(), (P, num_input_pts), device=dev, generator=generator)
+    sel = idx_in[pick]                                   # [P, npts] pixel indices
+    feats = torch.gather(rel.view(P, -1), 1, sel)        # [P, npts]
+    grid_points = get_sample_points(sampling_shape, scene_bounds, dev)
+    nq = grid_points.shape[0]
+    logits = torch.empty(P, nq, device=dev)
+    # every class has its own point sub-sample, so xyz is a per-class batch (B = P scenes of one patch each); the UNet
+    # runs once, only the implicit decoder walks the lattice in chunks
+    vol = net.feature_volume(xyz[sel].contiguous(), feats.view(P, 1, num_input_pts, 1).contiguous())
+    C = net.unet_num_channels
+    for j in range(0, nq, num_pts_per_pass):
+        q = grid_points[j : j + num_pts_per_pass]
+        out = net.visual_sampler.run([vol], C, net.vg, q.unsqueeze(0).expand(P, -1, -1).contiguous())
+        logits[:, j : j + q.shape[0]] = out.view(P, -1)
+    logits = logits.view(P, *sampling_shape)
+    return {"relevancies": rel, "logits": logits, "prediction": logits.argmax(dim=0)}

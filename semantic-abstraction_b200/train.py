@@ -201,19 +201,30 @@ class Lamb(torch.optim.Optimizer):
 
 
 def all_reduce_gradients(parameters: Iterable[torch.Tensor], world_size: Optional[int] = None):
-    """Data-parallel gradient averaging over NCCL (what DistributedDataParallel does at utils.py:255-258): one flat
-    bucket per call; parameters without a gradient contribute zeros on every rank so that all ranks make the same
-    skip decision. The reference sets NCCL_P2P_DISABLE=1 (utils.py:132); we do not."""
+    """Data-parallel gradient averaging over NCCL (what DistributedDataParallel(find_unused_parameters=True) does at
+    utils.py:255-258): one flat bucket per call.  A parameter that has a gradient on ANY rank ends up with the averaged
+    gradient on EVERY rank (ranks without one contribute zeros); a parameter unused everywhere keeps grad None on all
+    ranks — so LAMB's skip decision (arm/optim/lamb.py:71-72) is identical across ranks and the replicas stay in sync
+    (SURVEY.md §8e).  The reference sets NCCL_P2P_DISABLE=1 (utils.py:132); we do not."""
     if not (dist.is_available() and dist.is_initialized()):
         return
     world = world_size or dist.get_world_size()
     ps = list(parameters)
-    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in ps])
+    if not ps:
+        return
+    dev = ps[0].device
+    has = torch.tensor([0.0 if p.grad is None else 1.0 for p in ps], device=dev)
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in ps] + [has])
     dist.all_reduce(flat)
+    used = (flat[-len(ps):] > 0).tolist()
     flat /= world
     off = 0
-    for p in ps:
+    for p, u in zip(ps, used):
         n = p.numel()
-        if p.grad is not None:
-            p.grad.copy_(flat[off : off + n].view_as(p))
+        if u:
+            g = flat[off : off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
         off += n

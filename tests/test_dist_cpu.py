@@ -48,3 +48,37 @@ def test_shard_units_properties():
             parts = [shard_units(list(range(n)), r, world) for r in range(world)]
             assert sum(parts, []) == list(range(n))
             assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from semabs_b200 import train
+
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2)),
+          torch.nn.Parameter(torch.zeros(4))]
+    ps[0].grad = torch.full((5, 3), float(rank + 1))
+    ps[1].grad = torch.arange(7.0) * (rank + 1)
+    ps[2].grad = None                                   # unused on every rank (e.g. VOOL's completion-net sampler): stays None
+    ps[3].grad = torch.ones(4) if rank == 0 else None   # used on one rank only (a relation embedding): zeros from the other
+    train.all_reduce_gradients(ps)
+    out.put((rank, [None if p.grad is None else p.grad.clone() for p in ps]))
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_world2():
+    """DDP-style gradient averaging (utils.py:255-258) incl. the unused-parameter cases of SURVEY.md §8e."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda t: t[0])
+    [p.join(timeout=60) for p in procs]
+    for rank, g in res:
+        assert torch.equal(g[0], torch.full((5, 3), 1.5))
+        assert torch.equal(g[1], torch.arange(7.0) * 1.5)
+        assert g[2] is None
+        # used on one rank only: every rank gets the average, so every rank's LAMB updates it identically
+        assert torch.equal(g[3], torch.full((4,), 0.5))

@@ -1,0 +1,94 @@
+"""RGB-D -> relevancy -> OVSSC logits glue (semabs_b200.pipeline, BASELINE.json configs[4]).
+CPU: the geometry helpers against the numpy oracle (oracle/pipeline_oracle.py, pinned to the reference's point_cloud.py).
+GPU: the whole pipeline against the composition of the CPU oracles on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+BOUNDS = ((-1.0, -1.0, -0.1), (1.0, 1.0, 1.9))
+
+
+def _scene(seed, H, W):
+    rng = np.random.default_rng(seed)
+    depth = rng.uniform(0.4, 2.5, (H, W)).astype(np.float32)
+    K = np.array([[0.9 * W, 0, W / 2 - 0.5], [0, 0.9 * W, H / 2 - 0.5], [0, 0, 1]], dtype=np.float64)
+    T = np.array([[1.0, 0, 0, 0.05], [0, 0, 1, -1.2], [0, -1, 0, 0.9]])
+    return depth, K, T
+
+
+def test_geometry_helpers_match_oracle():
+    from oracle import pipeline_oracle as po
+    from semabs_b200 import pipeline
+
+    depth, K, T = _scene(0, 23, 31)
+    for pose in (None, T):
+        a = pipeline.back_project(torch.from_numpy(depth), K, pose).numpy()
+        b = po.get_pointcloud(depth, K, pose)
+        assert np.abs(a - b).max() < 2e-6 * np.abs(b).max()  # fp32 on our side, fp64 in numpy
+    pts = po.get_pointcloud(depth, K, T).astype(np.float32)
+    m = pipeline.filter_pts_bounds(torch.from_numpy(pts), BOUNDS).numpy()
+    assert (m == po.filter_pts_bounds(pts, np.array(BOUNDS))).all() and 0 < m.sum() < m.size
+    g = pipeline.get_sample_points((5, 6, 7), BOUNDS, "cpu").numpy()
+    assert np.array_equal(g, po.get_sample_points((5, 6, 7), BOUNDS))
+    assert pipeline.filter_pts_bounds(torch.from_numpy(g), BOUNDS).all()  # the assertion of visualize.py:171-173
+
+
+@pytest.mark.gpu
+def test_rgbd_to_ovssc_logits_matches_oracle_composition():
+    from oracle import clip_oracle, pipeline_oracle as po, unet_oracle
+    from oracle.gen_golden import PROMPT, synth_image
+    from semabs_b200 import pipeline
+    from semabs_b200.clip import ClipWrapper
+    from semabs_b200.clip.model import synthetic_clip_state_dict
+    from semabs_b200.clip.tokenizer import tokenize
+    from semabs_b200.net import SemAbs3D
+
+    dev = "cuda"
+    labels = ["television", "vase", "carpet"]
+    H = W = 64
+    img = synth_image(3, H, W)
+    depth, K, T = _scene(1, H, W)
+    cfg = dict(distractor_labels={}, horizontal_flipping=False, augmentations=0, positive_attn_only=True,
+               cropping_augmentations=[{"tile_size": 64, "stride": 16}, {"tile_size": 32, "stride": 16}])
+    ClipWrapper.reset()
+    ClipWrapper("ViT-B/32", dev, seed=0)
+    torch.manual_seed(40)
+    net = SemAbs3D(voxel_shape=(16, 16, 16), scene_bounds=BOUNDS, unet_num_channels=16, unet_f_maps=16, unet_num_groups=8,
+                   unet_num_levels=3, network_inputs=["saliency"], use_pts_feat_extractor=True,
+                   pts_feat_extractor_hidden_dim=128, reduce_method="max", device=dev, batch_size=1).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    shape = (8, 8, 8)
+    n_pts = 600
+    out = pipeline.rgbd_to_ovssc_logits(net, img, depth, K, T, labels, BOUNDS, cfg, sampling_shape=shape, num_input_pts=n_pts,
+                                        num_pts_per_pass=200, generator=gen)
+    # ---- oracle composition on the CPU, with the same point sub-sample ----
+    sd = clip_oracle.convert_weights_values(synthetic_clip_state_dict("ViT-B/32", seed=0))
+    with torch.no_grad():
+        Wt = clip_oracle.zeroshot_weights(sd, tokenize([PROMPT.format(c) for c in labels]), len(labels), 1)
+        rel = clip_oracle.get_clip_saliency(sd, img, Wt, cfg["cropping_augmentations"], positive_attn_only=True) * 50
+        rel = rel - rel.mean(dim=0, keepdim=True)
+    assert ((out["relevancies"].cpu() - rel).abs().max() / rel.abs().max()).item() < 2e-3
+    xyz = po.get_pointcloud(depth, K, T).astype(np.float32)
+    idx_in = np.nonzero(po.filter_pts_bounds(xyz, np.array(BOUNDS)))[0]
+    gen2 = torch.Generator(device=dev).manual_seed(7)
+    pick = torch.randint(0, len(idx_in), (len(labels), n_pts), device=dev, generator=gen2).cpu().numpy()
+    sel = idx_in[pick]
+    q = torch.from_numpy(po.get_sample_points(shape, BOUNDS))
+    nsd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    logits = []
+    with torch.no_grad():
+        for c in range(len(labels)):
+            feats = rel[c].reshape(-1)[torch.from_numpy(sel[c])].view(1, 1, n_pts, 1)
+            o = unet_oracle.semabs3d_forward(nsd, torch.from_numpy(xyz[sel[c]])[None], feats, q[None, None], BOUNDS, (16, 16, 16))
+            logits.append(o.view(*shape))
+    ref = torch.stack(logits)
+    got = out["logits"].cpu()
+    err = ((got - ref).abs().max() / ref.abs().max()).item()
+    print(f"pipeline logits max-rel err {err:.2e}")
+    assert err < 5e-3  # relevancy (1e-3 class) feeds a x50 amplified, mean-subtracted input: tolerances compound
+    # arg-max voxel labels: identical wherever the reference's top-2 margin exceeds the tolerance
+    top2 = ref.topk(2, dim=0).values
+    sure = (top2[0] - top2[1]) > 5e-3 * ref.abs().max()
+    assert sure.float().mean() > 0.5
+    assert (out["prediction"].cpu()[sure] == ref.argmax(dim=0)[sure]).all()
+    ClipWrapper.reset()
