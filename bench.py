@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-voxel", action="store_true")
     ap.add_argument("--skip-train", action="store_true")
+    ap.add_argument("--skip-pipeline", action="store_true")
     ap.add_argument("--train-descs", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -266,6 +267,9 @@ def main():
     if not args.skip_voxel:
         voxel = bench_voxel(dev, world, dist if world > 1 else None, pk)
 
+    pipe = None
+    if not args.skip_pipeline:
+        pipe = bench_pipeline(dev, rank, world, cfg, imgs[: min(2, len(imgs))])
     train = None
     if not args.skip_train:
         torch.cuda.empty_cache()
@@ -283,7 +287,7 @@ def main():
                            "tile_batch_size": TILE_BATCH, "fwd_splits": eng.fwd_splits, "bwd_splits": eng.bwd_splits},
                 "e2e": {"value": e2e_value, "unit": "relevancy-maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": "ClipWrapper.get_clip_saliency_convolve: host PIL tile preprocessing inside the timed region"},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "voxel": voxel, "train": train}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "voxel": voxel, "pipeline": pipe, "train": train}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -332,6 +336,49 @@ def bench_voxel(dev, world, dist, pk, C=32, N=4, steps=5, warmup=3):
                          "frac": per_gpu * UNET_GB_PER_GRID_FP32[C] / pk["hbm_gbs"], "traffic": None,
                          "tensor_tflops": per_gpu * UNET_GF_PER_GRID[C] / 1e3, "tensor_frac": per_gpu * UNET_GF_PER_GRID[C] / 1e3 / pk["tflops"],
                          "note": "whole-forward algorithmic bytes (BASELINE.md byte rule, fp32 I/O) / time"}}
+
+
+@torch.no_grad()
+def bench_pipeline(dev, rank, world, cfg, images):
+    """configs[4]: synthetic RGB-D -> 16-label relevancy (x50, minus label mean) -> depth back-projection -> SemAbs3D
+    (reference defaults: 128^3 grid, 16 channels, 6 levels, 80k input points per class) -> logits on a 128^3 query
+    lattice + class arg-max, device resident (semabs_b200.pipeline).  Timed per image through the public pipeline call
+    (host uint8 image and fp32 depth in, device logits out + D2H of the int64 arg-max volume)."""
+    import torch.distributed as dist
+
+    from semabs_b200 import pipeline
+    from semabs_b200.net import SemAbs3D
+
+    bounds = ((-1.0, -1.0, -0.1), (1.0, 1.0, 1.9))
+    torch.manual_seed(1)
+    net = SemAbs3D(voxel_shape=(128, 128, 128), scene_bounds=bounds, unet_num_channels=16, unet_f_maps=16, unet_num_groups=8,
+                   unet_num_levels=6, network_inputs=["saliency"], use_pts_feat_extractor=True,
+                   pts_feat_extractor_hidden_dim=128, reduce_method="max", device=str(dev), batch_size=1).to(dev)
+    rng = np.random.default_rng(5 + rank)
+    # a tilted synthetic depth plane seen by a camera 1.2 m in front of the scene volume
+    yy, xx = np.mgrid[0:IMG, 0:IMG].astype(np.float32)
+    depth = (1.0 + 0.6 * xx / IMG + 0.3 * yy / IMG + 0.02 * rng.standard_normal((IMG, IMG))).astype(np.float32)
+    K = np.array([[0.9 * IMG, 0, IMG / 2 - 0.5], [0, 0.9 * IMG, IMG / 2 - 0.5], [0, 0, 1]])
+    T = np.array([[1.0, 0, 0, 0.0], [0, 0, 1, -1.2], [0, -1, 0, 0.9]])
+    gen = torch.Generator(device=dev).manual_seed(3)
+    run = lambda im: pipeline.rgbd_to_ovssc_logits(net, im, depth, K, T, LABELS16, bounds, dict(positive_attn_only=True,
+                                                   tile_batch_size=TILE_BATCH, **cfg), generator=gen)["prediction"].cpu()
+    run(images[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for im in images:
+        pred = run(im)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    n = len(images)
+    return {"metric": "RGB-D images/s through relevancy -> OVSSC logits (336^2, 16 labels, 128^3 grid + 128^3 lattice)",
+            "value": world * n / dt.item(), "unit": "images/s (sum over GPUs)", "s_per_image": dt.item() / n,
+            "relevancy_maps_per_s": world * n * len(LABELS16) / dt.item(), "classes_in_prediction": int(pred.unique().numel()),
+            "h2d_bytes_per_image": IMG * IMG * 3 + IMG * IMG * 4 + 285 * 3 * 224 * 224 * 4, "d2h_bytes_per_image": 128**3 * 8}
 
 
 def bench_train(dev, rank, world, pk, C=16, num_descs=16, steps=2, warmup=2):
@@ -389,7 +436,7 @@ def bench_train(dev, rank, world, pk, C=16, num_descs=16, steps=2, warmup=2):
     return {"metric": "VOOL train steps/s (128^3, 16 ch, 16 descriptions/GPU)", "value": world * 1e3 / ms, "unit": "steps/s (sum over GPUs)",
             "ms_per_step": ms, "voxel_grids_trained_per_s": world * grids / (ms / 1e3), "descs_per_gpu": num_descs,
             "unet_kernel_launches_per_step": (unet.kernel_launches - l0) // steps,
-            "loss_trajectory": [float(x) for x in losses], "unet_algorithmic_tflops": tf, "tensor_frac": tf / world / pk["tflops"],
+            "loss_trajectory": [float(x.detach()) for x in losses], "unet_algorithmic_tflops": tf, "tensor_frac": tf / world / pk["tflops"],
             "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2**30,
             "note": "gradient all-reduce: one flat NCCL all-reduce after backward" if world > 1 else "single GPU: no collective"}
 
