@@ -70,11 +70,11 @@ def preprocess_tiles(tiles_u8: Sequence[np.ndarray], n_px: int) -> torch.Tensor:
     return torch.cat(list(_pool().map(lambda c: _preprocess_tiles_serial(c, n_px), chunks)), dim=0)
 
 
-def _preprocess_tiles_serial(tiles_u8: Sequence[np.ndarray], n_px: int) -> torch.Tensor:
-    """The reference's `_transform` (clip_explainability.py:98-108) on a list of uint8 crops: PIL bicubic resize of
-    the shorter side to 224 (hard-coded there), centre crop/pad to n_px, /255, normalise. Host side, like the
-    reference (it is the reference's declared bottleneck, __init__.py:275; a device version is a 'next' row)."""
-    out = torch.empty(len(tiles_u8), 3, n_px, n_px)
+def _preprocess_tiles_into(out: torch.Tensor, tiles_u8: Sequence[np.ndarray], n_px: int) -> torch.Tensor:
+    """The reference's `_transform` (clip_explainability.py:98-108) on a list of uint8 crops, written into `out`
+    [len(tiles), 3, n_px, n_px]: PIL bicubic resize of the shorter side to 224 (hard-coded there), centre crop/pad to
+    n_px, /255, normalise. Host side, like the reference (it is the reference's declared bottleneck, __init__.py:275;
+    a device version is a 'next' row)."""
     for i, t in enumerate(tiles_u8):
         img = Image.fromarray(t).convert("RGB")
         w, h = img.size
@@ -88,8 +88,38 @@ def _preprocess_tiles_serial(tiles_u8: Sequence[np.ndarray], n_px: int) -> torch
                 nh, nw = arr.shape[1:]
             top, left = int(round((nh - n_px) / 2.0)), int(round((nw - n_px) / 2.0))
             arr = arr[:, top : top + n_px, left : left + n_px]
-        out[i] = arr.float().div(255)
-    return (out - _MEAN) / _STD
+        # (x/255 - mean)/std with the same operation order as ToTensor + Normalize
+        out[i] = (arr.float().div(255) - _MEAN[0]) / _STD[0]
+    return out
+
+
+def _preprocess_tiles_serial(tiles_u8: Sequence[np.ndarray], n_px: int) -> torch.Tensor:
+    return _preprocess_tiles_into(torch.empty(len(tiles_u8), 3, n_px, n_px), tiles_u8, n_px)
+
+
+class _PinnedRing:
+    """A few pinned host batches [tile_batch, 3, R, R] that worker threads fill slice-wise and that are copied to the
+    device asynchronously; a buffer is reused only after its previous H2D copy has completed (CUDA event)."""
+
+    DEPTH = 4
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+        self.bufs = [torch.empty(self.shape).pin_memory() for _ in range(self.DEPTH)]
+        self.events = [None] * self.DEPTH
+        self.i = 0
+
+    def acquire(self):
+        k = self.i
+        self.i = (k + 1) % self.DEPTH
+        if self.events[k] is not None:
+            self.events[k].synchronize()
+            self.events[k] = None
+        return k, self.bufs[k]
+
+    def copied(self, k):
+        self.events[k] = torch.cuda.Event()
+        self.events[k].record()
 
 
 class ClipGradcam:
@@ -239,18 +269,56 @@ class ClipWrapper:
         st["ev"][i].record()
         return out
 
+    _ring = None
+    SUB_TILES = 12  # tiles per worker task: a 95-tile batch is preprocessed by 8 threads at once, not by one
+
+    @classmethod
+    def _device_batches(cls, crops, n_px, tile_batch_size):
+        """Generator of preprocessed tile batches already on their way to the device.  Every batch is cut into
+        SUB_TILES-sized worker tasks that fill slices of one pinned buffer, so the FIRST batch of an image is ready after
+        ~SUB_TILES tile-times instead of tile_batch_size (that latency was 140 ms of idle GPU per image); up to
+        DEPTH-1 batches are prepared ahead of the one the GPU is working on."""
+        from collections import deque
+
+        n = len(crops)
+        shape = (tile_batch_size, 3, n_px, n_px)
+        if cls._ring is None or cls._ring.shape != shape:
+            cls._ring = _PinnedRing(shape)
+        ring, pool = cls._ring, _pool()
+        starts = deque(range(0, n, tile_batch_size))
+        pending = deque()
+
+        def submit():
+            i = starts.popleft()
+            cnt = min(tile_batch_size, n - i)
+            k, buf = ring.acquire()
+            futs = [pool.submit(_preprocess_tiles_into, buf[j : min(j + cls.SUB_TILES, cnt)], crops[i + j : i + min(j + cls.SUB_TILES, cnt)], n_px)
+                    for j in range(0, cnt, cls.SUB_TILES)]
+            pending.append((k, buf, cnt, futs))
+
+        while starts and len(pending) < ring.DEPTH - 1:
+            submit()
+        while pending:
+            k, buf, cnt, futs = pending.popleft()
+            for f in futs:
+                f.result()
+            d = buf[:cnt].to(cls.device, non_blocking=True)
+            ring.copied(k)
+            if starts:
+                submit()
+            yield d
+
     @classmethod
     def get_clip_saliency_convolve(cls, text_labels, horizontal_flipping=False, positive_attn_only: bool = False,
                                    tile_batch_size=32, prompt_batch_size=32, tile_interpolate_batch_size=32, **kwargs):
-        """Reference: CLIP/clip/__init__.py:135-236. Host tile preprocessing runs in worker threads, one future per
-        tile batch, and overlaps with the GPU work of the batches already submitted."""
+        """Reference: CLIP/clip/__init__.py:135-236. Host tile preprocessing runs in worker threads and overlaps with the
+        GPU work of the batches already submitted (see _device_batches)."""
         tile_desc, crops, size_order = cls.enumerate_crops(**kwargs)
         n_px = cls.clip_gradcam.n_px
-        futs = [_pool().submit(_preprocess_tiles_serial, crops[i : i + tile_batch_size], n_px)
-                for i in range(0, len(crops), tile_batch_size)]
         H, W = kwargs["img"].shape[:2]
-        out = cls.get_clip_saliency_device((f.result() for f in futs), tile_desc, size_order, text_labels, H, W,
-                                           horizontal_flipping, positive_attn_only, tile_batch_size, prompt_batch_size)
+        out = cls.get_clip_saliency_device(cls._device_batches(crops, n_px, tile_batch_size), tile_desc, size_order,
+                                           text_labels, H, W, horizontal_flipping, positive_attn_only, tile_batch_size,
+                                           prompt_batch_size)
         return out if kwargs.get("keep_on_device", False) else out.cpu()
 
     @classmethod
