@@ -251,7 +251,8 @@ def main():
     _, wall_e2e = timed(step_e2e, max(1, args.steps // 2))
     e2e_steps = max(1, args.steps // 2)
     e2e_value = world * maps_per_step * e2e_steps / (wall_e2e / 1e3)
-    h2d = args.images * n_tiles * 3 * 224 * 224 * 4
+    # with device tile preprocessing only the uint8 image and the tile table cross PCIe; the host path ships fp32 tiles
+    h2d = args.images * (IMG * IMG * 3 + n_tiles * 5 * 4) if ClipWrapper.device_preprocessing else args.images * n_tiles * 3 * 224 * 224 * 4
     d2h = args.images * P * IMG * IMG * 4
 
     pk = peaks()
@@ -286,7 +287,9 @@ def main():
                            "l2_policy": "inputs larger than L2: per-step working set ~6 GB of saved activations + 1.4 GB tiles",
                            "tile_batch_size": TILE_BATCH, "fwd_splits": eng.fwd_splits, "bwd_splits": eng.bwd_splits},
                 "e2e": {"value": e2e_value, "unit": "relevancy-maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "note": "ClipWrapper.get_clip_saliency_convolve: host PIL tile preprocessing inside the timed region"},
+                        "note": ("ClipWrapper.get_clip_saliency_convolve on host uint8 images: tile crop / Pillow-exact bicubic / normalise on the GPU "
+                                 "(semabs_tile_preprocess), D2H of the fp32 maps") if ClipWrapper.device_preprocessing else
+                                "ClipWrapper.get_clip_saliency_convolve: host PIL tile preprocessing inside the timed region"},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "voxel": voxel, "pipeline": pipe, "train": train}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -378,7 +381,7 @@ def bench_pipeline(dev, rank, world, cfg, images):
     return {"metric": "RGB-D images/s through relevancy -> OVSSC logits (336^2, 16 labels, 128^3 grid + 128^3 lattice)",
             "value": world * n / dt.item(), "unit": "images/s (sum over GPUs)", "s_per_image": dt.item() / n,
             "relevancy_maps_per_s": world * n * len(LABELS16) / dt.item(), "classes_in_prediction": int(pred.unique().numel()),
-            "h2d_bytes_per_image": IMG * IMG * 3 + IMG * IMG * 4 + 285 * 3 * 224 * 224 * 4, "d2h_bytes_per_image": 128**3 * 8}
+            "h2d_bytes_per_image": IMG * IMG * 3 + IMG * IMG * 4 + 285 * 5 * 4, "d2h_bytes_per_image": 128**3 * 8}
 
 
 def bench_train(dev, rank, world, pk, C=16, num_descs=16, steps=2, warmup=2):

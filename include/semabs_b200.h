@@ -173,6 +173,16 @@ int semabs_tile_assemble(const float* rel, const int32_t* tile_desc, int32_t n_t
                          int32_t n_sizes, int32_t g, int32_t H, int32_t W, int32_t P, float* out, void* stream);
 int semabs_flip_average(float* rel, const float* rel_flipped, int64_t n_maps, int32_t g, void* stream);
 
+/* Tile preprocessing on the device (assemble.cu) — the reference's `_transform` per tile (clip_explainability.py:98-108,
+ * create_tiles __init__.py:257-281): crop a square tile out of a uint8 HWC image, Pillow-exact bicubic resize to RxR
+ * (Pillow's 8-bit two-pass fixed-point resampler, bit for bit), /255, (v-mean)/std -> out [n_tiles,3,R,R] fp32.
+ * images [n_images,H,W,3] uint8 (device); tiles int32 [n_tiles,5] = (image, row0, col0, size, size_id) (device);
+ * coef int32 [n_sizes,R,kmax], bounds int32 [n_sizes,R,2] = (first input index, window length) (device): Pillow's
+ * precompute_coeffs / normalize_coeffs_8bpc tables for size -> R (built by the host wrapper); mean3/std3 HOST. */
+int semabs_tile_preprocess(const uint8_t* images, int32_t n_images, int32_t H, int32_t W, const int32_t* tiles,
+                           int32_t n_tiles, const int32_t* coef, const int32_t* bounds, int32_t n_sizes, int32_t kmax,
+                           int32_t R, const float* mean3, const float* std3, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Residual 3-D UNet stages (conv3d.cu, unet_ops.cu) — reference unet3d.py.
  * Internal activation layout is channels-last: raw fp32 [N,D,H,W,C] and, as MMA operand, fp16

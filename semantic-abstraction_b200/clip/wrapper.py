@@ -97,6 +97,53 @@ def _preprocess_tiles_serial(tiles_u8: Sequence[np.ndarray], n_px: int) -> torch
     return _preprocess_tiles_into(torch.empty(len(tiles_u8), 3, n_px, n_px), tiles_u8, n_px)
 
 
+_PRECISION_BITS = 32 - 8 - 2  # Pillow: src/libImaging/Resample.c
+
+
+def _bicubic_filter(x: float) -> float:
+    a = -0.5
+    x = abs(x)
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pillow_bicubic_coeffs(in_size: int, out_size: int):
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc for Image.resize(..., BICUBIC) along one axis (what
+    `Resize(224, interpolation=BICUBIC)` of the reference's `_transform` runs, clip_explainability.py:98-108):
+    -> (coef int64 [out_size, ksize] 22-bit fixed point, bounds int64 [out_size, 2] = (first input index, window length)).
+    Same double-precision expressions in the same order as the C source; pinned bit-exactly against the installed Pillow in
+    tests/test_abi.py::test_pillow_resize_tables."""
+    import math
+
+    scale = filterscale = in_size / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    coef = np.zeros((out_size, ksize), np.int64)
+    bounds = np.zeros((out_size, 2), np.int64)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = [_bicubic_filter((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        for x in range(xmax):
+            k = w[x] / ww if ww != 0.0 else w[x]
+            coef[xx, x] = int(k * (1 << _PRECISION_BITS) - 0.5) if k < 0 else int(k * (1 << _PRECISION_BITS) + 0.5)
+        bounds[xx] = (xmin, xmax)
+    return coef, bounds
+
+
+_COEF_KMAX = 32  # window lengths up to 32 taps: tiles up to ~1600 px per side
+
+
 class _PinnedRing:
     """A few pinned host batches [tile_batch, 3, R, R] that worker threads fill slice-wise and that are copied to the
     device asynchronously; a buffer is reused only after its previous H2D copy has completed (CUDA event)."""
@@ -246,6 +293,7 @@ class ClipWrapper:
         return ops.tile_assemble(rel, desc, order, H, W, out)
 
     _staging = None
+    _last_images = None
 
     @classmethod
     def _to_device(cls, batch):
@@ -268,6 +316,48 @@ class ClipWrapper:
         st["ev"][i] = torch.cuda.Event()
         st["ev"][i].record()
         return out
+
+    device_preprocessing = True  # crop / Pillow-exact resize / normalise on the GPU (semabs_tile_preprocess)
+    _coef_cache: dict = {}
+
+    @classmethod
+    def _device_preprocessed_batches(cls, tile_desc, n_px, tile_batch_size):
+        """Tile preprocessing on the device: the uint8 image copies go up once (0.3 MB each instead of 0.6 MB per TILE of
+        fp32), every tile batch is one launch of semabs_tile_preprocess — bit-identical to the PIL host path (tests).
+        Returns None when the kernel's preconditions do not hold (non-224 input resolution, windows above 32 taps):
+        the host path, which is also what the reference does, takes over."""
+        images = cls._last_images
+        sizes = sorted({int(s) for s in tile_desc[:, 2]})
+        if n_px != 224 or not sizes or any(2 * int(np.ceil(2.0 * max(s / 224, 1.0))) + 1 > _COEF_KMAX for s in sizes):
+            return None
+        dev = cls.device
+        key = tuple(sizes)
+        if key not in cls._coef_cache:
+            coef = np.zeros((len(sizes), 224, _COEF_KMAX), np.int32)
+            bounds = np.zeros((len(sizes), 224, 2), np.int32)
+            for i, sz in enumerate(sizes):
+                c, b = pillow_bicubic_coeffs(sz, 224)
+                coef[i, :, : c.shape[1]] = c
+                bounds[i] = b
+            cls._coef_cache[key] = (torch.from_numpy(coef).to(dev), torch.from_numpy(bounds).to(dev))
+        coef_d, bounds_d = cls._coef_cache[key]
+        n = len(tile_desc)
+        per_img = n // len(images)
+        table = np.zeros((n, 5), np.int32)
+        table[:, 0] = np.arange(n) // per_img
+        table[:, 1:4] = tile_desc
+        table[:, 4] = np.searchsorted(np.asarray(sizes), tile_desc[:, 2])
+        imgs_d = torch.from_numpy(np.ascontiguousarray(np.stack(images))).pin_memory().to(dev, non_blocking=True)
+        table_d = torch.from_numpy(table).pin_memory().to(dev, non_blocking=True)
+        mean, std = [float(v) for v in _MEAN.flatten()], [float(v) for v in _STD.flatten()]
+
+        def gen():
+            for i in range(0, n, tile_batch_size):
+                cnt = min(tile_batch_size, n - i)
+                out = torch.empty(cnt, 3, 224, 224, device=dev)
+                yield ops.tile_preprocess(imgs_d, table_d[i : i + cnt], coef_d, bounds_d, out, mean, std)
+
+        return gen()
 
     _ring = None
     SUB_TILES = 12  # tiles per worker task: a 95-tile batch is preprocessed by 8 threads at once, not by one
@@ -316,9 +406,11 @@ class ClipWrapper:
         tile_desc, crops, size_order = cls.enumerate_crops(**kwargs)
         n_px = cls.clip_gradcam.n_px
         H, W = kwargs["img"].shape[:2]
-        out = cls.get_clip_saliency_device(cls._device_batches(crops, n_px, tile_batch_size), tile_desc, size_order,
-                                           text_labels, H, W, horizontal_flipping, positive_attn_only, tile_batch_size,
-                                           prompt_batch_size)
+        batches = cls._device_preprocessed_batches(tile_desc, n_px, tile_batch_size) if cls.device_preprocessing else None
+        if batches is None:
+            batches = cls._device_batches(crops, n_px, tile_batch_size)
+        out = cls.get_clip_saliency_device(batches, tile_desc, size_order, text_labels, H, W, horizontal_flipping,
+                                           positive_attn_only, tile_batch_size, prompt_batch_size)
         return out if kwargs.get("keep_on_device", False) else out.cpu()
 
     @classmethod
@@ -345,6 +437,7 @@ class ClipWrapper:
                         desc.append((int(x), int(y), int(ts)))
                         crops.append(im[x : x + ts, y : y + ts])
         size_order = list(dict.fromkeys(a["tile_size"] for a in cropping_augmentations))
+        cls._last_images = images  # the device preprocessing path uploads these instead of the tiles
         return np.array(desc, dtype=np.int32).reshape(-1, 3), crops, size_order
 
     @classmethod

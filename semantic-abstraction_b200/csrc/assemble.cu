@@ -88,3 +88,69 @@ extern "C" int semabs_flip_average(float* rel, const float* rel_flipped, int64_t
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tile preprocessing on the device: crop -> Pillow-exact bicubic resize to 224x224 -> /255 -> normalise
+// (reference: `_transform`, CLIP/clip/clip_explainability.py:98-108, applied per tile in create_tiles,
+// CLIP/clip/__init__.py:257-281 — the reference's self-declared bottleneck, :275).
+// Pillow's 8-bit resampler (ImagingResampleHorizontal/Vertical_8bpc) is integer arithmetic: per output coordinate a
+// window [xmin, xmin+xmax) of 22-bit fixed-point coefficients, accumulator initialised to 2^21, arithmetic shift by
+// 22, clip to [0,255]; horizontal pass first, its uint8 result feeds the vertical pass.  The coefficient tables are
+// built on the host exactly like precompute_coeffs / normalize_coeffs_8bpc (wrapper.pillow_bicubic_coeffs); this kernel
+// evaluates both passes on the fly per output pixel (window^2 taps, <= 49 at 336 -> 224), which reproduces Pillow bit
+// for bit, so the tiles — and everything downstream — are identical to the host path's.
+// ---------------------------------------------------------------------------------------------------------------
+namespace sb {
+
+__global__ void __launch_bounds__(256)
+tile_preprocess_kernel(const uint8_t* __restrict__ images, int H, int W, const int32_t* __restrict__ tiles,
+                       const int32_t* __restrict__ coef, const int32_t* __restrict__ bounds, int kmax, int R,
+                       float mean0, float mean1, float mean2, float std0, float std1, float std2,
+                       float* __restrict__ out) {
+  const int t = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= R * R) return;
+  const int yy = pix / R, xx = pix % R;
+  const int img = tiles[t * 5 + 0], row0 = tiles[t * 5 + 1], col0 = tiles[t * 5 + 2], sid = tiles[t * 5 + 4];
+  const int32_t* kx = coef + (size_t(sid) * R + xx) * kmax;
+  const int32_t* ky = coef + (size_t(sid) * R + yy) * kmax;
+  const int xmin = bounds[(sid * R + xx) * 2], xcnt = bounds[(sid * R + xx) * 2 + 1];
+  const int ymin = bounds[(sid * R + yy) * 2], ycnt = bounds[(sid * R + yy) * 2 + 1];
+  const uint8_t* base = images + (size_t(img) * H + row0) * W * 3 + size_t(col0) * 3;
+  int acc0 = 1 << 21, acc1 = 1 << 21, acc2 = 1 << 21;
+  for (int y = 0; y < ycnt; ++y) {
+    const uint8_t* rowp = base + size_t(ymin + y) * W * 3 + size_t(xmin) * 3;
+    int h0 = 1 << 21, h1 = 1 << 21, h2 = 1 << 21;
+    for (int x = 0; x < xcnt; ++x) {
+      const int k = kx[x];
+      h0 += int(rowp[3 * x]) * k, h1 += int(rowp[3 * x + 1]) * k, h2 += int(rowp[3 * x + 2]) * k;
+    }
+    h0 >>= 22, h1 >>= 22, h2 >>= 22;
+    h0 = min(max(h0, 0), 255), h1 = min(max(h1, 0), 255), h2 = min(max(h2, 0), 255);
+    const int k = ky[y];
+    acc0 += h0 * k, acc1 += h1 * k, acc2 += h2 * k;
+  }
+  acc0 >>= 22, acc1 >>= 22, acc2 >>= 22;
+  acc0 = min(max(acc0, 0), 255), acc1 = min(max(acc1, 0), 255), acc2 = min(max(acc2, 0), 255);
+  // ToTensor (/255) then Normalize ((v - mean) / std), IEEE fp32 like the host path
+  float* o = out + (size_t(t) * 3 * R + yy) * R + xx;
+  o[0] = __fdiv_rn(__fsub_rn(__fdiv_rn(float(acc0), 255.f), mean0), std0);
+  o[size_t(R) * R] = __fdiv_rn(__fsub_rn(__fdiv_rn(float(acc1), 255.f), mean1), std1);
+  o[size_t(2) * R * R] = __fdiv_rn(__fsub_rn(__fdiv_rn(float(acc2), 255.f), mean2), std2);
+}
+
+}  // namespace sb
+
+extern "C" int semabs_tile_preprocess(const uint8_t* images, int32_t n_images, int32_t H, int32_t W, const int32_t* tiles,
+                                      int32_t n_tiles, const int32_t* coef, const int32_t* bounds, int32_t n_sizes,
+                                      int32_t kmax, int32_t R, const float* mean3, const float* std3, float* out,
+                                      void* stream) {
+  SB_REQUIRE(images && tiles && coef && bounds && mean3 && std3 && out, "semabs_tile_preprocess: null pointer");
+  SB_REQUIRE(n_images > 0 && H > 0 && W > 0 && n_tiles > 0 && n_sizes > 0 && kmax > 0 && R > 0,
+             "semabs_tile_preprocess: bad arguments");
+  dim3 grid((R * R + 255) / 256, n_tiles);
+  sb::tile_preprocess_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(images, H, W, tiles, coef, bounds, kmax, R, mean3[0],
+                                                                    mean3[1], mean3[2], std3[0], std3[1], std3[2], out);
+  SB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

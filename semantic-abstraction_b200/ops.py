@@ -222,6 +222,19 @@ def tile_assemble(rel, tile_desc, size_order, H, W, out):
     return out
 
 
+def tile_preprocess(images_u8, tiles, coef, bounds, out, mean, std):
+    """images_u8 [n,H,W,3] uint8, tiles int32 [n_tiles,5], coef int32 [n_sizes,R,kmax], bounds int32 [n_sizes,R,2] (all on
+    the device) -> out [n_tiles,3,R,R] fp32; mean / std: 3 python floats each."""
+    n_img, H, W, _ = images_u8.shape
+    assert images_u8.dtype == torch.uint8 and images_u8.is_contiguous() and tiles.dtype == torch.int32 and tiles.is_contiguous()
+    assert coef.dtype == torch.int32 and bounds.dtype == torch.int32 and out.dtype == torch.float32 and out.is_contiguous()
+    n_sizes, R, kmax = coef.shape
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    check(lib().semabs_tile_preprocess(ptr(images_u8), i32(n_img), i32(H), i32(W), ptr(tiles), i32(tiles.shape[0]), ptr(coef),
+                                       ptr(bounds), i32(n_sizes), i32(kmax), i32(R), m3, s3, ptr(out), stream_ptr()))
+    return out
+
+
 def flip_average(rel, rel_flipped):
     g = rel.shape[-1]
     assert rel.is_contiguous() and rel_flipped.is_contiguous() and rel.shape == rel_flipped.shape

@@ -63,3 +63,35 @@ def test_convert_weights_and_positional_quirk():
     q = model.interpolate_positional_embedding(pos, 257)
     assert torch.equal(q, clip_oracle._positional_quirk(pos, 257))
     assert torch.equal(q[0], pos[0]) and q.shape == (257, 8)
+
+
+def test_pillow_resize_tables():
+    """Host side of semabs_tile_preprocess: the coefficient tables reproduce the installed Pillow's BICUBIC resize bit for
+    bit when evaluated with Pillow's integer two-pass scheme (numpy emulation of what the kernel does)."""
+    import numpy as np
+    from PIL import Image
+
+    from semabs_b200.clip.wrapper import pillow_bicubic_coeffs
+
+    def resize(img, out):
+        s = img.shape[0]
+        kk, b = pillow_bicubic_coeffs(s, out)
+
+        def one_pass(src):  # along axis 1
+            dst = np.zeros((src.shape[0], out, 3), np.uint8)
+            for xx in range(out):
+                xmin, cnt = b[xx]
+                acc = np.full((src.shape[0], 3), 1 << 21, np.int64)
+                for x in range(cnt):
+                    acc += src[:, xmin + x, :].astype(np.int64) * kk[xx, x]
+                dst[:, xx, :] = np.clip(acc >> 22, 0, 255)
+            return dst
+
+        tmp = one_pass(img)                                   # horizontal
+        return one_pass(tmp.transpose(1, 0, 2)).transpose(1, 0, 2)  # vertical
+
+    rng = np.random.default_rng(0)
+    for s in (336, 224, 168, 112, 84, 61, 500):
+        img = rng.integers(0, 256, (s, s, 3), dtype=np.uint8)
+        ref = np.array(Image.fromarray(img).resize((224, 224), Image.BICUBIC))
+        assert np.array_equal(resize(img, 224), ref), s

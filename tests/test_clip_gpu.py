@@ -141,3 +141,30 @@ def test_tile_assemble_vs_oracle():
     assert (out.cpu() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()  # one fp16 ulp of an accumulator at most
     assert ((out.cpu() - ref).abs() > 1e-6 * ref.abs().max()).float().mean().item() < 0.02  # ...and only rarely
     assert (out.cpu().flatten(1).argmax(1) == ref.flatten(1).argmax(1)).all()
+
+
+def test_device_tile_preprocessing_is_bit_identical_to_pil():
+    """semabs_tile_preprocess (crop + Pillow-exact bicubic + normalise on the GPU) vs the host path (`_transform` through
+    PIL, what the reference runs): identical bits for every tile of a 5-size pyramid and of jittered image copies."""
+    from semabs_b200.clip import ClipWrapper
+    from semabs_b200.clip import wrapper as w
+
+    ClipWrapper.reset()
+    ClipWrapper("ViT-B/32", "cuda", seed=0)
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (336, 336, 3), dtype=np.uint8)
+    img[:100, :120] = 255  # saturated / flat regions exercise the clipping and the negative bicubic lobes
+    img[200:, 250:] = 0
+    augs = [{"tile_size": s, "stride": s // 4} for s in (336, 224, 168, 112, 84)]
+    desc, crops, _ = ClipWrapper.enumerate_crops(img=img, augmentations=1, cropping_augmentations=augs)
+    assert len(crops) == 2 * 285
+    got = torch.cat(list(ClipWrapper._device_preprocessed_batches(desc, 224, 64))).cpu()
+    ref = w.preprocess_tiles(crops, 224)
+    assert got.shape == ref.shape
+    assert torch.equal(got, ref), (got - ref).abs().max()
+    # a 976-px image (the reference's matterport.png size): 19-tap windows
+    big = rng.integers(0, 256, (976, 976, 3), dtype=np.uint8)
+    desc, crops, _ = ClipWrapper.enumerate_crops(img=big, augmentations=0, cropping_augmentations=[{"tile_size": 976, "stride": 244}, {"tile_size": 650, "stride": 162}])
+    got = torch.cat(list(ClipWrapper._device_preprocessed_batches(desc, 224, 8))).cpu()
+    assert torch.equal(got, w.preprocess_tiles(crops, 224))
+    ClipWrapper.reset()
