@@ -11,6 +11,8 @@
 // sum / sum-of-squares for the NEXT GroupNorm kept in registers across tiles and flushed with fp64 atomics.
 // Transposed convolution = 8 output-parity classes, each an ordinary tap list over the input grid whose
 // results are scattered with stride 2.
+#include <stdlib.h>
+
 #include "../../include/semabs_b200.h"
 #include "common.cuh"
 #include "ptx.cuh"
@@ -48,25 +50,30 @@ struct ConvParams {
   int groups;                // G of the consumer GroupNorm
 };
 
-template <int BN, int KB>
+// FUSED (precise mode): the three precision terms x_hi W_hi + x_hi W_lo + x_lo W_hi run as TWO stages per (tap, K block)
+// instead of three: stage 0 = x_hi against [W_hi ; W_lo] stacked along N (one MMA of width 2 BN, accumulator columns
+// [0,BN) and [BN,2BN)), stage 1 = x_lo against W_hi (width BN, columns [0,BN)); the epilogue adds the two column halves.
+// The activation box — whose TMA cost (box rows, not bytes) bounds this kernel — is fetched twice per tap, not 3 times.
+template <int BN, int KB, bool FUSED>
 struct ConvCfg {
   static constexpr int A_BYTES = 128 * KB * 2;
   static constexpr int B_BYTES_RAW = BN * KB * 2;
-  static constexpr int B_BYTES = (B_BYTES_RAW + 1023) / 1024 * 1024;
+  static constexpr int B_BYTES = ((FUSED ? 2 : 1) * B_BYTES_RAW + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 512 + 1024;
   static constexpr uint64_t SWZ = (KB == 64) ? SW_128B : (KB == 32 ? SW_64B : SW_32B);
   static constexpr uint32_t SBO = 8 * KB * 2;  // 8 rows of one swizzle atom
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int ACC_COLS = (FUSED ? 2 : 1) * BN;  // columns of one accumulator buffer
+  static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
 };
 
-template <int BN, int KB>
+template <int BN, int KB, bool FUSED>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BN, KB>;
+  using Cfg = ConvCfg<BN, KB, FUSED>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -79,7 +86,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int spatial_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
   const int num_tiles = spatial_tiles * p.n_tiles_out;
   const int kblocks = p.C_in / KB;
-  const int ksteps = p.npass * p.ntaps * kblocks;
+  const int ksteps = (FUSED ? 2 : p.npass) * p.ntaps * kblocks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -125,22 +132,45 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int nb, x0, y0, z0, n0;
         decode(t, nb, x0, y0, z0, n0);
-        for (int ps = 0; ps < p.npass; ++ps) {
-          const int a_off = p.pass_a[ps] * p.C_in;
-          const int w_off = p.pass_w[ps] * p.w_slices;
+        if (FUSED) {
           for (int tp = 0; tp < p.ntaps; ++tp) {
             const int dz = p.tap[tp][0], dy = p.tap[tp][1], dx = p.tap[tp][2];
-            const int wk = (w_off + p.tap_w[tp]) * p.C_in;
+            const int wk_hi = p.tap_w[tp] * p.C_in, wk_lo = (p.w_slices + p.tap_w[tp]) * p.C_in;
             for (int kb = 0; kb < kblocks; ++kb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
-              uint8_t* sB = sA + Cfg::A_BYTES;
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES_RAW);
-              tma_load_5d(sA, &tmA, &full_bar[stage], a_off + kb * KB, x0 + dx, y0 + dy, z0 + dz, n0);
-              tma_load_2d(sB, &tmB, &full_bar[stage], wk + kb * KB, nb * BN);
-              if (++stage == Cfg::STAGES) {
-                stage = 0;
-                phase ^= 1;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+                uint8_t* sB = sA + Cfg::A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + (h == 0 ? 2 : 1) * Cfg::B_BYTES_RAW);
+                tma_load_5d(sA, &tmA, &full_bar[stage], h * p.C_in + kb * KB, x0 + dx, y0 + dy, z0 + dz, n0);
+                tma_load_2d(sB, &tmB, &full_bar[stage], wk_hi + kb * KB, nb * BN);
+                if (h == 0) tma_load_2d(sB + Cfg::B_BYTES_RAW, &tmB, &full_bar[stage], wk_lo + kb * KB, nb * BN);
+                if (++stage == Cfg::STAGES) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+          }
+        } else {
+          for (int ps = 0; ps < p.npass; ++ps) {
+            const int a_off = p.pass_a[ps] * p.C_in;
+            const int w_off = p.pass_w[ps] * p.w_slices;
+            for (int tp = 0; tp < p.ntaps; ++tp) {
+              const int dz = p.tap[tp][0], dy = p.tap[tp][1], dx = p.tap[tp][2];
+              const int wk = (w_off + p.tap_w[tp]) * p.C_in;
+              for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+                uint8_t* sB = sA + Cfg::A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES_RAW);
+                tma_load_5d(sA, &tmA, &full_bar[stage], a_off + kb * KB, x0 + dx, y0 + dy, z0 + dz, n0);
+                tma_load_2d(sB, &tmB, &full_bar[stage], wk + kb * KB, nb * BN);
+                if (++stage == Cfg::STAGES) {
+                  stage = 0;
+                  phase ^= 1;
+                }
               }
             }
           }
@@ -152,6 +182,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     {
       const uint32_t leader = elect_one() ? 1u : 0u;
       constexpr uint32_t idesc = make_idesc_f16(128, BN);
+      constexpr uint32_t idesc_wide = make_idesc_f16(128, FUSED ? 2 * BN : BN);  // x_hi * [W_hi ; W_lo]
       const uint64_t desc0 = make_smem_desc(0, 16, Cfg::SBO, Cfg::SWZ) + (smem_u32(smem) >> 4);
       int stage = 0;
       uint32_t phase = 0;
@@ -160,15 +191,17 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t da = desc0 + uint32_t(stage) * uint32_t(Cfg::STAGE_BYTES >> 4);
           const uint64_t db = da + uint32_t(Cfg::A_BYTES >> 4);
+          // FUSED: even stages are the wide ones (they also initialise all 2 BN columns at ks == 0)
+          const uint32_t id = (FUSED && (ks & 1) == 0) ? idesc_wide : idesc;
 #pragma unroll
           for (int k = 0; k < KB / 16; ++k)
-            umma_f16_elect(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (ks | k) != 0, leader);
+            umma_f16_elect(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), id, (ks | k) != 0, leader);
           umma_commit_elect(&empty_bar[stage], leader);
           if (++stage == Cfg::STAGES) {
             stage = 0;
@@ -228,13 +261,15 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
       for (int c = 0; c < BN / 16; ++c) {
         uint32_t rr[16];
-        tmem_ld_32x32b_x16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 16), rr);
+        tmem_ld_32x32b_x16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * Cfg::ACC_COLS + c * 16), rr);
+        uint32_t r2[16];
+        if (FUSED) tmem_ld_32x32b_x16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * Cfg::ACC_COLS + BN + c * 16), r2);
         tc_wait_ld();
         if (ok) {
           const int col0 = nb * BN + c * 16;
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+          for (int j = 0; j < 16; ++j) v[j] = FUSED ? __uint_as_float(rr[j]) + __uint_as_float(r2[j]) : __uint_as_float(rr[j]);
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -311,28 +346,36 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int KB>
+template <int BN, int KB, bool FUSED>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, KB>;
+  using Cfg = ConvCfg<BN, KB, FUSED>;
   static bool configured = false;
   if (!configured) {
-    SB_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<BN, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<BN, KB, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL));
     configured = true;
   }
   const int num_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n * p.n_tiles_out;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  conv3d_igemm_kernel<BN, KB><<<grid, CONV_THREADS, Cfg::TOTAL, st>>>(tmA, tmB, p);
+  conv3d_igemm_kernel<BN, KB, FUSED><<<grid, CONV_THREADS, Cfg::TOTAL, st>>>(tmA, tmB, p);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int KB>
-static int dispatch_bn(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
+static int dispatch_bn(int BN, bool fused, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
+  if (fused) {
+    switch (BN) {
+      case 16: return launch_conv<16, KB, true>(tmA, tmB, p, st);
+      case 32: return launch_conv<32, KB, true>(tmA, tmB, p, st);
+      case 64: return launch_conv<64, KB, true>(tmA, tmB, p, st);
+      default: return launch_conv<128, KB, true>(tmA, tmB, p, st);
+    }
+  }
   switch (BN) {
-    case 16: return launch_conv<16, KB>(tmA, tmB, p, st);
-    case 32: return launch_conv<32, KB>(tmA, tmB, p, st);
-    case 64: return launch_conv<64, KB>(tmA, tmB, p, st);
-    default: return launch_conv<128, KB>(tmA, tmB, p, st);
+    case 16: return launch_conv<16, KB, false>(tmA, tmB, p, st);
+    case 32: return launch_conv<32, KB, false>(tmA, tmB, p, st);
+    case 64: return launch_conv<64, KB, false>(tmA, tmB, p, st);
+    default: return launch_conv<128, KB, false>(tmA, tmB, p, st);
   }
 }
 
@@ -459,7 +502,12 @@ extern "C" int semabs_conv3d(const void* x16, int32_t a_splits, const void* w16,
     if (int rc = make_tmap_f16(&tmB, w16, 2, dims, str, box, swz)) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (KB == 64) return dispatch_bn<64>(BN, tmA, tmB, p, st);
-  if (KB == 32) return dispatch_bn<32>(BN, tmA, tmB, p, st);
-  return dispatch_bn<16>(BN, tmA, tmB, p, st);
+  static const bool fused_enabled = [] {
+    const char* e = getenv("SEMABS_CONV_FUSED");  // debugging switch: 0 = the original three-stage precise schedule
+    return !(e && e[0] == '0');
+  }();
+  const bool fused = precise != 0 && fused_enabled;
+  if (KB == 64) return dispatch_bn<64>(BN, fused, tmA, tmB, p, st);
+  if (KB == 32) return dispatch_bn<32>(BN, fused, tmA, tmB, p, st);
+  return dispatch_bn<16>(BN, fused, tmA, tmB, p, st);
 }

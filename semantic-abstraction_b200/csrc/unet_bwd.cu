@@ -490,6 +490,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3d_wgrad_kernel(const __gri
 }
 
 // grad[(a * Cb_real + b) * KT + slot_k[slot]] (+)= sum_split partial[split][slot][a][b] / scale
+// grid (ceil(Ca_real*Cb_real / 256), nslots): consecutive threads read consecutive b (coalesced) and add the splits in
+// a fixed order (deterministic)
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int nslots, int Ca, int Cb, int Ca_real, int Cb_real,
                     int KT, const int* __restrict__ slot_k, const float* __restrict__ scale, float* __restrict__ grad,
@@ -497,13 +499,19 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int nslots, i
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Ca_real * Cb_real) return;
   const int a = int(i / Cb_real), b = int(i % Cb_real);
+  const int s = blockIdx.y;
   const float inv_s = scale ? 1.f / *scale : 1.f;
-  for (int s = 0; s < nslots; ++s) {
-    float v = 0.f;
-    for (int k = 0; k < nsplit; ++k) v += partial[((size_t(k) * nslots + s) * Ca + a) * Cb + b];
-    float* o = grad + (size_t(a) * Cb_real + b) * KT + slot_k[s];
-    *o = (accumulate ? *o : 0.f) + v * inv_s;
+  const float* src = partial + (size_t(s) * Ca + a) * Cb + b;
+  const size_t stride = size_t(nslots) * Ca * Cb;
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= nsplit; k += 4) {
+    v0 += src[size_t(k) * stride], v1 += src[size_t(k + 1) * stride];
+    v2 += src[size_t(k + 2) * stride], v3 += src[size_t(k + 3) * stride];
   }
+  for (; k < nsplit; ++k) v0 += src[size_t(k) * stride];
+  float* o = grad + (size_t(a) * Cb_real + b) * KT + slot_k[s];
+  *o = (accumulate ? *o : 0.f) + ((v0 + v1) + (v2 + v3)) * inv_s;
 }
 
 template <int MA, int NB>
@@ -674,8 +682,9 @@ extern "C" int semabs_conv3d_wgrad(const void* A16, int32_t lda, int32_t Ca, int
   else rc = launch_wgrad<16, 16>(p, grid, st);
   if (rc) return rc;
   const long long outs = (long long)Ca_real * Cb_real;
-  wgrad_reduce_kernel<<<int((outs + 255) / 256), 256, 0, st>>>(p.partial, nsplit, nslots, Ca, Cb, Ca_real, Cb_real, KT,
-                                                               slot_k_dev, scale, grad, accumulate);
+  wgrad_reduce_kernel<<<dim3(unsigned((outs + 255) / 256), nslots), 256, 0, st>>>(p.partial, nsplit, nslots, Ca, Cb, Ca_real,
+                                                                                  Cb_real, KT, slot_k_dev, scale, grad,
+                                                                                  accumulate);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -124,18 +124,22 @@ def test_semabs3d_training_step_matches_oracle():
     labels = (torch.rand(B, P, n_out, generator=g) < 0.15).float()
     oob = torch.rand(B, P, n_out, generator=g) < 0.1
     frustum = torch.rand(B, P, n_out, generator=g) < 0.1
-    # oracle: reference forward restated on CPU + torch autograd + reference loss
-    sd = {k: v.detach().cpu().clone().requires_grad_(v.dtype.is_floating_point and k != "steps") for k, v in m.state_dict().items()}
-    out_ref = unet_oracle.semabs3d_forward(sd, xyz, feat, oxyz, BOUNDS, (16, 16, 16))
-    loss_ref, acc_ref = train_oracle.masked_bce(out_ref, labels, None, oob | frustum)
-    loss_ref.backward()
+    from tests._branches import branch_masks, oracle_on_our_branches, record_tapes
+
     batch = dict(input_xyz_pts=xyz.to(dev), input_feature_pts=feat.to(dev), tsdf_vol=torch.ones(B, 1, device=dev),
                  output_xyz_pts=oxyz.to(dev), output_label_pts=labels.to(dev), out_of_bounds_pts=oob.to(dev),
                  out_of_frustum_pts_mask=frustum.to(dev), patch_labels=[("a",), ("b",)])
-    stats, _ = train.get_losses_ovssc(m, batch)
+    with record_tapes() as tapes:
+        stats, _ = train.get_losses_ovssc(m, batch)
+    stats["loss"].backward()
+    # oracle: reference forward restated on CPU + torch autograd + reference loss, on our ReLU branches (tests/_branches.py)
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.dtype.is_floating_point and k != "steps") for k, v in m.state_dict().items()}
+    with oracle_on_our_branches(branch_masks(tapes, 3)):
+        out_ref = unet_oracle.semabs3d_forward(sd, xyz, feat, oxyz, BOUNDS, (16, 16, 16))
+    loss_ref, acc_ref = train_oracle.masked_bce(out_ref, labels, None, oob | frustum)
+    loss_ref.backward()
     assert abs(stats["loss"].item() - loss_ref.item()) < 1e-3 * abs(loss_ref.item())
     assert abs(stats["accuracy"].item() - acc_ref.item()) < 1e-3
-    stats["loss"].backward()
     print("SemAbs3D worst gradient error", _check_grads(m, sd))
     # optimiser: one LAMB step with clipping on both sides
     names = [n for n, p in m.named_parameters()]
@@ -163,16 +167,21 @@ def test_semabsvool_training_step_matches_oracle():
     labels = (torch.rand(B, D, n_out, generator=g) < 0.1).float()
     oob = torch.rand(B, D, n_out, generator=g) < 0.1
     rel = [["behind"], ["on the left of"], ["behind"]]
+    from tests._branches import branch_masks, oracle_on_our_branches, record_tapes
+
     sd = {k: t.detach().cpu().clone().requires_grad_(t.dtype.is_floating_point and not k.endswith("steps"))
           for k, t in v.state_dict().items()}
-    out_ref = unet_oracle.semabsvool_forward(sd, xyz, tgt, refsal, oxyz, rel, BOUNDS, (16, 16, 16), concat_xyz=True)
-    loss_ref = torch.nn.functional.binary_cross_entropy_with_logits(out_ref, labels)
-    loss_ref.backward()
     batch = dict(output_xyz_pts=oxyz.to(dev), spatial_relation_name=rel, input_xyz_pts=xyz.to(dev),
                  input_target_saliency_pts=tgt.to(dev), input_reference_saliency_pts=refsal.to(dev),
                  tsdf_vol=torch.ones(B, 1, device=dev), output_label_pts=labels.to(dev), out_of_bounds_pts=oob.to(dev))
     opt = train.Lamb(v.parameters(), lr=1e-3)
-    stats = train.train_step(v, batch, train.get_losses_vool, opt)
+    with record_tapes() as tapes:
+        stats = train.train_step(v, batch, train.get_losses_vool, opt)
+    assert len(tapes) == 2  # target and reference volumes
+    with oracle_on_our_branches(branch_masks(tapes, 3)):
+        out_ref = unet_oracle.semabsvool_forward(sd, xyz, tgt, refsal, oxyz, rel, BOUNDS, (16, 16, 16), concat_xyz=True)
+    loss_ref = torch.nn.functional.binary_cross_entropy_with_logits(out_ref, labels)
+    loss_ref.backward()
     assert abs(stats["loss"].item() - loss_ref.item()) < 1e-3 * abs(loss_ref.item())
     print("SemAbsVOOL worst gradient error", _check_grads(v, sd))
     # unused parameters (visual_sampler of the completion net, relations not named in the batch) stay untouched

@@ -196,21 +196,26 @@ def test_maxpool_backward_first_max_rule():
 def _unet_grads_vs_oracle(cin, cout, fmaps, levels, shape, N, seed, loss_scale=1.0):
     from oracle import unet_oracle
     from semabs_b200.unet3d import ResidualUNet3D
+    from tests._branches import branch_masks, oracle_on_our_branches, record_tapes
 
     torch.manual_seed(seed)
     m = ResidualUNet3D(in_channels=cin, out_channels=cout, f_maps=fmaps, num_groups=8, num_levels=levels).to(dev)
     g = torch.Generator().manual_seed(seed + 1)
     x = torch.randn(N, cin, *shape, generator=g)
     gy = torch.randn(N, cout, *shape, generator=g) * loss_scale
-    # oracle: autograd through the CPU restatement of the reference module
+    # ours: training-mode forward (tape) + hand-written backward
+    xg = x.to(dev).requires_grad_(True)
+    with record_tapes() as tapes:
+        y = m(xg)
+    y.backward(gy.to(dev))
+    # oracle: autograd through the CPU restatement of the reference module, on the ReLU branches our forward took
+    # (tests/_branches.py explains why)
     sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
     xo = x.clone().requires_grad_(True)
-    yo = unet_oracle.residual_unet3d(sd, xo)
+    with oracle_on_our_branches(branch_masks(tapes, levels)):
+        yo = unet_oracle.residual_unet3d(sd, xo)
     yo.backward(gy)
-    xg = x.to(dev).requires_grad_(True)
-    y = m(xg)
     assert ((y.detach().cpu() - yo.detach()).abs().max() / yo.detach().abs().max()).item() < 1e-3
-    y.backward(gy.to(dev))
     errs = {}
     for name, p in m.named_parameters():
         assert p.grad is not None, name
@@ -221,9 +226,8 @@ def _unet_grads_vs_oracle(cin, cout, fmaps, levels, shape, N, seed, loss_scale=1
     errs["<input>"] = _rel2(xg.grad.cpu(), xo.grad)
     ranked = sorted(errs.items(), key=lambda kv: -kv[1])
     print("gradient errors, worst first:", [(k, f"{v:.1e}") for k, v in ranked[:6]], "median", f"{ranked[len(ranked) // 2][1]:.1e}")
-    # ReLU kinks: a pre-activation within fp32 rounding of zero can take the other branch than the oracle (the forward
-    # outputs still agree to 1e-6); that flips ONE element of one unit's gradient by O(1) and shows up in that unit's
-    # (<= 4) strongly cancelling sums (tools/debug_unet_bwd.py: every other intermediate agrees to 5e-6)
+    # max-pool arg-max near-ties (two candidates within fp32 rounding) are the one remaining branch the oracle may take
+    # differently; allow it to show in the <= 4 tensors of one unit
     over = [kv for kv in ranked if kv[1] >= GRAD_TOL]
     assert len(over) <= 4 and ranked[0][1] < KINK_TOL, ranked[:6]
     assert ranked[len(ranked) // 2][1] < GRAD_TOL / 2
