@@ -22,6 +22,7 @@ else:
     torch.manual_seed(0)
     m = ResidualUNet3D(in_channels=C, out_channels=C, f_maps=C, num_groups=8, num_levels=6, precise=os.environ.get("UNET_FAST", "0") != "1").cuda()
     x = torch.randn(4, C, 128, 128, 128, device="cuda")
+    torch.set_grad_enabled(False)  # inference path (with grad enabled the module records a tape for backward)
     for _ in range(1 + reps):
         m(x)
     torch.cuda.synchronize()
