@@ -399,6 +399,23 @@ int semabs_lamb_step(const void* chunks, int32_t n_chunks, int32_t n_tensors, do
                      const double* grad_sumsq, float max_grad_norm, float lr, float beta1, float beta2, float eps,
                      float weight_decay, int32_t adam_mode, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Evaluation metrics on the device (metrics.cu) — utils.prediction_analysis (utils.py:338-380) and
+ * utils.voxelize_points (utils.py:617-665) as used by train_ovssc.get_detailed_stats (train_ovssc.py:20-78).
+ * pred / label / ignore: uint8 {0,1} [N, npts] (N = scenes x patches). counts: uint64 [N,7] =
+ * (true positives, predicted positives, label positives, union, false negatives, false positives, kept elements), from
+ * which iou = tp/union, precision = tp/pred_pos, recall = tp/label_pos, false_negative = fn/kept, false_positive = fp/kept.
+ * The voxelised variant first scatter-MAXes the three point features onto `shape` voxels (xyz [N/xyz_div, npts, 3];
+ * grid description as for semabs_points_to_voxels), ignores voxels that hold an ignored point or no point at all, and
+ * optionally returns the voxelised booleans [N, X*Y*Z]. flags_ws: uint32 [N, X*Y*Z] workspace.
+ * ---------------------------------------------------------------------------------------------------------- */
+int semabs_confusion_counts(const uint8_t* pred, const uint8_t* label, const uint8_t* ignore, int32_t N, int64_t npts,
+                            uint64_t* counts, void* stream);
+int semabs_voxelized_confusion_counts(const float* xyz, int32_t xyz_div, const uint8_t* pred, const uint8_t* label,
+                                      const uint8_t* ignore, int32_t N, int64_t npts, const float* neg_lc,
+                                      const float* scale, const int32_t* shape, uint32_t* flags_ws, uint64_t* counts,
+                                      uint8_t* vox_pred, uint8_t* vox_label, uint8_t* vox_ignore, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
