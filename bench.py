@@ -47,6 +47,13 @@ def synth_image(seed):
     return np.random.default_rng(seed).integers(0, 256, (IMG, IMG, 3), dtype=np.uint8)
 
 
+def measured_traffic():
+    """DRAM bytes from the committed ncu captures (profiles/r01_traffic.json, made with the commands in its `source` fields);
+    bench.py itself never runs under a profiler."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -257,8 +264,10 @@ def main():
 
     pk = peaks()
     flops_per_map = (GF_FWD_TILE + P * GF_BWD_TILE_LABEL) * 1e9 * n_tiles / P
+    tr = measured_traffic()
     roofline = {"bound": "tensor", "kernel": "gemm_f16_tn_kernel (tcgen05)", "achieved": gemm_prof["tflops"], "peak": pk["tflops"],
-                "unit": "TFLOP/s", "frac": gemm_prof["tflops"] / pk["tflops"], "traffic": None,
+                "unit": "TFLOP/s", "frac": gemm_prof["tflops"] / pk["tflops"], "traffic": tr.get("gemm_dram_bytes_per_launch"),
+                "traffic_note": tr.get("gemm_source"),
                 "peak_source": pk["src"] + " (sustained bf16 cuBLAS)", "gemm_launches": gemm_prof["launches"],
                 "gemm_time_share_of_step": gemm_prof["ms"] / ms_dev,
                 "whole_path_algorithmic_tflops": value / world * flops_per_map / 1e12,
@@ -275,6 +284,8 @@ def main():
     if not args.skip_train:
         torch.cuda.empty_cache()
         train = bench_train(dev, rank, world, pk, num_descs=args.train_descs)
+        torch.cuda.empty_cache()
+        train["amp_like"] = bench_train(dev, rank, world, pk, num_descs=args.train_descs, precise=False)
 
     if rank == 0:
         cpu = None if args.skip_cpu else cpu_relevancy_sample(2, 16)
@@ -364,7 +375,9 @@ def bench_voxel(dev, world, dist, pk, C=32, N=4, steps=5, warmup=3):
             "batch": N, "precise": m.precise, "gpu_launches": m.kernel_launches - l0,
             "e2e": {"value": e2e, "unit": "voxel-grids/s", "h2d_bytes_per_step": N * C * 128**3 * 4, "d2h_bytes_per_step": N * C * 128**3 * 4},
             "roofline": {"bound": "hbm", "achieved": per_gpu * UNET_GB_PER_GRID_FP32[C], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": per_gpu * UNET_GB_PER_GRID_FP32[C] / pk["hbm_gbs"], "traffic": None,
+                         "frac": per_gpu * UNET_GB_PER_GRID_FP32[C] / pk["hbm_gbs"],
+                         "traffic": (measured_traffic().get("unet_forward_dram_bytes") if C == 32 and N == 4 else None),
+                         "algorithmic_bytes": N * UNET_GB_PER_GRID_FP32[C] * 1e9,
                          "tensor_tflops": per_gpu * UNET_GF_PER_GRID[C] / 1e3, "tensor_frac": per_gpu * UNET_GF_PER_GRID[C] / 1e3 / pk["tflops"],
                          "note": "whole-forward algorithmic bytes (BASELINE.md byte rule, fp32 I/O) / time"}}
 
@@ -412,7 +425,7 @@ def bench_pipeline(dev, rank, world, cfg, images):
             "h2d_bytes_per_image": IMG * IMG * 3 + IMG * IMG * 4 + 285 * 5 * 4, "d2h_bytes_per_image": 128**3 * 8}
 
 
-def bench_train(dev, rank, world, pk, C=16, num_descs=16, steps=2, warmup=2):
+def bench_train(dev, rank, world, pk, C=16, num_descs=16, steps=2, warmup=2, precise=True):
     """configs[3]: SemAbsVOOL train step with the reference's defaults (utils.py:38-77: 128^3 grid, 16 channels, 6 levels,
     80k input / 400k output points, pointing_dim 64, decoder_concat_xyz_pts, LAMB lr 1e-3 wd 1e-5, grad_max_norm 2.0),
     batch 1 scene x `num_descs` descriptions per GPU = 2 x num_descs voxel grids through the UNet forward + backward,
@@ -427,7 +440,7 @@ def bench_train(dev, rank, world, pk, C=16, num_descs=16, steps=2, warmup=2):
     net = SemAbsVOOL(pointing_method="cosine_sim", pointing_dim=64, device=str(dev), decoder_concat_xyz_pts=True,
                      voxel_shape=(128, 128, 128), scene_bounds=bounds, unet_num_channels=C, unet_f_maps=C, unet_num_groups=8,
                      unet_num_levels=6, network_inputs=["saliency"], use_pts_feat_extractor=True,
-                     pts_feat_extractor_hidden_dim=128, reduce_method="max", batch_size=1).to(dev)
+                     pts_feat_extractor_hidden_dim=128, reduce_method="max", batch_size=1, precise=precise).to(dev)
     opt = train.Lamb(net.parameters(), lr=1e-3, weight_decay=1e-5)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     lo, hi = torch.tensor(bounds[0], device=dev), torch.tensor(bounds[1], device=dev)
@@ -465,6 +478,8 @@ def bench_train(dev, rank, world, pk, C=16, num_descs=16, steps=2, warmup=2):
     # forward + backward (data + weight gradients) = 3x the forward convolution FLOPs
     tf = world * grids * 3 * UNET_GF_PER_GRID[C] / 1e3 / (ms / 1e3)
     return {"metric": "VOOL train steps/s (128^3, 16 ch, 16 descriptions/GPU)", "value": world * 1e3 / ms, "unit": "steps/s (sum over GPUs)",
+            "precision": "fp32-accurate (3-term fp16 hi/lo convolutions forward and data-gradient)" if precise else
+                         "single fp16 operands, fp32 accumulation (the counterpart of the reference's --use_amp)",
             "ms_per_step": ms, "voxel_grids_trained_per_s": world * grids / (ms / 1e3), "descs_per_gpu": num_descs,
             "unet_kernel_launches_per_step": (unet.kernel_launches - l0) // steps,
             "loss_trajectory": [float(x.detach()) for x in losses], "unet_algorithmic_tflops": tf, "tensor_frac": tf / world / pk["tflops"],

@@ -59,7 +59,9 @@ class UNetBackward:
         # rounding of the adjoint WEIGHTS is a coherent error over all voxels, which single-pass operands turn into ~1e-2
         # relative errors of the (strongly cancelling) GroupNorm parameter gradients; the weight-gradient reduction only
         # sees per-voxel (incoherent) rounding and stays single pass
-        self.precise = True
+        # (follows the module's `precise` flag: precise=False = single fp16 operands everywhere, the counterpart of the
+        # reference's --use_amp training mode, utils.py:78,291-294)
+        self.precise = bool(unet.precise)
 
     # ---- tapes ------------------------------------------------------------------------------------------
     def new_tape(self) -> Tape:

@@ -193,16 +193,19 @@ def test_maxpool_backward_first_max_rule():
     assert abs(amax.view(torch.float32).item() - dx.abs().max().item()) < 1e-6
 
 
-def _unet_grads_vs_oracle(cin, cout, fmaps, levels, shape, N, seed, loss_scale=1.0):
+def _unet_grads_vs_oracle(cin, cout, fmaps, levels, shape, N, seed, loss_scale=1.0, precise=True):
     from oracle import unet_oracle
     from semabs_b200.unet3d import ResidualUNet3D
     from tests._branches import branch_masks, oracle_on_our_branches, record_tapes
 
     torch.manual_seed(seed)
-    m = ResidualUNet3D(in_channels=cin, out_channels=cout, f_maps=fmaps, num_groups=8, num_levels=levels).to(dev)
+    m = ResidualUNet3D(in_channels=cin, out_channels=cout, f_maps=fmaps, num_groups=8, num_levels=levels, precise=precise).to(dev)
     g = torch.Generator().manual_seed(seed + 1)
     x = torch.randn(N, cin, *shape, generator=g)
     gy = torch.randn(N, cout, *shape, generator=g) * loss_scale
+    # precise=False: single fp16 operands in every convolution, forward and backward (the --use_amp counterpart): the
+    # rounding is ~2^-11 per operand and layer instead of ~2^-22 (measured: worst tensor 2.2e-2, median 2.3e-3)
+    tol, kink_tol, fwd_tol = (GRAD_TOL, KINK_TOL, 1e-3) if precise else (5e-2, 5e-2, 5e-3)
     # ours: training-mode forward (tape) + hand-written backward
     xg = x.to(dev).requires_grad_(True)
     with record_tapes() as tapes:
@@ -215,7 +218,7 @@ def _unet_grads_vs_oracle(cin, cout, fmaps, levels, shape, N, seed, loss_scale=1
     with oracle_on_our_branches(branch_masks(tapes, levels)):
         yo = unet_oracle.residual_unet3d(sd, xo)
     yo.backward(gy)
-    assert ((y.detach().cpu() - yo.detach()).abs().max() / yo.detach().abs().max()).item() < 1e-3
+    assert ((y.detach().cpu() - yo.detach()).abs().max() / yo.detach().abs().max()).item() < fwd_tol
     errs = {}
     for name, p in m.named_parameters():
         assert p.grad is not None, name
@@ -228,9 +231,9 @@ def _unet_grads_vs_oracle(cin, cout, fmaps, levels, shape, N, seed, loss_scale=1
     print("gradient errors, worst first:", [(k, f"{v:.1e}") for k, v in ranked[:6]], "median", f"{ranked[len(ranked) // 2][1]:.1e}")
     # max-pool arg-max near-ties (two candidates within fp32 rounding) are the one remaining branch the oracle may take
     # differently; allow it to show in the <= 4 tensors of one unit
-    over = [kv for kv in ranked if kv[1] >= GRAD_TOL]
-    assert len(over) <= 4 and ranked[0][1] < KINK_TOL, ranked[:6]
-    assert ranked[len(ranked) // 2][1] < GRAD_TOL / 2
+    over = [kv for kv in ranked if kv[1] >= tol]
+    assert len(over) <= 4 and ranked[0][1] < kink_tol, ranked[:6]
+    assert ranked[len(ranked) // 2][1] < (tol / 2 if precise else 1e-2)
     return ranked[0], errs["<input>"]
 
 
@@ -247,3 +250,9 @@ def test_unet_backward_tiny_gradients_and_padded_input_channels():
 def test_unet_backward_halo_level():
     # W = 128 takes the halo-resident conv kernel for the data gradients
     _unet_grads_vs_oracle(16, 16, 16, 2, (4, 8, 128), 1, seed=4)
+
+
+def test_unet_backward_fast_mode():
+    # precise=False end to end (what bench.py reports as the "amp_like" train step)
+    _unet_grads_vs_oracle(16, 16, 16, 3, (16, 16, 16), 2, seed=6, precise=False)
+    _unet_grads_vs_oracle(16, 16, 16, 2, (4, 8, 128), 1, seed=7, precise=False)
