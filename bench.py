@@ -47,6 +47,14 @@ def synth_image(seed):
     return np.random.default_rng(seed).integers(0, 256, (IMG, IMG, 3), dtype=np.uint8)
 
 
+def _release():
+    """Drop dead modules / tapes / workspaces (autograd nodes and modules reference each other) and return the memory."""
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
 def measured_traffic():
     """DRAM bytes from the committed ncu captures (profiles/r01_traffic.json, made with the commands in its `source` fields);
     bench.py itself never runs under a profiler."""
@@ -169,6 +177,7 @@ def main():
     ap.add_argument("--skip-voxel", action="store_true")
     ap.add_argument("--skip-train", action="store_true")
     ap.add_argument("--skip-pipeline", action="store_true")
+    ap.add_argument("--skip-amp", action="store_true")
     ap.add_argument("--train-descs", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -280,12 +289,18 @@ def main():
     pipe = None
     if not args.skip_pipeline:
         pipe = bench_pipeline(dev, rank, world, cfg, imgs[: min(2, len(imgs))])
+    # the training step keeps ~80 GB of activations: release everything the earlier sections hold first
+    splits = (eng.fwd_splits, eng.bwd_splits)
+    del dev_tiles, pre, eng, gc
+    ClipWrapper.reset()
+    _release()
     train = None
     if not args.skip_train:
-        torch.cuda.empty_cache()
         train = bench_train(dev, rank, world, pk, num_descs=args.train_descs)
-        torch.cuda.empty_cache()
-        train["amp_like"] = bench_train(dev, rank, world, pk, num_descs=args.train_descs, precise=False)
+        _release()
+        if not args.skip_amp:
+            train["amp_like"] = bench_train(dev, rank, world, pk, num_descs=args.train_descs, precise=False)
+            _release()
 
     if rank == 0:
         cpu = None if args.skip_cpu else cpu_relevancy_sample(2, 16)
@@ -296,7 +311,7 @@ def main():
                 "config": {"workload": f"configs[1]: {MODEL} (seeded random init), {args.images} images 336x336 per GPU per step, "
                                        f"{n_tiles} tiles/image (5 crop sizes), {P} labels, no jitter/flip",
                            "l2_policy": "inputs larger than L2: per-step working set ~6 GB of saved activations + 1.4 GB tiles",
-                           "tile_batch_size": TILE_BATCH, "fwd_splits": eng.fwd_splits, "bwd_splits": eng.bwd_splits},
+                           "tile_batch_size": TILE_BATCH, "fwd_splits": splits[0], "bwd_splits": splits[1]},
                 "e2e": {"value": e2e_value, "unit": "relevancy-maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": ("ClipWrapper.get_clip_saliency_convolve on host uint8 images: tile crop / Pillow-exact bicubic / normalise on the GPU "
                                  "(semabs_tile_preprocess), D2H of the fp32 maps") if ClipWrapper.device_preprocessing else
@@ -371,8 +386,11 @@ def bench_voxel(dev, world, dist, pk, C=32, N=4, steps=5, warmup=3):
     e2e = K * N / (time.perf_counter() - t0) * world
     grids_s = world * N * steps / (ms / 1e3)
     per_gpu = grids_s / world
+    precise_mode, voxel_launches = m.precise, m.kernel_launches - l0
+    del m, xd, yh, xh, y
+    _release()
     return {"metric": "voxel-grids/sec/GPU (128^3, 32 ch)", "value": grids_s, "unit": "voxel-grids/s", "ms_per_step": ms / steps,
-            "batch": N, "precise": m.precise, "gpu_launches": m.kernel_launches - l0,
+            "batch": N, "precise": precise_mode, "gpu_launches": voxel_launches,
             "e2e": {"value": e2e, "unit": "voxel-grids/s", "h2d_bytes_per_step": N * C * 128**3 * 4, "d2h_bytes_per_step": N * C * 128**3 * 4},
             "roofline": {"bound": "hbm", "achieved": per_gpu * UNET_GB_PER_GRID_FP32[C], "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": per_gpu * UNET_GB_PER_GRID_FP32[C] / pk["hbm_gbs"],
@@ -419,6 +437,8 @@ def bench_pipeline(dev, rank, world, cfg, images):
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     n = len(images)
+    del net
+    _release()
     return {"metric": "RGB-D images/s through relevancy -> OVSSC logits (336^2, 16 labels, 128^3 grid + 128^3 lattice)",
             "value": world * n / dt.item(), "unit": "images/s (sum over GPUs)", "s_per_image": dt.item() / n,
             "relevancy_maps_per_s": world * n * len(LABELS16) / dt.item(), "classes_in_prediction": int(pred.unique().numel()),
@@ -457,6 +477,7 @@ def bench_train(dev, rank, world, pk, C=16, num_descs=16, steps=2, warmup=2, pre
         spatial_relation_name=[[rels[d % 6]] * B for d in range(num_descs)],
     )
     unet = net.completion_net.vol_feature_extractor
+    torch.cuda.reset_peak_memory_stats(dev)
     losses = []
     for _ in range(warmup):
         losses.append(train.train_step(net, batch, train.get_losses_vool, opt, grad_max_norm=2.0)["loss"])
@@ -474,6 +495,11 @@ def bench_train(dev, rank, world, pk, C=16, num_descs=16, steps=2, warmup=2, pre
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = ms.item() / steps
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 2**30
+    launches_per_step = (unet.kernel_launches - l0) // steps
+    loss_values = [float(x.detach()) for x in losses]
+    del losses, opt, net, unet, batch
+    _release()
     grids = 2 * num_descs * B  # target + reference volume per description
     # forward + backward (data + weight gradients) = 3x the forward convolution FLOPs
     tf = world * grids * 3 * UNET_GF_PER_GRID[C] / 1e3 / (ms / 1e3)
@@ -481,9 +507,9 @@ def bench_train(dev, rank, world, pk, C=16, num_descs=16, steps=2, warmup=2, pre
             "precision": "fp32-accurate (3-term fp16 hi/lo convolutions forward and data-gradient)" if precise else
                          "single fp16 operands, fp32 accumulation (the counterpart of the reference's --use_amp)",
             "ms_per_step": ms, "voxel_grids_trained_per_s": world * grids / (ms / 1e3), "descs_per_gpu": num_descs,
-            "unet_kernel_launches_per_step": (unet.kernel_launches - l0) // steps,
-            "loss_trajectory": [float(x.detach()) for x in losses], "unet_algorithmic_tflops": tf, "tensor_frac": tf / world / pk["tflops"],
-            "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2**30,
+            "unet_kernel_launches_per_step": launches_per_step,
+            "loss_trajectory": loss_values, "unet_algorithmic_tflops": tf, "tensor_frac": tf / world / pk["tflops"],
+            "peak_memory_gb": peak_gb,
             "note": "gradient all-reduce: one flat NCCL all-reduce after backward" if world > 1 else "single GPU: no collective"}
 
 

@@ -376,8 +376,10 @@ __device__ __forceinline__ uint32_t row_chunk_off(int row, int chunk) {
   return uint32_t(row) * (CH * 2) + uint32_t((chunk ^ ((row >> SH) & (CPR - 1))) * 16);
 }
 
+// 16 x 16 channel tiles need 96 registers and 63 KB of shared memory: two CTAs per SM (ncu: one CTA kept the mma.sync pipe
+// 25 % busy at 14 % warp occupancy — issue / latency bound, not L2 bound)
 template <int MA, int NB>
-__global__ void __launch_bounds__(WG_THREADS, 1) conv3d_wgrad_kernel(const __grid_constant__ WgradParams p) {
+__global__ void __launch_bounds__(WG_THREADS, (MA * NB <= 256) ? 2 : 1) conv3d_wgrad_kernel(const __grid_constant__ WgradParams p) {
   constexpr int MT = MA / 16, NT = NB / 8;
   constexpr int A_BYTES = WG_KB * MA * 2;
   constexpr int SEG_BYTES = WG_SEGROWS * NB * 2;
@@ -666,7 +668,8 @@ extern "C" int semabs_conv3d_wgrad(const void* A16, int32_t lda, int32_t Ca, int
   const int MA = Ca % 32 == 0 ? 32 : 16, NB = Cb % 32 == 0 ? 32 : 16;
   const int pairs = (Ca / MA) * (Cb / NB);
   const size_t per_split = size_t(nslots) * Ca * Cb * sizeof(float);
-  int nsplit = pairs >= num_sms() ? 1 : num_sms() / pairs;
+  const int cta_slots = num_sms() * ((MA * NB <= 256) ? 2 : 1);
+  int nsplit = pairs >= cta_slots ? 1 : cta_slots / pairs;
   if (nsplit > p.nchunks) nsplit = p.nchunks;
   if (size_t(nsplit) * per_split > size_t(workspace_bytes)) nsplit = int(size_t(workspace_bytes) / per_split);
   SB_REQUIRE(nsplit >= 1, "semabs_conv3d_wgrad: workspace of %lld bytes is too small (%zu per split)",
