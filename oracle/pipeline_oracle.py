@@ -67,3 +67,40 @@ def _pin():
 
 if __name__ == "__main__":
     _pin()
+
+
+def prediction_volumes_reference(logits, sampling_shape, scene_bounds, depth, cam_intr, cam_extr, cutoff=-3.0):
+    """TEST INFRASTRUCTURE: the tail of visualize.process_batch_ovssc (visualize.py:212-247) executed with the UNMODIFIED
+    reference classes fusion.TSDFVolume and point_cloud.check_pts_in_frustum (imported from /root/reference; used only by
+    the CPU pinning test, which is skipped where the checkout is absent)."""
+    import importlib.util, sys
+
+    import torch
+
+    mods = {}
+    for name in ("fusion", "point_cloud"):
+        for missing in ("pybullet", "pybullet_data", "matplotlib", "matplotlib.pyplot", "transforms3d", "skimage", "skimage.measure"):
+            sys.modules.setdefault(missing, type(sys)(missing))
+        spec = importlib.util.spec_from_file_location("ref_" + name, f"/root/reference/{name}.py")
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        mods[name] = m
+    grid_points = get_sample_points(sampling_shape, scene_bounds)
+    tsdf_vol = mods["fusion"].TSDFVolume(vol_bnds=np.array(scene_bounds).T,
+                                         voxel_size=(scene_bounds[1][0] - scene_bounds[0][0]) / sampling_shape[0])
+    tsdf_vol.integrate(color_im=np.zeros(depth.shape + (3,), np.uint8), depth_im=depth, cam_intr=cam_intr, cam_pose=cam_extr)
+    # get_volume()[0] is this array; the colour half of get_volume overflows uint8 under numpy 2 (fusion.py:199-203)
+    tsdf = tsdf_vol._tsdf_vol_cpu
+    logprobs = torch.as_tensor(logits).permute(*range(1, logits.ndim), 0)
+    prediction = logprobs.argmax(dim=-1)
+    empty = (logprobs < cutoff).all(dim=-1).view(*sampling_shape)
+    in_frustum = torch.from_numpy(mods["point_cloud"].check_pts_in_frustum(xyz_pts=grid_points, depth=depth, cam_pose=cam_extr,
+                                                                          cam_intr=cam_intr)).view(*sampling_shape)
+    out = []
+    for c in range(logits.shape[0]):
+        v = (prediction == c).float().view(*sampling_shape)
+        v[empty] = 0.0
+        v[~in_frustum] = 0.0
+        v[torch.from_numpy(tsdf > 0.0)] = 0.0
+        out.append(v)
+    return torch.stack(out), tsdf

@@ -5,8 +5,9 @@ mean over labels, back-projected depth, in-bounds mask, per-class point features
 sub-sample `num_input_pts` points per class, query lattice from `get_sample_points` :283-298, SemAbs3D logits) with
 the class arg-max of :236-238.  Differences, on purpose: the relevancy maps never leave the GPU; the UNet runs ONCE per
 image for all classes (the reference re-runs it for every 2^20-point chunk of the lattice, :182-211) and only the implicit
-decoder is chunked; the point sub-sample is drawn once per class instead of once per chunk.  TSDF / frustum masking
-(:212-247) is evaluation-side and not part of the hot path.
+decoder is chunked; the point sub-sample is drawn once per class instead of once per chunk.  The cutoff / frustum / TSDF
+masking of :212-247 is `prediction_volumes` below (bit-identical to the reference's fusion.TSDFVolume + check_pts_in_frustum,
+tests/test_pipeline.py).
 """
 from __future__ import annotations
 
@@ -73,7 +74,8 @@ def relevancy_point_features(rgb: np.ndarray, labels: Sequence[str], saliency_co
 def rgbd_to_ovssc_logits(net: SemAbs3D, rgb: np.ndarray, depth, cam_intr, cam_extr, labels: Sequence[str],
                          scene_bounds, saliency_config: dict, sampling_shape: Tuple[int, int, int] = (128, 128, 128),
                          num_input_pts: int = 80000, num_pts_per_pass: int = 2**20, subtract_mean: bool = True,
-                         generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
+                         generator: Optional[torch.Generator] = None, masked_volumes: bool = False,
+                         cutoff: float = -3.0) -> Dict[str, torch.Tensor]:
     """One image through the whole path. Returns {"relevancies" [P,H,W], "logits" [P, *sampling_shape],
     "prediction" int64 [*sampling_shape] (arg-max class, visualize.py:236)} — all on the device."""
     dev = next(net.parameters()).device
@@ -100,4 +102,73 @@ def rgbd_to_ovssc_logits(net: SemAbs3D, rgb: np.ndarray, depth, cam_intr, cam_ex
         out = net.visual_sampler.run([vol], C, net.vg, q.unsqueeze(0).expand(P, -1, -1).contiguous())
         logits[:, j : j + q.shape[0]] = out.view(P, -1)
     logits = logits.view(P, *sampling_shape)
-    return {"relevancies": rel, "logits": logits, "prediction": logits.argmax(dim=0)}
+    out = {"relevancies": rel, "logits": logits, "prediction": logits.argmax(dim=0)}
+    if masked_volumes:  # visualize.py:212-247: cutoff / frustum / TSDF masking of the per-class volumes
+        out["prediction_volumes"] = prediction_volumes(logits, sampling_shape, scene_bounds, depth_t, cam_intr, cam_extr, cutoff)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# post-processing of the dense sweep (visualize.process_batch_ovssc, visualize.py:212-247): empty / frustum / TSDF masks
+# ---------------------------------------------------------------------------------------------------------------------
+def check_pts_in_frustum(xyz_pts: torch.Tensor, depth_shape, cam_pose, cam_intr) -> torch.Tensor:
+    """point_cloud.check_pts_in_frustum (point_cloud.py:87-110): world points -> camera frame (inverse pose, fp64 like the
+    numpy original) -> pinhole projection; inside iff 0 <= x < w, 0 <= y < h and z > 0."""
+    dev = xyz_pts.device
+    T = torch.linalg.inv(torch.as_tensor(np.asarray(cam_pose), dtype=torch.float64, device=dev))
+    K = torch.as_tensor(np.asarray(cam_intr), dtype=torch.float64, device=dev)
+    p = xyz_pts.to(torch.float64) @ T[:3, :3].T + T[:3, 3]
+    z = p[:, 2]
+    px = (K[0, 0] / z) * p[:, 0] + K[0, 2]
+    py = (K[1, 1] / z) * p[:, 1] + K[1, 2]
+    h, w = depth_shape
+    return (px >= 0) & (px < w) & (py >= 0) & (py < h) & (z > 0)
+
+
+def tsdf_single_frame(scene_bounds, voxel_size: float, depth: torch.Tensor, cam_intr, cam_pose) -> torch.Tensor:
+    """fusion.TSDFVolume(vol_bnds, voxel_size).integrate(one frame).get_volume()[0] (fusion.py:10-173): the truncated signed
+    distance of every voxel to the observed surface along the camera ray, -1 where nothing was observed.  Same dtypes as
+    the original: voxel centres in fp32, camera transform in fp64, fp32 intrinsics, round-half-even pixel lookup."""
+    dev = depth.device
+    b = np.asarray(scene_bounds, dtype=np.float64).T.copy()                    # (3, 2) like vol_bnds
+    vol_dim = np.ceil((b[:, 1] - b[:, 0]) / float(voxel_size)).astype(int)
+    origin = torch.as_tensor(b[:, 0].astype(np.float32), device=dev)
+    trunc = 5 * float(voxel_size)
+    ijk = torch.stack(torch.meshgrid(*[torch.arange(int(n), device=dev) for n in vol_dim], indexing="ij"), dim=-1).reshape(-1, 3)
+    world = (origin.double() + float(voxel_size) * ijk.double()).float()       # vox2world writes fp32
+    T = torch.linalg.inv(torch.as_tensor(np.asarray(cam_pose), dtype=torch.float64, device=dev))
+    cam = world.double() @ T[:3, :3].T + T[:3, 3]
+    K = torch.as_tensor(np.asarray(cam_intr), dtype=torch.float32, device=dev).double()  # cam2pix casts intrinsics to fp32
+    z = cam[:, 2]
+    px = torch.round(cam[:, 0] * K[0, 0] / z + K[0, 2])
+    py = torch.round(cam[:, 1] * K[1, 1] / z + K[1, 2])
+    h, w = depth.shape
+    valid_pix = (px >= 0) & (px < w) & (py >= 0) & (py < h) & (z > 0)
+    pxi = torch.where(valid_pix, px, torch.zeros_like(px)).long()
+    pyi = torch.where(valid_pix, py, torch.zeros_like(py)).long()
+    depth_val = torch.where(valid_pix, depth.double()[pyi, pxi], torch.zeros_like(z))
+    diff = depth_val - z
+    valid = (depth_val > 0) & (diff >= -trunc)
+    dist = torch.clamp(diff / trunc, -1.0, 1.0)
+    tsdf = torch.where(valid, dist, torch.full_like(dist, -1.0)).float()
+    return tsdf.view(*[int(n) for n in vol_dim])
+
+
+@torch.no_grad()
+def prediction_volumes(logits: torch.Tensor, sampling_shape, scene_bounds, depth, cam_intr, cam_extr, cutoff: float = -3.0):
+    """The tail of visualize.process_batch_ovssc (visualize.py:212-247): arg-max class per lattice point, zeroed where every
+    class is below `cutoff`, outside the camera frustum, or in observed free space (TSDF > 0).  logits [P, *sampling_shape]
+    -> float volumes [P, *sampling_shape] (1 = the class is predicted there)."""
+    dev = logits.device
+    P = logits.shape[0]
+    depth_t = torch.as_tensor(depth, dtype=torch.float32, device=dev)
+    grid_points = get_sample_points(sampling_shape, scene_bounds, dev)
+    voxel_size = (scene_bounds[1][0] - scene_bounds[0][0]) / sampling_shape[0]
+    tsdf = tsdf_single_frame(scene_bounds, voxel_size, depth_t, cam_intr, cam_extr)
+    assert tuple(tsdf.shape) == tuple(sampling_shape), "the TSDF grid of visualize.py:212-216 must coincide with the lattice"
+    logprobs = logits.permute(*range(1, logits.dim()), 0)                      # [..., P]
+    prediction = logprobs.argmax(dim=-1)
+    empty = (logprobs < cutoff).all(dim=-1)
+    in_frustum = check_pts_in_frustum(grid_points, depth_t.shape, cam_extr, cam_intr).view(*sampling_shape)
+    keep = (~empty) & in_frustum & ~(tsdf > 0.0)
+    return torch.stack([((prediction == c) & keep).float() for c in range(P)])

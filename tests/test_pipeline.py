@@ -98,3 +98,27 @@ def test_rgbd_to_ovssc_logits_matches_oracle_composition():
     assert sure.float().mean() > 0.5
     assert (out["prediction"].cpu()[sure] == ref.argmax(dim=0)[sure]).all()
     ClipWrapper.reset()
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference"), reason="pins against the reference checkout (build container only)")
+def test_prediction_volume_masks_match_reference_classes():
+    """empty / frustum / TSDF masking of the dense sweep (visualize.py:212-247) against the unmodified fusion.TSDFVolume and
+    point_cloud.check_pts_in_frustum."""
+    from oracle import pipeline_oracle as po
+    from semabs_b200 import pipeline
+
+    rng = np.random.default_rng(4)
+    H, W = 48, 64
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    depth = (0.9 + 0.5 * xx / W + 0.4 * yy / H + 0.01 * rng.standard_normal((H, W))).astype(np.float32)
+    depth[:5, :7] = 0.0  # missing depth
+    K = np.array([[0.9 * W, 0, W / 2 - 0.5], [0, 0.9 * W, H / 2 - 0.5], [0, 0, 1]])
+    T = np.array([[1.0, 0, 0, 0.05], [0, 0, 1, -1.3], [0, -1, 0, 0.9], [0, 0, 0, 1]])
+    shape = (24, 24, 24)
+    logits = torch.from_numpy(rng.standard_normal((3,) + shape).astype(np.float32) * 3 - 2)
+    ref, tsdf_ref = po.prediction_volumes_reference(logits, shape, BOUNDS, depth, K, T)
+    tsdf = pipeline.tsdf_single_frame(BOUNDS, (BOUNDS[1][0] - BOUNDS[0][0]) / shape[0], torch.from_numpy(depth), K, T)
+    assert np.array_equal(tsdf.numpy(), tsdf_ref)
+    got = pipeline.prediction_volumes(logits, shape, BOUNDS, depth, K, T)
+    assert torch.equal(got, ref)
+    assert 0 < got.sum() < got.numel() / 3 and (tsdf_ref > 0).any() and (tsdf_ref == -1).any()
