@@ -141,6 +141,25 @@ def cpu_relevancy_sample(n_tiles=2, n_labels=16, repeats=1):
                       f"{torch.get_num_threads()} threads) in {t:.1f} s, extrapolated linearly in tile count"}
 
 
+def cpu_voxel_sample(C=32):
+    """The voxel half of the metric on the host: the oracle UNet (oracle/unet_oracle.py = the reference module restated with
+    torch CPU ops, fp32) on ONE 128^3 x C grid with all host threads — the same architecture / sizes as bench_voxel."""
+    from oracle import unet_oracle
+    from semabs_b200.unet3d import ResidualUNet3D
+
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    m = ResidualUNet3D(in_channels=C, out_channels=C, f_maps=C, num_groups=8, num_levels=6)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    x = torch.randn(1, C, 128, 128, 128, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        unet_oracle.residual_unet3d(sd, x)
+        dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "voxel-grids/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"1 grid 128^3 x {C} ch through the 6-level ResidualUNet3D (fp32, torch CPU, {torch.get_num_threads()} threads) in {dt:.1f} s"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -161,7 +180,8 @@ def run_reference(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: ViT-L/14, 336^2, 5-size pyramid (285 tiles), 16 labels; CPU: bounded sample",
                        "model_weights": "seeded random init"},
-            "cpu_baseline": r, "e2e": {"value": v, "unit": "relevancy-maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": r, "e2e": {"value": v, "unit": "relevancy-maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "voxel": dict(cpu_voxel_sample(), metric="voxel-grids/sec/GPU (128^3, 32 ch)")}
     print(json.dumps(line), flush=True)
 
 
@@ -304,6 +324,8 @@ def main():
 
     if rank == 0:
         cpu = None if args.skip_cpu else cpu_relevancy_sample(2, 16)
+        if voxel is not None and not args.skip_cpu:
+            voxel["cpu_baseline"] = cpu_voxel_sample()
         line = {"metric": "relevancy-maps/sec/GPU (336^2, 5 scales, 16 labels)", "value": value, "unit": "relevancy-maps/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 MMA / f32 accumulate (fwd hi+lo split)",
