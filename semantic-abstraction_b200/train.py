@@ -17,7 +17,6 @@ from typing import Iterable, List, Optional
 import torch
 import torch.distributed as dist
 
-from . import ops
 from ._lib import check, f32, i32, lib, ptr, stream_ptr
 
 CHUNK = 65536
