@@ -47,6 +47,28 @@ def synth_image(seed):
     return np.random.default_rng(seed).integers(0, 256, (IMG, IMG, 3), dtype=np.uint8)
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout; libraries (NCCL prints its version there when NCCL_DEBUG is set) write to
+    fd 1 behind Python's back, so fd 1 is pointed at stderr for the run and the line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def _release():
     """Drop dead modules / tapes / workspaces (autograd nodes and modules reference each other) and return the memory."""
     import gc
@@ -182,7 +204,7 @@ def run_reference(args):
                        "model_weights": "seeded random init"},
             "cpu_baseline": r, "e2e": {"value": v, "unit": "relevancy-maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "voxel": dict(cpu_voxel_sample(), metric="voxel-grids/sec/GPU (128^3, 32 ch)")}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -200,6 +222,7 @@ def main():
     ap.add_argument("--skip-amp", action="store_true")
     ap.add_argument("--train-descs", type=int, default=16)
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -339,7 +362,7 @@ def main():
                                  "(semabs_tile_preprocess), D2H of the fp32 maps") if ClipWrapper.device_preprocessing else
                                 "ClipWrapper.get_clip_saliency_convolve: host PIL tile preprocessing inside the timed region"},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "voxel": voxel, "pipeline": pipe, "train": train}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
