@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz by running the UNMODIFIED reference on CPU.
 
-Run in the build container (needs /root/reference):   python -m oracle.gen_golden [clip|unet|net|all]
+Run in the build container (needs /root/reference):   python -m oracle.gen_golden [clip|config0|unet|net|all]
 For every fixture it also asserts that the oracle restatement (oracle/*_oracle.py) reproduces the reference
 output, which is what pins the oracle.  Inputs and weights are regenerated from seeds by the tests, so only the
 reference OUTPUTS (plus checksums of the seeded inputs) are stored.
@@ -123,12 +123,58 @@ def gen_clip():
     print("wrote clip_golden.npz")
 
 
+def gen_config0():
+    """BASELINE.json configs[0]: the reference's own documented case — `generate_relevancy.py image`
+    on /root/reference/matterport.png (976^2), ViT-B/32, the first 4 typer default labels, the shipped
+    `saliency_configs["chefer_et_al"](976)` (one 976-px tile, no jitter / flip).  The input image is committed next to the
+    golden as a LOSSLESS re-encoding (tests/golden/matterport_976.webp, bit-identical pixels, checked below) because
+    /root/reference does not exist on the GPU box.  Stored: the reference maps sub-sampled 8x (the full 4x976^2 fp32
+    output is 15 MB), plus per-map peak index / peak value / float64 sum of the FULL maps; the GPU test additionally
+    compares the full maps with the oracle, which this function pins to the reference at full size."""
+    from PIL import Image
+
+    from semabs_b200.clip.model import synthetic_clip_state_dict
+
+    src = os.path.join(ref_import.REF_ROOT, "matterport.png")
+    img = np.array(Image.open(src).convert("RGB"))
+    assert img.shape == (976, 976, 3) and img.dtype == np.uint8
+    webp = os.path.join(GOLDEN, "matterport_976.webp")
+    Image.fromarray(img).save(webp, "WEBP", lossless=True, quality=100, method=6)
+    assert np.array_equal(np.array(Image.open(webp).convert("RGB")), img), "lossless re-encoding changed pixels"
+    sd_raw = synthetic_clip_state_dict("ViT-B/32", seed=0)
+    sd = clip_oracle.convert_weights_values(sd_raw)
+    wrapper = ref_import.make_reference_wrapper("ViT-B/32", sd_raw)
+    cfg = wrapper_cfg = import_saliency_configs()["chefer_et_al"](976)
+    t0 = time.time()
+    maps_ref, feats_ref = wrapper.get_clip_saliency(img=img, text_labels=np.array(LABELS4), prompts=[PROMPT], **cfg)
+    print("config[0] reference get_clip_saliency: %.2fs" % (time.time() - t0), tuple(maps_ref.shape))
+    W_ref = torch.cat([wrapper.clip_gradcam.class_to_language_feature[l] for l in LABELS4], dim=1)
+    maps_or = clip_oracle.get_clip_saliency(sd, img, W_ref, cfg["cropping_augmentations"], positive_attn_only=True)
+    e = rel_err(maps_or, maps_ref)
+    same_peak = bool((maps_or.flatten(1).argmax(1) == maps_ref.flatten(1).argmax(1)).all())
+    print("config[0] oracle-vs-reference", e, "argmax equal:", same_peak)
+    assert e < 1e-5 and same_peak
+    flat = maps_ref.flatten(1)
+    np.savez_compressed(os.path.join(GOLDEN, "config0_golden.npz"),
+                        maps_sub8=maps_ref[:, ::8, ::8].numpy(), peak_index=flat.argmax(1).numpy(),
+                        peak_value=flat.max(1).values.numpy(), map_sum=flat.double().sum(1).numpy(),
+                        n_at_peak=(flat == flat.max(1, keepdim=True).values).sum(1).numpy(),
+                        text_feats=feats_ref.numpy(), image_checksum=np.int64(img.astype(np.int64).sum()))
+    print("wrote config0_golden.npz; pixels tied at the reference peak per map:", (flat == flat.max(1, keepdim=True).values).sum(1).tolist())
+
+
+def import_saliency_configs():
+    return ref_import.import_reference_clip().saliency_configs
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     if what in ("clip", "all"):
         gen_clip()
+    if what in ("config0", "all"):
+        gen_config0()
     if what in ("unet", "net", "all"):
         from oracle import gen_golden_3d
 

@@ -239,10 +239,13 @@ def pack_clip_weights(name: str, state_dict: Dict[str, torch.Tensor], device, fi
     )  # fmt: skip
 
 
-def load_state_dict(name: str, download_root: Optional[str] = None, seed: int = 0) -> Dict[str, torch.Tensor]:
+def load_state_dict(name: str, download_root: Optional[str] = None, seed: Optional[int] = None,
+                    allow_synthetic: Optional[bool] = None) -> Dict[str, torch.Tensor]:
     """Checkpoint lookup mirroring `load` (reference clip_explainability.py:116-169) minus the network download:
-    a path, or `~/.cache/clip/<file>.pt`; when neither exists (no network here) a seeded synthetic model of the same
-    geometry is returned — and that is stated, not hidden: callers can check `.synthetic` on the engine."""
+    a path, or `~/.cache/clip/<file>.pt`.  When neither exists the reference would download or raise; here (no network)
+    this RAISES too unless the caller opted into seeded synthetic weights of the same geometry — explicitly, by passing
+    `seed=` / `allow_synthetic=True` or setting SEMABS_B200_ALLOW_SYNTHETIC=1 (tests and bench.py do; a user asking for
+    relevancy maps must never silently get maps of a random model)."""
     fname = {"ViT-B/32": "ViT-B-32.pt", "ViT-B/16": "ViT-B-16.pt", "ViT-L/14": "ViT-L-14.pt",
              "ViT-L/14@336px": "ViT-L-14-336px.pt"}  # fmt: skip
     path = None
@@ -255,11 +258,24 @@ def load_state_dict(name: str, download_root: Optional[str] = None, seed: int = 
     else:
         raise RuntimeError(f"Model {name} not found; available models = {available_models()}")
     if path is None:
-        sd = synthetic_clip_state_dict(name, seed)
+        if allow_synthetic is None:
+            allow_synthetic = seed is not None or os.environ.get("SEMABS_B200_ALLOW_SYNTHETIC", "0") == "1"
+        if not allow_synthetic:
+            raise RuntimeError(
+                f"CLIP checkpoint for {name} not found under {download_root or os.path.expanduser('~/.cache/clip')} "
+                "(no network download here). Place the checkpoint there, or opt into seeded random-init weights of the "
+                "same geometry with seed=<int> / allow_synthetic=True / SEMABS_B200_ALLOW_SYNTHETIC=1.")
+        import warnings
+
+        warnings.warn(f"semabs_b200: using SYNTHETIC seeded random-init weights for {name} (no checkpoint found); "
+                      "relevancy maps are meaningless except for parity / throughput measurements", stacklevel=2)
+        sd = synthetic_clip_state_dict(name, 0 if seed is None else seed)
         sd["__synthetic__"] = torch.tensor(1)
         return sd
     try:
         sd = torch.jit.load(path, map_location="cpu").state_dict()
     except RuntimeError:
-        sd = torch.load(path, map_location="cpu")
+        sd = torch.load(path, map_location="cpu", weights_only=True)
+        if "state_dict" in sd:
+            sd = sd["state_dict"]
     return {k: v for k, v in sd.items() if k not in ("input_resolution", "context_length", "vocab_size")}

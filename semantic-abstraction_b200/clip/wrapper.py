@@ -173,8 +173,8 @@ class ClipGradcam:
     """Drop-in for the reference class of the same name: `ClipGradcam(...)(x, o)` -> relevance [P,B,g,g]."""
 
     def __init__(self, clip_model_name: str, classes: List[str], templates: List[str], device, num_layers=10,
-                 positive_attn_only=False, fwd_splits=2, bwd_splits=1, seed=0, **load_kwargs):
-        sd = load_state_dict(clip_model_name, load_kwargs.get("download_root"), seed=seed)
+                 positive_attn_only=False, fwd_splits=2, bwd_splits=1, seed=None, allow_synthetic=None, **load_kwargs):
+        sd = load_state_dict(clip_model_name, load_kwargs.get("download_root"), seed=seed, allow_synthetic=allow_synthetic)
         self.synthetic = "__synthetic__" in sd
         sd.pop("__synthetic__", None)
         self.clip_model_name = clip_model_name

@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(256) scatter_finalize_kernel(float* __restrict
   }
   if (stats) {
     const int cpg = groups == 1 ? Cpad : C / groups;
-    const int g0 = (4 * cq) / cpg, g1 = (4 * cq + 2) / cpg;
+    // padded channels (>= C) hold zeros: clamp their group index instead of indexing past smst (C < Cpad, groups > 1)
+    const int g0 = min((4 * cq) / cpg, groups - 1), g1 = min((4 * cq + 2) / cpg, groups - 1);
     atomicAdd(&smst[2 * g0], s0), atomicAdd(&smst[2 * g0 + 1], q0);
     atomicAdd(&smst[2 * g1], s1), atomicAdd(&smst[2 * g1 + 1], q1);
     __syncthreads();

@@ -319,6 +319,9 @@ def _host3(vals, ctype):
 def points_to_voxels(xyz, feat, grid, *, N, npts, F, xyz_div, mlp, C_out, vol, cnt, Cpad, groups=1, stats=None):
     """grid = (neg_lc[3], scale[3], shape[3]) host values; mlp = None or (w1t,b1,w2t,b2,w3t,b3, hidden)."""
     neg_lc, scale, shape = grid
+    if stats is not None and groups > 1 and (C_out % groups != 0 or (C_out // groups) % 2 != 0):
+        # the finalize kernel accumulates the statistics channel pair by channel pair: a pair must not straddle two groups
+        raise ValueError(f"points_to_voxels: GroupNorm statistics need an even number of channels per group (C={C_out}, groups={groups})")
     w = mlp[:6] if mlp is not None else (None,) * 6
     hidden = mlp[6] if mlp is not None else 0
     check(

@@ -18,6 +18,7 @@ import torch
 import torch.distributed as dist
 
 from ._lib import check, f32, i32, lib, ptr, stream_ptr
+from .unet3d import bump_weights_epoch
 
 CHUNK = 65536
 
@@ -100,19 +101,26 @@ def get_losses_vool(net, batch: dict, balance_positive_negative: bool = False, *
     return {"loss": loss, "accuracy": acc}, None
 
 
-def train_step(net, batch: dict, get_losses_fn, optimizer, grad_max_norm: float = 1e5, **kwargs):
+def train_step(net, batch: dict, get_losses_fn, optimizer, grad_max_norm: float = 1e5, lr_scheduler=None, **kwargs):
     """One iteration of utils.loop's train branch (utils.py:404-422): losses -> zero_grad -> backward ->
-    [DDP gradient averaging] -> clip_grad_norm_ -> optimizer.step -> steps += 1.  With this module's Lamb the clip is
-    folded into the optimiser sweep."""
+    [DDP gradient averaging] -> clip_grad_norm_ -> optimizer.step -> lr_scheduler.step -> steps += 1 -> `gradnorm` stat.
+    With this module's Lamb the clip is folded into the optimiser sweep (the gradients themselves stay unclipped in
+    memory; `gradnorm` is reported as what utils.compute_grad_norm would see AFTER the reference's in-place clip)."""
     stats, _ = get_losses_fn(net=net, batch=batch, **kwargs)
     optimizer.zero_grad(set_to_none=True)
     stats["loss"].backward()
     all_reduce_gradients(net.parameters())
     if isinstance(optimizer, Lamb):
         optimizer.step(max_grad_norm=grad_max_norm)
+        total = optimizer.last_grad_norm
+        stats["gradnorm"] = total * torch.clamp(grad_max_norm / (total + 1e-6), max=1.0)
     else:
-        clip_grad_norm_(net.parameters(), grad_max_norm)
+        total = clip_grad_norm_(net.parameters(), grad_max_norm)
         optimizer.step()
+        bump_weights_epoch()
+        stats["gradnorm"] = total * torch.clamp(grad_max_norm / (total + 1e-6), max=1.0)
+    if lr_scheduler is not None:
+        lr_scheduler.step()
     net.steps += 1
     return stats
 
@@ -135,7 +143,14 @@ class _ChunkTable:
         self.n_tensors = len(params)
         dev = params[0].device
         self.table = torch.frombuffer(bytearray(b"".join(rec)), dtype=torch.uint8).to(dev)
-        self.key = tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(params, grads))
+        self.key = _table_key(params, grads, ms, vs)
+
+
+def _table_key(params, grads, ms, vs):
+    """identity of everything a table points at: parameter, gradient AND moment buffers (optimizer.load_state_dict replaces
+    the moments without touching the parameters)"""
+    dp = lambda t: 0 if t is None else t.data_ptr()
+    return tuple((dp(p), dp(g), dp(m), dp(v)) for p, g, m, v in zip(params, grads, ms, vs))
 
 
 def grad_sumsq(table: _ChunkTable) -> torch.Tensor:
@@ -167,13 +182,23 @@ class Lamb(torch.optim.Optimizer):
         if not 0.0 <= betas[1] < 1.0:
             raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
         self.adam = adam
-        self._table = None
+        self._tables = {}
+        self.last_grad_norm = None
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._tables = {}
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables = {}  # the moment buffers were replaced: never keep pointers into the old ones
 
     @torch.no_grad()
     def step(self, closure=None, max_grad_norm: Optional[float] = None):
         loss = closure() if closure is not None else None
-        for group in self.param_groups:
+        work = []
+        for gi, group in enumerate(self.param_groups):
             ps = [p for p in group["params"] if p.grad is not None]  # params without grad are skipped (lamb.py:71-72)
             if not ps:
                 continue
@@ -184,18 +209,30 @@ class Lamb(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p.data)
                     st["exp_avg_sq"] = torch.zeros_like(p.data)
                 st["step"] += 1
-            key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
-            if self._table is None or self._table.key != key:
-                self._table = _ChunkTable([p.data for p in ps], [p.grad.data for p in ps],
-                                          [self.state[p]["exp_avg"] for p in ps], [self.state[p]["exp_avg_sq"] for p in ps])
-            tb = self._table
+            params, grads = [p.data for p in ps], [p.grad.data for p in ps]
+            ms, vs = [self.state[p]["exp_avg"] for p in ps], [self.state[p]["exp_avg_sq"] for p in ps]
+            tb = self._tables.get(gi)
+            if tb is None or tb.key != _table_key(params, grads, ms, vs):
+                tb = self._tables[gi] = _ChunkTable(params, grads, ms, vs)
+            work.append((group, tb))
+        ss = None
+        if max_grad_norm is not None and work:
+            # clip_grad_norm_(net.parameters(), max) uses the GLOBAL norm over every parameter with a gradient
+            # (utils.py:415): one sum of squares over all groups, the same scalar for every group's sweep
+            ss = grad_sumsq(work[0][1])
+            for _, tb in work[1:]:
+                ss = ss + grad_sumsq(tb)
+            self.last_grad_norm = ss.sqrt().float()[0]
+        for group, tb in work:
             norms = torch.empty(2 * tb.n_tensors, dtype=torch.float64, device=tb.table.device)
-            ss = grad_sumsq(tb) if max_grad_norm is not None else None
             b1, b2 = group["betas"]
             check(lib().semabs_lamb_step(ptr(tb.table), i32(tb.n_chunks), i32(tb.n_tensors), ptr(norms), ptr(ss),
                                          f32(max_grad_norm or 0.0), f32(group["lr"]), f32(b1), f32(b2), f32(group["eps"]),
                                          f32(group["weight_decay"]), i32(int(self.adam)), stream_ptr()))
             self.last_norms = norms
+        # the update went through raw device pointers: torch's version counters did not move, so tell the modules that
+        # cache fp16 MMA-operand packs of their weights (ResidualUNet3D._packed, UNetBackward._packed) to rebuild them
+        bump_weights_epoch()
         return loss
 
 

@@ -21,6 +21,20 @@ from . import ops
 F16, F32, F64 = torch.float16, torch.float32, torch.float64
 
 
+_WEIGHTS_EPOCH = [0]
+
+
+def bump_weights_epoch() -> None:
+    """Called by optimisers that update parameters through raw device pointers (train.Lamb): such updates do not move
+    torch's tensor version counters, so the cached fp16 weight packs are additionally keyed on this epoch."""
+    _WEIGHTS_EPOCH[0] += 1
+
+
+def _params_key(module, device, precise):
+    ps = list(module.parameters())
+    return (str(device), precise, _WEIGHTS_EPOCH[0], tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+
+
 def number_of_features_per_level(init_channel_number, num_levels):
     return [init_channel_number * 2**k for k in range(num_levels)]
 
@@ -137,7 +151,7 @@ class ResidualUNet3D(nn.Module):
 
     def _packed(self, device):
         """fp16 (hi | lo) MMA-operand copies of the conv weights, rebuilt when a parameter changes."""
-        key = (str(device), self.precise, tuple(p._version for p in self.parameters()), tuple(p.data_ptr() for p in self.parameters()))
+        key = _params_key(self, device, self.precise)
         if key == self._pack_key:
             return self._pack
         s = 2 if self.precise else 1

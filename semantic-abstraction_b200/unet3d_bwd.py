@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import ops
-from .unet3d import F16, F32, F64, ExtResNetBlock, ResidualUNet3D, _pad16, _split_pack
+from .unet3d import F16, F32, F64, ExtResNetBlock, ResidualUNet3D, _pad16, _params_key, _split_pack
 
 I32 = torch.int32
 WGRAD_WS_BYTES = 256 << 20
@@ -74,7 +74,7 @@ class UNetBackward:
     # ---- adjoint weight packs -----------------------------------------------------------------------------
     def _packed(self, dev):
         u = self.unet
-        key = (str(dev), self.precise, tuple(p._version for p in u.parameters()), tuple(p.data_ptr() for p in u.parameters()))
+        key = _params_key(u, dev, self.precise)
         if key == self._bpk_key:
             return self._bpk
         pk: Dict[str, torch.Tensor] = {}

@@ -75,3 +75,26 @@ def oracle_on_our_branches(masks):
     finally:
         F.relu = orig
     assert next(it, None) is None, "the oracle ran fewer ReLUs than the CUDA forward recorded"
+
+
+@contextlib.contextmanager
+def count_branch_flips(masks, result: dict):
+    """Un-borrowed run: the oracle keeps its OWN ReLU branches; `result["n"]` receives the number of pre-activations whose
+    sign decision differs from the masks recorded on our tapes (a wrong mask in the CUDA backward would show up here as a
+    large count, fp32 rounding of the forward as a handful)."""
+    it = iter(masks)
+    orig = F.relu
+    result["n"] = 0
+
+    def relu(x, *a, **k):
+        m = next(it)
+        assert m.shape == x.shape, (m.shape, x.shape)
+        result["n"] += int(((x.detach() > 0).float() != m).sum())
+        return orig(x, *a, **k)
+
+    F.relu = relu
+    try:
+        yield
+    finally:
+        F.relu = orig
+    assert next(it, None) is None, "the oracle ran fewer ReLUs than the CUDA forward recorded"

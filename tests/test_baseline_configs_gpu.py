@@ -1,0 +1,271 @@
+"""Parity AT THE BASELINE.json CONFIG SIZES, CUDA path vs the CPU oracle (oracle/*.py, pinned bit-exactly to the unmodified
+reference by oracle/gen_golden*.py) — VERDICT r01 "next round" item 1:
+
+  (a) configs[2]: one 128^3 x 32-channel grid through the 6-level ResidualUNet3D (512 / 1024-channel convolutions, the
+      halo-resident kernel at 128^2, all five transposed convolutions)                         unet3d.py:596-621
+  (b) configs[1]: ViT-L/14, 16 labels, a 95-tile engine batch drawn from the real 5-size pyramid (one tile of every crop
+      size incl. 84 px is compared)                                                             clip_gradcam.py:58-132
+  (c) SemAbs3D.forward at the reference defaults (128^3, 16 channels, 6 levels, 80 k / 400 k points, 4 patches)
+                                                                                                net.py:383-439
+  (d) configs[0]: `generate_relevancy.py image` shape — matterport.png 976^2, ViT-B/32, 4 labels, "chefer_et_al" —
+      against the committed REFERENCE output (tests/golden/config0_golden.npz) and the oracle at full size
+  (e) configs[3] shape: one SemAbsVOOL training step with a 6-level UNet (64^3) vs torch autograd through the oracle,
+      with AND without borrowing our ReLU branches (the un-borrowed run reports how many pre-activations flipped).
+
+Tolerances are BASELINE.json north_star's: fp32 maps / logits within 1e-3 relative (max|d| / max|ref|); arg-max / peak
+indices bit-exact — every test PRINTS the measured error and the exact number of index mismatches, and a mismatch is
+accepted only when the reference's own margin at that position is below the fp32 noise of the comparison (a tie)."""
+import os
+import time
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+TOL = 1e-3
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+BOUNDS = ((-1.0, -1.0, -0.1), (1.0, 1.0, 1.9))
+PYRAMID = [{"tile_size": s, "stride": s // 4} for s in (336, 224, 168, 112, 84)]
+LABELS16 = ["basketball jersey", "nintendo switch", "television", "ping pong table", "vase", "fireplace",
+            "abstract painting of a vespa", "carpet", "wall", "microwave", "cabinet", "fire extinguisher", "mirror",
+            "woven chair", "globe", "leather sofa"]  # fmt: skip
+PROMPT = "a photograph of a {} in a home."
+
+
+def _maxrel(a, b):
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+def _argmax_report(name, ours, ref, dim, abs_err):
+    """Exact count of arg-max mismatches along `dim`; every mismatch must be a numerical tie of the REFERENCE (its top-2
+    margin at that position below 2x the measured max abs error of this comparison)."""
+    io, ir = ours.argmax(dim), ref.argmax(dim)
+    bad = io != ir
+    n_bad, n = int(bad.sum()), bad.numel()
+    top2 = ref.topk(2, dim=dim).values
+    margin = (top2.select(dim, 0) - top2.select(dim, 1)).abs()
+    worst = float(margin[bad].max()) if n_bad else 0.0
+    print(f"{name}: arg-max mismatches {n_bad} / {n}" + (f" (largest reference margin among them {worst:.2e}, "
+          f"comparison noise {abs_err:.2e})" if n_bad else " (bit-exact)"))
+    assert worst <= 2 * abs_err, f"{name}: an unambiguous reference arg-max was missed (margin {worst:.3e})"
+    return n_bad
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def test_a_unet_128cube_32ch_6levels_vs_oracle():
+    from oracle import unet_oracle
+    from semabs_b200.unet3d import ResidualUNet3D
+
+    torch.manual_seed(0)
+    m = ResidualUNet3D(in_channels=32, out_channels=32, f_maps=32, num_groups=8, num_levels=6).to(dev)
+    x = torch.randn(1, 32, 128, 128, 128, generator=torch.Generator().manual_seed(0))
+    y = m(x.to(dev)).cpu()
+    torch.set_num_threads(os.cpu_count())
+    t0 = time.time()
+    ref = unet_oracle.residual_unet3d({k: v.cpu() for k, v in m.state_dict().items()}, x)
+    err = _maxrel(y, ref)
+    print(f"(a) ResidualUNet3D 128^3 x 32 ch, 6 levels: max|d|/max|ref| = {err:.2e} (oracle {time.time() - t0:.1f} s on CPU)")
+    assert y.shape == ref.shape == (1, 32, 128, 128, 128)
+    assert err < TOL
+    _argmax_report("(a) voxel arg-max over 32 channels", y, ref, 1, float((y - ref).abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def test_b_vit_l14_16_labels_tile_batch_95_vs_oracle():
+    from oracle import clip_oracle
+    from semabs_b200.clip import ClipWrapper
+    from semabs_b200.clip.model import synthetic_clip_state_dict
+    from semabs_b200.clip.tokenizer import tokenize
+
+    ClipWrapper.reset()
+    ClipWrapper("ViT-L/14", dev, seed=0)
+    gc = ClipWrapper.clip_gradcam
+    gc.templates = [PROMPT]
+    gc.set_classes(LABELS16)
+    W = torch.cat([gc.class_to_language_feature[l] for l in LABELS16], dim=1).contiguous()
+    sd = clip_oracle.convert_weights_values(synthetic_clip_state_dict("ViT-L/14", seed=0))
+    torch.set_num_threads(os.cpu_count())
+    W_ref = clip_oracle.zeroshot_weights(sd, tokenize([PROMPT.format(l) for l in LABELS16]), 16, 1)
+    werr = _maxrel(W.cpu(), W_ref)
+    print(f"(b) zero-shot weights, 16 labels: {werr:.2e}")
+    assert werr < TOL
+    img = np.random.default_rng(0).integers(0, 256, (336, 336, 3), dtype=np.uint8)
+    desc, _, _ = ClipWrapper.enumerate_crops(img=img, augmentations=0, cropping_augmentations=PYRAMID)
+    assert len(desc) == 285
+    tiles = torch.cat(list(ClipWrapper._device_preprocessed_batches(desc, 224, 285)))
+    # one engine batch of 95 tiles (bench.py's tile_batch_size) holding every crop size: 336 (1), 224 (9), 168 (25),
+    # 112 (30 of 81), 84 (30 of 169)
+    first = {s: int(np.nonzero(desc[:, 2] == s)[0][0]) for s in (336, 224, 168, 112, 84)}
+    idx = [first[336]] + list(range(first[224], first[224] + 9)) + list(range(first[168], first[168] + 25)) + \
+        list(range(first[112], first[112] + 30)) + list(range(first[84] + 100, first[84] + 130))
+    assert len(idx) == 95
+    batch = tiles[idx].contiguous()
+    gc.positive_attn_only = True
+    rel = gc.engine.relevancy(batch, W, positive_attn_only=True).cpu()
+    assert rel.shape == (16, 95, 16, 16)
+    sel = [0, 5, 20, 50, 94]  # one tile per crop size: 336, 224, 168, 112, 84 px
+    assert [int(desc[idx[s], 2]) for s in sel] == [336, 224, 168, 112, 84]
+    t0 = time.time()
+    ref = clip_oracle.relevancy(sd, batch[sel].cpu(), W.cpu())
+    per_map = ((rel[:, sel] - ref).abs().amax(dim=(-1, -2)) / ref.abs().amax(dim=(-1, -2)))
+    print(f"(b) ViT-L/14 relevancy, 16 labels x 5 tiles of a 95-tile batch: max over maps of max|d|/max|ref| = "
+          f"{per_map.max().item():.2e}, median {per_map.median().item():.2e} (oracle {time.time() - t0:.1f} s on CPU)")
+    assert per_map.max().item() < TOL
+    ours, theirs = rel[:, sel].flatten(2), ref.flatten(2)
+    _argmax_report("(b) relevancy-peak cell of every (label, tile) map", ours, theirs, 2, float((ours - theirs).abs().max()))
+    ClipWrapper.reset()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def test_c_semabs3d_reference_defaults_vs_oracle():
+    from oracle import unet_oracle
+    from semabs_b200.net import SemAbs3D
+
+    torch.manual_seed(3)
+    m = SemAbs3D(voxel_shape=(128, 128, 128), scene_bounds=BOUNDS, unet_num_channels=16, unet_f_maps=16, unet_num_groups=8,
+                 unet_num_levels=6, network_inputs=["saliency"], use_pts_feat_extractor=True, pts_feat_extractor_hidden_dim=128,
+                 reduce_method="max", device=dev, batch_size=1).to(dev)
+    B, P, n_in, n_out = 1, 4, 80000, 400000
+    g = torch.Generator().manual_seed(4)
+    lo, hi = torch.tensor(BOUNDS[0]), torch.tensor(BOUNDS[1])
+    xyz = lo + (hi - lo) * torch.rand(B, n_in, 3, generator=g)
+    feat = torch.randn(B, P, n_in, 1, generator=g)
+    oxyz = lo + (hi - lo) * (torch.rand(B, P, n_out, 3, generator=g) * 1.04 - 0.02)  # a few queries outside the bounds
+    out = m(input_xyz_pts=xyz.to(dev), input_feature_pts=feat.to(dev), tsdf_vol=torch.ones(B, 1, device=dev),
+            output_xyz_pts=oxyz.to(dev)).cpu()
+    torch.set_num_threads(os.cpu_count())
+    t0 = time.time()
+    ref = unet_oracle.semabs3d_forward({k: v.cpu() for k, v in m.state_dict().items()}, xyz, feat, oxyz, BOUNDS, (128, 128, 128))
+    err = _maxrel(out, ref)
+    print(f"(c) SemAbs3D.forward at the reference defaults (128^3, C=16, 6 levels, 80k/400k pts, P=4): logits "
+          f"max|d|/max|ref| = {err:.2e} (oracle {time.time() - t0:.1f} s on CPU)")
+    assert out.shape == ref.shape == (1, 4, n_out)
+    assert err < TOL
+    _argmax_report("(c) label arg-max over the 4 patches at 400k query points", out, ref, 1, float((out - ref).abs().max()))
+    sign_flips = int(((out > 0) != (ref > 0)).sum())
+    print(f"(c) occupancy decisions (logit > 0) that differ: {sign_flips} / {out.numel()}")
+    assert ((out > 0) == (ref > 0))[(ref.abs() > 2 * (out - ref).abs().max())].all()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def test_d_config0_chefer_matterport_vit_b32_vs_reference_golden():
+    from PIL import Image
+
+    from oracle import clip_oracle
+    from semabs_b200.clip import ClipWrapper, saliency_configs
+    from semabs_b200.clip.model import synthetic_clip_state_dict
+    from semabs_b200.clip.tokenizer import tokenize
+
+    gold = np.load(os.path.join(GOLD, "config0_golden.npz"))
+    img = np.array(Image.open(os.path.join(GOLD, "matterport_976.webp")).convert("RGB"))
+    assert img.shape == (976, 976, 3) and int(img.astype(np.int64).sum()) == int(gold["image_checksum"])
+    labels = LABELS16[:4]
+    ClipWrapper.reset()
+    ClipWrapper("ViT-B/32", dev, seed=0)
+    maps, feats = ClipWrapper.get_clip_saliency(img=img, text_labels=np.array(labels), prompts=[PROMPT],
+                                                **saliency_configs["chefer_et_al"](976))
+    assert maps.shape == (4, 976, 976) and maps.dtype == torch.float32 and not maps.is_cuda
+    # 1) against the committed output of the unmodified reference
+    ref_sub = torch.from_numpy(gold["maps_sub8"])
+    per_map = (maps[:, ::8, ::8] - ref_sub).abs().amax(dim=(1, 2)) / ref_sub.abs().amax(dim=(1, 2))
+    print(f"(d) configs[0] maps vs REFERENCE golden (every 8th pixel): max|d|/max|ref| per map = {[f'{v:.2e}' for v in per_map.tolist()]}")
+    assert per_map.max().item() < TOL
+    sums = maps.flatten(1).double().sum(1).numpy()
+    assert np.all(np.abs(sums - gold["map_sum"]) < TOL * np.abs(gold["map_sum"]))
+    fr = torch.from_numpy(gold["text_feats"])
+    assert (feats - fr).abs().max().item() < TOL * fr.abs().max().item()
+    # 2) against the oracle at full size (pinned to the reference at this very size by oracle/gen_golden.py:gen_config0)
+    sd = clip_oracle.convert_weights_values(synthetic_clip_state_dict("ViT-B/32", seed=0))
+    W = clip_oracle.zeroshot_weights(sd, tokenize([PROMPT.format(l) for l in labels]), 4, 1)
+    ref = clip_oracle.get_clip_saliency(sd, img, W, saliency_configs["chefer_et_al"](976)["cropping_augmentations"])
+    assert np.array_equal(ref.flatten(1).argmax(1).numpy(), gold["peak_index"]), "oracle drifted from the reference golden"
+    full = ((maps - ref).abs().amax(dim=(1, 2)) / ref.abs().amax(dim=(1, 2)))
+    print(f"(d) full 976^2 maps vs oracle: {[f'{v:.2e}' for v in full.tolist()]}")
+    assert full.max().item() < TOL
+    # peak pixel: the reference's maximum is a plateau of fp16-equal pixels (n_at_peak in the golden; argmax returns the
+    # first); ours must be the same index, or — reported — another pixel of the reference's own plateau
+    ours = maps.flatten(1).argmax(1).numpy()
+    exact = int((ours == gold["peak_index"]).sum())
+    rflat = ref.flatten(1)
+    on_plateau = [bool(rflat[p, ours[p]] == gold["peak_value"][p]) for p in range(4)]
+    print(f"(d) relevancy-peak pixel index identical to the reference for {exact} / 4 maps; reference plateau sizes "
+          f"{gold['n_at_peak'].tolist()}; ours on the reference plateau: {on_plateau}")
+    assert all(on_plateau)
+    ClipWrapper.reset()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def test_e_vool_training_step_6_levels_vs_oracle_autograd():
+    from oracle import unet_oracle
+    from semabs_b200 import train
+    from semabs_b200.net import SemAbsVOOL
+    from tests._branches import branch_masks, count_branch_flips, oracle_on_our_branches, record_tapes
+
+    shape = (64, 64, 64)
+    args = dict(voxel_shape=shape, scene_bounds=BOUNDS, unet_num_channels=16, unet_f_maps=16, unet_num_groups=8,
+                unet_num_levels=6, network_inputs=["saliency"], use_pts_feat_extractor=True,
+                pts_feat_extractor_hidden_dim=128, reduce_method="max", device=dev, batch_size=1)
+    torch.manual_seed(41)
+    v = SemAbsVOOL(pointing_method="cosine_sim", pointing_dim=64, decoder_concat_xyz_pts=True, **args).to(dev)
+    B, D, n_in, n_out = 1, 3, 20000, 40000
+    g = torch.Generator().manual_seed(42)
+    lo, hi = torch.tensor(BOUNDS[0]), torch.tensor(BOUNDS[1])
+    xyz = lo + (hi - lo) * torch.rand(B, n_in, 3, generator=g)
+    oxyz = lo + (hi - lo) * (torch.rand(B, D, n_out, 3, generator=g) * 1.1 - 0.05)
+    tgt, refsal = torch.randn(B, D, n_in, 1, generator=g), torch.randn(B, D, n_in, 1, generator=g)
+    labels = (torch.rand(B, D, n_out, generator=g) < 0.1).float()
+    oob = torch.rand(B, D, n_out, generator=g) < 0.1
+    rel = [["behind"], ["on the left of"], ["in"]]
+    sd0 = {k: t.detach().cpu().clone() for k, t in v.state_dict().items()}
+    batch = dict(output_xyz_pts=oxyz.to(dev), spatial_relation_name=rel, input_xyz_pts=xyz.to(dev),
+                 input_target_saliency_pts=tgt.to(dev), input_reference_saliency_pts=refsal.to(dev),
+                 tsdf_vol=torch.ones(B, 1, device=dev), output_label_pts=labels.to(dev), out_of_bounds_pts=oob.to(dev))
+    with record_tapes() as tapes:
+        stats, _ = train.get_losses_vool(v, batch)
+    stats["loss"].backward()
+    masks = branch_masks(tapes, 6)
+    torch.set_num_threads(os.cpu_count())
+
+    def oracle_grads(ctx):
+        sd = {k: t.clone().requires_grad_(t.dtype.is_floating_point and not k.endswith("steps")) for k, t in sd0.items()}
+        with ctx:
+            out_ref = unet_oracle.semabsvool_forward(sd, xyz, tgt, refsal, oxyz, rel, BOUNDS, shape, concat_xyz=True)
+        loss_ref = torch.nn.functional.binary_cross_entropy_with_logits(out_ref, labels)
+        loss_ref.backward()
+        return sd, loss_ref, out_ref.detach()
+
+    def errors(sd):
+        errs = {}
+        for name, p in v.named_parameters():
+            r = sd[name].grad
+            if r is None:
+                assert p.grad is None, name
+                continue
+            assert p.grad is not None, name
+            if r.norm() > 0:
+                errs[name] = ((p.grad.cpu().double() - r.double()).norm() / r.double().norm()).item()
+        return sorted(errs.items(), key=lambda kv: -kv[1])
+
+    # 1) like with like: the oracle differentiates the ReLU branches our forward took
+    sd, loss_ref, out_ref = oracle_grads(oracle_on_our_branches(masks))
+    assert abs(stats["loss"].item() - loss_ref.item()) < TOL * abs(loss_ref.item())
+    ranked = errors(sd)
+    med = ranked[len(ranked) // 2][1]
+    print(f"(e) VOOL step, 6 levels, 64^3, 3 descriptions: loss {stats['loss'].item():.6f} vs {loss_ref.item():.6f}; "
+          f"gradient ||d||/||ref|| over {len(ranked)} tensors: worst {ranked[0][1]:.1e} ({ranked[0][0]}), median {med:.1e}, "
+          f"tensors above 2e-3: {sum(e >= 2e-3 for _, e in ranked)}")
+    assert med < 1e-3 and ranked[0][1] < 3e-2 and sum(e >= 2e-3 for _, e in ranked) <= 4
+    # 2) un-borrowed: the oracle takes its OWN branches; report how many pre-activations landed on the other side
+    flips = {}
+    sd2, _, _ = oracle_grads(count_branch_flips(masks, flips))
+    ranked2 = errors(sd2)
+    total = sum(m.numel() for m in masks)
+    print(f"(e) un-borrowed oracle: {flips['n']} of {total} ReLU pre-activations took the other branch "
+          f"({flips['n'] / total:.1e}); gradient errors then: worst {ranked2[0][1]:.1e} ({ranked2[0][0]}), "
+          f"median {ranked2[len(ranked2) // 2][1]:.1e}")
+    assert flips["n"] <= max(20, 2e-5 * total), "more flipped ReLU branches than fp32 rounding of the forward explains"
+    assert ranked2[len(ranked2) // 2][1] < 1e-3

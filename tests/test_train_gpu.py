@@ -188,3 +188,85 @@ def test_semabsvool_training_step_matches_oracle():
     assert v.completion_net.visual_sampler.mlp[0].weight.grad is None
     assert v.relation_embeddings["on"].grad is None and v.relation_embeddings["behind"].grad is not None
     assert float(v.steps) == 1.0
+
+
+def test_forward_after_optimizer_steps_uses_the_updated_weights():
+    """train.Lamb updates parameters through raw device pointers, which does not move torch's version
+    counters; the cached fp16 weight packs of the UNet (forward and adjoint) must be rebuilt anyway.  Three train steps,
+    then a forward that must match the oracle evaluated on the UPDATED master weights (and differ from step 0's)."""
+    from oracle import unet_oracle
+    from semabs_b200 import train
+    from semabs_b200.net import SemAbs3D
+
+    torch.manual_seed(51)
+    m = SemAbs3D(**_semabs_args()).to(dev)
+    B, P, n_in, n_out = 1, 2, 3000, 5000
+    xyz, feat, oxyz = _points(52, B, P, n_in, n_out)
+    g = torch.Generator().manual_seed(53)
+    labels = (torch.rand(B, P, n_out, generator=g) < 0.3).float()
+    batch = dict(input_xyz_pts=xyz.to(dev), input_feature_pts=feat.to(dev), tsdf_vol=torch.ones(B, 1, device=dev),
+                 output_xyz_pts=oxyz.to(dev), output_label_pts=labels.to(dev),
+                 out_of_bounds_pts=torch.zeros(B, P, n_out, dtype=torch.bool, device=dev),
+                 out_of_frustum_pts_mask=torch.zeros(B, P, n_out, dtype=torch.bool, device=dev), patch_labels=[("a",), ("b",)])
+    with torch.no_grad():
+        out0 = m(**batch).cpu()
+    opt = train.Lamb(m.parameters(), lr=2e-2, weight_decay=1e-5)
+    losses = [train.train_step(m, batch, train.get_losses_ovssc, opt, grad_max_norm=2.0)["loss"].item() for _ in range(3)]
+    with torch.no_grad():
+        out3 = m(**batch).cpu()
+        ref3 = unet_oracle.semabs3d_forward({k: v.cpu() for k, v in m.state_dict().items()}, xyz, feat, oxyz, BOUNDS, (16, 16, 16))
+    moved = ((out3 - out0).abs().max() / out0.abs().max()).item()
+    err = ((out3 - ref3).abs().max() / ref3.abs().max()).item()
+    print(f"after 3 LAMB steps: logits moved by {moved:.2e}, forward vs oracle on the updated weights {err:.2e}, losses {losses}")
+    assert moved > 1e-2, "the optimiser did not change the network output at all"
+    assert err < 1e-3, "forward after optimiser steps does not use the updated weights"
+    assert losses[2] < losses[0]
+    # the next training step must also see them (same check through the tape path): loss == oracle loss on updated weights
+    stats, _ = train.get_losses_ovssc(m, batch)
+    loss_ref = torch.nn.functional.binary_cross_entropy_with_logits(ref3, labels)
+    assert abs(stats["loss"].item() - loss_ref.item()) < 1e-3 * abs(loss_ref.item())
+
+
+def test_lamb_param_groups_global_clip_and_state_reload():
+    """ADVICE r01 (medium x2): the folded clip uses the GLOBAL gradient norm over all param groups (clip_grad_norm_ over
+    net.parameters(), utils.py:415), and optimizer.load_state_dict() after a step must not leave the kernel pointing at
+    the old moment buffers."""
+    import copy
+
+    from oracle import train_oracle
+    from semabs_b200 import train
+
+    g = torch.Generator().manual_seed(5)
+    shapes = [(3000,), (40, 30), (7,), (100000,)]
+    init = [torch.randn(*s, generator=g) for s in shapes]
+    cpu = [t.clone() for t in init]
+    state = [dict() for _ in cpu]
+    params = [torch.nn.Parameter(t.clone().to(dev)) for t in init]
+    wds = [0.01, 0.01, 0.0, 0.0]
+    opt = train.Lamb([{"params": params[:2], "weight_decay": 0.01}, {"params": params[2:], "weight_decay": 0.0}], lr=1e-2)
+
+    def one_step(optimizer, step):
+        grads = [torch.randn(*s, generator=g) * (5.0 if step % 2 == 0 else 1e-3) for s in shapes]
+        for p, gr in zip(params, grads):
+            p.grad = gr.clone().to(dev)
+        total, coef = train_oracle.clip_coefficient(grads, 2.0)
+        for i in range(len(cpu)):
+            train_oracle.lamb_step([cpu[i]], [grads[i] * coef], [state[i]], lr=1e-2, weight_decay=wds[i])
+        optimizer.step(max_grad_norm=2.0)
+        assert abs(optimizer.last_grad_norm.item() - total.item()) < 1e-4 * total.item()
+        for a, p in zip(cpu, params):
+            assert torch.allclose(a, p.data.cpu(), rtol=2e-5, atol=1e-6), (step, (a - p.data.cpu()).abs().max())
+
+    one_step(opt, 0)
+    one_step(opt, 1)
+    saved = copy.deepcopy(opt.state_dict())
+    opt2 = train.Lamb([{"params": params[:2], "weight_decay": 0.01}, {"params": params[2:], "weight_decay": 0.0}], lr=1e-2)
+    opt2.load_state_dict(saved)
+    one_step(opt2, 2)
+    # ... and reloading into an optimiser that has ALREADY stepped (cached tables) must switch to the loaded moments
+    old_m = [opt.state[p]["exp_avg"] for p in params]
+    opt.load_state_dict(copy.deepcopy(opt2.state_dict()))
+    assert all(opt.state[p]["exp_avg"].data_ptr() != o.data_ptr() for p, o in zip(params, old_m))
+    one_step(opt, 3)
+    for p in params:
+        assert torch.equal(opt.state[p]["exp_avg"], opt.state[p]["exp_avg"]) and opt.state[p]["step"] == 4
