@@ -66,39 +66,23 @@ def get_bce_weight(output_label_pts: torch.Tensor, balance_positive_negative: bo
     return w * (float(w.numel()) / w.sum())
 
 
-def get_losses_ovssc(net, batch: dict, balance_positive_negative: bool = False, **kwargs):
-    """Loss / accuracy of train_ovssc.get_losses (train_ovssc.py:81-150): padding patches (label ""), out-of-bounds and
-    out-of-frustum points are ignored; BCE-with-logits, mean over the kept points."""
-    import numpy as np
+def get_losses_ovssc(net, batch: dict, **kwargs):
+    """= semabs_b200.train_ovssc.get_losses (the reference's train_ovssc.get_losses contract: stats + per-cutoff DataFrame)."""
+    from .train_ovssc import get_losses
 
-    outputs = net(**batch)
-    labels = batch["output_label_pts"]
-    ignore = torch.zeros_like(outputs, dtype=torch.bool)
-    if "patch_labels" in batch:
-        pad = torch.from_numpy(np.array(batch["patch_labels"]).T == "").to(outputs.device)
-        ignore[pad] = True
-    ignore |= batch["out_of_bounds_pts"].view(outputs.shape).bool()
-    ignore |= batch["out_of_frustum_pts_mask"].view(outputs.shape).bool()
-    w = get_bce_weight(labels, balance_positive_negative)
-    loss, acc = _BceFn.apply(outputs.contiguous(), labels, w, ignore)
-    return {"loss": loss, "accuracy": acc}, None
+    batch.setdefault("scene_id", [f"scene_{i}" for i in range(batch["output_label_pts"].shape[0])])
+    return get_losses(net, batch, **kwargs)
 
 
-def get_losses_vool(net, batch: dict, balance_positive_negative: bool = False, **kwargs):
-    """train_vool.get_losses (train_vool.py:118-185): the loss runs over ALL points, only the accuracy honours the
-    padding ("[pad]" relations) / out-of-bounds mask."""
-    import numpy as np
+def get_losses_vool(net, batch: dict, **kwargs):
+    """= semabs_b200.train_vool.get_losses."""
+    from .train_vool import get_losses
 
-    outputs = net(**batch)
-    labels = batch["output_label_pts"]
-    w = get_bce_weight(labels, balance_positive_negative)
-    loss, _ = _BceFn.apply(outputs.contiguous(), labels, w, None)
-    ignore = torch.zeros_like(outputs, dtype=torch.bool)
-    pad = torch.from_numpy(np.array(batch["spatial_relation_name"]).T == "[pad]").to(outputs.device)
-    ignore[pad] = True
-    ignore |= batch["out_of_bounds_pts"].view(outputs.shape).bool()
-    _, acc, _ = bce_with_logits_masked(outputs.detach().contiguous(), labels, None, ignore, need_grad=False)
-    return {"loss": loss, "accuracy": acc}, None
+    B, D = batch["output_label_pts"].shape[:2]
+    batch.setdefault("scene_id", [f"scene_{i}" for i in range(B)])
+    for k in ("target_obj_name", "reference_obj_name"):
+        batch.setdefault(k, [[""] * B for _ in range(D)])
+    return get_losses(net, batch, **kwargs)
 
 
 def train_step(net, batch: dict, get_losses_fn, optimizer, grad_max_norm: float = 1e5, lr_scheduler=None, **kwargs):
