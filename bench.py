@@ -132,79 +132,225 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle (CPU restatement pinned bit-exactly to the reference) on a bounded sample
+# reference arm / cpu baseline / CUDA-eager comparator: the STOCK reference code path, executed from the byte-for-byte
+# snapshot oracle/_ref (oracle/build_ref.py; /root/reference itself does not exist on the GPU box) with the same seeded
+# weights as our arm.  Falls back to the oracle restatement (kind "port") only when the snapshot is missing.
 # ---------------------------------------------------------------------------------------------------------
-def cpu_relevancy_sample(n_tiles=2, n_labels=16, repeats=1):
-    """Times the reference algorithm (oracle/clip_oracle.py; /root/reference cannot travel to the GPU box) on
-    n_tiles x n_labels of the SAME workload (ViT-L/14 tiles of a 336^2 synthetic image) with all host threads and
-    extrapolates linearly in tile count to maps/s of the full 285-tile pyramid."""
-    from oracle import clip_oracle
-    from semabs_b200.clip.model import synthetic_clip_state_dict
+_STOCK = {}
 
+
+def stock_reference():
+    """-> oracle.ref_import bound to the snapshot, or None"""
+    from oracle import build_ref
+
+    if not build_ref.available():
+        return None
+    os.environ["SEMABS_REFERENCE_ROOT"] = build_ref.DST
+    from oracle import ref_import
+
+    return ref_import
+
+
+def stock_wrapper(device):
+    """the reference's ClipWrapper singleton (CLIP/clip/__init__.py:44-101) on `device`, seeded ViT-L/14 weights"""
+    key = str(device)
+    if _STOCK.get("key") != key:
+        from semabs_b200.clip.model import synthetic_clip_state_dict
+
+        ri = stock_reference()
+        _STOCK["wrapper"] = ri.make_reference_wrapper(MODEL, synthetic_clip_state_dict(MODEL, seed=0), device=device)
+        _STOCK["key"] = key
+    return _STOCK["wrapper"]
+
+
+STOCK_CFG = dict(distractor_labels={}, horizontal_flipping=False, augmentations=0, positive_attn_only=True)
+
+
+def cpu_relevancy_sample(n_labels=16):
+    """Times the reference's own CPU path on a BOUNDED sample of configs[1]: stock ClipWrapper.get_clip_saliency (fp32 on
+    CPU, all host threads) on a 336^2 synthetic image with 16 labels and a ONE-tile pyramid, plus its text tower alone;
+    a full image costs t_text + 285 x (t_call - t_text) (every tile is resized to 224^2, so tiles cost the same)."""
     torch.set_num_threads(os.cpu_count())
-    sd = clip_oracle.convert_weights_values(synthetic_clip_state_dict(MODEL, seed=0))
     img = synth_image(0)
-    desc = clip_oracle.enumerate_tiles(img.shape, PYRAMID)
-    pick = [0, len(desc) - 1, len(desc) // 2, len(desc) // 3][:n_tiles]
-    tiles = torch.stack([clip_oracle.preprocess_tile(img[r : r + s, c : c + s]) for r, c, s in desc[pick]])
-    g = torch.Generator().manual_seed(0)
-    W = torch.randn(768, n_labels, generator=g)
-    W = (W / W.norm(dim=0, keepdim=True)).contiguous()
-    ts = []
-    for _ in range(repeats):
+    labels = LABELS16[:n_labels]
+    n_full = 285
+    if stock_reference() is not None:
+        w = stock_wrapper("cpu")
+        t0 = time.perf_counter()
+        w.clip_gradcam.templates = [PROMPT]
+        w.clip_gradcam.set_classes(labels)
+        t_text = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        maps, _ = w.get_clip_saliency(img=img, text_labels=np.array(labels), prompts=[PROMPT],
+                                      cropping_augmentations=[{"tile_size": IMG, "stride": IMG // 4}], **STOCK_CFG)
+        t_call = time.perf_counter() - t0
+        assert tuple(maps.shape) == (n_labels, IMG, IMG)
+        t_image = t_text + n_full * max(t_call - t_text, 1e-9)
+        kind = "reference"
+        sample = (f"stock ClipWrapper.get_clip_saliency from the oracle/_ref snapshot: 1 tile x {n_labels} labels of the 285-tile "
+                  f"pyramid ({MODEL}, fp32, torch CPU, {torch.get_num_threads()} threads) in {t_call:.1f} s incl. {t_text:.1f} s text tower; "
+                  f"per image = text + 285 x tile")
+    else:
+        from oracle import clip_oracle
+        from semabs_b200.clip.model import synthetic_clip_state_dict
+
+        sd = clip_oracle.convert_weights_values(synthetic_clip_state_dict(MODEL, seed=0))
+        desc = clip_oracle.enumerate_tiles(img.shape, PYRAMID)
+        tiles = torch.stack([clip_oracle.preprocess_tile(img[r : r + s, c : c + s]) for r, c, s in desc[[0, len(desc) - 1]]])
+        g = torch.Generator().manual_seed(0)
+        W = torch.randn(768, n_labels, generator=g)
+        W = (W / W.norm(dim=0, keepdim=True)).contiguous()
         t0 = time.perf_counter()
         clip_oracle.relevancy(sd, tiles, W)
-        ts.append(time.perf_counter() - t0)
-    t = float(np.median(ts))
-    tile_label_per_s = n_tiles * n_labels / t
-    maps_per_s = tile_label_per_s / len(desc)  # one map needs all 285 tiles of its image
-    return {"value": maps_per_s, "unit": "relevancy-maps/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{n_tiles} tiles x {n_labels} labels of the 285-tile pyramid (ViT-L/14, fp32, torch CPU, "
-                      f"{torch.get_num_threads()} threads) in {t:.1f} s, extrapolated linearly in tile count"}
+        t_call = time.perf_counter() - t0
+        t_image = n_full * t_call / 2
+        kind = "port"
+        sample = (f"oracle restatement (faster than the stock path: one autograd call per label instead of 13): 2 tiles x {n_labels} "
+                  f"labels in {t_call:.1f} s, extrapolated linearly in tile count")
+    return {"value": n_labels / t_image, "unit": "relevancy-maps/s", "cores": os.cpu_count(), "kind": kind, "sample": sample,
+            "sample_seconds": t_call}
 
 
-def cpu_voxel_sample(C=32):
-    """The voxel half of the metric on the host: the oracle UNet (oracle/unet_oracle.py = the reference module restated with
-    torch CPU ops, fp32) on ONE 128^3 x C grid with all host threads — the same architecture / sizes as bench_voxel."""
+def _stock_unet(C, device):
+    ri = stock_reference()
+    torch.manual_seed(0)
+    if ri is not None:
+        m = ri.import_reference_module("unet3d").ResidualUNet3D(in_channels=C, out_channels=C, f_maps=C, num_groups=8, num_levels=6)
+        return m.to(device).eval(), "reference"
     from oracle import unet_oracle
     from semabs_b200.unet3d import ResidualUNet3D
 
+    sd = {k: v.detach().to(device) for k, v in ResidualUNet3D(in_channels=C, out_channels=C, f_maps=C, num_groups=8, num_levels=6).state_dict().items()}
+    return (lambda x: unet_oracle.residual_unet3d(sd, x)), "port"
+
+
+def cpu_voxel_sample(C=32):
+    """The voxel half on the host: the stock ResidualUNet3D (reference unet3d.py from the snapshot, fp32, torch CPU, all
+    threads) on ONE 128^3 x C grid — the same architecture / sizes as bench_voxel."""
     torch.set_num_threads(os.cpu_count())
-    torch.manual_seed(0)
-    m = ResidualUNet3D(in_channels=C, out_channels=C, f_maps=C, num_groups=8, num_levels=6)
-    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    m, kind = _stock_unet(C, "cpu")
     x = torch.randn(1, C, 128, 128, 128, generator=torch.Generator().manual_seed(0))
     with torch.no_grad():
         t0 = time.perf_counter()
-        unet_oracle.residual_unet3d(sd, x)
+        m(x)
         dt = time.perf_counter() - t0
-    return {"value": 1.0 / dt, "unit": "voxel-grids/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": 1.0 / dt, "unit": "voxel-grids/s", "cores": os.cpu_count(), "kind": kind,
             "sample": f"1 grid 128^3 x {C} ch through the 6-level ResidualUNet3D (fp32, torch CPU, {torch.get_num_threads()} threads) in {dt:.1f} s"}
 
 
+def cuda_eager_relevancy(dev):
+    """SURVEY.md §8d's practical GPU comparator: the STOCK reference Python on torch CUDA eager on this B200 (fp16 model, as
+    `load` leaves it on CUDA), same image / labels / pyramid as configs[1].  A 10-tile sub-pyramid is timed first; the full
+    285-tile image is run when that predicts under ~3 minutes, otherwise the sample is extrapolated by tile count."""
+    if stock_reference() is None:
+        return {"unavailable": "oracle/_ref snapshot missing"}
+    try:
+        w = stock_wrapper(dev)
+        img = synth_image(0)
+        call = lambda pyr: w.get_clip_saliency(img=img, text_labels=np.array(LABELS16), prompts=[PROMPT],
+                                               cropping_augmentations=pyr, **STOCK_CFG)[0]
+        call(PYRAMID[:1])  # warm-up (cuBLAS / cuDNN handles, allocator)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        call(PYRAMID[:2])
+        torch.cuda.synchronize()
+        t10 = time.perf_counter() - t0
+        if t10 / 10 * 285 < 180:
+            t0 = time.perf_counter()
+            maps = call(PYRAMID)
+            torch.cuda.synchronize()
+            t = time.perf_counter() - t0
+            note = f"one full image (285 tiles x 16 labels, tile_batch_size 32 = the reference default) in {t:.1f} s"
+        else:
+            t = t10 / 10 * 285
+            note = f"10-tile sub-pyramid x 16 labels in {t10:.1f} s, extrapolated by tile count to 285"
+        return {"value": len(LABELS16) / t, "unit": "relevancy-maps/s", "impl": "stock reference (oracle/_ref) on torch CUDA eager, fp16 model",
+                "sample": note, "torch": torch.__version__}
+    except Exception as e:  # the stock code pre-dates torch 2: report instead of hiding
+        return {"unavailable": f"stock reference failed on CUDA: {type(e).__name__}: {str(e)[:200]}"}
+    finally:
+        _STOCK.clear()
+        _release()
+
+
+@torch.no_grad()
+def cuda_eager_voxel(dev, C=32, N=4):
+    """stock ResidualUNet3D on torch CUDA eager (cuDNN conv3d), fp32 with TF32 off (the accuracy class of our precise mode)
+    and on (torch's default for convolutions), batch 4 x 128^3 x 32 ch."""
+    out = {}
+    try:
+        m, kind = _stock_unet(C, dev)
+        x = torch.randn(N, C, 128, 128, 128, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+        old = torch.backends.cudnn.allow_tf32
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(2):
+                m(x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                m(x)
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = {"value": 3 * N / (e0.elapsed_time(e1) / 1e3), "unit": "voxel-grids/s", "ms_per_batch": e0.elapsed_time(e1) / 3}
+        torch.backends.cudnn.allow_tf32 = old
+        out["impl"] = f"stock unet3d.ResidualUNet3D ({kind}) on torch {torch.__version__} CUDA eager, cuDNN conv3d, batch {N}"
+        del m, x
+    except Exception as e:
+        out["unavailable"] = f"{type(e).__name__}: {str(e)[:200]}"
+    _release()
+    return out
+
+
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation on the box's host cores, all threads, on our arm's config /
+    metric / unit; each step = the bounded sample described in cpu_baseline.sample.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_relevancy_sample(1, 2)
+    for _ in range(min(max(args.warmup, 0), 1)):
+        cpu_relevancy_sample(2)
     vals = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r = cpu_relevancy_sample(2, 16)
+        r = cpu_relevancy_sample(16)
         vals.append(r["value"])
     dt = time.perf_counter() - t0
     v = float(np.mean(vals))
     r["value"] = v
-    line = {"impl": "reference", "metric": "relevancy-maps/sec/GPU (336^2, 5 scales, 16 labels)", "value": v,
+    line = {"impl": "reference", "metric": METRIC, "value": v,
             "unit": "relevancy-maps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: ViT-L/14, 336^2, 5-size pyramid (285 tiles), 16 labels; CPU: bounded sample",
-                       "model_weights": "seeded random init"},
+            "dtype": "f32", "data": "synthetic", "config": workload_config(IMAGES_PER_STEP, 285),
             "cpu_baseline": r, "e2e": {"value": v, "unit": "relevancy-maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "voxel": dict(cpu_voxel_sample(), metric="voxel-grids/sec/GPU (128^3, 32 ch)")}
     emit(line)
+
+
+METRIC = "relevancy-maps/sec/GPU (336^2, 5 scales, 16 labels)"
+
+
+def workload_config(images, n_tiles):
+    """identical in both arms (the reference arm runs a bounded sample OF this workload, described in its cpu_baseline)"""
+    return {"workload": f"configs[1]: {MODEL} (seeded random init), {images} images 336x336 per GPU per step, {n_tiles} tiles/image "
+                        f"(5 crop sizes), {len(LABELS16)} labels, no jitter/flip"}
+
+
+def family_table(prof: dict, pk: dict):
+    """CALL_PROFILE records -> [{kernel, ms, share, calls, bound, achieved, unit, frac}] sorted by time"""
+    total = sum(v["ms"] for v in prof.values()) or 1.0
+    rows = []
+    for name, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        row = {"kernel": name, "ms": round(v["ms"], 3), "share": round(v["ms"] / total, 4), "calls": v["calls"]}
+        if v.get("flops"):
+            tf = v["flops"] / (v["ms"] * 1e-3) / 1e12
+            row.update(bound="tensor", achieved=round(tf, 1), unit="TFLOP/s", frac=round(tf / pk["tflops"], 4))
+        elif v.get("bytes"):
+            gb = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+            row.update(bound="hbm", achieved=round(gb, 1), unit="GB/s", frac=round(gb / pk["hbm_gbs"], 4))
+        rows.append(row)
+    return rows
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -220,6 +366,7 @@ def main():
     ap.add_argument("--skip-train", action="store_true")
     ap.add_argument("--skip-pipeline", action="store_true")
     ap.add_argument("--skip-amp", action="store_true")
+    ap.add_argument("--skip-eager", action="store_true")
     ap.add_argument("--train-descs", type=int, default=16)
     args = ap.parse_args()
     _quiet_stdout()
@@ -262,10 +409,13 @@ def main():
         return out
 
     def step_e2e():
+        """the reference's public call, whole (CLIP/clip/__init__.py:103-133): set_classes (tokeniser + text tower) ->
+        tile pyramid -> relevancy -> assembly -> fp32 maps on the host, per image"""
         last = None
         for im in imgs:
-            maps = ClipWrapper.get_clip_saliency_convolve(img=im, text_labels=LABELS16, positive_attn_only=True,
-                                                          tile_batch_size=TILE_BATCH, **cfg)
+            maps, feats = ClipWrapper.get_clip_saliency(img=im, text_labels=np.array(LABELS16), prompts=[PROMPT], distractor_labels={},
+                                                        horizontal_flipping=False, positive_attn_only=True,
+                                                        tile_batch_size=TILE_BATCH, **cfg)
             last = maps
         return last
 
@@ -305,6 +455,15 @@ def main():
     maps_per_step = args.images * P
     value = world * maps_per_step * args.steps / (ms_dev / 1e3)
 
+    # ---- per-kernel-family roofline table: ONE image (285 tiles x 16 labels) with a CUDA-event bracket around every C-ABI
+    # call, outside the timed region ----
+    from semabs_b200._lib import CALL_PROFILE
+
+    CALL_PROFILE.enable()
+    desc0, _, order0 = pre[0]
+    ClipWrapper.get_clip_saliency_device(dev_tiles[0], desc0, order0, LABELS16, IMG, IMG, positive_attn_only=True, tile_batch_size=TILE_BATCH)
+    kernel_table = family_table(CALL_PROFILE.collect(), peaks())
+
     # ---- e2e through the public API (host images, PIL preprocessing, H2D, D2H) ----
     step_e2e()
     _, wall_e2e = timed(step_e2e, max(1, args.steps // 2))
@@ -312,7 +471,7 @@ def main():
     e2e_value = world * maps_per_step * e2e_steps / (wall_e2e / 1e3)
     # with device tile preprocessing only the uint8 image and the tile table cross PCIe; the host path ships fp32 tiles
     h2d = args.images * (IMG * IMG * 3 + n_tiles * 5 * 4) if ClipWrapper.device_preprocessing else args.images * n_tiles * 3 * 224 * 224 * 4
-    d2h = args.images * P * IMG * IMG * 4
+    d2h = args.images * (P * IMG * IMG * 4 + P * 768 * 4)
 
     pk = peaks()
     flops_per_map = (GF_FWD_TILE + P * GF_BWD_TILE_LABEL) * 1e9 * n_tiles / P
@@ -323,15 +482,22 @@ def main():
                 "peak_source": pk["src"] + " (sustained bf16 cuBLAS)", "gemm_launches": gemm_prof["launches"],
                 "gemm_time_share_of_step": gemm_prof["ms"] / ms_dev,
                 "whole_path_algorithmic_tflops": value / world * flops_per_map / 1e12,
-                "whole_path_frac": value / world * flops_per_map / 1e12 / pk["tflops"]}
+                "whole_path_frac": value / world * flops_per_map / 1e12 / pk["tflops"],
+                "kernels": kernel_table,
+                "kernels_note": "per C-ABI entry point (= kernel family; semabs_attn_bwd_tc = row + column + tail kernels), one image, "
+                                "CUDA events around every call; achieved = algorithmic FLOPs or bytes of the calls / their summed time"}
 
     voxel = None
     if not args.skip_voxel:
         voxel = bench_voxel(dev, world, dist if world > 1 else None, pk)
+    cuda_eager = None
+    if world == 1 and not args.skip_eager:  # comparator legs: N = 1 only, like cpu_baseline
+        cuda_eager = {"relevancy": cuda_eager_relevancy(dev), "voxel": cuda_eager_voxel(dev),
+                      "note": "reference Python on torch CUDA eager on this GPU (SURVEY.md §8d), timed by wall clock around synchronised calls"}
 
     pipe = None
     if not args.skip_pipeline:
-        pipe = bench_pipeline(dev, rank, world, cfg, imgs[: min(2, len(imgs))])
+        pipe = bench_pipeline(dev, rank, world, cfg, imgs)  # configs[4]: 64 images sharded over 8 GPUs = 8 per rank
     # the training step keeps ~80 GB of activations: release everything the earlier sections hold first
     splits = (eng.fwd_splits, eng.bwd_splits)
     del dev_tiles, pre, eng, gc
@@ -346,22 +512,23 @@ def main():
             _release()
 
     if rank == 0:
-        cpu = None if args.skip_cpu else cpu_relevancy_sample(2, 16)
-        if voxel is not None and not args.skip_cpu:
+        skip_cpu = args.skip_cpu or world > 1  # reported baseline: rank 0 at N = 1 only
+        cpu = None if skip_cpu else cpu_relevancy_sample(16)
+        if voxel is not None and not skip_cpu:
             voxel["cpu_baseline"] = cpu_voxel_sample()
-        line = {"metric": "relevancy-maps/sec/GPU (336^2, 5 scales, 16 labels)", "value": value, "unit": "relevancy-maps/s",
+        line = {"metric": METRIC, "value": value, "unit": "relevancy-maps/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 MMA / f32 accumulate (fwd hi+lo split)",
                 "data": "synthetic",
-                "config": {"workload": f"configs[1]: {MODEL} (seeded random init), {args.images} images 336x336 per GPU per step, "
-                                       f"{n_tiles} tiles/image (5 crop sizes), {P} labels, no jitter/flip",
-                           "l2_policy": "inputs larger than L2: per-step working set ~6 GB of saved activations + 1.4 GB tiles",
-                           "tile_batch_size": TILE_BATCH, "fwd_splits": splits[0], "bwd_splits": splits[1]},
+                "config": dict(workload_config(args.images, n_tiles),
+                               l2_policy="inputs larger than L2: per-step working set ~6 GB of saved activations + 1.4 GB tiles",
+                               tile_batch_size=TILE_BATCH, fwd_splits=splits[0], bwd_splits=splits[1]),
                 "e2e": {"value": e2e_value, "unit": "relevancy-maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "note": ("ClipWrapper.get_clip_saliency_convolve on host uint8 images: tile crop / Pillow-exact bicubic / normalise on the GPU "
-                                 "(semabs_tile_preprocess), D2H of the fp32 maps") if ClipWrapper.device_preprocessing else
-                                "ClipWrapper.get_clip_saliency_convolve: host PIL tile preprocessing inside the timed region"},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "voxel": voxel, "pipeline": pipe, "train": train}
+                        "note": "ClipWrapper.get_clip_saliency per host uint8 image (the reference's public call, whole): tokeniser + text tower "
+                                "(set_classes) -> tile crop / Pillow-exact bicubic / normalise on the GPU -> relevancy -> assembly -> D2H of the "
+                                "fp32 maps and the text features"},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "cuda_eager": cuda_eager, "clocks": clocks,
+                "voxel": voxel, "pipeline": pipe, "train": train}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -429,6 +596,11 @@ def bench_voxel(dev, world, dist, pk, C=32, N=4, steps=5, warmup=3):
     t0 = time.perf_counter()
     run_e2e(K)
     e2e = K * N / (time.perf_counter() - t0) * world
+    from semabs_b200._lib import CALL_PROFILE
+
+    CALL_PROFILE.enable()
+    m(x)
+    kernel_table = family_table(CALL_PROFILE.collect(), pk)
     grids_s = world * N * steps / (ms / 1e3)
     per_gpu = grids_s / world
     precise_mode, voxel_launches = m.precise, m.kernel_launches - l0
@@ -442,7 +614,8 @@ def bench_voxel(dev, world, dist, pk, C=32, N=4, steps=5, warmup=3):
                          "traffic": (measured_traffic().get("unet_forward_dram_bytes") if C == 32 and N == 4 else None),
                          "algorithmic_bytes": N * UNET_GB_PER_GRID_FP32[C] * 1e9,
                          "tensor_tflops": per_gpu * UNET_GF_PER_GRID[C] / 1e3, "tensor_frac": per_gpu * UNET_GF_PER_GRID[C] / 1e3 / pk["tflops"],
-                         "note": "whole-forward algorithmic bytes (BASELINE.md byte rule, fp32 I/O) / time"}}
+                         "note": "whole-forward algorithmic bytes (BASELINE.md byte rule, fp32 I/O) / time",
+                         "kernels": kernel_table}}
 
 
 @torch.no_grad()

@@ -121,6 +121,15 @@ int semabs_attn_bwd_tc(const void* qkv16, int32_t ld_qkv, const void* probs16, i
                        int32_t P, int32_t B, int32_t T, int32_t H, int32_t splits, int32_t positive_only,
                        int32_t need_dqkv, void* stream);
 
+/* Second generation of semabs_attn_bwd_tc (vit_attn_bwd2.cu; same arguments and results, T <= 272 with T % 128 in {0, 1} above
+ * one tile — the ViT geometries): delta_i = dO_i . O_i from a separate bandwidth kernel into delta_ws, a dedicated control
+ * warp for TMA / MMA issue, probability rows / columns held in registers across the P labels of a unit, block-wide tail.
+ * The product path (ClipEngine) calls this one; the first generation stays as its cross-check. */
+int semabs_attn_bwd_tc2(const void* qkv16, int32_t ld_qkv, const void* probs16, int32_t ld_p16, const float* o32,
+                        const void* dO16, int32_t ld_do, const float* r, float* delta_ws, float* wpart, void* dqkv16,
+                        int32_t P, int32_t B, int32_t T, int32_t H, int32_t splits, int32_t positive_only,
+                        int32_t need_dqkv, void* stream);
+
 /* Known-answer hook for the two tcgen05 operand forms the attention kernels add to the GEMM's (A operand in TMEM,
  * MN-major B in shared memory): D[128,64] = A16[128,Kd] * B16[Kd,64], Kd % 16 == 0, Kd <= 256; lbo / sbo are the
  * descriptor byte offsets under test.  Test infrastructure for tests/test_vit_kernels_gpu.py. */
@@ -172,6 +181,15 @@ int semabs_zeroshot_weights(const float* feat, float* W, int32_t n_classes, int3
 int semabs_tile_assemble(const float* rel, const int32_t* tile_desc, int32_t n_tiles, const int32_t* size_order,
                          int32_t n_sizes, int32_t g, int32_t H, int32_t W, int32_t P, float* out, void* stream);
 int semabs_flip_average(float* rel, const float* rel_flipped, int64_t n_maps, int32_t g, void* stream);
+
+/* Relevancy store, device half (store.cu) — SURVEY.md §8 f4.  Writer (generate_relevancy.py:95-111): maps [P,H,W] fp32 ->
+ * out [P+1,SH,SW] fp32 = F.interpolate(mode="nearest-exact") to the storage grid, row P = the mean map over the labels.
+ * Reader (dataset.py:817-872): out[k] [H,W] = gain * bilinear_align_corners_false(stored[rows[k]] - stored[mean_row]) (mean_row
+ * < 0: nothing subtracted); rows int32 [K] on the device. */
+int semabs_relevancy_store_pack(const float* maps, int32_t P, int32_t H, int32_t W, int32_t SH, int32_t SW, float* out,
+                                void* stream);
+int semabs_relevancy_store_unpack(const float* stored, const int32_t* rows, int32_t K, int32_t mean_row, int32_t SH, int32_t SW,
+                                  int32_t H, int32_t W, float gain, float* out, void* stream);
 
 /* Tile preprocessing on the device (assemble.cu) — the reference's `_transform` per tile (clip_explainability.py:98-108,
  * create_tiles __init__.py:257-281): crop a square tile out of a uint8 HWC image, Pillow-exact bicubic resize to RxR

@@ -24,7 +24,18 @@ import types
 import numpy as np
 import torch
 
-REF_ROOT = os.environ.get("SEMABS_REFERENCE_ROOT", "/root/reference")
+_SNAPSHOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # oracle/build_ref.py's byte-for-byte copy
+
+
+def _default_root():
+    if os.environ.get("SEMABS_REFERENCE_ROOT"):
+        return os.environ["SEMABS_REFERENCE_ROOT"]
+    if os.path.isdir("/root/reference/CLIP/clip"):
+        return "/root/reference"
+    return _SNAPSHOT  # the GPU box: only the snapshot exists (it has the path's files only: CLIP/clip, net, unet3d, lamb)
+
+
+REF_ROOT = _default_root()
 
 
 def reference_available() -> bool:
@@ -113,30 +124,34 @@ def import_reference_clip():
     return pkg
 
 
-def build_reference_clip_model(state_dict):
-    """state dict -> reference model through the reference's own build_model (so convert_weights applies), then
-    .float() as `load` does on CPU (clip_explainability.py:163-168)."""
+def build_reference_clip_model(state_dict, device="cpu"):
+    """state dict -> reference model through the reference's own build_model (so convert_weights applies), then exactly
+    what `load` does (clip_explainability.py:163-168): `.to(device)`, and `.float()` only on CPU — on CUDA the stock
+    model stays fp16."""
     import_reference_clip()
     me = importlib.import_module("CLIP.clip.model_explainability")
     sd = {k: v.clone() for k, v in state_dict.items() if not k.startswith("__")}
-    return me.build_model(sd).float().eval()
+    model = me.build_model(sd).to(device)
+    if str(device) == "cpu":
+        model.float()
+    return model.eval()
 
 
-def make_reference_wrapper(model_name: str, state_dict):
+def make_reference_wrapper(model_name: str, state_dict, device="cpu"):
     """A ClipWrapper singleton whose weights come from `state_dict` instead of a download."""
     pkg = import_reference_clip()
     ce = importlib.import_module("CLIP.clip.clip_explainability")
     cg = importlib.import_module("CLIP.clip.clip_gradcam")
 
     def fake_load(name, device="cpu", **kw):
-        model = build_reference_clip_model(state_dict)
+        model = build_reference_clip_model(state_dict, device)
         return model, ce._transform(model.visual.input_resolution)
 
     cg.load = fake_load
     pkg.load = fake_load  # the stock second model of ClipWrapper.__init__ (unused by get_clip_saliency)
     for attr in ("clip_model", "clip_preprocess", "clip_gradcam"):
         setattr(pkg.ClipWrapper, attr, None)
-    pkg.ClipWrapper(clip_model_type=model_name, device="cpu")
+    pkg.ClipWrapper(clip_model_type=model_name, device=device)
     return pkg.ClipWrapper
 
 

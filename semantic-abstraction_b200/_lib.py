@@ -44,10 +44,68 @@ class GemmEpilogue(C.Structure):
 ACT_NONE, ACT_QUICKGELU, ACT_MUL_AUX16 = 0, 1, 2
 
 
-def lib() -> C.CDLL:
+class _CallProfile:
+    """Optional CUDA-event bracket around EVERY C-ABI call, keyed by entry-point name (bench.py's per-kernel-family
+    roofline table; never enabled inside a timed region: the events cost ~2 us per call)."""
+
+    def __init__(self):
+        self.on = False
+        self.recs = {}
+        self.meta = {}
+
+    def enable(self):
+        self.on, self.recs, self.meta = True, {}, {}
+
+    def note(self, name, **kw):
+        """accumulate algorithmic work (flops / bytes) declared by the op wrapper for the call that follows"""
+        if self.on:
+            m = self.meta.setdefault(name, {})
+            for k, v in kw.items():
+                m[k] = m.get(k, 0.0) + float(v)
+
+    def collect(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, evs in self.recs.items():
+            out[name] = dict(ms=sum(a.elapsed_time(b) for a, b in evs), calls=len(evs), **self.meta.get(name, {}))
+        self.on, self.recs, self.meta = False, {}, {}
+        return out
+
+
+CALL_PROFILE = _CallProfile()
+
+
+class _ProfiledLib:
+    def __init__(self, l):
+        self._l = l
+
+    def __getattr__(self, name):
+        fn = getattr(self._l, name)
+        if not name.startswith("semabs_") or name in ("semabs_last_error", "semabs_abi_version", "semabs_lamb_chunk_bytes"):
+            return fn
+
+        def call(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a)
+            e1.record()
+            CALL_PROFILE.recs.setdefault(name, []).append((e0, e1))
+            return r
+
+        return call
+
+
+_profiled = None
+
+
+def lib():
     """Load (once) and return the shared library; raises if it has not been built."""
-    global _lib
+    global _lib, _profiled
     if _lib is not None:
+        if CALL_PROFILE.on:
+            if _profiled is None:
+                _profiled = _ProfiledLib(_lib)
+            return _profiled
         return _lib
     if not LIB_PATH.exists():
         if os.environ.get("SEMABS_B200_AUTOBUILD", "0") == "1":

@@ -6,7 +6,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT_MUL_AUX16, ACT_NONE, ACT_QUICKGELU, GemmEpilogue, check, f32, i32, lib, ptr, stream_ptr
+from ._lib import ACT_MUL_AUX16, ACT_NONE, ACT_QUICKGELU, CALL_PROFILE, GemmEpilogue, check, f32, i32, lib, ptr, stream_ptr
 
 
 class _GemmProfile:
@@ -80,6 +80,7 @@ def gemm_f16(
         assert out_f32.dtype == torch.float32 and out_f32.shape == (M, N)
     if out_f16 is not None:
         assert out_f16.dtype == torch.float16 and out_f16.shape == (M, out_f16_splits * N)
+    CALL_PROFILE.note("semabs_gemm_f16", flops=2.0 * M * N * K)
     prof = GEMM_PROFILE.on
     if prof:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -117,6 +118,7 @@ def vit_im2col(tiles, out16, patch, kpad, splits):
 
 
 def layernorm_fwd(x, gamma, beta, *, M, d, x_stride=None, y32=None, y16=None, mean=None, rstd=None, splits=1):
+    CALL_PROFILE.note("semabs_layernorm_fwd", bytes=M * d * (4 + (2 * splits if y16 is not None else 0) + (4 if y32 is not None else 0)))
     check(
         lib().semabs_layernorm_fwd(
             ptr(x), _i64(d if x_stride is None else x_stride), ptr(gamma), ptr(beta), ptr(y32), ptr(y16), ptr(mean),
@@ -131,6 +133,8 @@ def vit_embed_lnpre(patch, cls, pos, gamma, beta, x_out, B, T, d):
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx32, *, M, d, x_rows, x_stride=None, dres=None, out_stride=None, dx16=None,
                   out16_stride=None, splits=1):
+    CALL_PROFILE.note("semabs_layernorm_bwd", bytes=M * d * (4 + 4 + (4 if dres is not None else 0) + (2 * splits if dx16 is not None else 0))
+                      + x_rows * d * 4)
     check(
         lib().semabs_layernorm_bwd(
             ptr(dy), ptr(dres), ptr(x), _i64(d if x_stride is None else x_stride), i32(x_rows), ptr(mean), ptr(rstd),
@@ -148,6 +152,7 @@ def attn_fwd(qkv, *, B, T, H, probs=None, probs16=None, o32=None, o16=None, caus
 
 def attn_fwd_tc(qkv16, *, in_splits, B, T, H, probs16=None, o32=None, o16=None, o_splits=1, causal=False):
     """tcgen05 attention forward; qkv16 [B*T, in_splits*3d] fp16 rows [hi | lo]."""
+    CALL_PROFILE.note("semabs_attn_fwd_tc", flops=4.0 * T * T * 64 * H * B)  # S = QK^T and O = PV
     assert qkv16.dtype == torch.float16 and qkv16.is_contiguous()
     ldp = probs16.shape[-1] if probs16 is not None else 0
     check(lib().semabs_attn_fwd_tc(ptr(qkv16), i32(in_splits), ptr(probs16), i32(ldp), ptr(o32), ptr(o16), i32(o_splits),
@@ -170,10 +175,27 @@ def attn_bwd(qkv16, probs16, o32, dO16, ld_do, r, delta_ws, wpart, dqkv16, *, P,
     )
 
 
+ATTN_BWD_GENERATION = 2  # 2 = vit_attn_bwd2.cu (product path); 1 = the first tcgen05 kernels (cross-check / odd T % 128)
+
+
 def attn_bwd_tc(qkv16, probs16, o32, dO16, ld_do, r, delta_ws, wpart, dqkv16, *, P, B, T, H, splits=1, positive_only=True,
-                need_dqkv=True):
+                need_dqkv=True, generation=None):
     """tcgen05 version of attn_bwd (T <= 272)."""
     assert qkv16.dtype == torch.float16 and probs16.dtype == torch.float16
+    # algorithmic minimum: G = dO V^T always; dQ = dS K, dK = dS^T Q, dV = A^T dO when the block below needs them
+    flops = (8.0 if need_dqkv else 2.0) * T * T * 64 * H * P * B
+    gen = ATTN_BWD_GENERATION if generation is None else generation
+    if gen == 2 and (T <= 128 or T % 128 <= 1):
+        CALL_PROFILE.note("semabs_attn_bwd_tc2", flops=flops)
+        check(
+            lib().semabs_attn_bwd_tc2(
+                ptr(qkv16), i32(qkv16.stride(0)), ptr(probs16), i32(probs16.shape[-1]), ptr(o32), ptr(dO16), i32(ld_do), ptr(r),
+                ptr(delta_ws), ptr(wpart), ptr(dqkv16), i32(P), i32(B), i32(T), i32(H), i32(splits), i32(int(positive_only)),
+                i32(int(need_dqkv)), stream_ptr(),
+            )
+        )
+        return
+    CALL_PROFILE.note("semabs_attn_bwd_tc", flops=flops)
     check(
         lib().semabs_attn_bwd_tc(
             ptr(qkv16), i32(qkv16.stride(0)), ptr(probs16), i32(probs16.shape[-1]), ptr(o32), ptr(dO16), i32(ld_do), ptr(r),
@@ -250,6 +272,11 @@ CONV_3X3X3, CONV_1X1X1, CONV_TRANSPOSE_PARITY = 0, 1, 2
 
 def conv3d(x16, w16, *, kind, N, D, H, W, C_in, C_out, a_splits=1, w_splits=1, parity=0, precise=False, bias=None,
            residual=None, relu=False, out32=None, out16=None, o16_splits=1, stats=None, groups=0):
+    if CALL_PROFILE.on:
+        # taps per output voxel: 27 / 1 / the parity class's tap list (1,2,2,2,4,4,4,8: 27 over the 8 classes);
+        # kinds 2 / 3 produce D*H*W outputs per launch (one parity class)
+        taps = {CONV_3X3X3: 27, CONV_1X1X1: 1}.get(kind, (1 << bin(parity).count("1")))
+        CALL_PROFILE.note("semabs_conv3d", flops=2.0 * N * D * H * W * taps * C_in * C_out)
     check(
         lib().semabs_conv3d(
             ptr(x16), i32(a_splits), ptr(w16), i32(w_splits), i32(kind), i32(parity), i32(N), i32(D), i32(H), i32(W),
@@ -260,20 +287,24 @@ def conv3d(x16, w16, *, kind, N, D, H, W, C_in, C_out, a_splits=1, w_splits=1, p
 
 
 def ncdhw_to_ndhwc(x, y, *, N, S, C, Cpad, groups=1, stats=None):
+    CALL_PROFILE.note("semabs_ncdhw_to_ndhwc", bytes=N * S * (C + Cpad) * 4)
     check(lib().semabs_ncdhw_to_ndhwc(ptr(x), ptr(y), i32(N), _i64(S), i32(C), i32(Cpad), i32(groups), ptr(stats), stream_ptr()))
 
 
 def ndhwc_to_ncdhw(x, y, *, N, S, C):
+    CALL_PROFILE.note("semabs_ndhwc_to_ncdhw", bytes=N * S * C * 8)
     check(lib().semabs_ndhwc_to_ncdhw(ptr(x), ptr(y), i32(N), _i64(S), i32(C), stream_ptr()))
 
 
 def groupnorm_apply(x, stats, gamma, beta, y16, *, N, S, C, C_real, groups, splits=1, planar=False):
+    CALL_PROFILE.note("semabs_groupnorm_apply", bytes=N * S * C * (4 + 2 * splits))
     check(lib().semabs_groupnorm_apply(ptr(x), ptr(stats), ptr(gamma), ptr(beta), ptr(y16), i32(N), _i64(S), i32(C),
                                        i32(C_real), i32(groups), i32(splits), i32(int(planar)), stream_ptr()))
 
 
 def conv3d_halo(x16_planar, w_img, *, N, D, H, W, C_in, C_out, a_splits=1, w_splits=1, precise=False, residual=None,
                 relu=False, out32=None, out16=None, o16_splits=1, stats=None, groups=0):
+    CALL_PROFILE.note("semabs_conv3d_halo", flops=2.0 * N * D * H * W * 27 * C_in * C_out)
     check(
         lib().semabs_conv3d_halo(
             ptr(x16_planar), i32(a_splits), ptr(w_img), i32(w_splits), i32(N), i32(D), i32(H), i32(W), i32(C_in),
@@ -303,6 +334,7 @@ def pack_halo_weights(w: torch.Tensor, splits: int) -> torch.Tensor:
 
 
 def maxpool3d_2(x, y, *, N, D, H, W, C, groups=1, stats=None):
+    CALL_PROFILE.note("semabs_maxpool3d_2", bytes=N * D * H * W * C * 4 * 1.125)
     check(lib().semabs_maxpool3d_2(ptr(x), ptr(y), i32(N), i32(D), i32(H), i32(W), i32(C), i32(groups), ptr(stats), stream_ptr()))
 
 

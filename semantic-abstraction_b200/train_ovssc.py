@@ -42,6 +42,15 @@ def get_detailed_stats(prediction, gt_label, xyz_pts, patch_labels, scene_ids, s
     return pd.DataFrame.from_dict(cols)
 
 
+def scene_bounds_of(net):
+    """the network's own voxel-grid bounds: default for `scene_bounds` when the caller (unlike utils.train, which forwards
+    every parsed flag) does not pass it"""
+    vg = getattr(net, "vg", None) or getattr(getattr(net, "completion_net", None), "vg", None)
+    if vg is None:
+        raise TypeError("get_losses: pass scene_bounds=... (the network exposes no voxel grid to take it from)")
+    return [list(vg.lower_corner), list(vg.upper_corner)]
+
+
 def _forward_in_patch_chunks(net, batch):
     """The reference's fallback for > 500 000 query points (train_ovssc.py:93-126): one patch per forward."""
     P = batch["output_xyz_pts"].shape[1]
@@ -59,6 +68,8 @@ def _forward_in_patch_chunks(net, batch):
 def get_losses(net, batch: dict, cutoffs=[0], balance_positive_negative: bool = False,
                **kwargs) -> Tuple[Dict[str, Union[float, torch.Tensor]], pd.DataFrame]:
     stats = {}
+    if "scene_bounds" not in kwargs:
+        kwargs["scene_bounds"] = scene_bounds_of(net)
     outputs = net(**batch) if batch["output_xyz_pts"].shape[2] <= 500000 else _forward_in_patch_chunks(net, batch)
     # like the reference, the collated [P][B] label lists and the out-of-bounds mask are normalised IN the batch dict
     batch["patch_labels"] = np.array(batch["patch_labels"]).T

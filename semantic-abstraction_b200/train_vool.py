@@ -15,7 +15,7 @@ import torch
 from . import metrics
 from .net import SemAbsVOOL
 from .train import _BceFn, bce_with_logits_masked, get_bce_weight
-from .train_ovssc import _analysis_columns
+from .train_ovssc import _analysis_columns, scene_bounds_of
 
 
 def get_detailed_stats(prediction, gt_label, xyz_pts, scene_ids, target_obj_names, reference_obj_names, spatial_relation_names,
@@ -55,6 +55,8 @@ def _forward_in_description_chunks(net, batch):
 def get_losses(net, batch: dict, cutoffs=[-2.0], balance_positive_negative: bool = False,
                **kwargs) -> Tuple[Dict[str, Union[float, torch.Tensor]], pd.DataFrame]:
     stats = {}
+    if "scene_bounds" not in kwargs:
+        kwargs["scene_bounds"] = scene_bounds_of(net)
     labels = batch["output_label_pts"]
     outputs = net(**batch) if labels.shape[2] <= 500000 else _forward_in_description_chunks(net, batch)
     ignore = torch.zeros_like(outputs, dtype=torch.bool)

@@ -9,8 +9,10 @@ reference by oracle/gen_golden*.py) — VERDICT r01 "next round" item 1:
                                                                                                 net.py:383-439
   (d) configs[0]: `generate_relevancy.py image` shape — matterport.png 976^2, ViT-B/32, 4 labels, "chefer_et_al" —
       against the committed REFERENCE output (tests/golden/config0_golden.npz) and the oracle at full size
-  (e) configs[3] shape: one SemAbsVOOL training step with a 6-level UNet (64^3) vs torch autograd through the oracle,
-      with AND without borrowing our ReLU branches (the un-borrowed run reports how many pre-activations flipped).
+  (e) configs[3] shape: one SemAbsVOOL training step at the reference defaults (128^3 grid, 6-level UNet, 80 k / 400 k
+      points; one description = two UNet passes, so that the CPU autograd oracle fits in host memory) vs torch autograd
+      through the oracle, with AND without borrowing our ReLU branches (the un-borrowed run reports how many
+      pre-activations flipped).
 
 Tolerances are BASELINE.json north_star's: fp32 maps / logits within 1e-3 relative (max|d| / max|ref|); arg-max / peak
 indices bit-exact — every test PRINTS the measured error and the exact number of index mismatches, and a mismatch is
@@ -205,13 +207,13 @@ def test_e_vool_training_step_6_levels_vs_oracle_autograd():
     from semabs_b200.net import SemAbsVOOL
     from tests._branches import branch_masks, count_branch_flips, oracle_on_our_branches, record_tapes
 
-    shape = (64, 64, 64)
+    shape = (128, 128, 128)  # 6 levels bottom out at 4^3, like the reference defaults (utils.py:38,59)
     args = dict(voxel_shape=shape, scene_bounds=BOUNDS, unet_num_channels=16, unet_f_maps=16, unet_num_groups=8,
                 unet_num_levels=6, network_inputs=["saliency"], use_pts_feat_extractor=True,
                 pts_feat_extractor_hidden_dim=128, reduce_method="max", device=dev, batch_size=1)
     torch.manual_seed(41)
     v = SemAbsVOOL(pointing_method="cosine_sim", pointing_dim=64, decoder_concat_xyz_pts=True, **args).to(dev)
-    B, D, n_in, n_out = 1, 3, 20000, 40000
+    B, D, n_in, n_out = 1, 1, 80000, 400000
     g = torch.Generator().manual_seed(42)
     lo, hi = torch.tensor(BOUNDS[0]), torch.tensor(BOUNDS[1])
     xyz = lo + (hi - lo) * torch.rand(B, n_in, 3, generator=g)
@@ -219,7 +221,7 @@ def test_e_vool_training_step_6_levels_vs_oracle_autograd():
     tgt, refsal = torch.randn(B, D, n_in, 1, generator=g), torch.randn(B, D, n_in, 1, generator=g)
     labels = (torch.rand(B, D, n_out, generator=g) < 0.1).float()
     oob = torch.rand(B, D, n_out, generator=g) < 0.1
-    rel = [["behind"], ["on the left of"], ["in"]]
+    rel = [["behind"]]
     sd0 = {k: t.detach().cpu().clone() for k, t in v.state_dict().items()}
     batch = dict(output_xyz_pts=oxyz.to(dev), spatial_relation_name=rel, input_xyz_pts=xyz.to(dev),
                  input_target_saliency_pts=tgt.to(dev), input_reference_saliency_pts=refsal.to(dev),
@@ -255,10 +257,12 @@ def test_e_vool_training_step_6_levels_vs_oracle_autograd():
     assert abs(stats["loss"].item() - loss_ref.item()) < TOL * abs(loss_ref.item())
     ranked = errors(sd)
     med = ranked[len(ranked) // 2][1]
-    print(f"(e) VOOL step, 6 levels, 64^3, 3 descriptions: loss {stats['loss'].item():.6f} vs {loss_ref.item():.6f}; "
+    print(f"(e) VOOL step, 6 levels, 128^3, 80k/400k points: loss {stats['loss'].item():.6f} vs {loss_ref.item():.6f}; "
           f"gradient ||d||/||ref|| over {len(ranked)} tensors: worst {ranked[0][1]:.1e} ({ranked[0][0]}), median {med:.1e}, "
           f"tensors above 2e-3: {sum(e >= 2e-3 for _, e in ranked)}")
-    assert med < 1e-3 and ranked[0][1] < 3e-2 and sum(e >= 2e-3 for _, e in ranked) <= 4
+    # gradient tolerance at FULL size (not part of north_star, which bounds maps / logits): the weight-gradient reductions run
+    # on single fp16 operands over 2 M voxels per grid; per tensor <= 1e-2, median <= 1e-3 (the 16^3 tests hold 2e-3 / 1e-3)
+    assert med < 1e-3 and ranked[0][1] < 1e-2, ranked[:5]
     # 2) un-borrowed: the oracle takes its OWN branches; report how many pre-activations landed on the other side
     flips = {}
     sd2, _, _ = oracle_grads(count_branch_flips(masks, flips))

@@ -116,10 +116,11 @@ def test_train_save_reload_continue(tmp_path, task):
         assert torch.equal(a, b), k
     for p, q in zip(net.parameters(), net2.parameters()):
         if p in opt.state:
-            assert opt2.state[q]["step"] == opt.state[p]["step"] == 3
+            assert opt2.state[q]["step"] == opt.state[p]["step"] <= 3  # (a relation embedding absent from a batch skips that step)
             assert torch.equal(opt.state[p]["exp_avg"], opt2.state[q]["exp_avg"]) and torch.equal(opt.state[p]["exp_avg_sq"], opt2.state[q]["exp_avg_sq"])
         else:
             assert q not in opt2.state or len(opt2.state[q]) == 0  # unused parameters never got optimiser state
+    assert max(st["step"] for st in opt.state.values() if st) == 3
     # step 4 on both (same batch, same learning rate)
     for g in opt2.param_groups:
         g["lr"] = opt.param_groups[0]["lr"]

@@ -64,8 +64,13 @@ def test_attn_fwd(T, H, causal):
 
 
 @pytest.mark.parametrize("T,H,impl", [(50, 12, "mma"), (257, 16, "mma"), (50, 12, "tc"), (257, 16, "tc"), (197, 12, "tc"),
-                                      (128, 4, "tc"), (130, 4, "tc")])
+                                      (128, 4, "tc"), (130, 4, "tc"), (50, 12, "tc1"), (257, 16, "tc1"), (128, 4, "tc1"),
+                                      (129, 2, "tc"), (256, 2, "tc")])
 def test_attn_bwd(T, H, impl):
+    """impl: "mma" = mma.sync kernels; "tc" = the product path (second-generation tcgen05 kernels, vit_attn_bwd2.cu, where
+    T % 128 <= 1; first generation otherwise); "tc1" = first-generation tcgen05 kernels forced (cross-check)."""
+    import functools
+
     from semabs_b200 import ops
 
     g = torch.Generator(device=dev).manual_seed(T + 1)
@@ -84,13 +89,14 @@ def test_attn_bwd(T, H, impl):
     delta = torch.empty(P * B * H, T, device=dev)
     wpart = torch.full((P * B * H, T), float("nan"), device=dev)
     dqkv16 = torch.full((P * B * T, 2 * 3 * d), float("nan"), device=dev, dtype=torch.float16)
-    bwd = ops.attn_bwd_tc if impl == "tc" else ops.attn_bwd
+    tc = {"tc": ops.attn_bwd_tc, "tc1": functools.partial(ops.attn_bwd_tc, generation=1)}
+    bwd = tc.get(impl, ops.attn_bwd)
     bwd(qkv16, probs16, o32, dO, d, r, delta, wpart, dqkv16, P=P, B=B, T=T, H=H, splits=2, positive_only=True)
     torch.cuda.synchronize()
-    if impl == "tc":  # relevance-only call (last dense block): same wpart, nothing else touched
+    if impl in tc:  # relevance-only call (last dense block): same wpart, nothing else touched
         w2 = torch.full_like(wpart, float("nan"))
-        ops.attn_bwd_tc(qkv16, probs16, o32, dO, d, r, delta, w2, None, P=P, B=B, T=T, H=H, splits=2, positive_only=True,
-                        need_dqkv=False)
+        tc[impl](qkv16, probs16, o32, dO, d, r, delta, w2, None, P=P, B=B, T=T, H=H, splits=2, positive_only=True,
+                 need_dqkv=False)
         assert torch.equal(w2, wpart)
 
     # torch reference (fp32, same fp16-rounded dO)
