@@ -182,6 +182,12 @@ int semabs_tile_assemble(const float* rel, const int32_t* tile_desc, int32_t n_t
                          int32_t n_sizes, int32_t g, int32_t H, int32_t W, int32_t P, float* out, void* stream);
 int semabs_flip_average(float* rel, const float* rel_flipped, int64_t n_maps, int32_t g, void* stream);
 
+/* ColorJitter on the device (jitter.cu) — the reference's test-time augmentation copies (CLIP/clip/__init__.py:55-57,246-247).
+ * One operation of torchvision's tensor implementation on a uint8 HWC image: op 0 brightness, 1 contrast, 2 saturation,
+ * 3 hue, `factor` as drawn by ColorJitter.get_params.  in / out [npix, 3] uint8 (may alias for ops 0-2 only when equal);
+ * scratch8: 8 bytes of device memory (contrast's grey-image sum). */
+int semabs_color_jitter_op(const uint8_t* in, uint8_t* out, int64_t npix, int32_t op, float factor, void* scratch8, void* stream);
+
 /* Relevancy store, device half (store.cu) — SURVEY.md §8 f4.  Writer (generate_relevancy.py:95-111): maps [P,H,W] fp32 ->
  * out [P+1,SH,SW] fp32 = F.interpolate(mode="nearest-exact") to the storage grid, row P = the mean map over the labels.
  * Reader (dataset.py:817-872): out[k] [H,W] = gain * bilinear_align_corners_false(stored[rows[k]] - stored[mean_row]) (mean_row

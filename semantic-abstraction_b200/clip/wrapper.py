@@ -342,12 +342,15 @@ class ClipWrapper:
             cls._coef_cache[key] = (torch.from_numpy(coef).to(dev), torch.from_numpy(bounds).to(dev))
         coef_d, bounds_d = cls._coef_cache[key]
         n = len(tile_desc)
-        per_img = n // len(images)
+        n_images = len(images) + len(cls._jitter_params)
+        per_img = n // n_images
         table = np.zeros((n, 5), np.int32)
         table[:, 0] = np.arange(n) // per_img
         table[:, 1:4] = tile_desc
         table[:, 4] = np.searchsorted(np.asarray(sizes), tile_desc[:, 2])
         imgs_d = torch.from_numpy(np.ascontiguousarray(np.stack(images))).pin_memory().to(dev, non_blocking=True)
+        if cls._jitter_params:  # the augmentation copies, made here on the device from the uploaded original
+            imgs_d = torch.stack([imgs_d[0]] + [ops.color_jitter(imgs_d[0], *prm) for prm in cls._jitter_params])
         table_d = torch.from_numpy(table).pin_memory().to(dev, non_blocking=True)
         mean, std = [float(v) for v in _MEAN.flatten()], [float(v) for v in _STD.flatten()]
 
@@ -408,43 +411,77 @@ class ClipWrapper:
         H, W = kwargs["img"].shape[:2]
         batches = cls._device_preprocessed_batches(tile_desc, n_px, tile_batch_size) if cls.device_preprocessing else None
         if batches is None:
+            if cls._jitter_params:  # host path: make the SAME jitter copies with PIL, like the reference
+                tile_desc, crops, size_order = cls.enumerate_crops(host_jitter=True, jitter_params=cls._all_jitter_params, **kwargs)
             batches = cls._device_batches(crops, n_px, tile_batch_size)
         out = cls.get_clip_saliency_device(batches, tile_desc, size_order, text_labels, H, W, horizontal_flipping,
                                            positive_attn_only, tile_batch_size, prompt_batch_size)
         return out if kwargs.get("keep_on_device", False) else out.cpu()
 
+    device_jitter = True  # ColorJitter copies of the "ours" TTA made on the GPU (semabs_color_jitter_op), not by PIL on the host
+    _jitter_params: list = []
+
+    @staticmethod
+    def _jitter_on_host(img_pil, params):
+        """what ColorJitter.forward does to a PIL image for drawn parameters (the reference's path, __init__.py:246-247)"""
+        import torchvision.transforms.functional as TF
+
+        fn_idx, b, c, s, h = params
+        for fn_id in fn_idx:
+            if fn_id == 0 and b is not None:
+                img_pil = TF.adjust_brightness(img_pil, b)
+            elif fn_id == 1 and c is not None:
+                img_pil = TF.adjust_contrast(img_pil, c)
+            elif fn_id == 2 and s is not None:
+                img_pil = TF.adjust_saturation(img_pil, s)
+            elif fn_id == 3 and h is not None:
+                img_pil = TF.adjust_hue(img_pil, h)
+        return img_pil
+
     @classmethod
-    def enumerate_crops(cls, img, augmentations, cropping_augmentations, **kwargs):
+    def enumerate_crops(cls, img, augmentations, cropping_augmentations, host_jitter=None, jitter_params=None, **kwargs):
         """Tile enumeration in the reference's order (__init__.py:238-282): image copies (original + ColorJitter
         draws) -> crop sizes -> column offset -> row offset. Returns (tile_desc int32 [n,3] = (row0,col0,size),
-        list of uint8 crops (views), size order)."""
+        list of uint8 crops (views), size order).  The jitter parameters are drawn exactly like ColorJitter.forward draws
+        them (same torch RNG consumption as the reference); with `device_jitter` the copies themselves are produced on the
+        GPU later (`_device_preprocessed_batches`) and the crop list only covers the original image."""
         assert type(img) == np.ndarray
         cls.check_initialized()
+        jt = cls.jittering_transforms
+        if host_jitter is None:
+            host_jitter = not (cls.device_preprocessing and cls.device_jitter)
+        if jitter_params is None:
+            jitter_params = [jt.get_params(jt.brightness, jt.contrast, jt.saturation, jt.hue) for _ in range(augmentations)]
         img_pil = Image.fromarray(img)
         images = [np.array(img_pil)]
-        for _ in range(augmentations):
-            images.append(np.array(cls.jittering_transforms(img_pil)))
+        if host_jitter:
+            images += [np.array(cls._jitter_on_host(img_pil, prm)) for prm in jitter_params]
         desc, crops = [], []
-        for im in images:
+        for k in range(1 + augmentations):
+            im = images[k] if k < len(images) else None
+            H_, W_ = images[0].shape[:2]
             for aug in cropping_augmentations:
                 ts, st = aug["tile_size"], aug["stride"]
-                for y in np.arange(0, im.shape[1] - ts + 1, st):
-                    if y >= im.shape[0]:
+                for y in np.arange(0, W_ - ts + 1, st):
+                    if y >= H_:
                         continue
-                    for x in np.arange(0, im.shape[0] - ts + 1, st):
-                        if x >= im.shape[1]:
+                    for x in np.arange(0, H_ - ts + 1, st):
+                        if x >= W_:
                             continue
                         desc.append((int(x), int(y), int(ts)))
-                        crops.append(im[x : x + ts, y : y + ts])
+                        if im is not None:
+                            crops.append(im[x : x + ts, y : y + ts])
         size_order = list(dict.fromkeys(a["tile_size"] for a in cropping_augmentations))
         cls._last_images = images  # the device preprocessing path uploads these instead of the tiles
+        cls._jitter_params = [] if host_jitter else list(jitter_params)
+        cls._all_jitter_params = list(jitter_params)
         return np.array(desc, dtype=np.int32).reshape(-1, 3), crops, size_order
 
     @classmethod
     def create_tiles(cls, img, augmentations, cropping_augmentations, **kwargs):
         """Eager variant of the reference's create_tiles: (tile_desc, preprocessed tiles [n,3,R,R] fp32 in pinned host
         memory, size order)."""
-        desc, crops, size_order = cls.enumerate_crops(img, augmentations, cropping_augmentations)
+        desc, crops, size_order = cls.enumerate_crops(img, augmentations, cropping_augmentations, host_jitter=True)
         tiles = preprocess_tiles(crops, cls.clip_gradcam.n_px)
         if torch.cuda.is_available():
             tiles = tiles.pin_memory()

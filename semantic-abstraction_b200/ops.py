@@ -257,6 +257,25 @@ def tile_preprocess(images_u8, tiles, coef, bounds, out, mean, std):
     return out
 
 
+def color_jitter(img_u8: torch.Tensor, fn_idx, brightness, contrast, saturation, hue) -> torch.Tensor:
+    """torchvision.transforms.ColorJitter.forward on a uint8 HWC device image with the parameters `ColorJitter.get_params`
+    drew (CLIP/clip/__init__.py:55-57,246-247): the four operations in the drawn order, each one launch of
+    semabs_color_jitter_op.  Returns a new [H,W,3] uint8 tensor."""
+    assert img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.dim() == 3 and img_u8.shape[2] == 3
+    cur = img_u8.contiguous()
+    npix = cur.shape[0] * cur.shape[1]
+    scratch = torch.empty(1, dtype=torch.int64, device=cur.device)
+    factors = {0: brightness, 1: contrast, 2: saturation, 3: hue}
+    for fn_id in [int(i) for i in fn_idx]:
+        f = factors[fn_id]
+        if f is None:
+            continue
+        nxt = torch.empty_like(cur)
+        check(lib().semabs_color_jitter_op(ptr(cur), ptr(nxt), _i64(npix), i32(fn_id), f32(f), ptr(scratch), stream_ptr()))
+        cur = nxt
+    return cur if cur is not img_u8 else img_u8.clone()
+
+
 def flip_average(rel, rel_flipped):
     g = rel.shape[-1]
     assert rel.is_contiguous() and rel_flipped.is_contiguous() and rel.shape == rel_flipped.shape

@@ -72,7 +72,8 @@ def get_losses(net, batch: dict, cutoffs=[0], balance_positive_negative: bool = 
         kwargs["scene_bounds"] = scene_bounds_of(net)
     outputs = net(**batch) if batch["output_xyz_pts"].shape[2] <= 500000 else _forward_in_patch_chunks(net, batch)
     # like the reference, the collated [P][B] label lists and the out-of-bounds mask are normalised IN the batch dict
-    batch["patch_labels"] = np.array(batch["patch_labels"]).T
+    if not isinstance(batch["patch_labels"], np.ndarray):  # (idempotent: a batch dict that is reused arrives normalised)
+        batch["patch_labels"] = np.array(batch["patch_labels"]).T
     batch["out_of_bounds_pts"] = batch["out_of_bounds_pts"].view(outputs.shape)
     ignore = torch.zeros_like(outputs, dtype=torch.bool)
     ignore[torch.from_numpy(batch["patch_labels"] == "").to(outputs.device)] = True          # padding patches

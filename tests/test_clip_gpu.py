@@ -156,7 +156,7 @@ def test_device_tile_preprocessing_is_bit_identical_to_pil():
     img[:100, :120] = 255  # saturated / flat regions exercise the clipping and the negative bicubic lobes
     img[200:, 250:] = 0
     augs = [{"tile_size": s, "stride": s // 4} for s in (336, 224, 168, 112, 84)]
-    desc, crops, _ = ClipWrapper.enumerate_crops(img=img, augmentations=1, cropping_augmentations=augs)
+    desc, crops, _ = ClipWrapper.enumerate_crops(img=img, augmentations=1, cropping_augmentations=augs, host_jitter=True)
     assert len(crops) == 2 * 285
     got = torch.cat(list(ClipWrapper._device_preprocessed_batches(desc, 224, 64))).cpu()
     ref = w.preprocess_tiles(crops, 224)
@@ -167,4 +167,67 @@ def test_device_tile_preprocessing_is_bit_identical_to_pil():
     desc, crops, _ = ClipWrapper.enumerate_crops(img=big, augmentations=0, cropping_augmentations=[{"tile_size": 976, "stride": 244}, {"tile_size": 650, "stride": 162}])
     got = torch.cat(list(ClipWrapper._device_preprocessed_batches(desc, 224, 8))).cpu()
     assert torch.equal(got, w.preprocess_tiles(crops, 224))
+    ClipWrapper.reset()
+
+
+def test_device_color_jitter_matches_torchvision_tensor_ops():
+    """semabs_color_jitter_op (the TTA copies of the "ours" config, CLIP/clip/__init__.py:55-57,246-247) vs torchvision's
+    tensor implementation on the same uint8 image with identical drawn parameters: brightness / saturation / hue
+    bit-identical; contrast within one LSB (exact integer mean here, float32 reduction there)."""
+    import torchvision
+    import torchvision.transforms.functional as TF
+
+    from semabs_b200 import ops
+
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    img[:20, :30] = 255
+    img[40:60, 50:80] = 0
+    img[70:, :40] = 128  # grey: the hue path's maxc == minc branch
+    d = torch.from_numpy(img).cuda()
+    chw = d.permute(2, 0, 1).contiguous()
+    fns = {0: TF.adjust_brightness, 1: TF.adjust_contrast, 2: TF.adjust_saturation, 3: TF.adjust_hue}
+    for op, factors in {0: (0.4, 1.0, 1.6), 1: (0.4, 1.37, 1.6), 2: (0.4, 0.93, 1.6), 3: (-0.1, 0.0, 0.033, 0.1)}.items():
+        for f in factors:
+            got = ops.color_jitter(d, [op], *[f if k == op else None for k in range(4)])
+            ref = fns[op](chw, f).permute(1, 2, 0)
+            diff = (got.int() - ref.int()).abs()
+            if op == 1:
+                assert diff.max().item() <= 1 and (diff > 0).float().mean().item() < 1e-3, (op, f, diff.max().item())
+            else:
+                assert diff.max().item() == 0, (op, f, diff.max().item(), (diff > 0).sum().item())
+    # whole transform: parameters drawn exactly like ColorJitter.forward draws them
+    jt = torchvision.transforms.ColorJitter(brightness=0.6, contrast=0.6, saturation=0.6, hue=0.1)
+    for seed in range(4):
+        torch.manual_seed(seed)
+        prm = jt.get_params(jt.brightness, jt.contrast, jt.saturation, jt.hue)
+        got = ops.color_jitter(d, *prm)
+        torch.manual_seed(seed)
+        ref = jt(chw).permute(1, 2, 0)
+        diff = (got.int() - ref.int()).abs()
+        assert diff.max().item() <= 2 and (diff > 0).float().mean().item() < 5e-3, (seed, diff.max().item(), (diff > 0).float().mean().item())
+
+
+def test_ours_config_runs_with_device_jitter():
+    """The reference-faithful "ours" TTA (5 jitter copies x 4 crop sizes x horizontal flip) end to end on a small image:
+    jitter copies on the device vs the PIL host path with the same drawn parameters — the two colour pipelines round
+    differently by construction, so the maps are only required to be close, finite and correctly shaped."""
+    from oracle.gen_golden import LABELS4, PROMPT, synth_image
+    from semabs_b200.clip import ClipWrapper, saliency_configs
+
+    ClipWrapper.reset()
+    ClipWrapper("ViT-B/32", "cuda", seed=0)
+    img = synth_image(7, 96, 96)
+    cfg = saliency_configs["ours"](96)
+    outs = []
+    for dev_jitter in (True, False):
+        ClipWrapper.device_jitter = dev_jitter
+        torch.manual_seed(123)
+        maps, _ = ClipWrapper.get_clip_saliency(img=img, text_labels=np.array(LABELS4), prompts=[PROMPT], **cfg)
+        assert maps.shape == (4, 96, 96) and torch.isfinite(maps).all() and (maps >= 0).all()
+        outs.append(maps)
+    ClipWrapper.device_jitter = True
+    rel = ((outs[0] - outs[1]).abs().amax(dim=(1, 2)) / outs[1].abs().amax(dim=(1, 2))).max().item()
+    print(f"'ours' config, device vs PIL jitter copies (same parameters): max relative map difference {rel:.2e}")
+    assert rel < 0.1
     ClipWrapper.reset()
