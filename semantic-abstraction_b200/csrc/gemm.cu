@@ -3,8 +3,11 @@
 //
 //   C[M,N] = epi( A[M, splits*K] * B[N,K]^T )           A, B fp16 K-major
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (warp w owns TMEM lanes [32*(w%4), +32)).
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+// warps 4..11 = epilogue: warp w owns TMEM lanes [32*(w%4), +32) and the column half (w-4)/4 of the tile, in 16-column chunks.
+// (Round 1 ran 4 epilogue warps over 32-column chunks: with K = 1024 a 128x256 tile is only 8192 tensor cycles long and the
+// one-row-per-thread epilogue — TMEM load, side-input loads, convert, store for 256 columns — did not always fit: ncu showed
+// the tensor pipe at 64 % (aux-multiplying dgrad) / 77 % (out-proj dgrad) on those shapes against 84-88 % for K >= 3072.)
 // Replaces F.linear call sites of the reference ViT (see include/semabs_b200.h for file:line).
 #include "../../include/semabs_b200.h"
 #include "common.cuh"
@@ -14,7 +17,9 @@ namespace sb {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 fp16 = 128 bytes = one swizzle-128B row
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_CW = 16;  // epilogue chunk width (columns)
 
 template <int BN>
 struct GemmSmem {
@@ -98,7 +103,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -175,7 +180,10 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp >= 4) {
     // ===== epilogue =====
-    const int q = warp & 3;
+    const int q = warp & 3, chalf = (warp - 4) >> 2;
+    constexpr int CW = GEMM_CW;
+    constexpr int HALF = BN / 2;       // columns per epilogue warp
+    constexpr int NC = HALF / CW;      // chunks per warp and tile
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -187,98 +195,97 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const bool row_ok = row < M;
       const __half* aux_row = nullptr;
       if (ep.act == SEMABS_ACT_MUL_AUX16 && row_ok) aux_row = ep.aux16 + size_t(row % ep.aux_rows) * ep.ld_aux;
-      // Software-pipelined over 32-column chunks: the TMEM load and the global side inputs (aux / residual) of chunk
-      // c+1 are in flight while chunk c is converted and stored; without this every chunk exposed a full
-      // tcgen05.ld + LDG round trip and the aux-multiplying dgrad epilogue, not the MMAs, bounded the K=1024 GEMMs.
-      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+      // Software-pipelined over 16-column chunks: the TMEM load and the global side inputs (aux / residual) of chunk
+      // c+1 are in flight while chunk c is converted and stored.
+      const int colbase = n_blk * BN + chalf * HALF;
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + chalf * HALF);
       const float* res_row = (ep.residual && row_ok) ? ep.residual + size_t(row) * ep.ld_out : nullptr;
       const bool wide = ep.wide != 0;
-      auto load_side = [&](int c, uint32_t(&au)[16], uint32_t(&rs)[32]) {
-        const int col0 = n_blk * BN + c * 32;
+      auto load_side = [&](int c, uint32_t(&au)[CW / 2], uint32_t(&rs)[CW]) {
+        const int col0 = colbase + c * CW;
         if (col0 < N) {
-          if (aux_row) ld_row_words<16>(aux_row + col0, au, wide);
-          if (res_row) ld_row_words<32>(res_row + col0, rs, wide);
+          if (aux_row) ld_row_words<CW / 2>(aux_row + col0, au, wide);
+          if (res_row) ld_row_words<CW>(res_row + col0, rs, wide);
         }
       };
-      auto process = [&](int c, const uint32_t(&r)[32], const uint32_t(&au)[16], const uint32_t(&rs)[32]) {
-        const int col0 = n_blk * BN + c * 32;
+      auto process = [&](int c, const uint32_t(&r)[CW], const uint32_t(&au)[CW / 2], const uint32_t(&rs)[CW]) {
+        const int col0 = colbase + c * CW;
         if (row_ok && col0 < N) {
-          float v[32];
+          float v[CW];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
           if (ep.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < CW; j += 4) {
               float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
               v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
             }
           }
           if (col0 < ep.scale_cols) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < CW; ++j)
               if (col0 + j < ep.scale_cols) v[j] *= ep.scale;
           }
           if (aux_row) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < CW / 2; ++j) {
               const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&au[j]));
               v[2 * j] *= f.x, v[2 * j + 1] *= f.y;
             }
           }
           if (res_row) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rs[j]);
+            for (int j = 0; j < CW; ++j) v[j] += __uint_as_float(rs[j]);
           }
           if (ep.out_f32) {
-            st_row_words<32>(ep.out_f32 + size_t(row) * ep.ld_out + col0, reinterpret_cast<const uint32_t*>(v), wide);
+            st_row_words<CW>(ep.out_f32 + size_t(row) * ep.ld_out + col0, reinterpret_cast<const uint32_t*>(v), wide);
           }
           if (ep.out_f16) {
-            __align__(16) __half2 h[16];
+            __align__(16) __half2 h[CW / 2];
             if (ep.act == SEMABS_ACT_QUICKGELU) {
               // one sigmoid gives both the activation and (for the backward sweep) its derivative
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
+              for (int j = 0; j < CW; j += 2) {
                 const float s0 = sigmoidf_precise(1.702f * v[j]), s1 = sigmoidf_precise(1.702f * v[j + 1]);
                 h[j >> 1] = __floats2half2_rn(s0 + 1.702f * v[j] * s0 * (1.0f - s0), s1 + 1.702f * v[j + 1] * s1 * (1.0f - s1));
                 v[j] *= s0, v[j + 1] *= s1;
               }
               if (ep.out_aux16) {
-                st_row_words<16>(ep.out_aux16 + size_t(row) * ep.ld_out_aux + col0, reinterpret_cast<const uint32_t*>(h), wide);
+                st_row_words<CW / 2>(ep.out_aux16 + size_t(row) * ep.ld_out_aux + col0, reinterpret_cast<const uint32_t*>(h), wide);
               }
             }
             __half* o = ep.out_f16 + size_t(row) * ep.ld_out16 + col0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-            st_row_words<16>(o, reinterpret_cast<const uint32_t*>(h), wide);
+            for (int j = 0; j < CW / 2; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            st_row_words<CW / 2>(o, reinterpret_cast<const uint32_t*>(h), wide);
             if (ep.out_f16_splits == 2) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
+              for (int j = 0; j < CW / 2; ++j) {
                 float2 f = __half22float2(h[j]);
                 h[j] = __floats2half2_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y);
               }
-              st_row_words<16>(o + N, reinterpret_cast<const uint32_t*>(h), wide);
+              st_row_words<CW / 2>(o + N, reinterpret_cast<const uint32_t*>(h), wide);
             }
           }
         }
       };
-      constexpr int NC = BN / 32;
-      uint32_t r0[32], r1[32];
-      uint32_t a0[16], a1[16];
-      uint32_t s0[32], s1[32];
-      tmem_ld_32x32b_x32(t_addr, r0);
+      uint32_t r0[CW], r1[CW];
+      uint32_t a0[CW / 2], a1[CW / 2];
+      uint32_t s0[CW], s1[CW];
+      tmem_ld_32x32b_x16(t_addr, r0);
       load_side(0, a0, s0);
 #pragma unroll 1
       for (int c = 0; c < NC; c += 2) {
         tc_wait_ld();
         if (c + 1 < NC) {
-          tmem_ld_32x32b_x32(t_addr + uint32_t((c + 1) * 32), r1);
+          tmem_ld_32x32b_x16(t_addr + uint32_t((c + 1) * CW), r1);
           load_side(c + 1, a1, s1);
         }
         process(c, r0, a0, s0);
         if (c + 1 < NC) {
           tc_wait_ld();
           if (c + 2 < NC) {
-            tmem_ld_32x32b_x32(t_addr + uint32_t((c + 2) * 32), r0);
+            tmem_ld_32x32b_x16(t_addr + uint32_t((c + 2) * CW), r0);
             load_side(c + 2, a0, s0);
           }
           process(c + 1, r1, a1, s1);

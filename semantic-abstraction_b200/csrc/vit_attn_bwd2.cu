@@ -31,29 +31,45 @@ constexpr int NCH_HALF = (TC_MAX_T / 16 + 1) / 2;  // 9 chunks of 16 strip colum
 // ---------------------------------------------------------------------------------------------------------
 // delta[pb, h, i] = sum_c dO[pb, i, h*64 + c] * O[b, i, h*64 + c]
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) attn_delta_kernel(AttnBwdTcArgs a) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)a.P * a.B * a.T * a.H;
-  if (t >= total) return;
-  const int h = int(t % a.H);
-  const long long row = t / a.H;  // (pb, i)
-  const int i = int(row % a.T);
-  const int pb = int(row / a.T), b = pb % a.B;
-  const __half* g = a.dO16 + size_t(row) * a.ld_do + h * TC_HD;
-  const float* o = a.o32 + (size_t(b) * a.T + i) * a.d + h * TC_HD;
-  uint32_t gv[32], ov[64];
+// block = 32 consecutive (pb, i) rows x H heads: reads are whole contiguous rows (thread = 128 B of dO + 256 B of O), the
+// results are transposed through shared memory so that each head's 32 deltas leave as one 128-byte segment (the first
+// version stored 4 bytes per thread at a stride of T floats: 0.36 ms for 0.8 GB of input, write-transaction bound)
+__global__ void __launch_bounds__(1024) attn_delta_kernel(AttnBwdTcArgs a) {
+  __shared__ float s[32][33];
+  const int H = a.H, tid = threadIdx.x;
+  const long long rows_total = (long long)a.P * a.B * a.T;
+  {
+    const int r = tid / H, h = tid - r * H;
+    const long long row = (long long)blockIdx.x * 32 + r;  // (pb, i)
+    if (row < rows_total) {
+      const int i = int(row % a.T);
+      const int pb = int(row / a.T), b = pb % a.B;
+      const __half* g = a.dO16 + size_t(row) * a.ld_do + h * TC_HD;
+      const float* o = a.o32 + (size_t(b) * a.T + i) * a.d + h * TC_HD;
+      uint32_t gv[32], ov[64];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) ld_global_256(g + 16 * e, gv + 8 * e);
+      for (int e = 0; e < 4; ++e) ld_global_256(g + 16 * e, gv + 8 * e);
 #pragma unroll
-  for (int e = 0; e < 8; ++e) ld_global_256(o + 8 * e, ov + 8 * e);
-  float acc0 = 0.f, acc1 = 0.f;
+      for (int e = 0; e < 8; ++e) ld_global_256(o + 8 * e, ov + 8 * e);
+      float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&gv[k]));
-    acc0 = fmaf(g2.x, __uint_as_float(ov[2 * k]), acc0);
-    acc1 = fmaf(g2.y, __uint_as_float(ov[2 * k + 1]), acc1);
+      for (int k = 0; k < 32; ++k) {
+        const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&gv[k]));
+        acc0 = fmaf(g2.x, __uint_as_float(ov[2 * k]), acc0);
+        acc1 = fmaf(g2.y, __uint_as_float(ov[2 * k + 1]), acc1);
+      }
+      s[r][h] = acc0 + acc1;
+    }
   }
-  a.delta[(size_t(pb) * a.H + h) * a.T + i] = acc0 + acc1;
+  __syncthreads();
+  {
+    const int h = tid >> 5, r = tid & 31;
+    const long long row = (long long)blockIdx.x * 32 + r;
+    if (row < rows_total) {
+      const int i = int(row % a.T), pb = int(row / a.T);
+      a.delta[(size_t(pb) * H + h) * a.T + i] = s[r][h];
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -499,22 +515,26 @@ constexpr int TAIL_PITCH = 72;                       // halfs per staged row (64
 constexpr int TAIL_ROWS = 264;                       // >= T (<= 257 + ...) rounded up
 constexpr int TAIL_TILE_BYTES = TAIL_ROWS * TAIL_PITCH * 2;
 struct TailSmem {
-  static constexpr int Q = 0, K = Q + TAIL_TILE_BYTES, V = K + TAIL_TILE_BYTES, DO = V + TAIL_TILE_BYTES;
-  static constexpr int DS = DO + TAIL_TILE_BYTES;    // float [2][TAIL_ROWS]: ds and a (column part) / ds (row part)
-  static constexpr int RED = DS + 2 * TAIL_ROWS * 4; // float [8 segments][3][64] partial sums
-  static constexpr int WRED = RED + 8 * 3 * 64 * 4;  // float [8] warp partials of the relevance sum
+  static constexpr int Q = 0, K = Q + TAIL_TILE_BYTES, V = K + TAIL_TILE_BYTES, DO = V + TAIL_TILE_BYTES;  // DO: 2 stages
+  static constexpr int DS = DO + 2 * TAIL_TILE_BYTES; // float [2][TAIL_ROWS]: ds and a (column part) / ds (row part)
+  static constexpr int RED = DS + 2 * TAIL_ROWS * 4;  // float [8 segments][3][64] partial sums
+  static constexpr int WRED = RED + 8 * 3 * 64 * 4;   // float [8] warp partials of the relevance sum
   static constexpr int TOTAL = WRED + 64;
 };
 
-__device__ __forceinline__ void tail_stage(__half* dst, const __half* src, int ld, int T, int tid) {
-  // rows [0, T) x 64 halfs, 16 bytes per thread-step: 8 steps per row
+// rows [0, T) x 64 halfs -> padded shared rows, 16 bytes per cp.async (no register round trip: every copy of the tile is
+// in flight at once; the first version staged through registers and spent 41 % of the kernel waiting on those loads)
+__device__ __forceinline__ void tail_stage_async(__half* dst, const __half* src, int ld, int T, int tid) {
   for (int idx = tid; idx < T * 8; idx += TC_SIMT) {
     const int r = idx >> 3, c = idx & 7;
-    *reinterpret_cast<uint4*>(dst + r * TAIL_PITCH + c * 8) = *reinterpret_cast<const uint4*>(src + size_t(r) * ld + c * 8);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + r * TAIL_PITCH + c * 8)),
+                 "l"(src + size_t(r) * ld + c * 8)
+                 : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ float tail_dot64(const __half* x, const __half* y) {  // two staged rows (16-byte aligned)
-  float acc = 0.f;
+  float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const uint4 ux = *reinterpret_cast<const uint4*>(x + c * 8), uy = *reinterpret_cast<const uint4*>(y + c * 8);
@@ -523,10 +543,10 @@ __device__ __forceinline__ float tail_dot64(const __half* x, const __half* y) { 
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float2 fx = __half22float2(hx[e]), fy = __half22float2(hy[e]);
-      acc = fmaf(fx.x, fy.x, acc), acc = fmaf(fx.y, fy.y, acc);
+      acc0 = fmaf(fx.x, fy.x, acc0), acc1 = fmaf(fx.y, fy.y, acc1);
     }
   }
-  return acc;
+  return acc0 + acc1;
 }
 
 __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArgs a) {
@@ -535,7 +555,6 @@ __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArg
   __half* sQ = reinterpret_cast<__half*>(smem + TailSmem::Q);
   __half* sK = reinterpret_cast<__half*>(smem + TailSmem::K);
   __half* sV = reinterpret_cast<__half*>(smem + TailSmem::V);
-  __half* sG = reinterpret_cast<__half*>(smem + TailSmem::DO);
   float* s_ds = reinterpret_cast<float*>(smem + TailSmem::DS);
   float* s_av = s_ds + TAIL_ROWS;
   float* s_red = reinterpret_cast<float*>(smem + TailSmem::RED);
@@ -547,25 +566,35 @@ __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArg
   const __half* qkv = a.qkv16 + size_t(b) * T * a.ldq + h * TC_HD;
   const __half* Ab = a.probs16 + size_t(bh) * T * a.ldp;
   const size_t ld = size_t(a.splits) * 3 * d;
-  tail_stage(sQ, qkv, a.ldq, T, tid);
-  tail_stage(sK, qkv + d, a.ldq, T, tid);
-  tail_stage(sV, qkv + 2 * d, a.ldq, T, tid);
+  auto dO_of = [&](int p) { return a.dO16 + size_t(p * a.B + b) * T * a.ld_do + h * TC_HD; };
+  auto sG_of = [&](int p) { return reinterpret_cast<__half*>(smem + TailSmem::DO + (p & 1) * TAIL_TILE_BYTES); };
+  tail_stage_async(sQ, qkv, a.ldq, T, tid);
+  tail_stage_async(sK, qkv + d, a.ldq, T, tid);
+  tail_stage_async(sV, qkv + 2 * d, a.ldq, T, tid);
+  tail_stage_async(sG_of(0), dO_of(0), a.ld_do, T, tid);
   // probability column x0 (rows i) and row x0 (columns j) of this head: per-thread registers, rows tid and tid + 256
   const int r1 = tid + TC_SIMT;
-  const float acol0 = __half2float(Ab[size_t(tid < T ? tid : 0) * a.ldp + x0]) * (tid < T ? 1.f : 0.f);
+  const float acol0 = tid < T ? __half2float(Ab[size_t(tid) * a.ldp + x0]) : 0.f;
   const float acol1 = r1 < T ? __half2float(Ab[size_t(r1) * a.ldp + x0]) : 0.f;
   const float arow0 = tid < T ? __half2float(Ab[size_t(x0) * a.ldp + tid]) : 0.f;
   const float arow1 = r1 < T ? __half2float(Ab[size_t(x0) * a.ldp + r1]) : 0.f;
   const int cp = tid & 31, seg = tid >> 5;  // reduction layout: channel pair (2 cp, 2 cp + 1) x 8 row segments
   const int rows_per_seg = (T + 7) / 8;
+  const int i_beg = seg * rows_per_seg, i_end = min(T, (seg + 1) * rows_per_seg);
   for (int p = 0; p < a.P; ++p) {
     const int pb = p * a.B + b;
-    const __half* dOb = a.dO16 + size_t(pb) * T * a.ld_do + h * TC_HD;
+    const __half* sG = sG_of(p);
     const float* dl = a.delta + (size_t(pb) * a.H + h) * T;
     const float* rp = a.r + size_t(pb) * T;
-    __syncthreads();  // previous label's readers of sG / s_ds are done (first pass: the Q / K / V staging is complete)
-    tail_stage(sG, dOb, a.ld_do, T, tid);
-    __syncthreads();
+    // per-label scalars: in flight while the staged tile lands
+    const float rv0 = tid < T ? rp[tid] : 0.f, rv1 = r1 < T ? rp[r1] : 0.f;
+    float dv0 = 0.f, dv1 = 0.f, dx0 = 0.f;
+    if (a.need_dqkv) {
+      dv0 = tid < T ? dl[tid] : 0.f, dv1 = r1 < T ? dl[r1] : 0.f, dx0 = dl[x0];
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // label p's dO (and, first pass, Q / K / V) visible; every reader of stage (p+1)&1 (label p-1) is done
+    if (p + 1 < a.P) tail_stage_async(sG_of(p + 1), dO_of(p + 1), a.ld_do, T, tid);  // overlaps this label's arithmetic
     // ---- column part, scalars: thread = query row(s) tid, tid + 256
     float wsum = 0.f;
     {
@@ -574,15 +603,15 @@ __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArg
         const float g = tail_dot64(sG + tid * TAIL_PITCH, v0);
         float x = g * acol0;
         if (a.positive_only) x = fmaxf(x, 0.f);
-        wsum = rp[tid] * x;
-        s_ds[tid] = acol0 * (g - (a.need_dqkv ? dl[tid] : 0.f)), s_av[tid] = acol0;
+        wsum = rv0 * x;
+        s_ds[tid] = acol0 * (g - dv0), s_av[tid] = acol0;
       }
       if (r1 < T) {
         const float g = tail_dot64(sG + r1 * TAIL_PITCH, v0);
         float x = g * acol1;
         if (a.positive_only) x = fmaxf(x, 0.f);
-        wsum = fmaf(rp[r1], x, wsum);
-        s_ds[r1] = acol1 * (g - (a.need_dqkv ? dl[r1] : 0.f)), s_av[r1] = acol1;
+        wsum = fmaf(rv1, x, wsum);
+        s_ds[r1] = acol1 * (g - dv1), s_av[r1] = acol1;
       }
     }
     wsum = warp_sum(wsum);
@@ -598,8 +627,8 @@ __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArg
     // ---- column part, vectors: dK_x0 = sum_i ds_i Q_i ; dV_x0 = sum_i a_i dO_i
     {
       float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
-      const int i_end = min(T, (seg + 1) * rows_per_seg);
-      for (int i = seg * rows_per_seg; i < i_end; ++i) {
+#pragma unroll 4
+      for (int i = i_beg; i < i_end; ++i) {
         const float ds = s_ds[i], av = s_av[i];
         const float2 fq = __half22float2(*reinterpret_cast<const __half2*>(sQ + i * TAIL_PITCH + 2 * cp));
         const float2 fg = __half22float2(*reinterpret_cast<const __half2*>(sG + i * TAIL_PITCH + 2 * cp));
@@ -613,15 +642,14 @@ __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArg
     // ---- row part, scalars: thread = key(s) j = tid, tid + 256
     {
       const __half* g0 = sG + x0 * TAIL_PITCH;
-      const float delta0 = dl[x0];
-      if (tid < T) s_ds[tid] = arow0 * (tail_dot64(g0, sV + tid * TAIL_PITCH) - delta0);
-      if (r1 < T) s_ds[r1] = arow1 * (tail_dot64(g0, sV + r1 * TAIL_PITCH) - delta0);
+      if (tid < T) s_ds[tid] = arow0 * (tail_dot64(g0, sV + tid * TAIL_PITCH) - dx0);
+      if (r1 < T) s_ds[r1] = arow1 * (tail_dot64(g0, sV + r1 * TAIL_PITCH) - dx0);
     }
     __syncthreads();
     {
       float q0 = 0.f, q1 = 0.f;
-      const int j_end = min(T, (seg + 1) * rows_per_seg);
-      for (int j = seg * rows_per_seg; j < j_end; ++j) {
+#pragma unroll 4
+      for (int j = i_beg; j < i_end; ++j) {
         const float ds = s_ds[j];
         const float2 fk = __half22float2(*reinterpret_cast<const __half2*>(sK + j * TAIL_PITCH + 2 * cp));
         q0 = fmaf(ds, fk.x, q0), q1 = fmaf(ds, fk.y, q1);
@@ -644,6 +672,7 @@ __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArg
       if (a.splits == 2) *reinterpret_cast<uint32_t*>(orow + 3 * d + col) = lo;
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace sb
@@ -689,8 +718,9 @@ extern "C" int semabs_attn_bwd_tc2(const void* qkv16, int32_t ld_qkv, const void
   const int n_units = B * H * a.n_full;
   const int grid = n_units < num_sms() ? n_units : num_sms();
   if (need_dqkv) {  // delta feeds dS in both passes and the tail; the relevance-only last step needs neither delta nor dQ
-    const long long threads = (long long)P * B * T * H;
-    attn_delta_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);
+    SB_REQUIRE(H <= 32, "semabs_attn_bwd_tc2: at most 32 heads");
+    const long long rows = (long long)P * B * T;
+    attn_delta_kernel<<<(unsigned)((rows + 31) / 32), 32 * H, 0, st>>>(a);
     SB_CHECK_CUDA(cudaGetLastError());
     attn_bwd_row_tc2_kernel<<<grid, TC_BWD_THREADS, RowSmem::TOTAL, st>>>(tm_qkv, tm_do, a);
     SB_CHECK_CUDA(cudaGetLastError());
