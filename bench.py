@@ -367,6 +367,7 @@ def main():
     ap.add_argument("--skip-pipeline", action="store_true")
     ap.add_argument("--skip-amp", action="store_true")
     ap.add_argument("--skip-eager", action="store_true")
+    ap.add_argument("--skip-ours", action="store_true")
     ap.add_argument("--train-descs", type=int, default=16)
     args = ap.parse_args()
     _quiet_stdout()
@@ -473,6 +474,25 @@ def main():
     h2d = args.images * (IMG * IMG * 3 + n_tiles * 5 * 4) if ClipWrapper.device_preprocessing else args.images * n_tiles * 3 * 224 * 224 * 4
     d2h = args.images * (P * IMG * IMG * 4 + P * 768 * 4)
 
+    # ---- R2' (SURVEY.md §8d): the reference-faithful `saliency_configs["ours"](336)` TTA — 204 tiles x (1 + 5 ColorJitter
+    # copies) x 2 flips = 2448 ViT passes per image — through the public call, one image (reported for fidelity, not the target)
+    faithful = None
+    if not args.skip_ours:
+        from semabs_b200.clip import saliency_configs
+
+        ours_cfg = saliency_configs["ours"](IMG)
+        torch.manual_seed(0)
+        call = lambda: ClipWrapper.get_clip_saliency(img=imgs[0], text_labels=np.array(LABELS16), prompts=[PROMPT],
+                                                     tile_batch_size=102, **ours_cfg)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        call()
+        torch.cuda.synchronize()
+        t_ours = time.perf_counter() - t0
+        faithful = {"metric": "relevancy-maps/s, saliency_configs['ours'](336): 204 tiles x 6 image copies (device ColorJitter) x 2 flips = 2448 passes/image",
+                    "value": world * P / t_ours, "unit": "relevancy-maps/s", "s_per_image": t_ours,
+                    "algorithmic_tflops": world * 2448 * (GF_FWD_TILE + P * GF_BWD_TILE_LABEL) / 1e3 / t_ours}
+
     pk = peaks()
     flops_per_map = (GF_FWD_TILE + P * GF_BWD_TILE_LABEL) * 1e9 * n_tiles / P
     tr = measured_traffic()
@@ -527,7 +547,7 @@ def main():
                         "note": "ClipWrapper.get_clip_saliency per host uint8 image (the reference's public call, whole): tokeniser + text tower "
                                 "(set_classes) -> tile crop / Pillow-exact bicubic / normalise on the GPU -> relevancy -> assembly -> D2H of the "
                                 "fp32 maps and the text features"},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "cuda_eager": cuda_eager, "clocks": clocks,
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "cuda_eager": cuda_eager, "faithful_ours": faithful, "clocks": clocks,
                 "voxel": voxel, "pipeline": pipe, "train": train}
         emit(line)
     if world > 1:
@@ -641,8 +661,10 @@ def bench_pipeline(dev, rank, world, cfg, images):
     K = np.array([[0.9 * IMG, 0, IMG / 2 - 0.5], [0, 0.9 * IMG, IMG / 2 - 0.5], [0, 0, 1]])
     T = np.array([[1.0, 0, 0, 0.0], [0, 0, 1, -1.2], [0, -1, 0, 0.9]])
     gen = torch.Generator(device=dev).manual_seed(3)
+    lattice = (240, 240, 240)  # the reference's dense-sweep lattice (visualize.py:163-164)
     run = lambda im: pipeline.rgbd_to_ovssc_logits(net, im, depth, K, T, LABELS16, bounds, dict(positive_attn_only=True,
-                                                   tile_batch_size=TILE_BATCH, **cfg), generator=gen)["prediction"].cpu()
+                                                   tile_batch_size=TILE_BATCH, **cfg), sampling_shape=lattice,
+                                                   generator=gen)["prediction"].cpu()
     run(images[0])
     torch.cuda.synchronize()
     if world > 1:
@@ -657,10 +679,11 @@ def bench_pipeline(dev, rank, world, cfg, images):
     n = len(images)
     del net
     _release()
-    return {"metric": "RGB-D images/s through relevancy -> OVSSC logits (336^2, 16 labels, 128^3 grid + 128^3 lattice)",
+    return {"metric": "RGB-D images/s through relevancy -> OVSSC logits (336^2, 16 labels, 128^3 grid, 240^3 query lattice)",
+            "images_per_gpu": n, "workload": "configs[4]: 64 synthetic RGB-D images sharded over 8 GPUs = 8 per GPU (weak scaling: every N runs 8 per rank)",
             "value": world * n / dt.item(), "unit": "images/s (sum over GPUs)", "s_per_image": dt.item() / n,
             "relevancy_maps_per_s": world * n * len(LABELS16) / dt.item(), "classes_in_prediction": int(pred.unique().numel()),
-            "h2d_bytes_per_image": IMG * IMG * 3 + IMG * IMG * 4 + 285 * 5 * 4, "d2h_bytes_per_image": 128**3 * 8}
+            "h2d_bytes_per_image": IMG * IMG * 3 + IMG * IMG * 4 + 285 * 5 * 4, "d2h_bytes_per_image": 240**3 * 8}
 
 
 def bench_train(dev, rank, world, pk, C=16, num_descs=16, steps=2, warmup=2, precise=True):

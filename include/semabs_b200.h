@@ -69,6 +69,11 @@ typedef struct semabs_gemm_epilogue {
 
 int semabs_gemm_f16(const void* A, int32_t lda, const void* B, int32_t ldb, int32_t M, int32_t N, int32_t K,
                     int32_t a_splits, const semabs_gemm_epilogue* ep, void* stream);
+/* Shapes that qualify for 128 x 256 tiles (N % 256 == 0 and at least two tiles per SM) run on CTA pairs by default
+ * (gemm2.cu: tcgen05.mma.cta_group::2, one 256 x 256 tile per pair); enable = 0 keeps them on the single-CTA kernel
+ * (A/B measurements and the cross-check in tests/test_gemm_gpu.py).  Process-wide switch, not thread-safe. */
+int semabs_set_gemm_pair(int32_t enable);
+
 
 /* ------------------------------------------------------------------------------------------------------------
  * CLIP ViT / text-transformer stages other than the GEMMs (vit_ops.cu, vit_attn.cu).

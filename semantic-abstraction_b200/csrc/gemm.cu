@@ -11,6 +11,7 @@
 // Replaces F.linear call sites of the reference ViT (see include/semabs_b200.h for file:line).
 #include "../../include/semabs_b200.h"
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include "ptx.cuh"
 
 namespace sb {
@@ -18,8 +19,6 @@ namespace sb {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 fp16 = 128 bytes = one swizzle-128B row
 constexpr int GEMM_THREADS = 384;
-constexpr int GEMM_EPI_WARPS = 8;
-constexpr int GEMM_CW = 16;  // epilogue chunk width (columns)
 
 template <int BN>
 struct GemmSmem {
@@ -33,45 +32,6 @@ struct GemmSmem {
   // round 1: -40 % on K=1024 shapes) steals it. Each thread owns one accumulator row and moves whole 32 B sectors.
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KiB alignment
 };
-
-struct EpiParams {
-  const float* bias;
-  const float* residual;
-  const __half* aux16;
-  int aux_rows;
-  int ld_aux;
-  __half* out_aux16;
-  int ld_out_aux;
-  float* out_f32;
-  int ld_out;
-  __half* out_f16;
-  int ld_out16;
-  int out_f16_splits;
-  int act;
-  int scale_cols;
-  float scale;
-  int wide;  // every row of every side input / output is 32-byte aligned: 256-bit global accesses
-  // aux-aware tile order (SEMABS_ACT_MUL_AUX16 with aux_rows < M): rows r, r + aux_rows, r + 2 aux_rows ... multiply by the
-  // same aux row, so their tiles are visited back to back and the aux tile is fetched from HBM once instead of once per
-  // repeat (ncu round 1: 1.34 GB read for 0.34 GB of operands on the fc2 dgrad)
-  int raster_rows;    // aux_rows, or 0 = plain row-major tile order
-  int raster_groups;  // ceil(aux_rows / 128)
-  int raster_reps;    // M / aux_rows
-};
-
-// virtual tile index -> (m_blk, n_blk); false = this virtual index maps to no tile (skipped by every role alike)
-__device__ __forceinline__ bool tile_coords(const EpiParams& ep, int t, int num_m, int num_n, int& m_blk, int& n_blk) {
-  n_blk = t % num_n;
-  const int u = t / num_n;
-  if (ep.raster_rows == 0) {
-    m_blk = u;
-    return true;
-  }
-  const int p = u % ep.raster_reps, g = u / ep.raster_reps;
-  m_blk = g + int((long long)p * ep.raster_rows / 128);
-  const int next = (p + 1 == ep.raster_reps) ? num_m : int((long long)(p + 1) * ep.raster_rows / 128);
-  return m_blk < next;
-}
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -123,7 +83,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int m_blk, n_blk;
-        if (!tile_coords(ep, t, num_m, num_n, m_blk, n_blk)) continue;
+        if (!tile_coords(ep, t, num_m, num_n, GEMM_BM, m_blk, n_blk)) continue;
         for (int kb = 0; kb < kblocks_total; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * S::STAGE_BYTES;
@@ -152,7 +112,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         {
           int m_blk, n_blk;
-          if (!tile_coords(ep, t, num_m, num_n, m_blk, n_blk)) continue;
+          if (!tile_coords(ep, t, num_m, num_n, GEMM_BM, m_blk, n_blk)) continue;
         }
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -180,117 +140,14 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp >= 4) {
     // ===== epilogue =====
-    const int q = warp & 3, chalf = (warp - 4) >> 2;
-    constexpr int CW = GEMM_CW;
-    constexpr int HALF = BN / 2;       // columns per epilogue warp
-    constexpr int NC = HALF / CW;      // chunks per warp and tile
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int m_blk, n_blk;
-      if (!tile_coords(ep, t, num_m, num_n, m_blk, n_blk)) continue;
+      if (!tile_coords(ep, t, num_m, num_n, GEMM_BM, m_blk, n_blk)) continue;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * GEMM_BM + q * 32 + lane;
-      const bool row_ok = row < M;
-      const __half* aux_row = nullptr;
-      if (ep.act == SEMABS_ACT_MUL_AUX16 && row_ok) aux_row = ep.aux16 + size_t(row % ep.aux_rows) * ep.ld_aux;
-      // Software-pipelined over 16-column chunks: the TMEM load and the global side inputs (aux / residual) of chunk
-      // c+1 are in flight while chunk c is converted and stored.
-      const int colbase = n_blk * BN + chalf * HALF;
-      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + chalf * HALF);
-      const float* res_row = (ep.residual && row_ok) ? ep.residual + size_t(row) * ep.ld_out : nullptr;
-      const bool wide = ep.wide != 0;
-      auto load_side = [&](int c, uint32_t(&au)[CW / 2], uint32_t(&rs)[CW]) {
-        const int col0 = colbase + c * CW;
-        if (col0 < N) {
-          if (aux_row) ld_row_words<CW / 2>(aux_row + col0, au, wide);
-          if (res_row) ld_row_words<CW>(res_row + col0, rs, wide);
-        }
-      };
-      auto process = [&](int c, const uint32_t(&r)[CW], const uint32_t(&au)[CW / 2], const uint32_t(&rs)[CW]) {
-        const int col0 = colbase + c * CW;
-        if (row_ok && col0 < N) {
-          float v[CW];
-#pragma unroll
-          for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
-          if (ep.bias) {
-#pragma unroll
-            for (int j = 0; j < CW; j += 4) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
-              v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
-            }
-          }
-          if (col0 < ep.scale_cols) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j)
-              if (col0 + j < ep.scale_cols) v[j] *= ep.scale;
-          }
-          if (aux_row) {
-#pragma unroll
-            for (int j = 0; j < CW / 2; ++j) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&au[j]));
-              v[2 * j] *= f.x, v[2 * j + 1] *= f.y;
-            }
-          }
-          if (res_row) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] += __uint_as_float(rs[j]);
-          }
-          if (ep.out_f32) {
-            st_row_words<CW>(ep.out_f32 + size_t(row) * ep.ld_out + col0, reinterpret_cast<const uint32_t*>(v), wide);
-          }
-          if (ep.out_f16) {
-            __align__(16) __half2 h[CW / 2];
-            if (ep.act == SEMABS_ACT_QUICKGELU) {
-              // one sigmoid gives both the activation and (for the backward sweep) its derivative
-#pragma unroll
-              for (int j = 0; j < CW; j += 2) {
-                const float s0 = sigmoidf_precise(1.702f * v[j]), s1 = sigmoidf_precise(1.702f * v[j + 1]);
-                h[j >> 1] = __floats2half2_rn(s0 + 1.702f * v[j] * s0 * (1.0f - s0), s1 + 1.702f * v[j + 1] * s1 * (1.0f - s1));
-                v[j] *= s0, v[j + 1] *= s1;
-              }
-              if (ep.out_aux16) {
-                st_row_words<CW / 2>(ep.out_aux16 + size_t(row) * ep.ld_out_aux + col0, reinterpret_cast<const uint32_t*>(h), wide);
-              }
-            }
-            __half* o = ep.out_f16 + size_t(row) * ep.ld_out16 + col0;
-#pragma unroll
-            for (int j = 0; j < CW / 2; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-            st_row_words<CW / 2>(o, reinterpret_cast<const uint32_t*>(h), wide);
-            if (ep.out_f16_splits == 2) {
-#pragma unroll
-              for (int j = 0; j < CW / 2; ++j) {
-                float2 f = __half22float2(h[j]);
-                h[j] = __floats2half2_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y);
-              }
-              st_row_words<CW / 2>(o + N, reinterpret_cast<const uint32_t*>(h), wide);
-            }
-          }
-        }
-      };
-      uint32_t r0[CW], r1[CW];
-      uint32_t a0[CW / 2], a1[CW / 2];
-      uint32_t s0[CW], s1[CW];
-      tmem_ld_32x32b_x16(t_addr, r0);
-      load_side(0, a0, s0);
-#pragma unroll 1
-      for (int c = 0; c < NC; c += 2) {
-        tc_wait_ld();
-        if (c + 1 < NC) {
-          tmem_ld_32x32b_x16(t_addr + uint32_t((c + 1) * CW), r1);
-          load_side(c + 1, a1, s1);
-        }
-        process(c, r0, a0, s0);
-        if (c + 1 < NC) {
-          tc_wait_ld();
-          if (c + 2 < NC) {
-            tmem_ld_32x32b_x16(t_addr + uint32_t((c + 2) * CW), r0);
-            load_side(c + 2, a0, s0);
-          }
-          process(c + 1, r1, a1, s1);
-        }
-      }
+      gemm_epilogue_tile<BN>(ep, tmem_base + uint32_t(acc * BN), m_blk * GEMM_BM, n_blk * BN, M, N, warp, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -323,7 +180,18 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
   return 0;
 }
 
+int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int kblocks_total, int kblocks_wrap_b,
+                     const EpiParams& ep, cudaStream_t stream);  // gemm2.cu
+static int g_gemm_pair = 1;
+
 }  // namespace sb
+
+// 1 (default): shapes that qualify for 128 x 256 tiles run on CTA pairs (gemm2.cu: 256 x 256 per pair); 0: single-CTA kernels
+// only (A/B measurements, cross-check in the tests)
+extern "C" int semabs_set_gemm_pair(int32_t enable) {
+  sb::g_gemm_pair = enable ? 1 : 0;
+  return 0;
+}
 
 extern "C" int semabs_gemm_f16(const void* A, int32_t lda, const void* B, int32_t ldb, int32_t M, int32_t N,
                                int32_t K, int32_t a_splits, const semabs_gemm_epilogue* e, void* stream) {
@@ -379,14 +247,24 @@ extern "C" int semabs_gemm_f16(const void* A, int32_t lda, const void* B, int32_
     ep.wide = ok32(ep.residual, 4LL * ep.ld_out) && ok32(ep.out_f32, 4LL * ep.ld_out) && ok32(ep.out_f16, 2LL * ep.ld_out16) &&
               ok32(ep.aux16, 2LL * ep.ld_aux) && ok32(ep.out_aux16, 2LL * ep.ld_out_aux);
   }
+  const bool pair = BN == 256 && g_gemm_pair;
+  const int tile_rows = pair ? 2 * GEMM_BM : GEMM_BM;
   ep.raster_rows = ep.raster_groups = ep.raster_reps = 0;
-  if (ep.act == SEMABS_ACT_MUL_AUX16 && ep.aux_rows >= GEMM_BM && ep.aux_rows < M && M % ep.aux_rows == 0) {
+  if (ep.act == SEMABS_ACT_MUL_AUX16 && ep.aux_rows >= tile_rows && ep.aux_rows < M && M % ep.aux_rows == 0) {
     ep.raster_rows = ep.aux_rows;
-    ep.raster_groups = (ep.aux_rows + GEMM_BM - 1) / GEMM_BM;
+    ep.raster_groups = (ep.aux_rows + tile_rows - 1) / tile_rows;
     ep.raster_reps = M / ep.aux_rows;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int kb_total = kblocks * a_splits;
+  if (pair) {
+    // B rows per CTA = 128: the pair kernel's B box is [64 x 128]
+    uint64_t dims[2] = {uint64_t(K), uint64_t(N)};
+    uint64_t str[1] = {uint64_t(ldb) * 2};
+    uint32_t box[2] = {GEMM_BK, 128};
+    if (int rc = make_tmap_f16(&tmB, B, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    return launch_gemm_pair(tmA, tmB, M, N, kb_total, kblocks, ep, st);
+  }
   if (BN == 256) return launch_gemm<256>(tmA, tmB, M, N, kb_total, kblocks, ep, st);
   if (BN == 128) return launch_gemm<128>(tmA, tmB, M, N, kb_total, kblocks, ep, st);
   if (BN == 64) return launch_gemm<64>(tmA, tmB, M, N, kb_total, kblocks, ep, st);

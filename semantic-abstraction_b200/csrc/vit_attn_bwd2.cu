@@ -31,44 +31,49 @@ constexpr int NCH_HALF = (TC_MAX_T / 16 + 1) / 2;  // 9 chunks of 16 strip colum
 // ---------------------------------------------------------------------------------------------------------
 // delta[pb, h, i] = sum_c dO[pb, i, h*64 + c] * O[b, i, h*64 + c]
 // ---------------------------------------------------------------------------------------------------------
-// block = 32 consecutive (pb, i) rows x H heads: reads are whole contiguous rows (thread = 128 B of dO + 256 B of O), the
-// results are transposed through shared memory so that each head's 32 deltas leave as one 128-byte segment (the first
-// version stored 4 bytes per thread at a stride of T floats: 0.36 ms for 0.8 GB of input, write-transaction bound)
-__global__ void __launch_bounds__(1024) attn_delta_kernel(AttnBwdTcArgs a) {
-  __shared__ float s[32][33];
+// block = 16 consecutive (b, i) rows x H heads, looping over the P labels: a thread keeps its 64 O values in registers and
+// reads 128 B of dO per label (whole contiguous rows per warp); each label's results are transposed through shared memory so
+// that a head's 16 deltas leave as one 64-byte segment.  (First version: one thread per (label, row, head) re-reading O
+// for every label and storing 4 bytes at a stride of T floats — 0.36 ms, L2-bandwidth bound on the 16x re-read of O.)
+constexpr int DELTA_ROWS = 16;
+__global__ void __launch_bounds__(512) attn_delta_kernel(AttnBwdTcArgs a) {
+  __shared__ float s[2][DELTA_ROWS][33];
   const int H = a.H, tid = threadIdx.x;
-  const long long rows_total = (long long)a.P * a.B * a.T;
-  {
-    const int r = tid / H, h = tid - r * H;
-    const long long row = (long long)blockIdx.x * 32 + r;  // (pb, i)
-    if (row < rows_total) {
-      const int i = int(row % a.T);
-      const int pb = int(row / a.T), b = pb % a.B;
-      const __half* g = a.dO16 + size_t(row) * a.ld_do + h * TC_HD;
-      const float* o = a.o32 + (size_t(b) * a.T + i) * a.d + h * TC_HD;
-      uint32_t gv[32], ov[64];
+  const int rows_total = a.B * a.T;
+  const int r = tid / H, h = tid - r * H;
+  const int row = blockIdx.x * DELTA_ROWS + r;  // (b, i)
+  const bool ok = row < rows_total;
+  const int i = ok ? row % a.T : 0, b = ok ? row / a.T : 0;
+  uint32_t ov[64];
+  if (ok) {
+    const float* o = a.o32 + (size_t(b) * a.T + i) * a.d + h * TC_HD;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) ld_global_256(g + 16 * e, gv + 8 * e);
+    for (int e = 0; e < 8; ++e) ld_global_256(o + 8 * e, ov + 8 * e);
+  }
+  const int h2 = tid / DELTA_ROWS, r2 = tid % DELTA_ROWS;
+  const int row2 = blockIdx.x * DELTA_ROWS + r2;
+  const int i2 = row2 % a.T, b2 = row2 / a.T;
+  uint32_t gv[32];
+  auto load_g = [&](int p) {
+    const __half* g = a.dO16 + (size_t(p * a.B + b) * a.T + i) * a.ld_do + h * TC_HD;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) ld_global_256(o + 8 * e, ov + 8 * e);
-      float acc0 = 0.f, acc1 = 0.f;
+    for (int e = 0; e < 4; ++e) ld_global_256(g + 16 * e, gv + 8 * e);
+  };
+  if (ok) load_g(0);
+  for (int p = 0; p < a.P; ++p) {
+    float acc0 = 0.f, acc1 = 0.f;
+    if (ok) {
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
         const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&gv[k]));
         acc0 = fmaf(g2.x, __uint_as_float(ov[2 * k]), acc0);
         acc1 = fmaf(g2.y, __uint_as_float(ov[2 * k + 1]), acc1);
       }
-      s[r][h] = acc0 + acc1;
+      if (p + 1 < a.P) load_g(p + 1);  // next label's row in flight across the transpose
+      s[p & 1][r][h] = acc0 + acc1;
     }
-  }
-  __syncthreads();
-  {
-    const int h = tid >> 5, r = tid & 31;
-    const long long row = (long long)blockIdx.x * 32 + r;
-    if (row < rows_total) {
-      const int i = int(row % a.T), pb = int(row / a.T);
-      a.delta[(size_t(pb) * H + h) * a.T + i] = s[r][h];
-    }
+    __syncthreads();  // (two buffers: the writes of label p+1 cannot overtake the reads of label p by more than one barrier)
+    if (row2 < rows_total) a.delta[(size_t(p * a.B + b2) * H + h2) * a.T + i2] = s[p & 1][r2][h2];
   }
 }
 
@@ -719,8 +724,8 @@ extern "C" int semabs_attn_bwd_tc2(const void* qkv16, int32_t ld_qkv, const void
   const int grid = n_units < num_sms() ? n_units : num_sms();
   if (need_dqkv) {  // delta feeds dS in both passes and the tail; the relevance-only last step needs neither delta nor dQ
     SB_REQUIRE(H <= 32, "semabs_attn_bwd_tc2: at most 32 heads");
-    const long long rows = (long long)P * B * T;
-    attn_delta_kernel<<<(unsigned)((rows + 31) / 32), 32 * H, 0, st>>>(a);
+    const int rows = B * T;
+    attn_delta_kernel<<<(rows + DELTA_ROWS - 1) / DELTA_ROWS, DELTA_ROWS * H, 0, st>>>(a);
     SB_CHECK_CUDA(cudaGetLastError());
     attn_bwd_row_tc2_kernel<<<grid, TC_BWD_THREADS, RowSmem::TOTAL, st>>>(tm_qkv, tm_do, a);
     SB_CHECK_CUDA(cudaGetLastError());

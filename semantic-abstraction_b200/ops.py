@@ -97,6 +97,11 @@ def gemm_f16(
     return out_f32 if out_f32 is not None else out_f16
 
 
+def set_gemm_pair(enable: bool) -> None:
+    """CTA-pair (cta_group::2) GEMM kernel for the large shapes on / off (default on); see semabs_set_gemm_pair."""
+    check(lib().semabs_set_gemm_pair(i32(int(enable))))
+
+
 def split_f16(x: torch.Tensor) -> torch.Tensor:
     """[M,K] fp32 -> [M,2K] fp16 (hi | lo). Test helper; product kernels emit the split in their epilogues."""
     hi = x.half()

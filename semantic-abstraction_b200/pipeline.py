@@ -72,12 +72,13 @@ def relevancy_point_features(rgb: np.ndarray, labels: Sequence[str], saliency_co
 
 @torch.no_grad()
 def rgbd_to_ovssc_logits(net: SemAbs3D, rgb: np.ndarray, depth, cam_intr, cam_extr, labels: Sequence[str],
-                         scene_bounds, saliency_config: dict, sampling_shape: Tuple[int, int, int] = (128, 128, 128),
+                         scene_bounds, saliency_config: dict, sampling_shape: Tuple[int, int, int] = (240, 240, 240),
                          num_input_pts: int = 80000, num_pts_per_pass: int = 2**20, subtract_mean: bool = True,
                          generator: Optional[torch.Generator] = None, masked_volumes: bool = False,
                          cutoff: float = -3.0) -> Dict[str, torch.Tensor]:
     """One image through the whole path. Returns {"relevancies" [P,H,W], "logits" [P, *sampling_shape],
-    "prediction" int64 [*sampling_shape] (arg-max class, visualize.py:236)} — all on the device."""
+    "prediction" int64 [*sampling_shape] (arg-max class, visualize.py:236)} — all on the device.  Defaults are the
+    reference's (visualize.py:163-164: a 240^3 lattice = 13.8 M query points per class in 2^20-point chunks)."""
     dev = next(net.parameters()).device
     P = len(labels)
     rel = relevancy_point_features(rgb, labels, saliency_config, subtract_mean)
@@ -172,3 +173,36 @@ def prediction_volumes(logits: torch.Tensor, sampling_shape, scene_bounds, depth
     in_frustum = check_pts_in_frustum(grid_points, depth_t.shape, cam_extr, cam_intr).view(*sampling_shape)
     keep = (~empty) & in_frustum & ~(tsdf > 0.0)
     return torch.stack([((prediction == c) & keep).float() for c in range(P)])
+
+
+@torch.no_grad()
+def process_batch_ovssc(net: SemAbs3D, batch: Dict, scene_bounds, device, num_input_pts: int,
+                        sampling_shape: Tuple[int, int, int] = (240, 240, 240), num_pts_per_pass: int = int(2**20),
+                        cutoff: float = -3.0, generator: Optional[torch.Generator] = None, return_logits: bool = False):
+    """visualize.process_batch_ovssc (visualize.py:157-248) with the reference's signature and batch keys
+    (`input_xyz_pts` [1, n, 3], `input_feature_pts` [1, P, n, 1] or [P, n], `ovssc_obj_classes`, `depth`, `cam_intr`,
+    `cam_extr`): per class a random sub-sample of `num_input_pts` input points (np.random.choice with replacement there; a
+    device draw here), logits on the `sampling_shape` lattice, then the arg-max / cutoff / frustum / TSDF masks.  Returns
+    {class label: float32 numpy volume [*sampling_shape]} like the reference.  The UNet runs once per class batch (the
+    reference re-runs it, with a fresh sub-sample, for each of the 14 lattice chunks); only the implicit decoder is chunked."""
+    dev = torch.device(device)
+    classes = list(batch["ovssc_obj_classes"])
+    P = len(classes)
+    xyz_all = torch.as_tensor(batch["input_xyz_pts"], dtype=torch.float32, device=dev).reshape(-1, 3)
+    feats_all = torch.as_tensor(batch["input_feature_pts"], dtype=torch.float32, device=dev).reshape(P, -1)
+    n = xyz_all.shape[0]
+    pick = torch.randint(0, n, (P, num_input_pts), device=dev, generator=generator)
+    feats = torch.gather(feats_all, 1, pick)
+    vol = net.feature_volume(xyz_all[pick].contiguous(), feats.view(P, 1, num_input_pts, 1).contiguous())
+    grid_points = get_sample_points(sampling_shape, scene_bounds, dev)
+    assert bool(filter_pts_bounds(grid_points, scene_bounds).all())
+    nq = grid_points.shape[0]
+    logits = torch.empty(P, nq, device=dev)
+    for j in range(0, nq, num_pts_per_pass):
+        q = grid_points[j : j + num_pts_per_pass]
+        out = net.visual_sampler.run([vol], net.unet_num_channels, net.vg, q.unsqueeze(0).expand(P, -1, -1).contiguous())
+        logits[:, j : j + q.shape[0]] = out.view(P, -1)
+    vols = prediction_volumes(logits.view(P, *sampling_shape), sampling_shape, scene_bounds, batch["depth"], batch["cam_intr"],
+                              batch["cam_extr"], cutoff)
+    out = {label: vols[c].cpu().numpy() for c, label in enumerate(classes)}
+    return (out, logits.view(P, *sampling_shape)) if return_logits else out

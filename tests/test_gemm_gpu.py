@@ -118,3 +118,66 @@ def test_gemm_unaligned_rows_use_narrow_accesses():
     ops.gemm_f16(a, b, residual=res[:, 4:], out_f32=out)
     assert torch.allclose(out, _ref(a, b) + res[:, 4:], atol=1e-4, rtol=1e-4)
     assert wide32[:, :4].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(9700, 1024, 512), (38000, 256, 1024), (8224, 3072, 1024)])
+def test_gemm_cta_pair_kernel_matches_single_cta_and_reference(M, N, K):
+    """Shapes with >= 2 x 148 tiles of 128 x 256 take the CTA-pair kernel (gemm2.cu, tcgen05.mma.cta_group::2, 256 x 256 tile
+    per pair; M deliberately not a multiple of 256): every epilogue flavour against fp64 torch and against the single-CTA
+    kernel on the same inputs."""
+    from semabs_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    base = _ref(a, b)
+    outs = {}
+    for pair in (True, False):
+        ops.set_gemm_pair(pair)
+        try:
+            o32 = torch.full((M, N), float("nan"), device="cuda")
+            o16 = torch.full((M, 2 * N), float("nan"), device="cuda", dtype=torch.float16)
+            ops.gemm_f16(a, b, bias=bias, residual=res, out_f32=o32, out_f16=o16, out_f16_splits=2, scale_cols=128, scale=0.125)
+            gq = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+            gg = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+            ops.gemm_f16(a, b, bias=bias, act=ops.ACT_QUICKGELU, out_f16=gq, out_aux16=gg)
+            a2 = ops.split_f16(a.float() * 1.0003)
+            osplit = torch.full((M, N), float("nan"), device="cuda")
+            ops.gemm_f16(a2, b, a_splits=2, out_f32=osplit)
+            torch.cuda.synchronize()
+        finally:
+            ops.set_gemm_pair(True)
+        outs[pair] = (o32, o16, gq, gg, osplit)
+    o32, o16, gq, gg, osplit = outs[True]
+    ref = base + bias
+    ref[:, :128] *= 0.125
+    ref = ref + res
+    assert torch.allclose(o32, ref, atol=2e-4, rtol=1e-5)
+    assert torch.allclose(o16[:, :N].float() + o16[:, N:].float(), o32, atol=1e-5, rtol=1e-5)
+    pre = base + bias
+    sg = torch.sigmoid(1.702 * pre)
+    assert torch.allclose(gq.float(), pre * sg, atol=3e-3, rtol=2e-3)
+    assert torch.allclose(gg.float(), sg + 1.702 * pre * sg * (1 - sg), atol=3e-3, rtol=2e-3)
+    ref_split = ((a.float() * 1.0003).double() @ b.double().t()).float()
+    assert (osplit - ref_split).abs().max().item() < 3e-5 * ref_split.abs().max().item()
+    for x, y in zip(outs[True], outs[False]):  # same K order of accumulation in both kernels: identical bits expected
+        assert torch.equal(x, y) or torch.allclose(x.float(), y.float(), atol=1e-5, rtol=1e-5)
+
+
+def test_gemm_cta_pair_aux_raster():
+    from semabs_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(99)
+    S, P, N, K = 5 * 257, 8, 1024, 256
+    M = S * P
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).half()
+    aux = torch.randn(S, N, device="cuda", generator=g).half()
+    d16 = torch.full((M, 2 * N), float("nan"), device="cuda", dtype=torch.float16)
+    ops.gemm_f16(a, b, aux16=aux, act=ops.ACT_MUL_AUX16, out_f16=d16, out_f16_splits=2)
+    ref = _ref(a, b) * aux.float().repeat(P, 1)
+    got = d16[:, :N].float() + d16[:, N:].float()
+    assert not torch.isnan(got).any()
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4)

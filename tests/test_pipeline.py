@@ -122,3 +122,40 @@ def test_prediction_volume_masks_match_reference_classes():
     got = pipeline.prediction_volumes(logits, shape, BOUNDS, depth, K, T)
     assert torch.equal(got, ref)
     assert 0 < got.sum() < got.numel() / 3 and (tsdf_ref > 0).any() and (tsdf_ref == -1).any()
+
+
+@pytest.mark.gpu
+def test_process_batch_ovssc_on_device():
+    """visualize.process_batch_ovssc mirror (reference signature / batch keys / return value) on the GPU: the device masks must
+    equal the same function evaluated on the CPU (which test_prediction_volume_masks_match_reference_classes pins to the
+    reference's fusion.TSDFVolume + check_pts_in_frustum in the build container), and chunking the lattice must not matter."""
+    from semabs_b200 import pipeline
+    from semabs_b200.net import SemAbs3D
+
+    dev = "cuda"
+    rng = np.random.default_rng(9)
+    H, W = 48, 64
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    depth = (0.9 + 0.5 * xx / W + 0.4 * yy / H + 0.01 * rng.standard_normal((H, W))).astype(np.float32)
+    K = np.array([[0.9 * W, 0, W / 2 - 0.5], [0, 0.9 * W, H / 2 - 0.5], [0, 0, 1]])
+    T = np.array([[1.0, 0, 0, 0.05], [0, 0, 1, -1.3], [0, -1, 0, 0.9], [0, 0, 0, 1]])
+    torch.manual_seed(41)
+    net = SemAbs3D(voxel_shape=(16, 16, 16), scene_bounds=BOUNDS, unet_num_channels=16, unet_f_maps=16, unet_num_groups=8,
+                   unet_num_levels=3, network_inputs=["saliency"], use_pts_feat_extractor=True,
+                   pts_feat_extractor_hidden_dim=128, reduce_method="max", device=dev, batch_size=1).to(dev)
+    classes = ["television", "vase", "carpet"]
+    xyz = pipeline.back_project(torch.from_numpy(depth), K, T[:3])
+    xyz = xyz[pipeline.filter_pts_bounds(xyz, BOUNDS)]
+    batch = dict(input_xyz_pts=xyz[None], input_feature_pts=torch.randn(1, 3, xyz.shape[0], 1, generator=torch.Generator().manual_seed(2)),
+                 ovssc_obj_classes=classes, depth=depth, cam_intr=K, cam_extr=T)
+    shape = (24, 24, 24)
+    vols, logits = pipeline.process_batch_ovssc(net, batch, BOUNDS, dev, num_input_pts=700, sampling_shape=shape, num_pts_per_pass=5000,
+                                                generator=torch.Generator(device=dev).manual_seed(3), return_logits=True)
+    assert list(vols) == classes and all(v.shape == shape and v.dtype == np.float32 for v in vols.values())
+    ref = pipeline.prediction_volumes(logits.cpu(), shape, BOUNDS, depth, K, T)
+    assert all(np.array_equal(vols[c], ref[i].numpy()) for i, c in enumerate(classes))
+    total = sum(v.sum() for v in vols.values())
+    assert 0 < total < np.prod(shape)
+    vols2 = pipeline.process_batch_ovssc(net, batch, BOUNDS, dev, num_input_pts=700, sampling_shape=shape, num_pts_per_pass=2**20,
+                                         generator=torch.Generator(device=dev).manual_seed(3))
+    assert all(np.array_equal(vols[c], vols2[c]) for c in classes)
