@@ -296,8 +296,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
+// (.relaxed: a releasing arrive on a shared::cluster address compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the
+//  arrive — measured: it throttled the peer's TMA producer to one K block per ~1.5 us and the pair GEMM to 32 % tensor-pipe
+//  utilisation.  Nothing these arrives publish is a generic-proxy store: the operand bytes are credited by the async proxy
+//  (TMA complete_tx), and the epilogue's accumulator reads have completed (tcgen05.wait::ld) before it arrives.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA tile load whose completion bytes are credited to an mbarrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
