@@ -262,6 +262,13 @@ int semabs_conv3d_halo(const void* x16_planar, int32_t a_splits, const void* w_i
                        int32_t D, int32_t H, int32_t W, int32_t C_in, int32_t C_out, int32_t precise,
                        const float* residual, int32_t relu, float* out32, void* out16, int32_t o16_splits,
                        double* stats, int32_t groups, void* stream);
+/* C_out = 32 shapes of semabs_conv3d_halo run on CTA pairs by default (conv3d_halo2.cu: tcgen05.mma.cta_group::2, each CTA
+ * keeps its own output row's planes and one 16-channel half of the weights, so every activation row is read from shared
+ * memory once for all 32 channels); enable = 0 forces the single-CTA kernel.  Process-wide switch, not thread-safe. */
+int semabs_set_halo_pair(int32_t enable);
+/* Debug aid of the pair kernel: copies and clears its barrier time-out records (up to 64 x 8 int32); returns their number. */
+int semabs_debug_halo_pair_dump(int32_t* out512);
+
 
 /* nn.MaxPool3d(2) (Encoder.forward, unet3d.py:298,313-317) + statistics of the pooled tensor. */
 int semabs_maxpool3d_2(const float* x, float* y, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C,

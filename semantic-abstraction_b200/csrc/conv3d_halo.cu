@@ -370,6 +370,17 @@ conv3d_halo_kernel(const __half* __restrict__ xplanar, const __half* __restrict_
 
 using namespace sb;
 
+int semabs_conv3d_halo_pair_try(const void* x16_planar, int32_t a_splits, const void* w_img, int32_t w_splits, int32_t N, int32_t D,
+                                int32_t H, int32_t C_in, int32_t C_out, int32_t precise, const float* residual, int32_t relu,
+                                float* out32, void* out16, int32_t o16_splits, double* stats, int32_t groups, void* stream);  // conv3d_halo2.cu
+static int g_halo_pair = 1;
+
+// 1 (default): C_out = 32 shapes run on CTA pairs (conv3d_halo2.cu); 0: single-CTA kernel only (A/B measurements, cross-check)
+extern "C" int semabs_set_halo_pair(int32_t enable) {
+  g_halo_pair = enable ? 1 : 0;
+  return 0;
+}
+
 extern "C" int semabs_conv3d_halo(const void* x16_planar, int32_t a_splits, const void* w_img, int32_t w_splits,
                                   int32_t N, int32_t D, int32_t H, int32_t W, int32_t C_in, int32_t C_out,
                                   int32_t precise, const float* residual, int32_t relu, float* out32, void* out16,
@@ -382,6 +393,11 @@ extern "C" int semabs_conv3d_halo(const void* x16_planar, int32_t a_splits, cons
   SB_REQUIRE(!stats || (groups >= 1 && groups <= 8 && C_out % groups == 0 && (C_out / groups) >= 2),
              "semabs_conv3d_halo: bad GroupNorm groups");
   SB_REQUIRE(N > 0 && D > 0 && H > 0, "semabs_conv3d_halo: bad grid");
+  if (g_halo_pair) {
+    const int rc = semabs_conv3d_halo_pair_try(x16_planar, a_splits, w_img, w_splits, N, D, H, C_in, C_out, precise, residual, relu,
+                                               out32, out16, o16_splits, stats, groups, stream);
+    if (rc >= 0) return rc;  // ran (0) or failed with an error (> 0); -1 = shape does not qualify for the pair kernel
+  }
   HaloParams p{};
   p.N = N, p.D = D, p.H = H, p.C_in = C_in, p.C_out = C_out;
   p.nchunks = a_splits * C_in / 8;

@@ -1,0 +1,453 @@
+// CTA-pair (cta_group::2) variant of the halo-resident 3x3x3 convolution of conv3d_halo.cu for the full-resolution UNet
+// level (W = 128) with C_out = 32 and hi/lo (precise) or single-pass operands.
+//
+// conv3d_halo.cu gives a CTA 16 output channels because three activation planes (150 KB) plus the [W_hi ; W_lo] image of all
+// 32 channels (108 KB) exceed 227 KB, so every activation row is read from shared memory twice (once per channel half) and
+// ncu shows the kernel bound by A-operand reads of N = 32 / 16 MMAs (tensor pipe 19 %, profiles/r01_ncu_full_halo_v2.txt).
+// Here two CTAs form a pair: each keeps its OWN output row's planes (the A operand: M = 256 = 2 x 128 voxels) and ONE 16-channel
+// half of the weights (the B operand is split over the pair along N), and the leader issues tcgen05.mma.cta_group::2:
+//     x_hi * B1,  B1 = [W_hi[0:16] ; W_lo[0:16] | W_hi[16:32] ; W_lo[16:32]]   (N = 64; "|" = CTA boundary)
+//     x_lo * B2,  B2 = [W_hi[0:16] | W_hi[16:32]]                              (N = 32: the first 16 rows of each CTA's image)
+// so each CTA produces all 32 channels of its own row from ONE pass over its planes: half the A reads, half the plane
+// traffic, a quarter of the MMA instructions.  The per-CTA weight image is exactly the per-half image of
+// ops.pack_halo_weights (CTA rank r loads half r), shared memory per CTA is unchanged.
+//
+// Pair protocol (leader = cluster rank 0; cf. gemm2.cu):
+//   plane_full[s]   in the leader, count 2 x 128 producers: the peer's producer threads arrive remotely after
+//                   cp.async.wait_group + fence.proxy.async (their bytes sit in the peer's shared memory, which the
+//                   leader's MMAs read through the pair's operand path);
+//   plane_empty[s]  one per CTA, count 1, multicast tcgen05.commit;   tmem_full[a] likewise;
+//   tmem_empty[a]   in the leader, count 2 x 4 epilogue warps (remote arrives from the peer);
+//   weights         loaded once per CTA, then one cluster barrier before the first MMA.
+// The two CTAs of a pair walk items (n, y, z segment) 2k and 2k+1 in lock step (the item count must be even).
+#include <stdlib.h>
+
+#include "../../include/semabs_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sb {
+
+constexpr int H2_THREADS = 384;                    // 8 role warps + 4 plane-producer warps
+constexpr int H2_PRODUCERS = 128;
+constexpr int H2_W = 128;
+constexpr int H2_XP = H2_W + 2;
+constexpr int H2_CHUNK_DATA = 3 * H2_XP * 16;
+constexpr int H2_CHUNK_BYTES = (H2_CHUNK_DATA + 127) / 128 * 128;
+
+struct Halo2Params {
+  int N, D, H;
+  int C_in;               // 16 or 32
+  int nchunks;            // a_splits * C_in / 8
+  int nplanes;            // ring depth (3 or 4)
+  int zseg, nseg;
+  int plane_bytes;
+  int wres_bytes;         // resident weight image per CTA (one 16-channel half): 27 * (C_in/16) * wk_bytes
+  int wk_bytes;
+  const float* residual;
+  int relu;
+  float* out32;
+  __half* out16;
+  int o16_splits;
+  double* stats;
+  int groups;
+};
+
+// Debuggable waits: a time-out (2 s) records who waited for what in a device buffer, raises a grid-wide abort flag that makes
+// every other waiter fall through, and the kernel terminates normally so that the host can read the record
+// (semabs_debug_halo_pair_dump).  tag: 1 plane_empty, 2 plane_full(start), 3 tmem_empty, 4 plane_full, 5 tmem_full.
+__device__ int g_h2_abort = 0;
+__device__ int g_h2_n = 0;
+__device__ int g_h2_rec[64 * 8];
+__device__ __noinline__ void wait_report(int tag, int idx, uint32_t parity, int extra) {
+  const int k = atomicAdd(&g_h2_n, 1);
+  if (k < 64) {
+    int* r = g_h2_rec + 8 * k;
+    r[0] = int(blockIdx.x), r[1] = int(cluster_ctarank()), r[2] = int(threadIdx.x >> 5), r[3] = tag, r[4] = idx, r[5] = int(parity),
+    r[6] = extra, r[7] = 1;
+  }
+  atomicExch(&g_h2_abort, 1);
+}
+__device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, int tag, int idx, int extra = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0) {
+      if (*reinterpret_cast<volatile int*>(&g_h2_abort)) return;
+      if (global_timer_ns() - t0 > 2000000000ull) {
+        if ((threadIdx.x & 31) == 0) wait_report(tag, idx, parity, extra);
+        return;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void bulk_load2(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int KSTEPS, bool PRECISE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2_THREADS, 1)
+conv3d_halo_pair_kernel(const __half* __restrict__ xplanar, const __half* __restrict__ wimg,
+                        const __grid_constant__ Halo2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* planes = smem;
+  uint8_t* wres = planes + p.nplanes * p.plane_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wres + p.wres_bytes);
+  uint64_t* plane_full = bars;        // [4]  (used in the leader)
+  uint64_t* plane_empty = bars + 4;   // [4]
+  uint64_t* w_full = bars + 8;        // [1]
+  uint64_t* tmem_full = bars + 9;     // [2]
+  uint64_t* tmem_empty = bars + 11;   // [2]  (used in the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NP = p.nplanes;
+  const uint32_t rank = cluster_ctarank();
+  const bool is_leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int items = p.N * p.H * p.nseg;   // even (host-checked): the pair takes items 2k, 2k+1
+  const int pair_items = items >> 1;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 4; ++s) mbar_init(&plane_full[s], 2 * H2_PRODUCERS), mbar_init(&plane_empty[s], 1);
+    mbar_init(w_full, 1);
+    for (int a = 0; a < 2; ++a) mbar_init(&tmem_full[a], 1), mbar_init(&tmem_empty[a], 8);
+    fence_barrier_init();
+  }
+  // accumulators per buffer: NPART partial sums of [x_hi B1] (64 columns) and [x_lo B2] (32 columns)
+  constexpr int NPART = 2;
+  constexpr int HI_COLS = PRECISE ? 64 : 32, LO_COLS = PRECISE ? 32 : 0;
+  constexpr int ACC_COLS = NPART * (HI_COLS + LO_COLS);  // 192 (precise) / 64
+  constexpr int TMEM_COLS = 512;
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  __syncthreads();  // w_full is initialised (by warp 1) before warp 0 arms it — without this the two raced
+  if (warp == 0 && lane == 0) {
+    // resident weights of THIS CTA's 16-channel half
+    mbar_arrive_expect_tx(w_full, p.wres_bytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(wimg) + size_t(rank) * p.wres_bytes;
+    for (int off = 0; off < p.wres_bytes; off += 16384) {
+      const int n = min(16384, p.wres_bytes - off);
+      bulk_load2(wres + off, src + off, n, w_full);
+    }
+  }
+  if (warp == 0) mbar_wait(w_full, 0);  // ... landed before the cluster barrier below
+  tc_fence_before();
+  cluster_sync_all();                   // barrier inits, TMEM allocation and both weight halves visible pair-wide
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int item, int& n, int& y, int& z0) {
+    const int zs = item % p.nseg;
+    y = (item / p.nseg) % p.H;
+    n = item / (p.nseg * p.H);
+    z0 = zs * p.zseg;
+  };
+
+  if (warp >= 8) {
+    // ===== producers (both CTAs): this CTA's activation planes with 16-byte cp.async (zero-fill = conv padding) =====
+    const int pw = warp - 8;
+    const int nseg = p.nchunks * 3;
+    uint32_t pc = 0;
+    int prev_slot = -1;
+    auto publish = [&](int slot) {
+      fence_proxy_async_smem();
+      mbar_arrive_cluster(mapa_u32(smem_u32(&plane_full[slot]), 0));
+    };
+    for (int pi = pair; pi < pair_items; pi += num_pairs) {
+      int n, y, z0;
+      decode(2 * pi + int(rank), n, y, z0);
+      for (int k = 0; k < p.zseg + 2; ++k, ++pc) {
+        const int slot = pc % NP;
+        const uint32_t phase = (pc / NP) & 1;
+        const int z = z0 - 1 + k;
+        mbar_wait_tag(&plane_empty[slot], phase ^ 1, 1, slot, int(pc));
+        const uint32_t dst0 = smem_u32(planes + slot * p.plane_bytes);
+        const bool z_ok = z >= 0 && z < p.D;
+        for (int sg = pw; sg < nseg; sg += 4) {
+          const int c = sg / 3, yy = sg - 3 * c;
+          const int gy = y - 1 + yy;
+          const bool row_ok = z_ok && gy >= 0 && gy < p.H;
+          const __half* srow = xplanar + ((((size_t(n) * p.nchunks + c) * p.D + (z_ok ? z : 0)) * p.H + (row_ok ? gy : 0)) * H2_W) * 8 - 8;
+          const uint32_t drow = dst0 + uint32_t(c) * H2_CHUNK_BYTES + uint32_t(yy * H2_XP) * 16u;
+#pragma unroll
+          for (int xx = lane; xx < H2_XP; xx += 32) {
+            const bool ok = row_ok && xx >= 1 && xx <= H2_W;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(drow + uint32_t(xx) * 16u),
+                         "l"(ok ? srow + xx * 8 : xplanar), "r"(ok ? 16u : 0u)
+                         : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (prev_slot >= 0) {
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+          publish(prev_slot);
+        }
+        prev_slot = slot;
+      }
+    }
+    if (prev_slot >= 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      publish(prev_slot);
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader only (warp-convergent, elected lane issues) =====
+    if (is_leader) {
+      const uint32_t leader = elect_one() ? 1u : 0u;
+      const uint32_t idesc_hi = make_idesc_f16(256, HI_COLS);
+      const uint32_t idesc_lo = make_idesc_f16(256, 32);
+      const uint64_t a_desc0 = make_smem_desc(0, H2_CHUNK_BYTES, 128, SW_NONE);
+      const uint64_t b_desc0 = make_smem_desc(0, 128, 256, SW_NONE) + (smem_u32(wres) >> 4);
+      constexpr uint32_t KS_STEP = 2 * H2_CHUNK_BYTES / 16;
+      const uint32_t lo_off = uint32_t(p.C_in / 8) * H2_CHUNK_BYTES / 16;
+      const uint32_t wk16 = uint32_t(p.wk_bytes) >> 4;
+      uint32_t pc = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int pi = pair; pi < pair_items; pi += num_pairs) {
+        for (int k = 0; k < 2; ++k) mbar_wait_tag(&plane_full[(pc + k) % NP], ((pc + k) / NP) & 1, 2, int((pc + k) % NP), int(pc));
+        for (int i = 0; i < p.zseg; ++i) {
+          mbar_wait_tag(&tmem_empty[acc], acc_phase ^ 1, 3, acc, int(pc) + i);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+          uint64_t bd = b_desc0;
+#pragma unroll
+          for (int dz = 0; dz < 3; ++dz) {
+            const uint32_t pidx = pc + i + dz;
+            if (dz == 2) mbar_wait_tag(&plane_full[pidx % NP], (pidx / NP) & 1, 4, int(pidx % NP), int(pidx));
+            tc_fence_after();
+            const uint64_t ad = a_desc0 + (smem_u32(planes + (pidx % NP) * p.plane_bytes) >> 4);
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                  const int mi = ((dz * 3 + dy) * 3 + dx) * KSTEPS + ks;  // compile-time
+                  const int part = mi % NPART;
+                  const uint32_t accum = mi >= NPART ? 1u : 0u;
+                  const uint64_t a_hi = ad + uint32_t(dy * H2_XP + dx) + uint32_t(ks) * KS_STEP;
+                  umma_f16_pair_elect(d_tmem + part * HI_COLS, a_hi, bd, idesc_hi, accum, leader);
+                  if (PRECISE) umma_f16_pair_elect(d_tmem + NPART * HI_COLS + part * LO_COLS, a_hi + lo_off, bd, idesc_lo, accum, leader);
+                  bd += wk16;
+                }
+              }
+            }
+            if (dz == 0) umma_commit_pair_elect(&plane_empty[(pc + i) % NP], 3u, leader);
+          }
+          umma_commit_pair_elect(&tmem_full[acc], 3u, leader);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+        umma_commit_pair_elect(&plane_empty[(pc + p.zseg) % NP], 3u, leader);
+        umma_commit_pair_elect(&plane_empty[(pc + p.zseg + 1) % NP], 3u, leader);
+        pc += p.zseg + 2;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs): thread = voxel x of this CTA's output row; all 32 output channels in two groups of 16 =====
+    const int q = warp & 3;
+    const int x = q * 32 + lane;
+    constexpr int MAXG = 8;
+    float gs[2][MAXG], gq[2][MAXG];
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int i = 0; i < MAXG; ++i) gs[g][i] = gq[g][i] = 0.f;
+    int stat_n = -1;
+    const int cpg = p.stats ? 32 / p.groups : 16;
+    const int per = cpg >= 16 ? 1 : 16 / cpg;  // groups inside 16 channels
+    auto flush = [&]() {
+      if (stat_n < 0) return;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int gfirst = (g * 16) / cpg;
+#pragma unroll
+        for (int i = 0; i < MAXG; ++i) {
+          if (i < per) {
+            const float s = warp_sum(gs[g][i]), s2 = warp_sum(gq[g][i]);
+            // cpg == 32: both channel groups feed statistics group 0
+            if (lane == 0) {
+              double* dst = p.stats + (size_t(stat_n) * p.groups + gfirst + i) * 2;
+              atomicAdd(dst, double(s));
+              atomicAdd(dst + 1, double(s2));
+            }
+          }
+          gs[g][i] = gq[g][i] = 0.f;
+        }
+      }
+    };
+    const uint32_t empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0), empty1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int pi = pair; pi < pair_items; pi += num_pairs) {
+      int n, y, z0;
+      decode(2 * pi + int(rank), n, y, z0);
+      if (p.stats && n != stat_n) {
+        flush();
+        stat_n = n;
+      }
+      for (int i = 0; i < p.zseg; ++i) {
+        const int z = z0 + i;
+        mbar_wait_tag(&tmem_full[acc], acc_phase, 5, acc, i);
+        tc_fence_after();
+        const size_t ovox = ((size_t(n) * p.D + z) * p.H + y) * H2_W + x;
+        const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * ACC_COLS);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {  // output channels [16 g, 16 g + 16)
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+#pragma unroll
+          for (int part = 0; part < NPART; ++part) {
+            uint32_t rh[16];
+            // x_hi * W_hi: columns [32 g, +16) of the hi block (single-pass: [16 g, +16))
+            tmem_ld_32x32b_x16(trow + part * HI_COLS + (PRECISE ? 32 * g : 16 * g), rh);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(rh[j]);
+            if (PRECISE) {
+              uint32_t r2[16], r3[16];
+              tmem_ld_32x32b_x16(trow + part * HI_COLS + 32 * g + 16, r2);             // x_hi * W_lo
+              tmem_ld_32x32b_x16(trow + NPART * HI_COLS + part * LO_COLS + 16 * g, r3);  // x_lo * W_hi
+              tc_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r2[j]) + __uint_as_float(r3[j]);
+            }
+          }
+          if (g == 1) {
+            // accumulator drained: hand it back before the second group's global-memory work
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc ? empty1 : empty0);
+          }
+          const int col0 = 16 * g;
+          if (p.residual) {
+            const float* rs = p.residual + ovox * 32 + col0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(rs + j);
+              v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.out32) {
+            float* o = p.out32 + ovox * 32 + col0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          if (p.out16) {
+            __half* o = p.out16 + ovox * size_t(p.o16_splits) * 32 + col0;
+            __align__(16) __half2 hh[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(hh)[0];
+            reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(hh)[1];
+            if (p.o16_splits == 2) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 f = __half22float2(hh[j]);
+                hh[j] = __floats2half2_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+              }
+              reinterpret_cast<uint4*>(o + 32)[0] = reinterpret_cast<const uint4*>(hh)[0];
+              reinterpret_cast<uint4*>(o + 32)[1] = reinterpret_cast<const uint4*>(hh)[1];
+            }
+          }
+          if (p.stats) {
+            float ps[8], pq[8];
+            group_sums16(v, cpg, ps, pq);
+#pragma unroll
+            for (int i = 0; i < MAXG; ++i)
+              if (i < per) gs[g][i] += ps[i], gq[g][i] += pq[i];
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    if (p.stats) flush();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+// debug: copies the time-out records of the last pair-kernel launches (8 ints each: cta, rank, warp, tag, index, parity, extra,
+// valid) and clears them; returns the number of records
+extern "C" int semabs_debug_halo_pair_dump(int32_t* out512) {
+  int n = 0, zero = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_h2_n, sizeof(int));
+  cudaMemcpyFromSymbol(out512, g_h2_rec, sizeof(int) * 512);
+  cudaMemcpyToSymbol(g_h2_n, &zero, sizeof(int));
+  cudaMemcpyToSymbol(g_h2_abort, &zero, sizeof(int));
+  return n;
+}
+
+// Returns 0 on success, -1 when the shape does not qualify (the caller then uses the single-CTA kernel), > 0 on error.
+int semabs_conv3d_halo_pair_try(const void* x16_planar, int32_t a_splits, const void* w_img, int32_t w_splits, int32_t N, int32_t D,
+                                int32_t H, int32_t C_in, int32_t C_out, int32_t precise, const float* residual, int32_t relu,
+                                float* out32, void* out16, int32_t o16_splits, double* stats, int32_t groups, void* stream) {
+  if (C_out != 32 || !(C_in == 16 || C_in == 32)) return -1;
+  if (stats && (32 % groups != 0 || 32 / groups < 2)) return -1;
+  Halo2Params p{};
+  p.N = N, p.D = D, p.H = H, p.C_in = C_in;
+  p.nchunks = a_splits * C_in / 8;
+  p.wk_bytes = (precise ? 4 : 2) * 256;
+  p.wres_bytes = 27 * (C_in / 16) * p.wk_bytes;
+  p.plane_bytes = p.nchunks * H2_CHUNK_BYTES;
+  p.nplanes = (size_t(4) * p.plane_bytes + p.wres_bytes + 1024 <= size_t(227) * 1024) ? 4 : 3;
+  const size_t smem = size_t(p.nplanes) * p.plane_bytes + p.wres_bytes + 256 + 128;
+  if (smem > 227 * 1024) return -1;
+  int pairs_hw = num_sms() / 2;
+  if (const char* e = getenv("SEMABS_HALO_PAIRS")) pairs_hw = atoi(e) > 0 ? atoi(e) : pairs_hw;  // (tests: force several items per pair)
+  int zseg = D;
+  while (zseg > 16 && (long long)N * H * (D / zseg) < 12LL * pairs_hw && zseg % 2 == 0) zseg /= 2;
+  p.zseg = zseg, p.nseg = D / zseg;
+  if (p.zseg * p.nseg != D) return -1;
+  const int items = N * H * p.nseg;
+  if (items % 2 != 0 || items < 2) return -1;
+  p.residual = residual, p.relu = relu, p.out32 = out32, p.out16 = (__half*)out16, p.o16_splits = o16_splits;
+  p.stats = stats, p.groups = groups;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pair_items = items / 2;
+  const int pairs = pair_items < pairs_hw ? pair_items : pairs_hw;
+  const __half* xp = (const __half*)x16_planar;
+  const __half* wp = (const __half*)w_img;
+#define SB_HALO2_LAUNCH(KS, PR)                                                                                         \
+  do {                                                                                                                  \
+    static bool cfg = false;                                                                                            \
+    if (!cfg) {                                                                                                         \
+      SB_CHECK_CUDA(cudaFuncSetAttribute(conv3d_halo_pair_kernel<KS, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         227 * 1024));                                                                  \
+      cfg = true;                                                                                                       \
+    }                                                                                                                   \
+    conv3d_halo_pair_kernel<KS, PR><<<2 * pairs, H2_THREADS, smem, st>>>(xp, wp, p);                                    \
+  } while (0)
+  if (C_in == 32 && precise) SB_HALO2_LAUNCH(2, true);
+  else if (C_in == 32) SB_HALO2_LAUNCH(2, false);
+  else if (precise) SB_HALO2_LAUNCH(1, true);
+  else SB_HALO2_LAUNCH(1, false);
+#undef SB_HALO2_LAUNCH
+  SB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -338,6 +338,11 @@ def conv3d_halo(x16_planar, w_img, *, N, D, H, W, C_in, C_out, a_splits=1, w_spl
     )
 
 
+def set_halo_pair(enable: bool) -> None:
+    """CTA-pair variant of the halo-resident convolution on / off (default on); see semabs_set_halo_pair."""
+    check(lib().semabs_set_halo_pair(i32(int(enable))))
+
+
 def pack_halo_weights(w: torch.Tensor, splits: int) -> torch.Tensor:
     """conv.weight [Co, Ci, 3,3,3] fp32 -> resident UMMA no-swizzle core-matrix images for semabs_conv3d_halo, fp16:
     [Co/16 halves][27 taps][Ci/16 k-blocks][N/8 groups][2 k-chunks][8 rows][8 elems], where the N rows of a half are

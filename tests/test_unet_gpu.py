@@ -212,11 +212,18 @@ def test_semabsvool_matches_reference(gold):
     assert out.shape == ref.shape and err < TOL
 
 
+@pytest.mark.parametrize("pair", [True, False])
 @pytest.mark.parametrize("N,D,H,Ci,Co,precise", [(1, 4, 6, 16, 16, True), (2, 8, 8, 32, 32, True), (1, 16, 5, 32, 16, False),
-                                                  (1, 32, 4, 16, 32, True)])
-def test_conv_halo_resident(N, D, H, Ci, Co, precise):
-    """semabs_conv3d_halo (W = 128 level): chunk-planar input via groupnorm_apply(planar), per-tap weight images."""
+                                                  (1, 32, 4, 16, 32, True), (3, 6, 10, 32, 32, False), (1, 4, 5, 32, 32, True),
+                                                  (2, 64, 12, 32, 32, True), (1, 8, 6, 16, 32, False)])
+def test_conv_halo_resident(N, D, H, Ci, Co, precise, pair, request):
+    """semabs_conv3d_halo (W = 128 level): chunk-planar input via groupnorm_apply(planar), per-tap weight images.
+    pair=True: C_out = 32 shapes with an even item count take the CTA-pair kernel (conv3d_halo2.cu, cta_group::2 MMAs); the
+    (1, 4, 5, ...) case has an odd item count and exercises the fall-back to the single-CTA kernel."""
     from semabs_b200 import ops
+
+    ops.set_halo_pair(pair)
+    request.addfinalizer(lambda: ops.set_halo_pair(True))
 
     W = 128
     g = torch.Generator(device=dev).manual_seed(D * 10 + Ci + Co)
