@@ -103,6 +103,11 @@ int semabs_vit_embed_lnpre(const float* patch, const float* cls, const float* po
 int semabs_layernorm_bwd(const float* dy, const float* dres, const float* x, int64_t x_stride, int32_t x_rows,
                          const float* mean, const float* rstd, const float* gamma, float* dx32, int64_t out_stride,
                          void* dx16, int64_t out16_stride, int32_t M, int32_t d, int32_t splits, void* stream);
+/* Same operator with the cotangent dy given as fp16 rows [M, d] (the dgrad GEMM's out_f16): the LayerNorm backward is
+ * HBM-bound at 14 bytes per element; an fp16 dy makes it 12 and halves the producing GEMM's output write. */
+int semabs_layernorm_bwd_h(const void* dy16, const float* dres, const float* x, int64_t x_stride, int32_t x_rows,
+                           const float* mean, const float* rstd, const float* gamma, float* dx32, int64_t out_stride,
+                           void* dx16, int64_t out16_stride, int32_t M, int32_t d, int32_t splits, void* stream);
 
 /* Multi-head self-attention forward, head dim 64 (multi_head_attention_forward, CLIP/clip/auxiliary.py:260-337).
  * qkv [B*T, 3d] fp32 with q pre-scaled (auxiliary.py:207); softmax(q k^T) — what the reference stores through its

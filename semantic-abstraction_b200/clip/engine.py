@@ -53,6 +53,9 @@ class ClipEngine:
         self.sparse_last_block = True
         self.tc_attention = True  # tcgen05 attention forward (T <= 272); False = the mma.sync kernel of vit_attn.cu
         self.tc_attention_bwd = True  # tcgen05 attention backward (T <= 272); False = the mma.sync kernels
+        # dense-block LayerNorm cotangents as fp16 (one more fp16 rounding of the class every dgrad operand already has with
+        # bwd_splits = 1; with bwd_splits = 2 — the fp32-grade backward — they stay fp32)
+        self.ln_bwd_f16 = bwd_splits == 1
 
     # ------------------------------------------------------------------------------------------------
     def _block_forward(self, blk: BlockWeights, x, x_next, *, n_seq, T, H, d, causal, saved: Optional[dict]):
@@ -211,7 +214,9 @@ class ClipEngine:
         self.kernel_launches += 6
 
         du16 = ws.get("du16", (Mb, sb * 4 * d), F16)
-        dh = ws.get("dh", (Mb, d))
+        # cotangent of the LayerNorm outputs: fp16 straight from the dgrad GEMM epilogue (the LayerNorm backward is HBM-bound)
+        dh = ws.get("dh16", (Mb, d), F16) if self.ln_bwd_f16 else ws.get("dh", (Mb, d))
+        dh_out = dict(out_f16=dh) if self.ln_bwd_f16 else dict(out_f32=dh)
         dxm = ws.get("dx_mid", (Mb, d))
         dxm16 = ws.get("dx_mid16", (Mb, sb * d), F16)
         dO16 = ws.get("dO16", (Mb, d), F16)
@@ -251,7 +256,7 @@ class ClipEngine:
             if need:
                 dxm.zero_()
                 dxm.view(PB, T, d)[:, 0, :].copy_(dxmc)  # scatter of the class-token rows (data movement)
-                ops.gemm_f16(dqkv16, blk.w_inT, a_splits=sb, out_f32=dh)
+                ops.gemm_f16(dqkv16, blk.w_inT, a_splits=sb, **dh_out)
                 ops.layernorm_bwd(dh, sv["x_in"], sv["mean1"], sv["rstd1"], blk.ln1_g, dx, M=Mb, d=d, x_rows=B * T,
                                   dres=dxm, dx16=dx16, splits=sb)
                 self.kernel_launches += 2
@@ -267,7 +272,7 @@ class ClipEngine:
             # x_out = x_mid + c_proj(quickgelu(c_fc(ln_2(x_mid))))
             ops.gemm_f16(dx16, blk.w_projT, a_splits=sb, aux16=sv["gelu_grad16"], act=ops.ACT_MUL_AUX16, out_f16=du16,
                          out_f16_splits=sb)
-            ops.gemm_f16(du16, blk.w_fcT, a_splits=sb, out_f32=dh)
+            ops.gemm_f16(du16, blk.w_fcT, a_splits=sb, **dh_out)
             ops.layernorm_bwd(dh, sv["x_mid"], sv["mean2"], sv["rstd2"], blk.ln2_g, dxm, M=Mb, d=d, x_rows=B * T,
                               dres=dx, dx16=dxm16, splits=sb)
             # x_mid = x_in + out_proj(attn(ln_1(x_in)))
@@ -279,7 +284,7 @@ class ClipEngine:
             ops.rollout_update(r, wpart, PB, H, T)
             self.kernel_launches += 8 if need else 7
             if need:
-                ops.gemm_f16(dqkv16, blk.w_inT, a_splits=sb, out_f32=dh)
+                ops.gemm_f16(dqkv16, blk.w_inT, a_splits=sb, **dh_out)
                 ops.layernorm_bwd(dh, sv["x_in"], sv["mean1"], sv["rstd1"], blk.ln1_g, dx, M=Mb, d=d, x_rows=B * T,
                                   dres=dxm, dx16=dx16, splits=sb)
                 self.kernel_launches += 2

@@ -255,11 +255,26 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         stat_n = n_w < p.N ? n_w : -1;
         stat_nb = nb;
       }
+      const size_t ovox = ((size_t(n) * p.Do + (z * p.os + p.oz)) * p.Ho + (y * p.os + p.oy)) * p.Wo + (x * p.os + p.ox);
+      // the residual (decoder skip / block input) does not depend on the accumulator: chunk 0 is requested BEFORE waiting for
+      // the MMAs and chunk c+1 while chunk c is processed.  (ncu, round 2: the transposed convolutions into the 128^3 level ran at
+      // 1 TB/s with the tensor pipe 2-17 % busy — one exposed global-load round trip per 16-channel chunk of every tile.)
+      float4 rs_cur[4], rs_nxt[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rs_cur[j] = rs_nxt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* rs_row = (p.residual && ok) ? p.residual + ovox * p.C_out + nb * BN : nullptr;
+      if (rs_row) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rs_cur[j] = *reinterpret_cast<const float4*>(rs_row + 4 * j);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const size_t ovox = ((size_t(n) * p.Do + (z * p.os + p.oz)) * p.Ho + (y * p.os + p.oy)) * p.Wo + (x * p.os + p.ox);
 #pragma unroll 1
       for (int c = 0; c < BN / 16; ++c) {
+        if (rs_row && c + 1 < BN / 16) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rs_nxt[j] = *reinterpret_cast<const float4*>(rs_row + (c + 1) * 16 + 4 * j);
+        }
         uint32_t rr[16];
         tmem_ld_32x32b_x16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * Cfg::ACC_COLS + c * 16), rr);
         uint32_t r2[16];
@@ -278,10 +293,9 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if (p.residual) {
-            const float* rs = p.residual + ovox * p.C_out + col0;
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(rs + j);
+              const float4 b = rs_cur[j >> 2];
               v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
             }
           }
@@ -328,6 +342,8 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rs_cur[j] = rs_nxt[j];
       }
       tc_fence_before();
       __syncwarp();

@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(LnFwdArgs a) {
 // gradient of ln_post into the [P*B, T, d] token grid).
 // ---------------------------------------------------------------------------------------------------------
 struct LnBwdArgs {
-  const float* dy;       // [M, d]
+  const float* dy;       // [M, d] fp32, or null when dy16 is given
+  const __half* dy16;    // [M, d] fp16 (the dgrad GEMM's fp16 output: 2 instead of 4 bytes per element each way)
   const float* dres;     // optional [M, d] (row stride = out_stride)
   const float* x;        // forward input rows, x + (r % x_rows) * x_stride
   long long x_stride;
@@ -133,10 +134,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(LnBwdArgs a) {
   const int fr = row % a.x_rows;
   const float mean = a.mean[fr], rstd = a.rstd[fr];
   const float* x = a.x + size_t(fr) * a.x_stride;
-  const float* dy = a.dy + size_t(row) * a.d;
+  const float* dy = a.dy ? a.dy + size_t(row) * a.d : nullptr;
+  const __half* dyh = a.dy16 ? a.dy16 + size_t(row) * a.d : nullptr;
   float s1 = 0.f, s2 = 0.f;
   for (int i = threadIdx.x; i < a.d; i += blockDim.x) {
-    const float gi = dy[i] * a.gamma[i];
+    const float gi = (dy ? dy[i] : __half2float(dyh[i])) * a.gamma[i];
     const float xi = (x[i] - mean) * rstd;
     g[i] = gi;
     xh[i] = xi;
@@ -211,13 +213,22 @@ __global__ void __launch_bounds__(128, 4) layernorm_bwd_warp_kernel(LnBwdArgs a)
   const int fr = row % a.x_rows;
   const float mean = a.mean[fr], rstd = a.rstd[fr];
   const float* x = a.x + size_t(fr) * a.x_stride;
-  const float* dy = a.dy + size_t(row) * a.d;
+  const float* dy = a.dy ? a.dy + size_t(row) * a.d : nullptr;
+  const __half* dyh = a.dy16 ? a.dy16 + size_t(row) * a.d : nullptr;
   float4 g[NV], xh[NV];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int col = (k * 32 + lane) * 4;
-    const float4 d4 = *reinterpret_cast<const float4*>(dy + col), w4 = *reinterpret_cast<const float4*>(a.gamma + col);
+    float4 d4;
+    if (dy) {
+      d4 = *reinterpret_cast<const float4*>(dy + col);
+    } else {
+      const uint2 u = *reinterpret_cast<const uint2*>(dyh + col);
+      const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      d4 = make_float4(f0.x, f0.y, f1.x, f1.y);
+    }
+    const float4 w4 = *reinterpret_cast<const float4*>(a.gamma + col);
     const float4 x4 = *reinterpret_cast<const float4*>(x + col);
     g[k] = make_float4(d4.x * w4.x, d4.y * w4.y, d4.z * w4.z, d4.w * w4.w);
     xh[k] = make_float4((x4.x - mean) * rstd, (x4.y - mean) * rstd, (x4.z - mean) * rstd, (x4.w - mean) * rstd);
@@ -380,13 +391,13 @@ extern "C" int semabs_vit_embed_lnpre(const float* patch, const float* cls, cons
   return 0;
 }
 
-extern "C" int semabs_layernorm_bwd(const float* dy, const float* dres, const float* x, int64_t x_stride,
-                                    int32_t x_rows, const float* mean, const float* rstd, const float* gamma,
-                                    float* dx32, int64_t out_stride, void* dx16, int64_t out16_stride, int32_t M,
-                                    int32_t d, int32_t splits, void* stream) {
-  SB_REQUIRE(dy && x && mean && rstd && gamma && dx32 && M > 0 && x_rows > 0, "semabs_layernorm_bwd: bad arguments");
+static int layernorm_bwd_impl(const float* dy, const void* dy16, const float* dres, const float* x, int64_t x_stride,
+                              int32_t x_rows, const float* mean, const float* rstd, const float* gamma,
+                              float* dx32, int64_t out_stride, void* dx16, int64_t out16_stride, int32_t M,
+                              int32_t d, int32_t splits, void* stream) {
+  SB_REQUIRE((dy || dy16) && x && mean && rstd && gamma && dx32 && M > 0 && x_rows > 0, "semabs_layernorm_bwd: bad arguments");
   LnBwdArgs a{};
-  a.dy = dy, a.dres = dres, a.x = x, a.x_stride = x_stride, a.x_rows = x_rows, a.mean = mean, a.rstd = rstd;
+  a.dy = dy, a.dy16 = (const __half*)dy16, a.dres = dres, a.x = x, a.x_stride = x_stride, a.x_rows = x_rows, a.mean = mean, a.rstd = rstd;
   a.gamma = gamma, a.dx32 = dx32, a.out_stride = out_stride, a.dx16 = (__half*)dx16, a.out16_stride = out16_stride;
   a.M = M, a.d = d, a.splits = splits;
   const bool aligned = (x_stride % 4 == 0) && (out_stride % 4 == 0) && (out16_stride % 4 == 0);
@@ -395,6 +406,23 @@ extern "C" int semabs_layernorm_bwd(const float* dy, const float* dres, const fl
     layernorm_bwd_kernel<<<M, 256, 2 * d * sizeof(float), (cudaStream_t)stream>>>(a);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int semabs_layernorm_bwd(const float* dy, const float* dres, const float* x, int64_t x_stride,
+                                    int32_t x_rows, const float* mean, const float* rstd, const float* gamma,
+                                    float* dx32, int64_t out_stride, void* dx16, int64_t out16_stride, int32_t M,
+                                    int32_t d, int32_t splits, void* stream) {
+  return layernorm_bwd_impl(dy, nullptr, dres, x, x_stride, x_rows, mean, rstd, gamma, dx32, out_stride, dx16, out16_stride, M, d,
+                            splits, stream);
+}
+
+// same operator with the cotangent given as fp16 rows [M, d] (what the dgrad GEMM emits with out_f16)
+extern "C" int semabs_layernorm_bwd_h(const void* dy16, const float* dres, const float* x, int64_t x_stride,
+                                      int32_t x_rows, const float* mean, const float* rstd, const float* gamma,
+                                      float* dx32, int64_t out_stride, void* dx16, int64_t out16_stride, int32_t M,
+                                      int32_t d, int32_t splits, void* stream) {
+  return layernorm_bwd_impl(nullptr, dy16, dres, x, x_stride, x_rows, mean, rstd, gamma, dx32, out_stride, dx16, out16_stride, M, d,
+                            splits, stream);
 }
 
 extern "C" int semabs_clip_logit_seed(const float* f, const float* W, float* logits, void* seed16, int32_t B,

@@ -138,10 +138,14 @@ def vit_embed_lnpre(patch, cls, pos, gamma, beta, x_out, B, T, d):
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx32, *, M, d, x_rows, x_stride=None, dres=None, out_stride=None, dx16=None,
                   out16_stride=None, splits=1):
-    CALL_PROFILE.note("semabs_layernorm_bwd", bytes=M * d * (4 + 4 + (4 if dres is not None else 0) + (2 * splits if dx16 is not None else 0))
+    """dy: fp32 [M, d] or fp16 [M, d] (semabs_layernorm_bwd_h)."""
+    half = dy.dtype == torch.float16
+    CALL_PROFILE.note("semabs_layernorm_bwd_h" if half else "semabs_layernorm_bwd",
+                      bytes=M * d * ((2 if half else 4) + 4 + (4 if dres is not None else 0) + (2 * splits if dx16 is not None else 0))
                       + x_rows * d * 4)
+    fn = lib().semabs_layernorm_bwd_h if half else lib().semabs_layernorm_bwd
     check(
-        lib().semabs_layernorm_bwd(
+        fn(
             ptr(dy), ptr(dres), ptr(x), _i64(d if x_stride is None else x_stride), i32(x_rows), ptr(mean), ptr(rstd),
             ptr(gamma), ptr(dx32), _i64(d if out_stride is None else out_stride), ptr(dx16),
             _i64(splits * d if out16_stride is None else out16_stride), i32(M), i32(d), i32(splits), stream_ptr(),
