@@ -271,6 +271,15 @@ int semabs_conv3d_halo(const void* x16_planar, int32_t a_splits, const void* w_i
  * keeps its own output row's planes and one 16-channel half of the weights, so every activation row is read from shared
  * memory once for all 32 channels); enable = 0 forces the single-CTA kernel.  Process-wide switch, not thread-safe. */
 int semabs_set_halo_pair(int32_t enable);
+/* One sample, C_out = 32, CTA-pair kernel, with the GroupNorm of the CONSUMED tensor folded into the convolution (inference path
+ * of ResidualUNet3D at the 128-wide level): w_img = pack of W * (gamma * rstd) of this sample, bias_cls [27][32] = the shift term
+ * sum_taps W (beta - mean * gamma * rstd) for each of the 3 x 3 x 3 border classes (which taps fall inside the grid); the operand
+ * x16_planar is then the RAW tensor as chunk-planar hi | lo fp16, written by the producing convolution through out_planar.
+ * res_planar: residual read from such a tensor.  bias_cls / residual / res_planar / out32 / out16 / out_planar / stats optional. */
+int semabs_conv3d_halo_fused(const void* x16_planar, int32_t a_splits, const void* w_img, int32_t w_splits, int32_t D, int32_t H,
+                             int32_t C_in, int32_t precise, const float* bias_cls, const float* residual, const void* res_planar,
+                             int32_t relu, float* out32, void* out16, int32_t o16_splits, void* out_planar, double* stats,
+                             int32_t groups, void* stream);
 /* Debug aid of the pair kernel: copies and clears its barrier time-out records (up to 64 x 8 int32); returns their number. */
 int semabs_debug_halo_pair_dump(int32_t* out512);
 

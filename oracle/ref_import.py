@@ -17,6 +17,7 @@ The shims below are the ones SURVEY.md §8c lists; none of them changes referenc
 from __future__ import annotations
 
 import importlib
+import importlib.util
 import os
 import sys
 import types
@@ -45,6 +46,14 @@ def reference_available() -> bool:
 def _stub(name, **attrs):
     if name in sys.modules:
         return sys.modules[name]
+    if not attrs and "." not in name:
+        # only stand in for what is really absent: a stub of an installed package (filelock, imageio ...) would break every
+        # later import of it in the same process
+        try:
+            if importlib.util.find_spec(name) is not None:
+                return importlib.import_module(name)
+        except (ImportError, ValueError):
+            pass
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
     sys.modules[name] = m

@@ -372,7 +372,8 @@ using namespace sb;
 
 int semabs_conv3d_halo_pair_try(const void* x16_planar, int32_t a_splits, const void* w_img, int32_t w_splits, int32_t N, int32_t D,
                                 int32_t H, int32_t C_in, int32_t C_out, int32_t precise, const float* residual, int32_t relu,
-                                float* out32, void* out16, int32_t o16_splits, double* stats, int32_t groups, void* stream);  // conv3d_halo2.cu
+                                float* out32, void* out16, int32_t o16_splits, double* stats, int32_t groups, void* stream,
+                                const float* bias_cls, const void* res_planar, void* out_planar);  // conv3d_halo2.cu
 static int g_halo_pair = 1;
 
 // 1 (default): C_out = 32 shapes run on CTA pairs (conv3d_halo2.cu); 0: single-CTA kernel only (A/B measurements, cross-check)
@@ -395,7 +396,7 @@ extern "C" int semabs_conv3d_halo(const void* x16_planar, int32_t a_splits, cons
   SB_REQUIRE(N > 0 && D > 0 && H > 0, "semabs_conv3d_halo: bad grid");
   if (g_halo_pair) {
     const int rc = semabs_conv3d_halo_pair_try(x16_planar, a_splits, w_img, w_splits, N, D, H, C_in, C_out, precise, residual, relu,
-                                               out32, out16, o16_splits, stats, groups, stream);
+                                               out32, out16, o16_splits, stats, groups, stream, nullptr, nullptr, nullptr);
     if (rc >= 0) return rc;  // ran (0) or failed with an error (> 0); -1 = shape does not qualify for the pair kernel
   }
   HaloParams p{};

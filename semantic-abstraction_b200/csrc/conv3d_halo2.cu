@@ -51,6 +51,12 @@ struct Halo2Params {
   int o16_splits;
   double* stats;
   int groups;
+  // fused GroupNorm of the CONSUMED tensor (inference, one sample per launch): the weights carry gamma * rstd, the shift term
+  // sum_taps W b depends on which taps fall inside the grid -> 27 border classes x 32 channels, added in the epilogue
+  const float* bias_cls;      // [27][32] or null
+  const __half* res_planar;   // residual given as chunk-planar hi | lo fp16 of the raw tensor (instead of `residual`), or null
+  __half* out_planar;         // raw output as chunk-planar hi | lo fp16 = the next convolution's operand, or null
+  long long S;                // D * H * 128
 };
 
 // Debuggable waits: a time-out (2 s) records who waited for what in a device buffer, raises a grid-wide abort flag that makes
@@ -330,6 +336,32 @@ conv3d_halo_pair_kernel(const __half* __restrict__ xplanar, const __half* __rest
             if (lane == 0) mbar_arrive_cluster(acc ? empty1 : empty0);
           }
           const int col0 = 16 * g;
+          if (p.bias_cls) {
+            const int cz = z == 0 ? 0 : (z == p.D - 1 ? 2 : 1), cy = y == 0 ? 0 : (y == p.H - 1 ? 2 : 1);
+            const int cx = x == 0 ? 0 : (x == H2_W - 1 ? 2 : 1);
+            const float* bc = p.bias_cls + ((cz * 3 + cy) * 3 + cx) * 32 + col0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(bc + j);
+              v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+            }
+          }
+          if (p.res_planar) {
+            // chunk-planar [chunk][voxel][8]: 4 hi chunks then 4 lo chunks of the 32 channels (one sample per launch)
+            const size_t vox = (size_t(z) * p.H + y) * H2_W + x;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint4 uh = *reinterpret_cast<const uint4*>(p.res_planar + (size_t(2 * g + k) * p.S + vox) * 8);
+              const uint4 ul = *reinterpret_cast<const uint4*>(p.res_planar + (size_t(4 + 2 * g + k) * p.S + vox) * 8);
+              const __half2* hh2 = reinterpret_cast<const __half2*>(&uh);
+              const __half2* hl2 = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 fh = __half22float2(hh2[e]), fl = __half22float2(hl2[e]);
+                v[8 * k + 2 * e] += fh.x + fl.x, v[8 * k + 2 * e + 1] += fh.y + fl.y;
+              }
+            }
+          }
           if (p.residual) {
             const float* rs = p.residual + ovox * 32 + col0;
 #pragma unroll
@@ -362,6 +394,21 @@ conv3d_halo_pair_kernel(const __half* __restrict__ xplanar, const __half* __rest
               }
               reinterpret_cast<uint4*>(o + 32)[0] = reinterpret_cast<const uint4*>(hh)[0];
               reinterpret_cast<uint4*>(o + 32)[1] = reinterpret_cast<const uint4*>(hh)[1];
+            }
+          }
+          if (p.out_planar) {
+            const size_t vox = (size_t(z) * p.H + y) * H2_W + x;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              __align__(16) __half2 hh[4], hl[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                hh[e] = __floats2half2_rn(v[8 * k + 2 * e], v[8 * k + 2 * e + 1]);
+                const float2 f = __half22float2(hh[e]);
+                hl[e] = __floats2half2_rn(v[8 * k + 2 * e] - f.x, v[8 * k + 2 * e + 1] - f.y);
+              }
+              *reinterpret_cast<uint4*>(p.out_planar + (size_t(2 * g + k) * p.S + vox) * 8) = *reinterpret_cast<const uint4*>(hh);
+              *reinterpret_cast<uint4*>(p.out_planar + (size_t(4 + 2 * g + k) * p.S + vox) * 8) = *reinterpret_cast<const uint4*>(hl);
             }
           }
           if (p.stats) {
@@ -406,7 +453,8 @@ extern "C" int semabs_debug_halo_pair_dump(int32_t* out512) {
 // Returns 0 on success, -1 when the shape does not qualify (the caller then uses the single-CTA kernel), > 0 on error.
 int semabs_conv3d_halo_pair_try(const void* x16_planar, int32_t a_splits, const void* w_img, int32_t w_splits, int32_t N, int32_t D,
                                 int32_t H, int32_t C_in, int32_t C_out, int32_t precise, const float* residual, int32_t relu,
-                                float* out32, void* out16, int32_t o16_splits, double* stats, int32_t groups, void* stream) {
+                                float* out32, void* out16, int32_t o16_splits, double* stats, int32_t groups, void* stream,
+                                const float* bias_cls, const void* res_planar, void* out_planar) {
   if (C_out != 32 || !(C_in == 16 || C_in == 32)) return -1;
   if (stats && (32 % groups != 0 || 32 / groups < 2)) return -1;
   Halo2Params p{};
@@ -428,6 +476,8 @@ int semabs_conv3d_halo_pair_try(const void* x16_planar, int32_t a_splits, const 
   if (items % 2 != 0 || items < 2) return -1;
   p.residual = residual, p.relu = relu, p.out32 = out32, p.out16 = (__half*)out16, p.o16_splits = o16_splits;
   p.stats = stats, p.groups = groups;
+  p.bias_cls = bias_cls, p.res_planar = (const __half*)res_planar, p.out_planar = (__half*)out_planar;
+  p.S = (long long)D * H * H2_W;
   cudaStream_t st = (cudaStream_t)stream;
   const int pair_items = items / 2;
   const int pairs = pair_items < pairs_hw ? pair_items : pairs_hw;
@@ -450,4 +500,23 @@ int semabs_conv3d_halo_pair_try(const void* x16_planar, int32_t a_splits, const 
 #undef SB_HALO2_LAUNCH
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// One sample (N = 1), C_out = 32, on the CTA-pair kernel with the GroupNorm of the consumed tensor folded in: `w_img` holds
+// W * (gamma * rstd) of THIS sample (ops.pack_halo_weights layout), bias_cls [27][32] the per-border-class shift term; the
+// operand `x16_planar` is then the RAW tensor (hi | lo), which the producing convolution wrote itself through `out_planar` —
+// no GroupNorm-apply pass and no fp32 copy in between.  res_planar: residual read from such a raw planar tensor.  Any of
+// bias_cls / res_planar / out_planar may be null (plain behaviour).  Inference path of ResidualUNet3D at the 128-wide level.
+extern "C" int semabs_conv3d_halo_fused(const void* x16_planar, int32_t a_splits, const void* w_img, int32_t w_splits, int32_t D,
+                                        int32_t H, int32_t C_in, int32_t precise, const float* bias_cls, const float* residual,
+                                        const void* res_planar, int32_t relu, float* out32, void* out16, int32_t o16_splits,
+                                        void* out_planar, double* stats, int32_t groups, void* stream) {
+  SB_REQUIRE(x16_planar && w_img && (out32 || out16 || out_planar), "semabs_conv3d_halo_fused: null pointer");
+  SB_REQUIRE(precise ? (a_splits == 2 && w_splits == 2) : (a_splits == 1 && w_splits == 1), "semabs_conv3d_halo_fused: operand splits must match the precision mode");
+  SB_REQUIRE(!(residual && res_planar), "semabs_conv3d_halo_fused: one residual at most");
+  SB_REQUIRE((!res_planar && !out_planar) || a_splits == 2, "semabs_conv3d_halo_fused: planar residual / output are hi | lo tensors");
+  const int rc = semabs_conv3d_halo_pair_try(x16_planar, a_splits, w_img, w_splits, 1, D, H, C_in, 32, precise, residual, relu, out32,
+                                             out16, o16_splits, stats, groups, stream, bias_cls, res_planar, out_planar);
+  SB_REQUIRE(rc >= 0, "semabs_conv3d_halo_fused: shape not supported by the CTA-pair kernel (C_in %d, D %d, H %d)", C_in, D, H);
+  return rc;
 }

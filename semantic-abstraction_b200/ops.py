@@ -342,6 +342,19 @@ def conv3d_halo(x16_planar, w_img, *, N, D, H, W, C_in, C_out, a_splits=1, w_spl
     )
 
 
+def conv3d_halo_fused(x16_planar, w_img, *, D, H, C_in, a_splits, w_splits, precise, bias_cls=None, residual=None, res_planar=None,
+                      relu=False, out32=None, out16=None, o16_splits=1, out_planar=None, stats=None, groups=0):
+    """One sample, C_out = 32, CTA-pair kernel with the consumed tensor's GroupNorm folded in (see semabs_conv3d_halo_fused)."""
+    CALL_PROFILE.note("semabs_conv3d_halo_fused", flops=2.0 * D * H * 128 * 27 * C_in * 32)
+    check(
+        lib().semabs_conv3d_halo_fused(
+            ptr(x16_planar), i32(a_splits), ptr(w_img), i32(w_splits), i32(D), i32(H), i32(C_in), i32(int(precise)), ptr(bias_cls),
+            ptr(residual), ptr(res_planar), i32(int(relu)), ptr(out32), ptr(out16), i32(o16_splits), ptr(out_planar), ptr(stats),
+            i32(groups), stream_ptr(),
+        )
+    )
+
+
 def set_halo_pair(enable: bool) -> None:
     """CTA-pair variant of the halo-resident convolution on / off (default on); see semabs_set_halo_pair."""
     check(lib().semabs_set_halo_pair(i32(int(enable))))

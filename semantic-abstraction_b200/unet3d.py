@@ -108,6 +108,12 @@ class ResidualUNet3D(nn.Module):
         self.in_channels, self.out_channels, self.num_groups = in_channels, out_channels, num_groups
         self.precise = precise
         self.use_halo = True  # halo-resident conv kernel at the 128-wide level (conv3d_halo.cu)
+        # inference, 128-wide level, 32 channels, precise mode: conv2 / conv3 of a block consume the RAW output of their producer
+        # (written chunk-planar hi | lo by its epilogue) with the GroupNorm folded into per-sample weights + a border-class bias
+        # (semabs_conv3d_halo_fused) instead of a GroupNorm-apply pass over an fp32 copy.  Off by default: measured on B200 it
+        # moves 46.0 instead of 49.4 GB per 4-grid forward but is not faster (29.2 vs 27.7 ms) while the per-sample weight fold
+        # runs as ~300 small torch kernels
+        self.fold_groupnorm = False
         encoders = []
         for i, out_f in enumerate(f_maps):
             encoders.append(Encoder(in_channels if i == 0 else f_maps[i - 1], out_f, apply_pooling=i > 0,
@@ -182,6 +188,8 @@ class ResidualUNet3D(nn.Module):
                 co, ci = sc.conv.weight.shape[:2]
                 if co in (16, 32) and _pad16(ci) in (16, 32):
                     pk[f"{prefix}.wh{j}"] = halo_w(sc.conv.weight)
+                    if co == 32 and ci == 32:
+                        pk[f"{prefix}.wraw{j}"] = sc.conv.weight.detach().to(device, F32).contiguous()
                 pk[f"{prefix}.g{j}"], pk[f"{prefix}.b{j}"] = gn(sc.groupnorm, _pad16(sc.groupnorm.num_channels))
 
         for i, enc in enumerate(self.encoders):
@@ -207,6 +215,10 @@ class ResidualUNet3D(nn.Module):
         S = D * H * W
         s = 2 if self.precise else 1
         c_out = blk.conv1.conv.out_channels
+        if (tape is None and self.fold_groupnorm and self.use_halo and self.precise and W == 128 and c_out == 32 and c_in_pad in (16, 32)
+                and blk.conv2.num_groups * 2 <= 32 and H % 2 == 0 and f"{prefix}.wraw2" in pk):
+            return self._res_block_folded(pk, prefix, blk, x_raw, x_stats, N=N, dims=dims, c_in_pad=c_in_pad, c_in_real=c_in_real,
+                                          lvl=lvl, dev=dev, want32=want32, want16=want16)
         xn = self._buf(f"l{lvl}_xn", (N, S, s * max(c_in_pad, c_out)), F16, dev)
         o1 = self._alloc(tape, f"l{lvl}_o1", f"{prefix}.o1", (N, S, c_out), F32, dev)
         o2 = self._alloc(tape, f"l{lvl}_o2", f"{prefix}.o2", (N, S, c_out), F32, dev)
@@ -235,6 +247,60 @@ class ResidualUNet3D(nn.Module):
         if tape is not None:
             tape.blocks[prefix] = dict(x=x_raw, x_stats=x_stats, o1=o1, o2=o2, st=st, out=out32, dims=dims,
                                        c_in_pad=c_in_pad, c_in_real=c_in_real, c_out=c_out)
+        return out32, out16
+
+    # border classes of the folded GroupNorm shift: along one axis, first voxel -> taps {1, 2} inside, interior -> all, last -> {0, 1}
+    _TAP_VALID = ((0.0, 1.0, 1.0), (1.0, 1.0, 1.0), (1.0, 1.0, 0.0))
+
+    def _fold_gn(self, w, gamma, beta, stats, S, groups, s):
+        """GroupNorm(x) = a x + b per (sample, channel) with a = gamma rstd, b = beta - mean a, so conv(GroupNorm(x)) =
+        conv_{W a}(x) + sum over the taps that fall inside the grid of (W b): -> (weight images [N, 2 halves, ...] of W a,
+        bias table [N, 27 border classes, C_out]).  Same statistics arithmetic as gn_apply_kernel (fp64 mean / variance, eps
+        1e-5, fp32 scale / shift)."""
+        N = stats.shape[0]
+        co, ci = w.shape[:2]
+        cpg = ci // groups
+        cnt = float(S) * cpg
+        mean = stats[:, :groups, 0] / cnt
+        var = (stats[:, :groups, 1] / cnt - mean * mean).clamp_min(0.0)
+        rstd = (1.0 / torch.sqrt(var + 1e-5)).float()
+        a = rstd.repeat_interleave(cpg, dim=1) * gamma[None, :ci]
+        b = beta[None, :ci] - mean.float().repeat_interleave(cpg, dim=1) * a
+        imgs = torch.stack([ops.pack_halo_weights(w * a[n].view(1, ci, 1, 1, 1), s) for n in range(N)])
+        T = torch.einsum("oczyx,nc->nozyx", w, b)
+        M = torch.tensor(self._TAP_VALID, device=w.device)
+        bias = torch.einsum("nozyx,az,by,cx->nabco", T, M, M, M).reshape(N, 27, co).contiguous()
+        return imgs, bias
+
+    def _res_block_folded(self, pk, prefix, blk, x_raw, x_stats, *, N, dims, c_in_pad, c_in_real, lvl, dev, want32, want16):
+        """ExtResNetBlock.forward at the 128-wide level with 32 channels, inference: conv1 reads GroupNorm-applied x (its
+        producer is not a halo convolution), conv2 / conv3 read the raw planar output of conv1 / conv2 with folded GroupNorm;
+        o1 / o2 exist only as chunk-planar hi | lo fp16, the residual of conv3 is read from o1's planar copy."""
+        D, H, W = dims
+        S = D * H * W
+        c = 32
+        g2, g3 = blk.conv2.num_groups, blk.conv3.num_groups
+        xn = self._buf(f"l{lvl}_xn", (N, S, 2 * max(c_in_pad, c)), F16, dev)
+        o1p = self._buf(f"l{lvl}_o1p", (N, 2 * c * S), F16, dev)
+        o2p = self._buf(f"l{lvl}_o2p", (N, 2 * c * S), F16, dev)
+        st = self._buf(f"l{lvl}_st", (2, N, 8, 2), F64, dev)
+        st.zero_()
+        ops.groupnorm_apply(x_raw, x_stats, pk[f"{prefix}.g1"], pk[f"{prefix}.b1"], xn, N=N, S=S, C=c_in_pad, C_real=c_in_real,
+                            groups=blk.conv1.num_groups, splits=2, planar=True)
+        xn_n = xn.view(N, -1)
+        kw = dict(D=D, H=H, a_splits=2, w_splits=2, precise=True)
+        for n in range(N):
+            ops.conv3d_halo_fused(xn_n[n], pk[f"{prefix}.wh1"], C_in=c_in_pad, relu=True, out_planar=o1p[n], stats=st[0, n], groups=g2, **kw)
+        w2, bias2 = self._fold_gn(pk[f"{prefix}.wraw2"], pk[f"{prefix}.g2"], pk[f"{prefix}.b2"], st[0], S, g2, 2)
+        for n in range(N):
+            ops.conv3d_halo_fused(o1p[n], w2[n], C_in=c, bias_cls=bias2[n], relu=True, out_planar=o2p[n], stats=st[1, n], groups=g3, **kw)
+        w3, bias3 = self._fold_gn(pk[f"{prefix}.wraw3"], pk[f"{prefix}.g3"], pk[f"{prefix}.b3"], st[1], S, g3, 2)
+        out32 = self._buf(f"l{lvl}_out32", (N, S, c), F32, dev) if want32 else None
+        out16 = self._buf(f"l{lvl}_out16", (N, S, 2 * c), F16, dev) if want16 else None
+        for n in range(N):
+            ops.conv3d_halo_fused(o2p[n], w3[n], C_in=c, bias_cls=bias3[n], res_planar=o1p[n], relu=True,
+                                  out32=out32[n] if want32 else None, out16=out16[n] if want16 else None, o16_splits=2, **kw)
+        self.kernel_launches += 1 + 3 * N
         return out32, out16
 
     def forward_channels_last(self, x_raw, x_stats, N, dims, dev, tape=None):

@@ -275,3 +275,31 @@ def test_unet_full_resolution_row_path():
     m.use_halo = False
     y2 = m(x.to(dev)).cpu()
     assert _maxrel(y2, ref) < TOL
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 16, 128), (2, 8, 32, 128)])
+def test_unet_folded_groupnorm_matches_unfused_and_oracle(shape):
+    """128-wide level with 32 channels, inference: conv2 / conv3 of every block read the producer's RAW planar output with
+    the GroupNorm folded into per-sample weights + a 27-class border bias (semabs_conv3d_halo_fused).  Against the oracle and
+    against the un-folded path (GroupNorm-apply passes) of the same module."""
+    from oracle import unet_oracle
+    from semabs_b200.unet3d import ResidualUNet3D
+
+    N, D, H, W = shape
+    torch.manual_seed(13)
+    m = ResidualUNet3D(in_channels=32, out_channels=32, f_maps=32, num_groups=8, num_levels=3).to(dev)
+    x = torch.randn(N, 32, D, H, W, generator=torch.Generator().manual_seed(14)) * 1.5 + 0.2
+    m.fold_groupnorm = True
+    l0 = m.kernel_launches
+    y = m(x.to(dev)).cpu()
+    folded_launches = m.kernel_launches - l0
+    with torch.no_grad():
+        ref = unet_oracle.residual_unet3d({k: v.cpu() for k, v in m.state_dict().items()}, x)
+    err = _maxrel(y, ref)
+    m.fold_groupnorm = False
+    l0 = m.kernel_launches
+    y2 = m(x.to(dev)).cpu()
+    assert m.kernel_launches - l0 != folded_launches, "the folded path was not taken"
+    err2, diff = _maxrel(y2, ref), _maxrel(y, y2)
+    print(f"UNet {shape} folded GroupNorm: vs oracle {err:.2e} (un-folded path {err2:.2e}), folded vs un-folded {diff:.2e}")
+    assert err < TOL and err2 < TOL and diff < 1e-4
