@@ -140,6 +140,15 @@ int semabs_attn_bwd_tc2(const void* qkv16, int32_t ld_qkv, const void* probs16, 
                         int32_t P, int32_t B, int32_t T, int32_t H, int32_t splits, int32_t positive_only,
                         int32_t need_dqkv, void* stream);
 
+/* Third generation (vit_attn_bwd3.cu; same arguments, results and shape rules as semabs_attn_bwd_tc2): the strip of each
+ * (unit, label) item is cut into two column chunks that flow through  G -> element-wise -> dQ | dK, dV  as a software pipeline
+ * (tcgen05.mma executes in issue order, so the next item's G chunk is queued right behind the product that reads the chunk),
+ * K / V double-buffered over units in the row pass.  The product path (ClipEngine) calls this one. */
+int semabs_attn_bwd_tc3(const void* qkv16, int32_t ld_qkv, const void* probs16, int32_t ld_p16, const float* o32,
+                        const void* dO16, int32_t ld_do, const float* r, float* delta_ws, float* wpart, void* dqkv16,
+                        int32_t P, int32_t B, int32_t T, int32_t H, int32_t splits, int32_t positive_only,
+                        int32_t need_dqkv, void* stream);
+
 /* Known-answer hook for the two tcgen05 operand forms the attention kernels add to the GEMM's (A operand in TMEM,
  * MN-major B in shared memory): D[128,64] = A16[128,Kd] * B16[Kd,64], Kd % 16 == 0, Kd <= 256; lbo / sbo are the
  * descriptor byte offsets under test.  Test infrastructure for tests/test_vit_kernels_gpu.py. */

@@ -680,6 +680,25 @@ __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArg
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// launch helpers shared with the third generation (vit_attn_bwd3.cu reuses the delta and tail kernels)
+int launch_attn_delta(const AttnBwdTcArgs& a, cudaStream_t st) {
+  SB_REQUIRE(a.H <= 32, "attention backward: at most 32 heads");
+  const int rows = a.B * a.T;
+  attn_delta_kernel<<<(rows + DELTA_ROWS - 1) / DELTA_ROWS, DELTA_ROWS * a.H, 0, st>>>(a);
+  SB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_attn_tail2(const AttnBwdTcArgs& a, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    SB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tail2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TailSmem::TOTAL + 16));
+    configured = true;
+  }
+  attn_bwd_tail2_kernel<<<a.B * a.H, TC_SIMT, TailSmem::TOTAL + 16, st>>>(a);
+  SB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace sb
 
 using namespace sb;

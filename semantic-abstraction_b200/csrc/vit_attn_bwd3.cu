@@ -1,0 +1,584 @@
+// Attention backward + relevance on tcgen05, third generation: the row / column passes of vit_attn_bwd2.cu (same math, same
+// TMEM strip layout, same operand descriptors — see the derivations in vit_attn_tc.cu) re-scheduled as a two-chunk software
+// pipeline.  Reference: ClipGradcam.interpret, CLIP/clip/clip_gradcam.py:90-126 over the autograd graph of
+// auxiliary.multi_head_attention_forward, CLIP/clip/auxiliary.py:306-345.
+//
+// What the second generation measured (profiles/r02_ncu_full_attn_bwd2.txt): tensor pipe 17-19 % busy, ~4.9 k cycles per
+// (unit, label) item in the row pass against ~1.1 k cycles of MMA work, because the four phases of an item
+//     G = dO V^T  ->  element-wise dS  ->  dQ = dS K  ->  epilogue
+// run back to back: the single strip of 272 TMEM columns is the output of the first MMA and the A operand of the second, so
+// the tensor pipe idles during the element-wise phase and the element-wise warps idle during both MMAs.
+//
+// Here the strip is cut into two column chunks (ViT-L/14: 144 + 128 of the 272 columns) with their own barriers:
+//   * element-wise warps 0-3 own chunk 0, warps 4-7 chunk 1 (the same column split as before, so the register-resident
+//     probability rows / columns are unchanged) and never wait for each other;
+//   * the control warp issues  dX(n, c) ; G(n+1, c)  as soon as chunk c of item n has been packed: tcgen05.mma instructions
+//     execute in issue order, so G(n+1, c) may overwrite the chunk that dX(n, c) reads without a round trip through a barrier;
+//     while one half of the warps runs its element-wise phase the tensor pipe works on the other chunk;
+//   * row pass: two dQ accumulators (the epilogue of item n-1 runs after the element-wise phase of item n), K / V double
+//     buffered over units and three dO stages, so nothing on the tensor side waits at a unit boundary;
+//   * column pass: dK + dV accumulators are single (272 + 2 x 128 columns do not fit TMEM); chunk-0 warps drain dK of item
+//     n-1 after their element-wise phase of item n, chunk-1 warps drain dV of item n before theirs of item n+1;
+//     {delta_i, r_i} staging and the relevance partial sums are per chunk owner.
+// delta and the one-row / one-key tail are the second generation's kernels (launch helpers in vit_attn_bwd2.cu).
+#include "vit_attn_tc.cuh"
+
+namespace sb {
+
+int launch_attn_delta(const AttnBwdTcArgs& a, cudaStream_t st);  // vit_attn_bwd2.cu
+int launch_attn_tail2(const AttnBwdTcArgs& a, cudaStream_t st);  // vit_attn_bwd2.cu
+
+constexpr int T3_THREADS = 288;  // 8 element-wise warps (2 per TMEM lane quadrant: chunk 0 / chunk 1) + 1 control warp
+constexpr int T3_SIMT = 256;
+constexpr int T3_NCH = (TC_MAX_T / 16 + 1) / 2;  // 9 chunks of 16 strip columns per thread at most
+
+struct Row3Smem {
+  static constexpr int KVBUF = 2 * TC_KV_BYTES;          // K then V of one unit
+  static constexpr int KV = 0;                           // 2 buffers (unit parity)
+  static constexpr int DO = 2 * KVBUF;                   // 3 stages of one 136-row box
+  static constexpr int BARS = DO + 3 * TC_BOX_BYTES;
+  static constexpr int TOTAL = BARS + 256 + 1024;
+};
+static_assert(Row3Smem::TOTAL <= 232448, "row pass shared memory");
+
+// ---------------------------------------------------------------------------------------------------------
+// row pass: thread = query row i.  G = dO V^T -> dS = A o (G - delta) packed in place -> dQ = scale dS K
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(T3_THREADS, 1)
+attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, AttnBwdTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Row3Smem::BARS);
+  uint64_t *bar_kv = bars /* [2] */, *bar_do = bars + 2 /* [3] */, *bar_s = bars + 5 /* [2] */, *bar_p = bars + 7 /* [2] */;
+  uint64_t *bar_o = bars + 9 /* [2] */, *bar_e = bars + 11 /* [2] */;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = a.T, d = a.d, P = a.P;
+  const int ncol = (T + 15) & ~15;
+  const int nch = ncol / 16, c_split = (nch + 1) / 2;
+  const int nA = c_split * 16, nB = ncol - nA;  // strip columns of chunk 0 / chunk 1
+  const int n_units = a.B * a.H * a.n_full;
+  const int n_my = (n_units - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int N = n_my * P;  // items of this CTA: unit-major, label fastest
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_kv[i], 1), mbar_init(&bar_s[i], 1), mbar_init(&bar_o[i], 1);
+      mbar_init(&bar_p[i], T3_SIMT / 2), mbar_init(&bar_e[i], T3_SIMT);
+    }
+    for (int i = 0; i < 3; ++i) mbar_init(&bar_do[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base + TC_COL_S;
+
+  auto item = [&](int n, int& bh, int& mt, int& p) {
+    const int u = int(blockIdx.x) + (n / P) * int(gridDim.x);
+    p = n % P, bh = u / a.n_full, mt = u % a.n_full;
+  };
+
+  if (warp == 8) {
+    // ===== control warp: TMA + MMA issue (convergent; only the elected lane's instructions take effect) =====
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t idesc_gA = make_idesc_f16(128, nA), idesc_gB = make_idesc_f16(128, nB ? nB : 16);
+    constexpr uint32_t idesc_o = make_idesc_f16(128, TC_HD, false, true);
+    auto load_do = [&](int n) {
+      int bh, mt, p;
+      item(n, bh, mt, p);
+      const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+      mbar_arrive_expect_tx(&bar_do[n % 3], TC_BOX_BYTES);
+      tma_load_2d(smem + Row3Smem::DO + (n % 3) * TC_BOX_BYTES, &tm_do, &bar_do[n % 3], h * TC_HD, pb * T + mt * 128);
+    };
+    auto load_kv = [&](int u) {  // u = index of the unit within this CTA's list
+      int bh, mt, p;
+      item(u * P, bh, mt, p);
+      const int b = bh / a.H, h = bh % a.H;
+      uint8_t* buf = smem + Row3Smem::KV + (u & 1) * Row3Smem::KVBUF;
+      mbar_arrive_expect_tx(&bar_kv[u & 1], 2u * TC_KV_BYTES);
+      for (int bx = 0; bx < 2; ++bx) {
+        tma_load_2d(buf + bx * TC_BOX_BYTES, &tm_qkv, &bar_kv[u & 1], d + h * TC_HD, b * T + bx * TC_BOX_ROWS);
+        tma_load_2d(buf + TC_KV_BYTES + bx * TC_BOX_BYTES, &tm_qkv, &bar_kv[u & 1], 2 * d + h * TC_HD, b * T + bx * TC_BOX_ROWS);
+      }
+    };
+    auto issue_g = [&](int n, int c) {
+      const int u = n / P;
+      if (c == 0) {
+        if (n % P == 0) mbar_wait(&bar_kv[u & 1], (u >> 1) & 1);
+        mbar_wait(&bar_do[n % 3], (n / 3) & 1);
+        tc_fence_after();
+      }
+      if (c == 0 || nB) {
+        const uint64_t dDO = desc_kmajor(sbase + Row3Smem::DO + (n % 3) * TC_BOX_BYTES);
+        const uint64_t dV = desc_kmajor(sbase + Row3Smem::KV + (u & 1) * Row3Smem::KVBUF + TC_KV_BYTES + (c ? nA * 128 : 0));
+#pragma unroll
+        for (int k = 0; k < TC_HD / 16; ++k)
+          umma_f16_elect(tS + uint32_t(c ? nA : 0), dDO + uint64_t(2 * k), dV + uint64_t(2 * k), c ? idesc_gB : idesc_gA, k != 0, leader);
+      }
+      umma_commit_elect(&bar_s[c], leader);
+    };
+    auto issue_q = [&](int n, int c) {
+      const int u = n / P;
+      const uint64_t dK = desc_mnmajor(sbase + Row3Smem::KV + (u & 1) * Row3Smem::KVBUF, 16);
+      const uint32_t tO = tmem_base + uint32_t((n & 1) ? TC_COL_O2 : TC_COL_O);
+      const int s0 = c ? c_split : 0, s1 = c ? nch : c_split;
+      for (int s = s0; s < s1; ++s) umma_f16_ts_elect(tO, tS + uint32_t(16 * s), dK + uint64_t(s) * (2048 >> 4), idesc_o, s > 0, leader);
+      if (c == 1) umma_commit_elect(&bar_o[n & 1], leader);
+    };
+    if (N > 0) {
+      if (leader) {
+        load_kv(0);
+        if (n_my > 1) load_kv(1);
+        load_do(0);
+        if (N > 1) load_do(1);
+      }
+      __syncwarp();
+      issue_g(0, 0);
+      issue_g(0, 1);
+    }
+    for (int n = 0; n < N; ++n) {
+      // dO stage (n + 2) % 3 held item n - 1, whose G chunks were both consumed (bar_p waits of the previous iteration)
+      if (leader && n + 2 < N) load_do(n + 2);
+      __syncwarp();
+      mbar_wait(&bar_p[0], n & 1);  // chunk 0 of the strip holds packed dS(n)
+      if (n >= 2) mbar_wait(&bar_e[n & 1], ((n - 2) >> 1) & 1);  // accumulator n & 1 drained by the epilogue of item n - 2
+      tc_fence_after();
+      issue_q(n, 0);
+      if (n + 1 < N) issue_g(n + 1, 0);  // in issue order behind dQ(n, 0): may overwrite chunk 0
+      mbar_wait(&bar_p[1], n & 1);
+      tc_fence_after();
+      issue_q(n, 1);
+      if (n + 1 < N) issue_g(n + 1, 1);
+      if (n % P == 0 && n > 0) {
+        // unit n / P has started; the previous unit's K / V buffer is free once dQ(n - 1) has completed (long ago)
+        mbar_wait(&bar_o[(n - 1) & 1], ((n - 1) >> 1) & 1);
+        const int u = n / P;
+        if (leader && u + 1 < n_my) load_kv(u + 1);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== element-wise warps: half 0 owns strip chunk 0, half 1 chunk 1 =====
+    const int q = warp & 3, half = warp >> 2, rr = q * 32 + lane;
+    const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16);
+    const int c0 = half ? c_split : 0, c1 = half ? nch : c_split;
+    uint32_t arow[T3_NCH][8];  // this thread's half of its probability row (kept across the P labels of a unit)
+    float dnext = 0.f;
+    auto delta_of = [&](int n) -> float {
+      int bh, mt, p;
+      item(n, bh, mt, p);
+      const int i = mt * 128 + rr;
+      if (i >= T) return 0.f;
+      const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+      return a.delta[(size_t(pb) * a.H + h) * T + i];
+    };
+    auto epilogue = [&](int m) {
+      int bh, mt, p;
+      item(m, bh, mt, p);
+      const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+      const int i = mt * 128 + rr;
+      mbar_wait(&bar_o[m & 1], (m >> 1) & 1);
+      tc_fence_after();
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(t_row + uint32_t(((m & 1) ? TC_COL_O2 : TC_COL_O) + 32 * half), o);
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&bar_e[m & 1]);
+      if (i < T)
+        store_row_f16(a.dqkv16 + (size_t(pb) * T + i) * size_t(a.splits) * 3 * d + h * TC_HD + 32 * half, 3 * d, a.splits, o, 32, a.scale);
+    };
+    if (N > 0) dnext = delta_of(0);
+    for (int n = 0; n < N; ++n) {
+      int bh, mt, p;
+      item(n, bh, mt, p);
+      const int i = mt * 128 + rr;
+      const bool valid = i < T;
+      if (p == 0) {
+        const __half* prow = a.probs16 + (size_t(bh) * T + (valid ? i : 0)) * a.ldp;
+#pragma unroll
+        for (int cc = 0; cc < T3_NCH; ++cc) {
+          if (c0 + cc < c1) {
+            if (valid) {
+              ld_global_256(prow + (c0 + cc) * 16, arow[cc]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) arow[cc][e] = 0u;
+            }
+          }
+        }
+      }
+      const float delta = dnext;
+      if (n + 1 < N) dnext = delta_of(n + 1);  // in flight during this item's element-wise phase
+
+      mbar_wait(&bar_s[half], n & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < T3_NCH; cc += 2) {
+        const bool v0 = c0 + cc < c1, v1 = (cc + 1 < T3_NCH) && (c0 + cc + 1 < c1);  // warp-uniform
+        uint32_t g0[16], g1[16], w[8];
+        if (v0) tmem_ld_32x32b_x16(t_row + uint32_t(TC_COL_S + (c0 + cc) * 16), g0);
+        if (v1) tmem_ld_32x32b_x16(t_row + uint32_t(TC_COL_S + (c0 + cc + 1) * 16), g1);
+        tc_wait_ld();
+        if (v0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&arow[cc][e]));
+            w[e] = pack_h2(a2.x * (__uint_as_float(g0[2 * e]) - delta), a2.y * (__uint_as_float(g0[2 * e + 1]) - delta));
+          }
+          tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + (c0 + cc) * 16), w);
+        }
+        if (v1) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&arow[(cc + 1) % T3_NCH][e]));
+            w[e] = pack_h2(a2.x * (__uint_as_float(g1[2 * e]) - delta), a2.y * (__uint_as_float(g1[2 * e + 1]) - delta));
+          }
+          tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + (c0 + cc + 1) * 16), w);
+        }
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bar_p[half]);
+      if (n >= 1) epilogue(n - 1);  // its dQ has had the whole element-wise phase of item n to complete
+    }
+    if (N > 0) epilogue(N - 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// column pass: thread = key j.  G^T = V dO^T -> relevance column sums, dS^T and A^T packed in place -> dK = dS^T Q, dV = A^T dO
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(T3_THREADS, 1)
+attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                        const __grid_constant__ CUtensorMap tm_pr, AttnBwdTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ColSmem::BARS);
+  uint64_t *bar_kv = bars, *bar_do = bars + 1 /* [2] */, *bar_s = bars + 3 /* [2] */, *bar_p = bars + 5 /* [2] */;
+  uint64_t *bar_o = bars + 7, *bar_e = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float2* s_dr = reinterpret_cast<float2*>(smem + ColSmem::DR);  // [2 items][272 query rows] {delta_i, r_i}
+  float* s_w = reinterpret_cast<float*>(smem + ColSmem::W);      // [2 items][2 halves][128 keys]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = a.T, d = a.d, P = a.P;
+  const int ncol = (T + 15) & ~15;  // query columns of G^T
+  const int nch = ncol / 16, c_split = (nch + 1) / 2;
+  const int nA = c_split * 16, nB = ncol - nA;
+  const int n_units = a.B * a.H * a.n_full;
+  const int n_my = (n_units - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int N = n_my * P;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_pr);
+    mbar_init(bar_kv, 1), mbar_init(&bar_do[0], 1), mbar_init(&bar_do[1], 1), mbar_init(bar_o, 1), mbar_init(bar_e, T3_SIMT);
+    for (int i = 0; i < 2; ++i) mbar_init(&bar_s[i], 1), mbar_init(&bar_p[i], T3_SIMT / 2);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  auto item = [&](int n, int& bh, int& mt, int& p) {
+    const int u = int(blockIdx.x) + (n / P) * int(gridDim.x);
+    p = n % P, bh = u / a.n_full, mt = u % a.n_full;
+  };
+  // {delta_i, r_i} of item n, staged by the owner of the chunk the query row i belongs to: chunk 0 rows t and t + 128
+  // (< nA), chunk 1 row nA + t, for t = thread index within its half
+  const int half_t = int(threadIdx.x) & 127, my_half = (int(threadIdx.x) >> 7) & 1;
+  const int row_a = my_half ? nA + half_t : half_t;
+  const int row_b = my_half ? ncol : half_t + 128;  // second row of a chunk-0 thread (valid when < nA)
+  auto fetch_dr = [&](int n, float2& v0, float2& v1) {
+    int bh, mt, p;
+    item(n, bh, mt, p);
+    const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+    v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+    if (row_a < T) {
+      v0.x = a.need_dqkv ? a.delta[(size_t(pb) * a.H + h) * T + row_a] : 0.f;
+      v0.y = a.r[size_t(pb) * T + row_a];
+    }
+    if (row_b < nA && row_b < T) {
+      v1.x = a.need_dqkv ? a.delta[(size_t(pb) * a.H + h) * T + row_b] : 0.f;
+      v1.y = a.r[size_t(pb) * T + row_b];
+    }
+  };
+  auto store_dr = [&](int n, const float2& v0, const float2& v1) {
+    if (row_a < ncol) s_dr[(n & 1) * TC_MAX_T + row_a] = v0;
+    if (row_b < nA) s_dr[(n & 1) * TC_MAX_T + row_b] = v1;
+  };
+  if (warp < 8 && N > 0) {
+    float2 v0, v1;
+    fetch_dr(0, v0, v1);
+    store_dr(0, v0, v1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base + TC_COL_S, tK = tmem_base + TC_COL_O, tV = tmem_base + TC_COL_O2;
+
+  if (warp == 8) {
+    // ===== control warp =====
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t sbase = smem_u32(smem);
+    const uint64_t dVt = desc_kmajor(sbase + ColSmem::V), dQm = desc_mnmajor(sbase + ColSmem::Q, 16);
+    const uint32_t idesc_gA = make_idesc_f16(128, nA), idesc_gB = make_idesc_f16(128, nB ? nB : 16);
+    constexpr uint32_t idesc_o = make_idesc_f16(128, TC_HD, false, true);
+    auto load_do = [&](int n) {
+      int bh, mt, p;
+      item(n, bh, mt, p);
+      const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+      mbar_arrive_expect_tx(&bar_do[n & 1], TC_KV_BYTES);
+      for (int bx = 0; bx < 2; ++bx)
+        tma_load_2d(smem + ColSmem::DO + (n & 1) * TC_KV_BYTES + bx * TC_BOX_BYTES, &tm_do, &bar_do[n & 1], h * TC_HD,
+                    pb * T + bx * TC_BOX_ROWS);
+    };
+    auto load_unit = [&](int n) {
+      int bh, mt, p;
+      item(n, bh, mt, p);
+      const int b = bh / a.H, h = bh % a.H;
+      mbar_arrive_expect_tx(bar_kv, 7u * TC_BOX_BYTES);
+      for (int bx = 0; bx < 2; ++bx)
+        tma_load_2d(smem + ColSmem::Q + bx * TC_BOX_BYTES, &tm_qkv, bar_kv, h * TC_HD, b * T + bx * TC_BOX_ROWS);
+      tma_load_2d(smem + ColSmem::V, &tm_qkv, bar_kv, 2 * d + h * TC_HD, b * T + mt * 128);
+      for (int cb = 0; cb < 2; ++cb)
+        for (int bx = 0; bx < 2; ++bx)
+          tma_load_2d(smem + ColSmem::PR + (cb * 2 + bx) * TC_BOX_BYTES, &tm_pr, bar_kv, mt * 128 + cb * 64, bh * T + bx * TC_BOX_ROWS);
+    };
+    auto issue_g = [&](int n, int c) {
+      if (c == 0) {
+        if (n % P == 0) mbar_wait(bar_kv, (n / P) & 1);
+        mbar_wait(&bar_do[n & 1], (n >> 1) & 1);
+        tc_fence_after();
+      }
+      if (c == 0 || nB) {
+        const uint64_t dDOk = desc_kmajor(sbase + ColSmem::DO + (n & 1) * TC_KV_BYTES + (c ? nA * 128 : 0));
+#pragma unroll
+        for (int k = 0; k < TC_HD / 16; ++k)
+          umma_f16_elect(tS + uint32_t(c ? nA : 0), dVt + uint64_t(2 * k), dDOk + uint64_t(2 * k), c ? idesc_gB : idesc_gA, k != 0, leader);
+      }
+      umma_commit_elect(&bar_s[c], leader);
+    };
+    auto issue_kv = [&](int n, int c) {
+      if (a.need_dqkv) {
+        const uint64_t dDOm = desc_mnmajor(sbase + ColSmem::DO + (n & 1) * TC_KV_BYTES, 16);
+        const int s0 = c ? c_split : 0, s1 = c ? nch : c_split;
+        for (int s = s0; s < s1; ++s) {
+          const uint64_t kadv = uint64_t(s) * (2048 >> 4);
+          umma_f16_ts_elect(tK, tS + uint32_t(16 * s), dQm + kadv, idesc_o, s > 0, leader);
+          umma_f16_ts_elect(tV, tS + uint32_t(16 * s + 8), dDOm + kadv, idesc_o, s > 0, leader);
+        }
+      }
+      if (c == 1) umma_commit_elect(bar_o, leader);
+    };
+    if (N > 0) {
+      if (leader) {
+        load_unit(0);
+        load_do(0);
+        if (N > 1) load_do(1);
+      }
+      __syncwarp();
+      issue_g(0, 0);
+      issue_g(0, 1);
+    }
+    for (int n = 0; n < N; ++n) {
+      const bool more = n + 1 < N, boundary = (n + 1) % P == 0;
+      mbar_wait(&bar_p[0], n & 1);
+      if (n >= 1) mbar_wait(bar_e, (n - 1) & 1);  // dK / dV accumulators drained by the epilogues of item n - 1
+      tc_fence_after();
+      issue_kv(n, 0);
+      if (more && !boundary) issue_g(n + 1, 0);
+      mbar_wait(&bar_p[1], n & 1);
+      tc_fence_after();
+      issue_kv(n, 1);
+      if (more && !boundary) issue_g(n + 1, 1);
+      // dO stage n & 1 (B operand of dV(n)) and, at a unit boundary, Q / V / the probability tile are free once item n's
+      // MMAs have completed; the next item's G chunks are already queued behind them
+      mbar_wait(bar_o, n & 1);
+      tc_fence_after();
+      if (leader && n + 2 < N) load_do(n + 2);
+      if (more && boundary) {
+        if (leader) load_unit(n + 1);
+        __syncwarp();
+        issue_g(n + 1, 0);
+        issue_g(n + 1, 1);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== element-wise warps: half 0 owns query chunk 0 and drains dK, half 1 owns chunk 1 and drains dV =====
+    const int q = warp & 3, half = warp >> 2, jj = q * 32 + lane;
+    const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16);
+    const int c0 = half ? c_split : 0, c1 = half ? nch : c_split;
+    // probability tile addressing: element (i, jj) sits at  i*128 + (((jj%64)/8 ^ (i%8)) << 4) + (jj%8)*2  inside column
+    // block jj/64 (the two 136-row TMA boxes of a column block are contiguous and 136 % 8 == 0)
+    const uint8_t* pcol = smem + ColSmem::PR + (jj >> 6) * (2 * TC_BOX_BYTES) + (jj & 7) * 2;
+    const float invH = 1.0f / a.H;
+    uint32_t acol[T3_NCH][8];  // A[i, j] for this thread's key j and its chunk of the query rows i, packed pairs
+    auto epilogue = [&](int m) {
+      int bh, mt, p;
+      item(m, bh, mt, p);
+      const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+      const int j = mt * 128 + jj;
+      const bool valid = j < T;
+      mbar_wait(bar_o, m & 1);  // item m's MMAs are complete (and, transitively, both halves' s_w partial sums are visible)
+      tc_fence_after();
+      float wsum = 0.f;
+      if (half == 0) wsum = (s_w[(m & 1) * 256 + jj] + s_w[(m & 1) * 256 + 128 + jj]) * invH;
+      if (a.need_dqkv) {
+        const uint32_t col = half ? TC_COL_O2 : TC_COL_O;
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32b_x32(t_row + col, o0);
+        tmem_ld_32x32b_x32(t_row + col + 32, o1);
+        tc_wait_ld();
+        tc_fence_before();
+        mbar_arrive(bar_e);
+        if (valid) {
+          __half* orow = a.dqkv16 + (size_t(pb) * T + j) * size_t(a.splits) * 3 * d + (half ? 2 * d : d) + h * TC_HD;
+          store_row_f16(orow, 3 * d, a.splits, o0, 32, 1.0f);
+          store_row_f16(orow + 32, 3 * d, a.splits, o1, 32, 1.0f);
+        }
+      } else {
+        mbar_arrive(bar_e);
+      }
+      if (half == 0 && valid) a.wpart[(size_t(pb) * a.H + h) * T + j] = wsum;
+    };
+    for (int n = 0; n < N; ++n) {
+      int bh, mt, p;
+      item(n, bh, mt, p);
+      float2 nx0, nx1;
+      if (n + 1 < N) fetch_dr(n + 1, nx0, nx1);  // global loads in flight during the element-wise phase
+      if (p == 0) {
+        mbar_wait(bar_kv, (n / P) & 1);  // the tile is read with ordinary loads: every thread acquires the TMA writes
+#pragma unroll
+        for (int cc = 0; cc < T3_NCH; ++cc) {
+          if (c0 + cc < c1) {
+            const uint8_t* prow = pcol + (c0 + cc) * 2048;
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const int k0 = e & 7, k1 = (e + 1) & 7;
+              uint32_t lo = *reinterpret_cast<const uint16_t*>(prow + (e >> 3) * 1024 + k0 * 128 + ((((jj & 63) >> 3) ^ k0) << 4));
+              uint32_t hi = *reinterpret_cast<const uint16_t*>(prow + ((e + 1) >> 3) * 1024 + k1 * 128 + ((((jj & 63) >> 3) ^ k1) << 4));
+              const int i0 = (c0 + cc) * 16 + e;
+              if (i0 >= T) lo = 0u;      // rows past T belong to the next head
+              if (i0 + 1 >= T) hi = 0u;
+              acol[cc][e >> 1] = lo | (hi << 16);
+            }
+          }
+        }
+      }
+      mbar_wait(&bar_s[half], n & 1);
+      tc_fence_after();
+      const float2* dr = s_dr + (n & 1) * TC_MAX_T;
+      float w = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < T3_NCH; ++cc) {
+        if (c0 + cc < c1) {
+          const int c = c0 + cc;
+          uint32_t g[16], ds[8];
+          tmem_ld_32x32b_x16(t_row + uint32_t(TC_COL_S + c * 16), g);
+          const float4* dr4 = reinterpret_cast<const float4*>(dr + c * 16);
+          tc_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const float2 av = __half22float2(*reinterpret_cast<const __half2*>(&acol[cc][e >> 1]));
+            const float4 d4 = dr4[e >> 1];  // {delta_i, r_i, delta_i+1, r_i+1}
+            const float g0 = __uint_as_float(g[e]), g1 = __uint_as_float(g[e + 1]);
+            float x0 = g0 * av.x, x1 = g1 * av.y;
+            if (a.positive_only) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f);
+            w = fmaf(d4.y, x0, w);
+            w = fmaf(d4.w, x1, w);
+            ds[e >> 1] = pack_h2(av.x * (g0 - d4.x), av.y * (g1 - d4.z));
+          }
+          tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + c * 16), ds);
+          tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + c * 16 + 8), acol[cc]);
+        }
+      }
+      s_w[(n & 1) * 256 + half * 128 + jj] = w;
+      if (n + 1 < N) store_dr(n + 1, nx0, nx1);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bar_p[half]);
+      // chunk-1 owners drain dV(n) now (their next chunk is queued behind dK / dV(n, 1) anyway); chunk-0 owners drain
+      // dK(n - 1), which completed during their element-wise phase of item n
+      if (half == 1) epilogue(n);
+      else if (n >= 1) epilogue(n - 1);
+    }
+    if (N > 0 && half == 0) epilogue(N - 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+// Third-generation attention backward: same contract as semabs_attn_bwd_tc2 (include/semabs_b200.h).
+extern "C" int semabs_attn_bwd_tc3(const void* qkv16, int32_t ld_qkv, const void* probs16, int32_t ld_p16, const float* o32,
+                                   const void* dO16, int32_t ld_do, const float* r, float* delta_ws, float* wpart,
+                                   void* dqkv16, int32_t P, int32_t B, int32_t T, int32_t H, int32_t splits,
+                                   int32_t positive_only, int32_t need_dqkv, void* stream) {
+  SB_REQUIRE(qkv16 && probs16 && o32 && dO16 && r && delta_ws && wpart, "semabs_attn_bwd_tc3: null pointer");
+  SB_REQUIRE(!need_dqkv || dqkv16, "semabs_attn_bwd_tc3: dqkv16 missing");
+  SB_REQUIRE(P > 0 && B > 0 && T > 0 && H > 0 && T <= TC_MAX_T, "semabs_attn_bwd_tc3: bad shape (T <= %d)", TC_MAX_T);
+  SB_REQUIRE(ld_p16 % 16 == 0 && ld_p16 >= ((T + 15) / 16) * 16, "semabs_attn_bwd_tc3: bad probs16 pitch %d", ld_p16);
+  const int d = H * TC_HD;
+  SB_REQUIRE(ld_qkv >= 3 * d && ld_qkv % 8 == 0 && ld_do >= d && ld_do % 16 == 0, "semabs_attn_bwd_tc3: bad pitch");
+  SB_REQUIRE(splits == 1 || splits == 2, "semabs_attn_bwd_tc3: splits must be 1 or 2");
+  const int rem = T % 128;
+  SB_REQUIRE(T <= 128 || rem <= 1, "semabs_attn_bwd_tc3: T %% 128 must be 0 or 1 above one tile (got T=%d)", T);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tm_qkv, tm_do, tm_pr;
+  if (int rc = make_tile_tmap(&tm_qkv, qkv16, (long long)B * T, 3LL * d, ld_qkv)) return rc;
+  if (int rc = make_tile_tmap(&tm_do, dO16, (long long)P * B * T, d, ld_do)) return rc;
+  if (int rc = make_tile_tmap(&tm_pr, probs16, (long long)B * H * T, ld_p16, ld_p16)) return rc;
+  AttnBwdTcArgs a{};
+  a.qkv16 = (const __half*)qkv16, a.ldq = ld_qkv;
+  a.probs16 = (const __half*)probs16, a.ldp = ld_p16, a.o32 = o32, a.dO16 = (const __half*)dO16, a.ld_do = ld_do;
+  a.delta = delta_ws, a.r = r, a.wpart = wpart, a.dqkv16 = (__half*)dqkv16;
+  a.P = P, a.B = B, a.T = T, a.H = H, a.d = d, a.splits = splits, a.scale = 0.125f;
+  a.positive_only = positive_only, a.need_dqkv = need_dqkv;
+  a.n_tail = (T > 128 && rem == 1) ? 1 : 0;
+  a.n_full = a.n_tail ? T / 128 : (T + 127) / 128;
+  static bool configured = false;
+  if (!configured) {
+    SB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_row_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Row3Smem::TOTAL));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_col_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ColSmem::TOTAL));
+    configured = true;
+  }
+  const int n_units = B * H * a.n_full;
+  const int grid = n_units < num_sms() ? n_units : num_sms();
+  if (need_dqkv) {  // delta feeds dS in both passes and the tail; the relevance-only last step needs neither delta nor dQ
+    if (int rc = launch_attn_delta(a, st)) return rc;
+    attn_bwd_row_tc3_kernel<<<grid, T3_THREADS, Row3Smem::TOTAL, st>>>(tm_qkv, tm_do, a);
+    SB_CHECK_CUDA(cudaGetLastError());
+  }
+  attn_bwd_col_tc3_kernel<<<grid, T3_THREADS, ColSmem::TOTAL, st>>>(tm_qkv, tm_do, tm_pr, a);
+  SB_CHECK_CUDA(cudaGetLastError());
+  if (a.n_tail)
+    if (int rc = launch_attn_tail2(a, st)) return rc;
+  return 0;
+}

@@ -184,7 +184,8 @@ def attn_bwd(qkv16, probs16, o32, dO16, ld_do, r, delta_ws, wpart, dqkv16, *, P,
     )
 
 
-ATTN_BWD_GENERATION = 2  # 2 = vit_attn_bwd2.cu (product path); 1 = the first tcgen05 kernels (cross-check / odd T % 128)
+ATTN_BWD_GENERATION = 3  # 3 = vit_attn_bwd3.cu (product path: chunk-pipelined passes); 2 = vit_attn_bwd2.cu; 1 = the first tcgen05
+# kernels (cross-checks; generation 1 also takes T % 128 > 1)
 
 
 def attn_bwd_tc(qkv16, probs16, o32, dO16, ld_do, r, delta_ws, wpart, dqkv16, *, P, B, T, H, splits=1, positive_only=True,
@@ -194,10 +195,11 @@ def attn_bwd_tc(qkv16, probs16, o32, dO16, ld_do, r, delta_ws, wpart, dqkv16, *,
     # algorithmic minimum: G = dO V^T always; dQ = dS K, dK = dS^T Q, dV = A^T dO when the block below needs them
     flops = (8.0 if need_dqkv else 2.0) * T * T * 64 * H * P * B
     gen = ATTN_BWD_GENERATION if generation is None else generation
-    if gen == 2 and (T <= 128 or T % 128 <= 1):
-        CALL_PROFILE.note("semabs_attn_bwd_tc2", flops=flops)
+    if gen in (2, 3) and (T <= 128 or T % 128 <= 1):
+        name = f"semabs_attn_bwd_tc{gen}"
+        CALL_PROFILE.note(name, flops=flops)
         check(
-            lib().semabs_attn_bwd_tc2(
+            getattr(lib(), name)(
                 ptr(qkv16), i32(qkv16.stride(0)), ptr(probs16), i32(probs16.shape[-1]), ptr(o32), ptr(dO16), i32(ld_do), ptr(r),
                 ptr(delta_ws), ptr(wpart), ptr(dqkv16), i32(P), i32(B), i32(T), i32(H), i32(splits), i32(int(positive_only)),
                 i32(int(need_dqkv)), stream_ptr(),

@@ -65,10 +65,11 @@ def test_attn_fwd(T, H, causal):
 
 @pytest.mark.parametrize("T,H,impl", [(50, 12, "mma"), (257, 16, "mma"), (50, 12, "tc"), (257, 16, "tc"), (197, 12, "tc"),
                                       (128, 4, "tc"), (130, 4, "tc"), (50, 12, "tc1"), (257, 16, "tc1"), (128, 4, "tc1"),
-                                      (129, 2, "tc"), (256, 2, "tc")])
+                                      (129, 2, "tc"), (256, 2, "tc"), (50, 12, "tc2"), (257, 16, "tc2"), (129, 2, "tc2"),
+                                      (16, 2, "tc"), (8, 2, "tc")])
 def test_attn_bwd(T, H, impl):
-    """impl: "mma" = mma.sync kernels; "tc" = the product path (second-generation tcgen05 kernels, vit_attn_bwd2.cu, where
-    T % 128 <= 1; first generation otherwise); "tc1" = first-generation tcgen05 kernels forced (cross-check)."""
+    """impl: "mma" = mma.sync kernels; "tc" = the product path (third-generation tcgen05 kernels, vit_attn_bwd3.cu, where
+    T % 128 <= 1; first generation otherwise); "tc2" / "tc1" = second / first generation forced (cross-checks)."""
     import functools
 
     from semabs_b200 import ops
@@ -89,7 +90,7 @@ def test_attn_bwd(T, H, impl):
     delta = torch.empty(P * B * H, T, device=dev)
     wpart = torch.full((P * B * H, T), float("nan"), device=dev)
     dqkv16 = torch.full((P * B * T, 2 * 3 * d), float("nan"), device=dev, dtype=torch.float16)
-    tc = {"tc": ops.attn_bwd_tc, "tc1": functools.partial(ops.attn_bwd_tc, generation=1)}
+    tc = {"tc": ops.attn_bwd_tc, "tc1": functools.partial(ops.attn_bwd_tc, generation=1), "tc2": functools.partial(ops.attn_bwd_tc, generation=2)}
     bwd = tc.get(impl, ops.attn_bwd)
     bwd(qkv16, probs16, o32, dO, d, r, delta, wpart, dqkv16, P=P, B=B, T=T, H=H, splits=2, positive_only=True)
     torch.cuda.synchronize()
@@ -116,6 +117,41 @@ def test_attn_bwd(T, H, impl):
     got = dqkv16[:, : 3 * d].float() + dqkv16[:, 3 * d :].float()
     scale = ref.abs().max().item()
     assert (got - ref).abs().max().item() < 4e-3 * scale, ((got - ref).abs().max().item(), scale)
+
+
+@pytest.mark.parametrize("B,T,H,P", [(12, 257, 16, 3), (40, 50, 12, 5), (7, 257, 16, 16)])
+def test_attn_bwd_pipelined_matches_second_generation_over_unit_boundaries(B, T, H, P):
+    """More units than SMs, so every CTA of the chunk-pipelined passes (vit_attn_bwd3.cu) crosses unit boundaries (K / V double
+    buffer, probability reload, accumulator hand-over).  Same arithmetic in the same order as the second generation: the
+    results must be bit-identical."""
+    from semabs_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(B * T + P)
+    d = H * 64
+    qkv = torch.randn(B * T, 3 * d, device=dev, generator=g)
+    qkv[:, :d] *= 0.125 * 1.5
+    Tp = (T + 15) // 16 * 16
+    probs16 = torch.empty(B * H, T, Tp, device=dev, dtype=torch.float16)
+    o32 = torch.empty(B * T, d, device=dev)
+    ops.attn_fwd(qkv, B=B, T=T, H=H, probs=None, probs16=probs16, o32=o32)
+    qkv16 = qkv.half()
+    dO = torch.randn(P * B * T, d, device=dev, generator=g).half()
+    r = torch.rand(P * B, T, device=dev, generator=g)
+    out = {}
+    for gen in (2, 3):
+        delta = torch.empty(P * B * H, T, device=dev)
+        wpart = torch.full((P * B * H, T), float("nan"), device=dev)
+        dqkv16 = torch.full((P * B * T, 2 * 3 * d), float("nan"), device=dev, dtype=torch.float16)
+        ops.attn_bwd_tc(qkv16, probs16, o32, dO, d, r, delta, wpart, dqkv16, P=P, B=B, T=T, H=H, splits=2, positive_only=True, generation=gen)
+        w2 = torch.full_like(wpart, float("nan"))
+        ops.attn_bwd_tc(qkv16, probs16, o32, dO, d, r, delta, w2, None, P=P, B=B, T=T, H=H, splits=2, positive_only=True,
+                        need_dqkv=False, generation=gen)
+        torch.cuda.synchronize()
+        assert torch.equal(w2, wpart)
+        out[gen] = (wpart, dqkv16)
+    assert torch.isfinite(out[3][0]).all() and torch.isfinite(out[3][1].float()).all()
+    assert torch.equal(out[2][0], out[3][0]), (out[2][0] - out[3][0]).abs().max().item()
+    assert torch.equal(out[2][1], out[3][1]), (out[2][1].float() - out[3][1].float()).abs().max().item()
 
 
 def test_logit_seed():
