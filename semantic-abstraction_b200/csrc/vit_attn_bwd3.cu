@@ -32,6 +32,14 @@ constexpr int T3_THREADS = 288;  // 8 element-wise warps (2 per TMEM lane quadra
 constexpr int T3_SIMT = 256;
 constexpr int T3_NCH = (TC_MAX_T / 16 + 1) / 2;  // 9 chunks of 16 strip columns per thread at most
 
+// dS pair = A o (G - delta) as the fp16 MMA operand: the difference is formed in fp32, rounded to fp16 and multiplied by the
+// (fp16) probabilities with one packed multiply — 4 instructions per pair instead of 7 (two unpacks, two subtracts, two
+// multiplies, one pack); the element-wise warps are issue-bound, not the tensor pipe.  One extra fp16 rounding of a factor.
+__device__ __forceinline__ uint32_t ds_pair(uint32_t a_pair, float x0, float x1) {
+  const __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&a_pair), __floats2half2_rn(x0, x1));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
 struct Row3Smem {
   static constexpr int KVBUF = 2 * TC_KV_BYTES;          // K then V of one unit
   static constexpr int KV = 0;                           // 2 buffers (unit parity)
@@ -82,9 +90,11 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base + TC_COL_S;
 
-  auto item = [&](int n, int& bh, int& mt, int& p) {
-    const int u = int(blockIdx.x) + (n / P) * int(gridDim.x);
-    p = n % P, bh = u / a.n_full, mt = u % a.n_full;
+  // unit ul of this CTA -> (sequence b, head h, 128-row tile mt); the divisions run once per unit, not per item
+  auto unit_coord = [&](int ul, int& bh, int& b, int& h, int& mt) {
+    const int u = int(blockIdx.x) + ul * int(gridDim.x);
+    bh = u / a.n_full, mt = u - bh * a.n_full;
+    b = bh / a.H, h = bh - b * a.H;
   };
 
   if (warp == 8) {
@@ -93,43 +103,55 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const uint32_t sbase = smem_u32(smem);
     const uint32_t idesc_gA = make_idesc_f16(128, nA), idesc_gB = make_idesc_f16(128, nB ? nB : 16);
     constexpr uint32_t idesc_o = make_idesc_f16(128, TC_HD, false, true);
-    auto load_do = [&](int n) {
-      int bh, mt, p;
-      item(n, bh, mt, p);
-      const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
-      mbar_arrive_expect_tx(&bar_do[n % 3], TC_BOX_BYTES);
-      tma_load_2d(smem + Row3Smem::DO + (n % 3) * TC_BOX_BYTES, &tm_do, &bar_do[n % 3], h * TC_HD, pb * T + mt * 128);
-    };
-    auto load_kv = [&](int u) {  // u = index of the unit within this CTA's list
-      int bh, mt, p;
-      item(u * P, bh, mt, p);
-      const int b = bh / a.H, h = bh % a.H;
-      uint8_t* buf = smem + Row3Smem::KV + (u & 1) * Row3Smem::KVBUF;
-      mbar_arrive_expect_tx(&bar_kv[u & 1], 2u * TC_KV_BYTES);
-      for (int bx = 0; bx < 2; ++bx) {
-        tma_load_2d(buf + bx * TC_BOX_BYTES, &tm_qkv, &bar_kv[u & 1], d + h * TC_HD, b * T + bx * TC_BOX_ROWS);
-        tma_load_2d(buf + TC_KV_BYTES + bx * TC_BOX_BYTES, &tm_qkv, &bar_kv[u & 1], 2 * d + h * TC_HD, b * T + bx * TC_BOX_ROWS);
+    // dO loader position (runs two items ahead of the main loop)
+    int l_n = 0, l_p = 0, l_ul = 0, l_b = 0, l_h = 0, l_mt = 0, l_bh = 0;
+    unit_coord(0, l_bh, l_b, l_h, l_mt);
+    auto load_do = [&]() {
+      if (leader) {
+        const int st = l_n % 3;
+        mbar_arrive_expect_tx(&bar_do[st], TC_BOX_BYTES);
+        tma_load_2d(smem + Row3Smem::DO + st * TC_BOX_BYTES, &tm_do, &bar_do[st], l_h * TC_HD, (l_p * a.B + l_b) * T + l_mt * 128);
+      }
+      ++l_n;
+      if (++l_p == P) {
+        l_p = 0, ++l_ul;
+        if (l_ul < n_my) unit_coord(l_ul, l_bh, l_b, l_h, l_mt);
       }
     };
-    auto issue_g = [&](int n, int c) {
-      const int u = n / P;
+    auto load_kv = [&](int ul) {
+      int bh, b, h, mt;
+      unit_coord(ul, bh, b, h, mt);
+      uint8_t* buf = smem + Row3Smem::KV + (ul & 1) * Row3Smem::KVBUF;
+      mbar_arrive_expect_tx(&bar_kv[ul & 1], 2u * TC_KV_BYTES);
+      for (int bx = 0; bx < 2; ++bx) {
+        tma_load_2d(buf + bx * TC_BOX_BYTES, &tm_qkv, &bar_kv[ul & 1], d + h * TC_HD, b * T + bx * TC_BOX_ROWS);
+        tma_load_2d(buf + TC_KV_BYTES + bx * TC_BOX_BYTES, &tm_qkv, &bar_kv[ul & 1], 2 * d + h * TC_HD, b * T + bx * TC_BOX_ROWS);
+      }
+    };
+    // G issue position: item g_n = label g_p of unit g_ul (both chunks of an item, then the next item)
+    int g_n = 0, g_p = 0, g_ul = 0;
+    auto issue_g = [&](int c) {
+      const int st = g_n % 3;
       if (c == 0) {
-        if (n % P == 0) mbar_wait(&bar_kv[u & 1], (u >> 1) & 1);
-        mbar_wait(&bar_do[n % 3], (n / 3) & 1);
+        if (g_p == 0) mbar_wait(&bar_kv[g_ul & 1], (g_ul >> 1) & 1);
+        mbar_wait(&bar_do[st], (g_n / 3) & 1);
         tc_fence_after();
       }
       if (c == 0 || nB) {
-        const uint64_t dDO = desc_kmajor(sbase + Row3Smem::DO + (n % 3) * TC_BOX_BYTES);
-        const uint64_t dV = desc_kmajor(sbase + Row3Smem::KV + (u & 1) * Row3Smem::KVBUF + TC_KV_BYTES + (c ? nA * 128 : 0));
+        const uint64_t dDO = desc_kmajor(sbase + Row3Smem::DO + st * TC_BOX_BYTES);
+        const uint64_t dV = desc_kmajor(sbase + Row3Smem::KV + (g_ul & 1) * Row3Smem::KVBUF + TC_KV_BYTES + (c ? nA * 128 : 0));
 #pragma unroll
         for (int k = 0; k < TC_HD / 16; ++k)
           umma_f16_elect(tS + uint32_t(c ? nA : 0), dDO + uint64_t(2 * k), dV + uint64_t(2 * k), c ? idesc_gB : idesc_gA, k != 0, leader);
       }
       umma_commit_elect(&bar_s[c], leader);
+      if (c == 1) {
+        ++g_n;
+        if (++g_p == P) g_p = 0, ++g_ul;
+      }
     };
-    auto issue_q = [&](int n, int c) {
-      const int u = n / P;
-      const uint64_t dK = desc_mnmajor(sbase + Row3Smem::KV + (u & 1) * Row3Smem::KVBUF, 16);
+    auto issue_q = [&](int n, int ul, int c) {
+      const uint64_t dK = desc_mnmajor(sbase + Row3Smem::KV + (ul & 1) * Row3Smem::KVBUF, 16);
       const uint32_t tO = tmem_base + uint32_t((n & 1) ? TC_COL_O2 : TC_COL_O);
       const int s0 = c ? c_split : 0, s1 = c ? nch : c_split;
       for (int s = s0; s < s1; ++s) umma_f16_ts_elect(tO, tS + uint32_t(16 * s), dK + uint64_t(s) * (2048 >> 4), idesc_o, s > 0, leader);
@@ -139,54 +161,61 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       if (leader) {
         load_kv(0);
         if (n_my > 1) load_kv(1);
-        load_do(0);
-        if (N > 1) load_do(1);
       }
+      load_do();
+      if (N > 1) load_do();
       __syncwarp();
-      issue_g(0, 0);
-      issue_g(0, 1);
+      issue_g(0);
+      issue_g(1);
     }
+    int m_p = 0, m_ul = 0;  // main position: item n = label m_p of unit m_ul
     for (int n = 0; n < N; ++n) {
       // dO stage (n + 2) % 3 held item n - 1, whose G chunks were both consumed (bar_p waits of the previous iteration)
-      if (leader && n + 2 < N) load_do(n + 2);
+      if (n + 2 < N) load_do();
       __syncwarp();
       mbar_wait(&bar_p[0], n & 1);  // chunk 0 of the strip holds packed dS(n)
       if (n >= 2) mbar_wait(&bar_e[n & 1], ((n - 2) >> 1) & 1);  // accumulator n & 1 drained by the epilogue of item n - 2
       tc_fence_after();
-      issue_q(n, 0);
-      if (n + 1 < N) issue_g(n + 1, 0);  // in issue order behind dQ(n, 0): may overwrite chunk 0
+      issue_q(n, m_ul, 0);
+      if (n + 1 < N) issue_g(0);  // in issue order behind dQ(n, 0): may overwrite chunk 0
       mbar_wait(&bar_p[1], n & 1);
       tc_fence_after();
-      issue_q(n, 1);
-      if (n + 1 < N) issue_g(n + 1, 1);
-      if (n % P == 0 && n > 0) {
-        // unit n / P has started; the previous unit's K / V buffer is free once dQ(n - 1) has completed (long ago)
+      issue_q(n, m_ul, 1);
+      if (n + 1 < N) issue_g(1);
+      if (m_p == 0 && n > 0) {
+        // unit m_ul has started; the previous unit's K / V buffer is free once dQ(n - 1) has completed (long ago)
         mbar_wait(&bar_o[(n - 1) & 1], ((n - 1) >> 1) & 1);
-        const int u = n / P;
-        if (leader && u + 1 < n_my) load_kv(u + 1);
+        if (leader && m_ul + 1 < n_my) load_kv(m_ul + 1);
         __syncwarp();
       }
+      if (++m_p == P) m_p = 0, ++m_ul;
     }
   } else {
     // ===== element-wise warps: half 0 owns strip chunk 0, half 1 chunk 1 =====
     const int q = warp & 3, half = warp >> 2, rr = q * 32 + lane;
     const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16);
     const int c0 = half ? c_split : 0, c1 = half ? nch : c_split;
+    const size_t S3 = size_t(a.splits) * 3 * d;
+    const size_t d_stride = size_t(a.B) * a.H * T;   // delta: label p -> p + 1
+    const size_t o_stride = size_t(a.B) * T * S3;    // dqkv16 rows: label p -> p + 1
     uint32_t arow[T3_NCH][8];  // this thread's half of its probability row (kept across the P labels of a unit)
-    float dnext = 0.f;
-    auto delta_of = [&](int n) -> float {
-      int bh, mt, p;
-      item(n, bh, mt, p);
-      const int i = mt * 128 + rr;
-      if (i >= T) return 0.f;
-      const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
-      return a.delta[(size_t(pb) * a.H + h) * T + i];
+    struct Unit {
+      bool valid;
+      const __half* prow;
+      const float* dptr;
+      __half* optr;
     };
-    auto epilogue = [&](int m) {
-      int bh, mt, p;
-      item(m, bh, mt, p);
-      const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+    auto setup = [&](int ul, Unit& U) {
+      int bh, b, h, mt;
+      unit_coord(ul, bh, b, h, mt);
       const int i = mt * 128 + rr;
+      U.valid = i < T;
+      const int ic = U.valid ? i : 0;
+      U.prow = a.probs16 + (size_t(bh) * T + ic) * a.ldp;
+      U.dptr = a.delta + (size_t(b) * a.H + h) * T + ic;
+      U.optr = a.dqkv16 + (size_t(b) * T + ic) * S3 + h * TC_HD + 32 * half;
+    };
+    auto epilogue = [&](int m, __half* orow, bool valid) {
       mbar_wait(&bar_o[m & 1], (m >> 1) & 1);
       tc_fence_after();
       uint32_t o[32];
@@ -194,22 +223,24 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       tc_wait_ld();
       tc_fence_before();
       mbar_arrive(&bar_e[m & 1]);
-      if (i < T)
-        store_row_f16(a.dqkv16 + (size_t(pb) * T + i) * size_t(a.splits) * 3 * d + h * TC_HD + 32 * half, 3 * d, a.splits, o, 32, a.scale);
+      if (valid) store_row_f16(orow, 3 * d, a.splits, o, 32, a.scale);
     };
-    if (N > 0) dnext = delta_of(0);
+    Unit cur{}, nxt{};
+    int p = 0, ul = 0;
+    float dnext = 0.f;
+    __half* prev_o = nullptr;
+    bool prev_valid = false;
+    if (N > 0) {
+      setup(0, cur);
+      dnext = cur.valid ? cur.dptr[0] : 0.f;
+    }
     for (int n = 0; n < N; ++n) {
-      int bh, mt, p;
-      item(n, bh, mt, p);
-      const int i = mt * 128 + rr;
-      const bool valid = i < T;
       if (p == 0) {
-        const __half* prow = a.probs16 + (size_t(bh) * T + (valid ? i : 0)) * a.ldp;
 #pragma unroll
         for (int cc = 0; cc < T3_NCH; ++cc) {
           if (c0 + cc < c1) {
-            if (valid) {
-              ld_global_256(prow + (c0 + cc) * 16, arow[cc]);
+            if (cur.valid) {
+              ld_global_256(cur.prow + (c0 + cc) * 16, arow[cc]);
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e) arow[cc][e] = 0u;
@@ -218,7 +249,13 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         }
       }
       const float delta = dnext;
-      if (n + 1 < N) dnext = delta_of(n + 1);  // in flight during this item's element-wise phase
+      // next item's scalar in flight during this item's element-wise phase
+      if (p + 1 < P) {
+        dnext = cur.valid ? cur.dptr[size_t(p + 1) * d_stride] : 0.f;
+      } else if (n + 1 < N) {
+        setup(ul + 1, nxt);
+        dnext = nxt.valid ? nxt.dptr[0] : 0.f;
+      }
 
       mbar_wait(&bar_s[half], n & 1);
       tc_fence_after();
@@ -231,27 +268,24 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         tc_wait_ld();
         if (v0) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&arow[cc][e]));
-            w[e] = pack_h2(a2.x * (__uint_as_float(g0[2 * e]) - delta), a2.y * (__uint_as_float(g0[2 * e + 1]) - delta));
-          }
+          for (int e = 0; e < 8; ++e) w[e] = ds_pair(arow[cc][e], __uint_as_float(g0[2 * e]) - delta, __uint_as_float(g0[2 * e + 1]) - delta);
           tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + (c0 + cc) * 16), w);
         }
         if (v1) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&arow[(cc + 1) % T3_NCH][e]));
-            w[e] = pack_h2(a2.x * (__uint_as_float(g1[2 * e]) - delta), a2.y * (__uint_as_float(g1[2 * e + 1]) - delta));
-          }
+          for (int e = 0; e < 8; ++e)
+            w[e] = ds_pair(arow[(cc + 1) % T3_NCH][e], __uint_as_float(g1[2 * e]) - delta, __uint_as_float(g1[2 * e + 1]) - delta);
           tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + (c0 + cc + 1) * 16), w);
         }
       }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&bar_p[half]);
-      if (n >= 1) epilogue(n - 1);  // its dQ has had the whole element-wise phase of item n to complete
+      if (n >= 1) epilogue(n - 1, prev_o, prev_valid);  // its dQ has had the whole element-wise phase of item n to complete
+      prev_o = cur.optr + size_t(p) * o_stride, prev_valid = cur.valid;
+      if (++p == P) p = 0, ++ul, cur = nxt;
     }
-    if (N > 0) epilogue(N - 1);
+    if (N > 0) epilogue(N - 1, prev_o, prev_valid);
   }
   tc_fence_before();
   __syncthreads();
@@ -297,36 +331,33 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  auto item = [&](int n, int& bh, int& mt, int& p) {
-    const int u = int(blockIdx.x) + (n / P) * int(gridDim.x);
-    p = n % P, bh = u / a.n_full, mt = u % a.n_full;
+  auto unit_coord = [&](int ul, int& bh, int& b, int& h, int& mt) {
+    const int u = int(blockIdx.x) + ul * int(gridDim.x);
+    bh = u / a.n_full, mt = u - bh * a.n_full;
+    b = bh / a.H, h = bh - b * a.H;
   };
-  // {delta_i, r_i} of item n, staged by the owner of the chunk the query row i belongs to: chunk 0 rows t and t + 128
+  // {delta_i, r_i} of an item, staged by the owner of the chunk the query row i belongs to: chunk 0 rows t and t + 128
   // (< nA), chunk 1 row nA + t, for t = thread index within its half
   const int half_t = int(threadIdx.x) & 127, my_half = (int(threadIdx.x) >> 7) & 1;
   const int row_a = my_half ? nA + half_t : half_t;
   const int row_b = my_half ? ncol : half_t + 128;  // second row of a chunk-0 thread (valid when < nA)
-  auto fetch_dr = [&](int n, float2& v0, float2& v1) {
-    int bh, mt, p;
-    item(n, bh, mt, p);
-    const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+  const bool ok_a = row_a < T && (my_half || row_a < nA), ok_b = row_b < nA && row_b < T;
+  const size_t d_stride = size_t(a.B) * a.H * T;  // delta / wpart: label p -> p + 1
+  const size_t r_stride = size_t(a.B) * T;        // r: label p -> p + 1
+  auto fetch_dr = [&](const float* dbase, const float* rbase, float2& v0, float2& v1) {
     v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
-    if (row_a < T) {
-      v0.x = a.need_dqkv ? a.delta[(size_t(pb) * a.H + h) * T + row_a] : 0.f;
-      v0.y = a.r[size_t(pb) * T + row_a];
-    }
-    if (row_b < nA && row_b < T) {
-      v1.x = a.need_dqkv ? a.delta[(size_t(pb) * a.H + h) * T + row_b] : 0.f;
-      v1.y = a.r[size_t(pb) * T + row_b];
-    }
+    if (ok_a) v0 = make_float2(a.need_dqkv ? dbase[row_a] : 0.f, rbase[row_a]);
+    if (ok_b) v1 = make_float2(a.need_dqkv ? dbase[row_b] : 0.f, rbase[row_b]);
   };
   auto store_dr = [&](int n, const float2& v0, const float2& v1) {
-    if (row_a < ncol) s_dr[(n & 1) * TC_MAX_T + row_a] = v0;
+    if (my_half ? row_a < ncol : row_a < nA) s_dr[(n & 1) * TC_MAX_T + row_a] = v0;  // own chunk only: the halves run apart
     if (row_b < nA) s_dr[(n & 1) * TC_MAX_T + row_b] = v1;
   };
   if (warp < 8 && N > 0) {
+    int bh, b, h, mt;
+    unit_coord(0, bh, b, h, mt);
     float2 v0, v1;
-    fetch_dr(0, v0, v1);
+    fetch_dr(a.delta + (size_t(b) * a.H + h) * T, a.r + size_t(b) * T, v0, v1);
     store_dr(0, v0, v1);
   }
   tc_fence_before();
@@ -342,19 +373,26 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const uint64_t dVt = desc_kmajor(sbase + ColSmem::V), dQm = desc_mnmajor(sbase + ColSmem::Q, 16);
     const uint32_t idesc_gA = make_idesc_f16(128, nA), idesc_gB = make_idesc_f16(128, nB ? nB : 16);
     constexpr uint32_t idesc_o = make_idesc_f16(128, TC_HD, false, true);
-    auto load_do = [&](int n) {
-      int bh, mt, p;
-      item(n, bh, mt, p);
-      const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
-      mbar_arrive_expect_tx(&bar_do[n & 1], TC_KV_BYTES);
-      for (int bx = 0; bx < 2; ++bx)
-        tma_load_2d(smem + ColSmem::DO + (n & 1) * TC_KV_BYTES + bx * TC_BOX_BYTES, &tm_do, &bar_do[n & 1], h * TC_HD,
-                    pb * T + bx * TC_BOX_ROWS);
+    // dO loader position (two items ahead of the main loop)
+    int l_n = 0, l_p = 0, l_ul = 0, l_b = 0, l_h = 0, l_mt = 0, l_bh = 0;
+    unit_coord(0, l_bh, l_b, l_h, l_mt);
+    auto load_do = [&]() {
+      if (leader) {
+        const int st = l_n & 1;
+        mbar_arrive_expect_tx(&bar_do[st], TC_KV_BYTES);
+        for (int bx = 0; bx < 2; ++bx)
+          tma_load_2d(smem + ColSmem::DO + st * TC_KV_BYTES + bx * TC_BOX_BYTES, &tm_do, &bar_do[st], l_h * TC_HD,
+                      (l_p * a.B + l_b) * T + bx * TC_BOX_ROWS);
+      }
+      ++l_n;
+      if (++l_p == P) {
+        l_p = 0, ++l_ul;
+        if (l_ul < n_my) unit_coord(l_ul, l_bh, l_b, l_h, l_mt);
+      }
     };
-    auto load_unit = [&](int n) {
-      int bh, mt, p;
-      item(n, bh, mt, p);
-      const int b = bh / a.H, h = bh % a.H;
+    auto load_unit = [&](int ul) {
+      int bh, b, h, mt;
+      unit_coord(ul, bh, b, h, mt);
       mbar_arrive_expect_tx(bar_kv, 7u * TC_BOX_BYTES);
       for (int bx = 0; bx < 2; ++bx)
         tma_load_2d(smem + ColSmem::Q + bx * TC_BOX_BYTES, &tm_qkv, bar_kv, h * TC_HD, b * T + bx * TC_BOX_ROWS);
@@ -363,19 +401,24 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         for (int bx = 0; bx < 2; ++bx)
           tma_load_2d(smem + ColSmem::PR + (cb * 2 + bx) * TC_BOX_BYTES, &tm_pr, bar_kv, mt * 128 + cb * 64, bh * T + bx * TC_BOX_ROWS);
     };
-    auto issue_g = [&](int n, int c) {
+    int g_n = 0, g_p = 0, g_ul = 0;  // G issue position
+    auto issue_g = [&](int c) {
       if (c == 0) {
-        if (n % P == 0) mbar_wait(bar_kv, (n / P) & 1);
-        mbar_wait(&bar_do[n & 1], (n >> 1) & 1);
+        if (g_p == 0) mbar_wait(bar_kv, g_ul & 1);
+        mbar_wait(&bar_do[g_n & 1], (g_n >> 1) & 1);
         tc_fence_after();
       }
       if (c == 0 || nB) {
-        const uint64_t dDOk = desc_kmajor(sbase + ColSmem::DO + (n & 1) * TC_KV_BYTES + (c ? nA * 128 : 0));
+        const uint64_t dDOk = desc_kmajor(sbase + ColSmem::DO + (g_n & 1) * TC_KV_BYTES + (c ? nA * 128 : 0));
 #pragma unroll
         for (int k = 0; k < TC_HD / 16; ++k)
           umma_f16_elect(tS + uint32_t(c ? nA : 0), dVt + uint64_t(2 * k), dDOk + uint64_t(2 * k), c ? idesc_gB : idesc_gA, k != 0, leader);
       }
       umma_commit_elect(&bar_s[c], leader);
+      if (c == 1) {
+        ++g_n;
+        if (++g_p == P) g_p = 0, ++g_ul;
+      }
     };
     auto issue_kv = [&](int n, int c) {
       if (a.need_dqkv) {
@@ -390,38 +433,38 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       if (c == 1) umma_commit_elect(bar_o, leader);
     };
     if (N > 0) {
-      if (leader) {
-        load_unit(0);
-        load_do(0);
-        if (N > 1) load_do(1);
-      }
+      if (leader) load_unit(0);
+      load_do();
+      if (N > 1) load_do();
       __syncwarp();
-      issue_g(0, 0);
-      issue_g(0, 1);
+      issue_g(0);
+      issue_g(1);
     }
+    int m_p = 0, m_ul = 0;
     for (int n = 0; n < N; ++n) {
-      const bool more = n + 1 < N, boundary = (n + 1) % P == 0;
+      const bool more = n + 1 < N, boundary = m_p + 1 == P;
       mbar_wait(&bar_p[0], n & 1);
       if (n >= 1) mbar_wait(bar_e, (n - 1) & 1);  // dK / dV accumulators drained by the epilogues of item n - 1
       tc_fence_after();
       issue_kv(n, 0);
-      if (more && !boundary) issue_g(n + 1, 0);
+      if (more && !boundary) issue_g(0);
       mbar_wait(&bar_p[1], n & 1);
       tc_fence_after();
       issue_kv(n, 1);
-      if (more && !boundary) issue_g(n + 1, 1);
+      if (more && !boundary) issue_g(1);
       // dO stage n & 1 (B operand of dV(n)) and, at a unit boundary, Q / V / the probability tile are free once item n's
       // MMAs have completed; the next item's G chunks are already queued behind them
       mbar_wait(bar_o, n & 1);
       tc_fence_after();
-      if (leader && n + 2 < N) load_do(n + 2);
+      if (n + 2 < N) load_do();
       if (more && boundary) {
-        if (leader) load_unit(n + 1);
+        if (leader) load_unit(m_ul + 1);
         __syncwarp();
-        issue_g(n + 1, 0);
-        issue_g(n + 1, 1);
+        issue_g(0);
+        issue_g(1);
       }
       __syncwarp();
+      if (++m_p == P) m_p = 0, ++m_ul;
     }
   } else {
     // ===== element-wise warps: half 0 owns query chunk 0 and drains dK, half 1 owns chunk 1 and drains dV =====
@@ -432,42 +475,65 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     // block jj/64 (the two 136-row TMA boxes of a column block are contiguous and 136 % 8 == 0)
     const uint8_t* pcol = smem + ColSmem::PR + (jj >> 6) * (2 * TC_BOX_BYTES) + (jj & 7) * 2;
     const float invH = 1.0f / a.H;
+    const float clamp_lo = a.positive_only ? 0.f : -INFINITY;
+    const size_t S3 = size_t(a.splits) * 3 * d;
+    const size_t o_stride = size_t(a.B) * T * S3;
     uint32_t acol[T3_NCH][8];  // A[i, j] for this thread's key j and its chunk of the query rows i, packed pairs
-    auto epilogue = [&](int m) {
-      int bh, mt, p;
-      item(m, bh, mt, p);
-      const int b = bh / a.H, h = bh % a.H, pb = p * a.B + b;
+    struct Unit {
+      bool valid;
+      const float* dbase;  // delta of label 0, query row 0 of this (sequence, head)
+      const float* rbase;  // r of label 0, query row 0 of this sequence
+      float* wptr;         // wpart of label 0, this key
+      __half* optr;        // dK (half 0) / dV (half 1) row of label 0, this key
+    };
+    auto setup = [&](int ul, Unit& U) {
+      int bh, b, h, mt;
+      unit_coord(ul, bh, b, h, mt);
       const int j = mt * 128 + jj;
-      const bool valid = j < T;
+      U.valid = j < T;
+      const int jc = U.valid ? j : 0;
+      U.dbase = a.delta + (size_t(b) * a.H + h) * T;
+      U.rbase = a.r + size_t(b) * T;
+      U.wptr = a.wpart + (size_t(b) * a.H + h) * T + jc;
+      U.optr = a.dqkv16 + (size_t(b) * T + jc) * S3 + (half ? 2 * d : d) + h * TC_HD;
+    };
+    auto epilogue = [&](int m, const Unit& U, int pm) {
       mbar_wait(bar_o, m & 1);  // item m's MMAs are complete (and, transitively, both halves' s_w partial sums are visible)
       tc_fence_after();
       float wsum = 0.f;
       if (half == 0) wsum = (s_w[(m & 1) * 256 + jj] + s_w[(m & 1) * 256 + 128 + jj]) * invH;
       if (a.need_dqkv) {
         const uint32_t col = half ? TC_COL_O2 : TC_COL_O;
-        uint32_t o0[32], o1[32];
-        tmem_ld_32x32b_x32(t_row + col, o0);
-        tmem_ld_32x32b_x32(t_row + col + 32, o1);
+        // two 32-column loads one after the other: the thread's 72 probability registers stay live across items
+        __half* orow = U.optr + size_t(pm) * o_stride;
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(t_row + col, o);
+        tc_wait_ld();
+        if (U.valid) store_row_f16(orow, 3 * d, a.splits, o, 32, 1.0f);
+        tmem_ld_32x32b_x32(t_row + col + 32, o);
         tc_wait_ld();
         tc_fence_before();
         mbar_arrive(bar_e);
-        if (valid) {
-          __half* orow = a.dqkv16 + (size_t(pb) * T + j) * size_t(a.splits) * 3 * d + (half ? 2 * d : d) + h * TC_HD;
-          store_row_f16(orow, 3 * d, a.splits, o0, 32, 1.0f);
-          store_row_f16(orow + 32, 3 * d, a.splits, o1, 32, 1.0f);
-        }
+        if (U.valid) store_row_f16(orow + 32, 3 * d, a.splits, o, 32, 1.0f);
       } else {
         mbar_arrive(bar_e);
       }
-      if (half == 0 && valid) a.wpart[(size_t(pb) * a.H + h) * T + j] = wsum;
+      if (half == 0 && U.valid) U.wptr[size_t(pm) * d_stride] = wsum;
     };
+    Unit cur{}, nxt{}, prev{};
+    int p = 0, ul = 0, prev_p = 0;
+    if (N > 0) setup(0, cur);
     for (int n = 0; n < N; ++n) {
-      int bh, mt, p;
-      item(n, bh, mt, p);
       float2 nx0, nx1;
-      if (n + 1 < N) fetch_dr(n + 1, nx0, nx1);  // global loads in flight during the element-wise phase
+      // {delta, r} of the next item: global loads in flight during the element-wise phase
+      if (p + 1 < P) {
+        fetch_dr(cur.dbase + size_t(p + 1) * d_stride, cur.rbase + size_t(p + 1) * r_stride, nx0, nx1);
+      } else if (n + 1 < N) {
+        setup(ul + 1, nxt);
+        fetch_dr(nxt.dbase, nxt.rbase, nx0, nx1);
+      }
       if (p == 0) {
-        mbar_wait(bar_kv, (n / P) & 1);  // the tile is read with ordinary loads: every thread acquires the TMA writes
+        mbar_wait(bar_kv, ul & 1);  // the tile is read with ordinary loads: every thread acquires the TMA writes
 #pragma unroll
         for (int cc = 0; cc < T3_NCH; ++cc) {
           if (c0 + cc < c1) {
@@ -488,7 +554,7 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       mbar_wait(&bar_s[half], n & 1);
       tc_fence_after();
       const float2* dr = s_dr + (n & 1) * TC_MAX_T;
-      float w = 0.f;
+      float w0 = 0.f, w1 = 0.f;
 #pragma unroll
       for (int cc = 0; cc < T3_NCH; ++cc) {
         if (c0 + cc < c1) {
@@ -502,27 +568,28 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             const float2 av = __half22float2(*reinterpret_cast<const __half2*>(&acol[cc][e >> 1]));
             const float4 d4 = dr4[e >> 1];  // {delta_i, r_i, delta_i+1, r_i+1}
             const float g0 = __uint_as_float(g[e]), g1 = __uint_as_float(g[e + 1]);
-            float x0 = g0 * av.x, x1 = g1 * av.y;
-            if (a.positive_only) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f);
-            w = fmaf(d4.y, x0, w);
-            w = fmaf(d4.w, x1, w);
-            ds[e >> 1] = pack_h2(av.x * (g0 - d4.x), av.y * (g1 - d4.z));
+            // relevance term r_i max(g a, 0) = r_i (a max(g, 0)) since a >= 0
+            w0 = fmaf(d4.y, av.x * fmaxf(g0, clamp_lo), w0);
+            w1 = fmaf(d4.w, av.y * fmaxf(g1, clamp_lo), w1);
+            ds[e >> 1] = ds_pair(acol[cc][e >> 1], g0 - d4.x, g1 - d4.z);
           }
           tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + c * 16), ds);
           tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + c * 16 + 8), acol[cc]);
         }
       }
-      s_w[(n & 1) * 256 + half * 128 + jj] = w;
+      s_w[(n & 1) * 256 + half * 128 + jj] = w0 + w1;
       if (n + 1 < N) store_dr(n + 1, nx0, nx1);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&bar_p[half]);
       // chunk-1 owners drain dV(n) now (their next chunk is queued behind dK / dV(n, 1) anyway); chunk-0 owners drain
       // dK(n - 1), which completed during their element-wise phase of item n
-      if (half == 1) epilogue(n);
-      else if (n >= 1) epilogue(n - 1);
+      if (half == 1) epilogue(n, cur, p);
+      else if (n >= 1) epilogue(n - 1, prev, prev_p);
+      prev = cur, prev_p = p;
+      if (++p == P) p = 0, ++ul, cur = nxt;
     }
-    if (N > 0 && half == 0) epilogue(N - 1);
+    if (N > 0 && half == 0) epilogue(N - 1, prev, prev_p);
   }
   tc_fence_before();
   __syncthreads();

@@ -63,6 +63,15 @@ struct AttnBwdTcArgs {
 
 __device__ __forceinline__ void store_row_f16(__half* dst, int lo_off, int splits, const uint32_t* o, int n, float scale) {
   // n fp32 values (multiple of 16) -> fp16 hi (and lo at +lo_off elements)
+  if (splits != 2) {  // single-precision rows: no residual to form
+    for (int e0 = 0; e0 < n; e0 += 16) {
+      uint32_t hi[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) hi[e] = pack_h2(__uint_as_float(o[e0 + 2 * e]) * scale, __uint_as_float(o[e0 + 2 * e + 1]) * scale);
+      st_global_256(dst + e0, hi);
+    }
+    return;
+  }
   for (int e0 = 0; e0 < n; e0 += 16) {
     uint32_t hi[8], lo[8];
 #pragma unroll

@@ -122,8 +122,10 @@ def test_attn_bwd(T, H, impl):
 @pytest.mark.parametrize("B,T,H,P", [(12, 257, 16, 3), (40, 50, 12, 5), (7, 257, 16, 16)])
 def test_attn_bwd_pipelined_matches_second_generation_over_unit_boundaries(B, T, H, P):
     """More units than SMs, so every CTA of the chunk-pipelined passes (vit_attn_bwd3.cu) crosses unit boundaries (K / V double
-    buffer, probability reload, accumulator hand-over).  Same arithmetic in the same order as the second generation: the
-    results must be bit-identical."""
+    buffer, probability reload, accumulator hand-over).  The first version of these kernels did the same arithmetic in the
+    same order as the second generation and matched it bit for bit (commit c8e4e9d); since then dS is formed with one packed
+    fp16 multiply (one more rounding of a factor) and the relevance sum runs in two chains, so the comparison carries the
+    fp16-operand tolerance; a scheduling error (stale chunk, wrong accumulator, wrong label) would be O(1)."""
     from semabs_b200 import ops
 
     g = torch.Generator(device=dev).manual_seed(B * T + P)
@@ -150,8 +152,13 @@ def test_attn_bwd_pipelined_matches_second_generation_over_unit_boundaries(B, T,
         assert torch.equal(w2, wpart)
         out[gen] = (wpart, dqkv16)
     assert torch.isfinite(out[3][0]).all() and torch.isfinite(out[3][1].float()).all()
-    assert torch.equal(out[2][0], out[3][0]), (out[2][0] - out[3][0]).abs().max().item()
-    assert torch.equal(out[2][1], out[3][1]), (out[2][1].float() - out[3][1].float()).abs().max().item()
+    w2_, w3_ = out[2][0], out[3][0]
+    assert (w2_ - w3_).abs().max().item() < 1e-5 * w2_.abs().max().item()
+    g2 = out[2][1][:, : 3 * d].float() + out[2][1][:, 3 * d :].float()
+    g3 = out[3][1][:, : 3 * d].float() + out[3][1][:, 3 * d :].float()
+    err = (g2 - g3).abs().max().item() / g2.abs().max().item()
+    print(f"attention backward gen 3 vs gen 2 (B={B}, T={T}, H={H}, P={P}): max|d|/max = {err:.2e}")
+    assert err < 1.5e-3
 
 
 def test_logit_seed():
