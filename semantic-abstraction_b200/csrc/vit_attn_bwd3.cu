@@ -199,22 +199,6 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const size_t d_stride = size_t(a.B) * a.H * T;   // delta: label p -> p + 1
     const size_t o_stride = size_t(a.B) * T * S3;    // dqkv16 rows: label p -> p + 1
     uint32_t arow[T3_NCH][8];  // this thread's half of its probability row (kept across the P labels of a unit)
-    struct Unit {
-      bool valid;
-      const __half* prow;
-      const float* dptr;
-      __half* optr;
-    };
-    auto setup = [&](int ul, Unit& U) {
-      int bh, b, h, mt;
-      unit_coord(ul, bh, b, h, mt);
-      const int i = mt * 128 + rr;
-      U.valid = i < T;
-      const int ic = U.valid ? i : 0;
-      U.prow = a.probs16 + (size_t(bh) * T + ic) * a.ldp;
-      U.dptr = a.delta + (size_t(b) * a.H + h) * T + ic;
-      U.optr = a.dqkv16 + (size_t(b) * T + ic) * S3 + h * TC_HD + 32 * half;
-    };
     auto epilogue = [&](int m, __half* orow, bool valid) {
       mbar_wait(&bar_o[m & 1], (m >> 1) & 1);
       tc_fence_after();
@@ -225,22 +209,29 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       mbar_arrive(&bar_e[m & 1]);
       if (valid) store_row_f16(orow, 3 * d, a.splits, o, 32, a.scale);
     };
-    Unit cur{}, nxt{};
+    // per-unit state, advanced by pointer additions per label (no per-item multiplies, nothing carried for the next unit:
+    // the register file is full of probabilities and a spill reload on this path stalls the whole element-wise warp)
+    bool valid = false, prev_valid = false;
+    const float* dptr = nullptr;
+    __half *optr = nullptr, *prev_o = nullptr;
     int p = 0, ul = 0;
     float dnext = 0.f;
-    __half* prev_o = nullptr;
-    bool prev_valid = false;
-    if (N > 0) {
-      setup(0, cur);
-      dnext = cur.valid ? cur.dptr[0] : 0.f;
-    }
     for (int n = 0; n < N; ++n) {
       if (p == 0) {
+        int bh, b, h, mt;
+        unit_coord(ul, bh, b, h, mt);
+        const int i = mt * 128 + rr;
+        valid = i < T;
+        const int ic = valid ? i : 0;
+        const __half* prow = a.probs16 + (size_t(bh) * T + ic) * a.ldp;
+        dptr = a.delta + (size_t(b) * a.H + h) * T + ic;
+        optr = a.dqkv16 + (size_t(b) * T + ic) * S3 + h * TC_HD + 32 * half;
+        dnext = valid ? *dptr : 0.f;
 #pragma unroll
         for (int cc = 0; cc < T3_NCH; ++cc) {
           if (c0 + cc < c1) {
-            if (cur.valid) {
-              ld_global_256(cur.prow + (c0 + cc) * 16, arow[cc]);
+            if (valid) {
+              ld_global_256(prow + (c0 + cc) * 16, arow[cc]);
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e) arow[cc][e] = 0u;
@@ -249,12 +240,9 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         }
       }
       const float delta = dnext;
-      // next item's scalar in flight during this item's element-wise phase
-      if (p + 1 < P) {
-        dnext = cur.valid ? cur.dptr[size_t(p + 1) * d_stride] : 0.f;
-      } else if (n + 1 < N) {
-        setup(ul + 1, nxt);
-        dnext = nxt.valid ? nxt.dptr[0] : 0.f;
+      if (p + 1 < P) {  // next label's scalar in flight during this item's element-wise phase
+        dptr += d_stride;
+        dnext = valid ? *dptr : 0.f;
       }
 
       mbar_wait(&bar_s[half], n & 1);
@@ -282,8 +270,9 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       tc_fence_before();
       mbar_arrive(&bar_p[half]);
       if (n >= 1) epilogue(n - 1, prev_o, prev_valid);  // its dQ has had the whole element-wise phase of item n to complete
-      prev_o = cur.optr + size_t(p) * o_stride, prev_valid = cur.valid;
-      if (++p == P) p = 0, ++ul, cur = nxt;
+      prev_o = optr, prev_valid = valid;
+      optr += o_stride;
+      if (++p == P) p = 0, ++ul;
     }
     if (N > 0) epilogue(N - 1, prev_o, prev_valid);
   }
@@ -479,58 +468,58 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const size_t S3 = size_t(a.splits) * 3 * d;
     const size_t o_stride = size_t(a.B) * T * S3;
     uint32_t acol[T3_NCH][8];  // A[i, j] for this thread's key j and its chunk of the query rows i, packed pairs
-    struct Unit {
-      bool valid;
-      const float* dbase;  // delta of label 0, query row 0 of this (sequence, head)
-      const float* rbase;  // r of label 0, query row 0 of this sequence
-      float* wptr;         // wpart of label 0, this key
-      __half* optr;        // dK (half 0) / dV (half 1) row of label 0, this key
-    };
-    auto setup = [&](int ul, Unit& U) {
-      int bh, b, h, mt;
-      unit_coord(ul, bh, b, h, mt);
-      const int j = mt * 128 + jj;
-      U.valid = j < T;
-      const int jc = U.valid ? j : 0;
-      U.dbase = a.delta + (size_t(b) * a.H + h) * T;
-      U.rbase = a.r + size_t(b) * T;
-      U.wptr = a.wpart + (size_t(b) * a.H + h) * T + jc;
-      U.optr = a.dqkv16 + (size_t(b) * T + jc) * S3 + (half ? 2 * d : d) + h * TC_HD;
-    };
-    auto epilogue = [&](int m, const Unit& U, int pm) {
+    // per-unit state advanced by pointer additions per label; the epilogue of the previous item (chunk-0 owners) gets its
+    // two pointers and the validity flag from copies taken before the advance
+    bool valid = false, prev_valid = false;
+    const float *dbase = nullptr, *rbase = nullptr;  // delta / r of the NEXT item to stage, query row 0
+    float *wptr = nullptr, *prev_w = nullptr;          // wpart of this key, current label
+    __half *optr = nullptr, *prev_o = nullptr;         // dK (half 0) / dV (half 1) row of this key, current label
+    auto epilogue = [&](int m, __half* orow, float* wrow, bool ok) {
       mbar_wait(bar_o, m & 1);  // item m's MMAs are complete (and, transitively, both halves' s_w partial sums are visible)
       tc_fence_after();
       float wsum = 0.f;
       if (half == 0) wsum = (s_w[(m & 1) * 256 + jj] + s_w[(m & 1) * 256 + 128 + jj]) * invH;
       if (a.need_dqkv) {
-        const uint32_t col = half ? TC_COL_O2 : TC_COL_O;
         // two 32-column loads one after the other: the thread's 72 probability registers stay live across items
-        __half* orow = U.optr + size_t(pm) * o_stride;
+        const uint32_t col = half ? TC_COL_O2 : TC_COL_O;
         uint32_t o[32];
         tmem_ld_32x32b_x32(t_row + col, o);
         tc_wait_ld();
-        if (U.valid) store_row_f16(orow, 3 * d, a.splits, o, 32, 1.0f);
+        if (ok) store_row_f16(orow, 3 * d, a.splits, o, 32, 1.0f);
         tmem_ld_32x32b_x32(t_row + col + 32, o);
         tc_wait_ld();
         tc_fence_before();
         mbar_arrive(bar_e);
-        if (U.valid) store_row_f16(orow + 32, 3 * d, a.splits, o, 32, 1.0f);
+        if (ok) store_row_f16(orow + 32, 3 * d, a.splits, o, 32, 1.0f);
       } else {
         mbar_arrive(bar_e);
       }
-      if (half == 0 && U.valid) U.wptr[size_t(pm) * d_stride] = wsum;
+      if (half == 0 && ok) *wrow = wsum;
     };
-    Unit cur{}, nxt{}, prev{};
-    int p = 0, ul = 0, prev_p = 0;
-    if (N > 0) setup(0, cur);
+    int p = 0, ul = 0;
     for (int n = 0; n < N; ++n) {
-      float2 nx0, nx1;
-      // {delta, r} of the next item: global loads in flight during the element-wise phase
-      if (p + 1 < P) {
-        fetch_dr(cur.dbase + size_t(p + 1) * d_stride, cur.rbase + size_t(p + 1) * r_stride, nx0, nx1);
-      } else if (n + 1 < N) {
-        setup(ul + 1, nxt);
-        fetch_dr(nxt.dbase, nxt.rbase, nx0, nx1);
+      if (p == 0) {
+        int bh, b, h, mt;
+        unit_coord(ul, bh, b, h, mt);
+        const int j = mt * 128 + jj;
+        valid = j < T;
+        const int jc = valid ? j : 0;
+        dbase = a.delta + (size_t(b) * a.H + h) * T;
+        rbase = a.r + size_t(b) * T;
+        wptr = a.wpart + (size_t(b) * a.H + h) * T + jc;
+        optr = a.dqkv16 + (size_t(b) * T + jc) * S3 + (half ? 2 * d : d) + h * TC_HD;
+      }
+      float2 nx0 = make_float2(0.f, 0.f), nx1 = nx0;
+      bool have_next = false;
+      if (p + 1 < P) {  // {delta, r} of the next label: global loads in flight during the element-wise phase
+        dbase += d_stride, rbase += r_stride;
+        fetch_dr(dbase, rbase, nx0, nx1);
+        have_next = true;
+      } else if (n + 1 < N) {  // first label of the next unit (once per unit: the divisions are off the per-item path)
+        int bh, b, h, mt;
+        unit_coord(ul + 1, bh, b, h, mt);
+        fetch_dr(a.delta + (size_t(b) * a.H + h) * T, a.r + size_t(b) * T, nx0, nx1);
+        have_next = true;
       }
       if (p == 0) {
         mbar_wait(bar_kv, ul & 1);  // the tile is read with ordinary loads: every thread acquires the TMA writes
@@ -578,18 +567,19 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         }
       }
       s_w[(n & 1) * 256 + half * 128 + jj] = w0 + w1;
-      if (n + 1 < N) store_dr(n + 1, nx0, nx1);
+      if (have_next) store_dr(n + 1, nx0, nx1);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&bar_p[half]);
       // chunk-1 owners drain dV(n) now (their next chunk is queued behind dK / dV(n, 1) anyway); chunk-0 owners drain
       // dK(n - 1), which completed during their element-wise phase of item n
-      if (half == 1) epilogue(n, cur, p);
-      else if (n >= 1) epilogue(n - 1, prev, prev_p);
-      prev = cur, prev_p = p;
-      if (++p == P) p = 0, ++ul, cur = nxt;
+      if (half == 1) epilogue(n, optr, wptr, valid);
+      else if (n >= 1) epilogue(n - 1, prev_o, prev_w, prev_valid);
+      prev_o = optr, prev_w = wptr, prev_valid = valid;
+      optr += o_stride, wptr += d_stride;
+      if (++p == P) p = 0, ++ul;
     }
-    if (N > 0 && half == 0) epilogue(N - 1, prev, prev_p);
+    if (N > 0 && half == 0) epilogue(N - 1, prev_o, prev_w, prev_valid);
   }
   tc_fence_before();
   __syncthreads();

@@ -64,6 +64,7 @@ struct AttnBwdTcArgs {
 __device__ __forceinline__ void store_row_f16(__half* dst, int lo_off, int splits, const uint32_t* o, int n, float scale) {
   // n fp32 values (multiple of 16) -> fp16 hi (and lo at +lo_off elements)
   if (splits != 2) {  // single-precision rows: no residual to form
+#pragma unroll
     for (int e0 = 0; e0 < n; e0 += 16) {
       uint32_t hi[8];
 #pragma unroll
@@ -72,6 +73,7 @@ __device__ __forceinline__ void store_row_f16(__half* dst, int lo_off, int split
     }
     return;
   }
+#pragma unroll
   for (int e0 = 0; e0 < n; e0 += 16) {
     uint32_t hi[8], lo[8];
 #pragma unroll
