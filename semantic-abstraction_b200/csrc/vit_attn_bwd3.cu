@@ -40,6 +40,50 @@ __device__ __forceinline__ uint32_t ds_pair(uint32_t a_pair, float x0, float x1)
   return *reinterpret_cast<const uint32_t*>(&r);
 }
 
+// Shared-memory load the compiler may schedule freely (not volatile: a volatile one is issued right in front of its first use
+// and its latency shows up 72 times per item).  Ordering against the barrier that publishes the data comes from the address:
+// the caller passes it through order_after_wait() once the wait has returned.
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint32_t order_after_wait(uint32_t x) {
+  asm volatile("" : "+r"(x)::"memory");
+  return x;
+}
+
+// Element-wise phase of the column pass over NC 16-query chunks of one thread's (= one key's) strip range; {delta_i, r_i} come
+// from shared memory (warp-uniform addresses).  NC > 0: compile-time chunk count (ViT-L/14: 9 and 8), NC == 0: run-time count.
+// Measured alternatives at the bench shape (1.62 ms as written): steps of 8 queries 1.83 ms, 32 columns per TMEM round trip
+// 1.84 ms, a prefetching second 16-register buffer 1.62 ms — ptxas folds the two buffers into one: the 72 probability
+// registers of a thread leave no room under the 168-register cap of a 9-warp CTA, which is what bounds this phase.
+template <int NC>
+__device__ __forceinline__ void col_elementwise(uint32_t t_strip, uint32_t dr_addr, const uint32_t (&acol)[T3_NCH][8], int nc,
+                                                float clamp_lo, float& w0, float& w1) {
+  constexpr int MAXC = NC ? NC : T3_NCH;
+#pragma unroll
+  for (int cc = 0; cc < MAXC; ++cc) {
+    if (NC == 0 && cc >= nc) break;
+    uint32_t g[16], out[8];
+    tmem_ld_32x32b_x16(t_strip + uint32_t(cc * 16), g);
+    tc_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t ap = acol[cc][e];
+      const float2 av = __half22float2(*reinterpret_cast<const __half2*>(&ap));
+      const float4 d4 = lds128(dr_addr + uint32_t(cc * 16 + 2 * e) * 8);  // {delta_i, r_i, delta_i+1, r_i+1}
+      const float g0 = __uint_as_float(g[2 * e]), g1 = __uint_as_float(g[2 * e + 1]);
+      // relevance term r_i max(g a, 0) = r_i (a max(g, 0)) since a >= 0
+      w0 = fmaf(d4.y, av.x * fmaxf(g0, clamp_lo), w0);
+      w1 = fmaf(d4.w, av.y * fmaxf(g1, clamp_lo), w1);
+      out[e] = ds_pair(ap, g0 - d4.x, g1 - d4.z);
+    }
+    tmem_st_32x32b_x8(t_strip + uint32_t(cc * 16), out);
+    tmem_st_32x32b_x8(t_strip + uint32_t(cc * 16 + 8), acol[cc]);
+  }
+}
+
 struct Row3Smem {
   static constexpr int KVBUF = 2 * TC_KV_BYTES;          // K then V of one unit
   static constexpr int KV = 0;                           // 2 buffers (unit parity)
@@ -247,23 +291,24 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 
       mbar_wait(&bar_s[half], n & 1);
       tc_fence_after();
+      // TMEM loads run one 16-column chunk ahead of the arithmetic (two register buffers)
+      uint32_t gbuf[2][16];
+      tmem_ld_32x32b_x16(t_row + uint32_t(TC_COL_S + c0 * 16), gbuf[0]);
+      tc_wait_ld();
 #pragma unroll
-      for (int cc = 0; cc < T3_NCH; cc += 2) {
-        const bool v0 = c0 + cc < c1, v1 = (cc + 1 < T3_NCH) && (c0 + cc + 1 < c1);  // warp-uniform
-        uint32_t g0[16], g1[16], w[8];
-        if (v0) tmem_ld_32x32b_x16(t_row + uint32_t(TC_COL_S + (c0 + cc) * 16), g0);
-        if (v1) tmem_ld_32x32b_x16(t_row + uint32_t(TC_COL_S + (c0 + cc + 1) * 16), g1);
-        tc_wait_ld();
-        if (v0) {
+      for (int cc = 0; cc < T3_NCH; ++cc) {
+        if (c0 + cc < c1) {
+          const int c = c0 + cc;
+          const bool has_next = (cc + 1 < T3_NCH) && (c + 1 < c1);  // warp-uniform
+          uint32_t dtok = __float_as_uint(delta);  // ordering token: this chunk's arithmetic stays behind the prefetch
+          if (has_next) tmem_ld_32x32b_x16_tok(t_row + uint32_t(TC_COL_S + (c + 1) * 16), gbuf[(cc + 1) & 1], dtok);
+          const float dl = __uint_as_float(dtok);
+          const uint32_t(&g)[16] = gbuf[cc & 1];
+          uint32_t w[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) w[e] = ds_pair(arow[cc][e], __uint_as_float(g0[2 * e]) - delta, __uint_as_float(g0[2 * e + 1]) - delta);
-          tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + (c0 + cc) * 16), w);
-        }
-        if (v1) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            w[e] = ds_pair(arow[(cc + 1) % T3_NCH][e], __uint_as_float(g1[2 * e]) - delta, __uint_as_float(g1[2 * e + 1]) - delta);
-          tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + (c0 + cc + 1) * 16), w);
+          for (int e = 0; e < 8; ++e) w[e] = ds_pair(arow[cc][e], __uint_as_float(g[2 * e]) - dl, __uint_as_float(g[2 * e + 1]) - dl);
+          tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + c * 16), w);
+          if (has_next) tc_wait_ld();
         }
       }
       tc_wait_st();
@@ -470,10 +515,21 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     uint32_t acol[T3_NCH][8];  // A[i, j] for this thread's key j and its chunk of the query rows i, packed pairs
     // per-unit state advanced by pointer additions per label; the epilogue of the previous item (chunk-0 owners) gets its
     // two pointers and the validity flag from copies taken before the advance
-    bool valid = false, prev_valid = false;
+    // Output pointers describe the item whose epilogue comes next: the current item for chunk-1 owners, the previous one
+    // for chunk-0 owners (they are set / advanced after that epilogue).
+    bool valid = false;
     const float *dbase = nullptr, *rbase = nullptr;  // delta / r of the NEXT item to stage, query row 0
-    float *wptr = nullptr, *prev_w = nullptr;          // wpart of this key, current label
-    __half *optr = nullptr, *prev_o = nullptr;         // dK (half 0) / dV (half 1) row of this key, current label
+    float* wptr = nullptr;                            // wpart of this key
+    __half* optr = nullptr;                           // dK (half 0) / dV (half 1) row of this key
+    auto set_out = [&](int u_local) {
+      int bh, b, h, mt;
+      unit_coord(u_local, bh, b, h, mt);
+      const int j = mt * 128 + jj;
+      valid = j < T;
+      const int jc = valid ? j : 0;
+      wptr = a.wpart + (size_t(b) * a.H + h) * T + jc;
+      optr = a.dqkv16 + (size_t(b) * T + jc) * S3 + (half ? 2 * d : d) + h * TC_HD;
+    };
     auto epilogue = [&](int m, __half* orow, float* wrow, bool ok) {
       mbar_wait(bar_o, m & 1);  // item m's MMAs are complete (and, transitively, both halves' s_w partial sums are visible)
       tc_fence_after();
@@ -501,13 +557,8 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       if (p == 0) {
         int bh, b, h, mt;
         unit_coord(ul, bh, b, h, mt);
-        const int j = mt * 128 + jj;
-        valid = j < T;
-        const int jc = valid ? j : 0;
         dbase = a.delta + (size_t(b) * a.H + h) * T;
         rbase = a.r + size_t(b) * T;
-        wptr = a.wpart + (size_t(b) * a.H + h) * T + jc;
-        optr = a.dqkv16 + (size_t(b) * T + jc) * S3 + (half ? 2 * d : d) + h * TC_HD;
       }
       float2 nx0 = make_float2(0.f, 0.f), nx1 = nx0;
       bool have_next = false;
@@ -542,28 +593,15 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       }
       mbar_wait(&bar_s[half], n & 1);
       tc_fence_after();
-      const float2* dr = s_dr + (n & 1) * TC_MAX_T;
+      const uint32_t dr_addr = order_after_wait(smem_u32(s_dr + (n & 1) * TC_MAX_T));
       float w0 = 0.f, w1 = 0.f;
-#pragma unroll
-      for (int cc = 0; cc < T3_NCH; ++cc) {
-        if (c0 + cc < c1) {
-          const int c = c0 + cc;
-          uint32_t g[16], ds[8];
-          tmem_ld_32x32b_x16(t_row + uint32_t(TC_COL_S + c * 16), g);
-          const float4* dr4 = reinterpret_cast<const float4*>(dr + c * 16);
-          tc_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            const float2 av = __half22float2(*reinterpret_cast<const __half2*>(&acol[cc][e >> 1]));
-            const float4 d4 = dr4[e >> 1];  // {delta_i, r_i, delta_i+1, r_i+1}
-            const float g0 = __uint_as_float(g[e]), g1 = __uint_as_float(g[e + 1]);
-            // relevance term r_i max(g a, 0) = r_i (a max(g, 0)) since a >= 0
-            w0 = fmaf(d4.y, av.x * fmaxf(g0, clamp_lo), w0);
-            w1 = fmaf(d4.w, av.y * fmaxf(g1, clamp_lo), w1);
-            ds[e >> 1] = ds_pair(acol[cc][e >> 1], g0 - d4.x, g1 - d4.z);
-          }
-          tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + c * 16), ds);
-          tmem_st_32x32b_x8(t_row + uint32_t(TC_COL_S + c * 16 + 8), acol[cc]);
+      {
+        const uint32_t t_strip = t_row + uint32_t(TC_COL_S + c0 * 16), dr0 = dr_addr + uint32_t(c0 * 16) * 8;
+        if (nch == 17) {  // ViT-L/14 (T = 257): 9 + 8 chunks
+          if (half == 0) col_elementwise<9>(t_strip, dr0, acol, 9, clamp_lo, w0, w1);
+          else col_elementwise<8>(t_strip, dr0, acol, 8, clamp_lo, w0, w1);
+        } else {
+          col_elementwise<0>(t_strip, dr0, acol, c1 - c0, clamp_lo, w0, w1);
         }
       }
       s_w[(n & 1) * 256 + half * 128 + jj] = w0 + w1;
@@ -573,13 +611,20 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       mbar_arrive(&bar_p[half]);
       // chunk-1 owners drain dV(n) now (their next chunk is queued behind dK / dV(n, 1) anyway); chunk-0 owners drain
       // dK(n - 1), which completed during their element-wise phase of item n
-      if (half == 1) epilogue(n, optr, wptr, valid);
-      else if (n >= 1) epilogue(n - 1, prev_o, prev_w, prev_valid);
-      prev_o = optr, prev_w = wptr, prev_valid = valid;
-      optr += o_stride, wptr += d_stride;
+      if (half == 1) {
+        if (p == 0) set_out(ul);
+        epilogue(n, optr, wptr, valid);
+        optr += o_stride, wptr += d_stride;
+      } else {
+        if (n >= 1) {  // the pointers still describe item n - 1
+          epilogue(n - 1, optr, wptr, valid);
+          optr += o_stride, wptr += d_stride;
+        }
+        if (p == 0) set_out(ul);
+      }
       if (++p == P) p = 0, ++ul;
     }
-    if (N > 0 && half == 0) epilogue(N - 1, prev_o, prev_w, prev_valid);
+    if (N > 0 && half == 0) epilogue(N - 1, optr, wptr, valid);
   }
   tc_fence_before();
   __syncthreads();
