@@ -149,6 +149,10 @@ int semabs_attn_bwd_tc3(const void* qkv16, int32_t ld_qkv, const void* probs16, 
                         int32_t P, int32_t B, int32_t T, int32_t H, int32_t splits, int32_t positive_only,
                         int32_t need_dqkv, void* stream);
 
+/* Debug aid of semabs_attn_bwd_tc3: device buffer of 2 x 16 x 64 int64 that the next launches fill with clock64 time stamps of
+ * CTA 0's pipeline events (tools/attn_trace.py prints the timeline); null = off (default). */
+int semabs_debug_attn_trace(long long* device_buf);
+
 /* Known-answer hook for the two tcgen05 operand forms the attention kernels add to the GEMM's (A operand in TMEM,
  * MN-major B in shared memory): D[128,64] = A16[128,Kd] * B16[Kd,64], Kd % 16 == 0, Kd <= 256; lbo / sbo are the
  * descriptor byte offsets under test.  Test infrastructure for tests/test_vit_kernels_gpu.py. */

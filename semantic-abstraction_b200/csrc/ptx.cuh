@@ -77,6 +77,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Low-latency wait for fine-grained pipelines: mbarrier.test_wait never suspends the warp, so the hand-over costs tens of
+// cycles.  (try_wait parks the warp for an implementation-defined time slice: measured on B200 in the attention backward, the
+// wake-ups after a completed phase arrived 230 - 2000 cycles late, quantised — four such hand-overs per item.)  Same trap.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
+  uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if ((++spins & 0xffff) == 0 && global_timer_ns() - t0 > SB_MBAR_TIMEOUT_NS) __trap();
+  }
+}
+
 // ----------------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------------

@@ -177,8 +177,8 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     auto issue_g = [&](int c) {
       const int st = g_n % 3;
       if (c == 0) {
-        if (g_p == 0) mbar_wait(&bar_kv[g_ul & 1], (g_ul >> 1) & 1);
-        mbar_wait(&bar_do[st], (g_n / 3) & 1);
+        if (g_p == 0) mbar_wait_spin(&bar_kv[g_ul & 1], (g_ul >> 1) & 1);
+        mbar_wait_spin(&bar_do[st], (g_n / 3) & 1);
         tc_fence_after();
       }
       if (c == 0 || nB) {
@@ -217,18 +217,23 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       // dO stage (n + 2) % 3 held item n - 1, whose G chunks were both consumed (bar_p waits of the previous iteration)
       if (n + 2 < N) load_do();
       __syncwarp();
-      mbar_wait(&bar_p[0], n & 1);  // chunk 0 of the strip holds packed dS(n)
-      if (n >= 2) mbar_wait(&bar_e[n & 1], ((n - 2) >> 1) & 1);  // accumulator n & 1 drained by the epilogue of item n - 2
+      mbar_wait_spin(&bar_p[0], n & 1);  // chunk 0 of the strip holds packed dS(n)
+      tc_trace(a, 0, 0, n);
+      if (n >= 2) mbar_wait_spin(&bar_e[n & 1], ((n - 2) >> 1) & 1);  // accumulator n & 1 drained by the epilogue of item n - 2
       tc_fence_after();
+      tc_trace(a, 0, 1, n);
       issue_q(n, m_ul, 0);
       if (n + 1 < N) issue_g(0);  // in issue order behind dQ(n, 0): may overwrite chunk 0
-      mbar_wait(&bar_p[1], n & 1);
+      tc_trace(a, 0, 2, n);
+      mbar_wait_spin(&bar_p[1], n & 1);
       tc_fence_after();
+      tc_trace(a, 0, 3, n);
       issue_q(n, m_ul, 1);
       if (n + 1 < N) issue_g(1);
+      tc_trace(a, 0, 4, n);
       if (m_p == 0 && n > 0) {
         // unit m_ul has started; the previous unit's K / V buffer is free once dQ(n - 1) has completed (long ago)
-        mbar_wait(&bar_o[(n - 1) & 1], ((n - 1) >> 1) & 1);
+        mbar_wait_spin(&bar_o[(n - 1) & 1], ((n - 1) >> 1) & 1);
         if (leader && m_ul + 1 < n_my) load_kv(m_ul + 1);
         __syncwarp();
       }
@@ -244,7 +249,7 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const size_t o_stride = size_t(a.B) * T * S3;    // dqkv16 rows: label p -> p + 1
     uint32_t arow[T3_NCH][8];  // this thread's half of its probability row (kept across the P labels of a unit)
     auto epilogue = [&](int m, __half* orow, bool valid) {
-      mbar_wait(&bar_o[m & 1], (m >> 1) & 1);
+      mbar_wait_spin(&bar_o[m & 1], (m >> 1) & 1);
       tc_fence_after();
       uint32_t o[32];
       tmem_ld_32x32b_x32(t_row + uint32_t(((m & 1) ? TC_COL_O2 : TC_COL_O) + 32 * half), o);
@@ -289,8 +294,10 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         dnext = valid ? *dptr : 0.f;
       }
 
-      mbar_wait(&bar_s[half], n & 1);
+      if (q == 0) tc_trace(a, 0, 5 + 5 * half, n);  // loop top
+      mbar_wait_spin(&bar_s[half], n & 1);
       tc_fence_after();
+      if (q == 0) tc_trace(a, 0, 6 + 5 * half, n);  // G chunk seen
       // TMEM loads run one 16-column chunk ahead of the arithmetic (two register buffers)
       uint32_t gbuf[2][16];
       tmem_ld_32x32b_x16(t_row + uint32_t(TC_COL_S + c0 * 16), gbuf[0]);
@@ -314,7 +321,9 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&bar_p[half]);
+      if (q == 0) tc_trace(a, 0, 7 + 5 * half, n);  // chunk packed, arrived
       if (n >= 1) epilogue(n - 1, prev_o, prev_valid);  // its dQ has had the whole element-wise phase of item n to complete
+      if (q == 0) tc_trace(a, 0, 8 + 5 * half, n);  // epilogue of item n - 1 done
       prev_o = optr, prev_valid = valid;
       optr += o_stride;
       if (++p == P) p = 0, ++ul;
@@ -438,8 +447,8 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     int g_n = 0, g_p = 0, g_ul = 0;  // G issue position
     auto issue_g = [&](int c) {
       if (c == 0) {
-        if (g_p == 0) mbar_wait(bar_kv, g_ul & 1);
-        mbar_wait(&bar_do[g_n & 1], (g_n >> 1) & 1);
+        if (g_p == 0) mbar_wait_spin(bar_kv, g_ul & 1);
+        mbar_wait_spin(&bar_do[g_n & 1], (g_n >> 1) & 1);
         tc_fence_after();
       }
       if (c == 0 || nB) {
@@ -477,19 +486,25 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     int m_p = 0, m_ul = 0;
     for (int n = 0; n < N; ++n) {
       const bool more = n + 1 < N, boundary = m_p + 1 == P;
-      mbar_wait(&bar_p[0], n & 1);
-      if (n >= 1) mbar_wait(bar_e, (n - 1) & 1);  // dK / dV accumulators drained by the epilogues of item n - 1
+      mbar_wait_spin(&bar_p[0], n & 1);
+      tc_trace(a, 1, 0, n);
+      if (n >= 1) mbar_wait_spin(bar_e, (n - 1) & 1);  // dK / dV accumulators drained by the epilogues of item n - 1
       tc_fence_after();
+      tc_trace(a, 1, 1, n);
       issue_kv(n, 0);
       if (more && !boundary) issue_g(0);
-      mbar_wait(&bar_p[1], n & 1);
+      tc_trace(a, 1, 2, n);
+      mbar_wait_spin(&bar_p[1], n & 1);
       tc_fence_after();
+      tc_trace(a, 1, 3, n);
       issue_kv(n, 1);
       if (more && !boundary) issue_g(1);
+      tc_trace(a, 1, 4, n);
       // dO stage n & 1 (B operand of dV(n)) and, at a unit boundary, Q / V / the probability tile are free once item n's
       // MMAs have completed; the next item's G chunks are already queued behind them
-      mbar_wait(bar_o, n & 1);
+      mbar_wait_spin(bar_o, n & 1);
       tc_fence_after();
+      tc_trace(a, 1, 15, n);
       if (n + 2 < N) load_do();
       if (more && boundary) {
         if (leader) load_unit(m_ul + 1);
@@ -531,7 +546,7 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       optr = a.dqkv16 + (size_t(b) * T + jc) * S3 + (half ? 2 * d : d) + h * TC_HD;
     };
     auto epilogue = [&](int m, __half* orow, float* wrow, bool ok) {
-      mbar_wait(bar_o, m & 1);  // item m's MMAs are complete (and, transitively, both halves' s_w partial sums are visible)
+      mbar_wait_spin(bar_o, m & 1);  // item m's MMAs are complete (and, transitively, both halves' s_w partial sums are visible)
       tc_fence_after();
       float wsum = 0.f;
       if (half == 0) wsum = (s_w[(m & 1) * 256 + jj] + s_w[(m & 1) * 256 + 128 + jj]) * invH;
@@ -573,7 +588,7 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         have_next = true;
       }
       if (p == 0) {
-        mbar_wait(bar_kv, ul & 1);  // the tile is read with ordinary loads: every thread acquires the TMA writes
+        mbar_wait_spin(bar_kv, ul & 1);  // the tile is read with ordinary loads: every thread acquires the TMA writes
 #pragma unroll
         for (int cc = 0; cc < T3_NCH; ++cc) {
           if (c0 + cc < c1) {
@@ -591,8 +606,10 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
           }
         }
       }
-      mbar_wait(&bar_s[half], n & 1);
+      if (q == 0) tc_trace(a, 1, 5 + 5 * half, n);  // loop top (after the next item's scalar fetch / unit set-up)
+      mbar_wait_spin(&bar_s[half], n & 1);
       tc_fence_after();
+      if (q == 0) tc_trace(a, 1, 6 + 5 * half, n);  // G^T chunk seen
       const uint32_t dr_addr = order_after_wait(smem_u32(s_dr + (n & 1) * TC_MAX_T));
       float w0 = 0.f, w1 = 0.f;
       {
@@ -609,6 +626,7 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&bar_p[half]);
+      if (q == 0) tc_trace(a, 1, 7 + 5 * half, n);  // chunk packed, arrived
       // chunk-1 owners drain dV(n) now (their next chunk is queued behind dK / dV(n, 1) anyway); chunk-0 owners drain
       // dK(n - 1), which completed during their element-wise phase of item n
       if (half == 1) {
@@ -622,6 +640,7 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         }
         if (p == 0) set_out(ul);
       }
+      if (q == 0) tc_trace(a, 1, 8 + 5 * half, n);  // epilogue done
       if (++p == P) p = 0, ++ul;
     }
     if (N > 0 && half == 0) epilogue(N - 1, optr, wptr, valid);
@@ -637,6 +656,15 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 }  // namespace sb
 
 using namespace sb;
+
+static long long* g_attn_trace = nullptr;
+// Debug aid: device buffer of 2 x 16 x 64 int64 that the NEXT semabs_attn_bwd_tc3 launches fill with clock64 time stamps of
+// CTA 0's pipeline events (kernel 0 = row pass, 1 = column pass; event slots: 0-4 control warp, 5-8 / 10-13 first warp of
+// chunk 0 / chunk 1 owners, 15 column-pass MMAs complete); null switches it off.  tools/attn_trace.py prints the timeline.
+extern "C" int semabs_debug_attn_trace(long long* device_buf) {
+  g_attn_trace = device_buf;
+  return 0;
+}
 
 // Third-generation attention backward: same contract as semabs_attn_bwd_tc2 (include/semabs_b200.h).
 extern "C" int semabs_attn_bwd_tc3(const void* qkv16, int32_t ld_qkv, const void* probs16, int32_t ld_p16, const float* o32,
@@ -665,6 +693,7 @@ extern "C" int semabs_attn_bwd_tc3(const void* qkv16, int32_t ld_qkv, const void
   a.positive_only = positive_only, a.need_dqkv = need_dqkv;
   a.n_tail = (T > 128 && rem == 1) ? 1 : 0;
   a.n_full = a.n_tail ? T / 128 : (T + 127) / 128;
+  a.trace = g_attn_trace;
   static bool configured = false;
   if (!configured) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_row_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Row3Smem::TOTAL));

@@ -59,7 +59,14 @@ struct AttnBwdTcArgs {
   int positive_only, need_dqkv;
   int n_full;             // 128-row MMA tiles per (sequence, head)
   int n_tail;             // rows / keys left to the SIMT tail kernel
+  long long* trace;       // debug: clock64 time stamps of CTA 0's pipeline events (null in production), see semabs_debug_attn_trace
 };
+constexpr int TC_TRACE_ITEMS = 64;   // items of CTA 0 recorded
+constexpr int TC_TRACE_EVENTS = 16;  // event slots per kernel
+__device__ __forceinline__ void tc_trace(const AttnBwdTcArgs& a, int kernel, int event, int n) {
+  if (a.trace && blockIdx.x == 0 && n < TC_TRACE_ITEMS && (threadIdx.x & 31) == 0)
+    a.trace[(kernel * TC_TRACE_EVENTS + event) * TC_TRACE_ITEMS + n] = clock64();
+}
 
 __device__ __forceinline__ void store_row_f16(__half* dst, int lo_off, int splits, const uint32_t* o, int n, float scale) {
   // n fp32 values (multiple of 16) -> fp16 hi (and lo at +lo_off elements)
