@@ -21,6 +21,21 @@
 //     n-1 after their element-wise phase of item n, chunk-1 warps drain dV of item n before theirs of item n+1;
 //     {delta_i, r_i} staging and the relevance partial sums are per chunk owner.
 // delta and the one-row / one-key tail are the second generation's kernels (launch helpers in vit_attn_bwd2.cu).
+//
+// Measured on B200 while tuning (tools/ubench/*.cu, tools/attn_trace.py = clock64 time stamps of CTA 0 through
+// semabs_debug_attn_trace, ncu source-level stall samples under profiles/r02_ncu_full_attn_bwd3.txt):
+//   * one thread issues a tcgen05.mma every max(N / 2, ~36 + N / 4) cycles when A comes from shared memory (N = 64: 48, 144: 72,
+//     256: 128) and every N / 2 cycles when A comes from TMEM (N = 64: 32); the instruction does not return before the pipe
+//     accepts it, so the issuing warp's own bookkeeping between two MMAs is tensor idle time (compile-time chunk geometry took
+//     the row pass's control warp from ~70 to ~45 cycles per MMA); a TMA issue costs its thread ~500 cycles;
+//   * tcgen05.ld x16 + wait::ld is a 23-cycle round trip on an idle SM (3.4 KB / clk / SM with 16 warps), but ~120 cycles
+//     while the tensor pipe is busy; steps of 8 or 32 columns were both slower than 16;
+//   * the element-wise warps are the limit: 72 probability registers per thread + 16 strip values + the 168-register cap of a
+//     9-warp CTA leave ptxas no room to run loads ahead (it folds a second prefetch buffer into the first), so each warp is a
+//     serial chain at ~0.4 instructions / cycle, two warps per scheduler.  Four pipeline chunks instead of two, test_wait spin
+//     loops instead of try_wait, and a separate TMA-issue warp were each built and measured: 0.60 / 1.89 ms against 0.56 /
+//     1.76 ms (row / column) for this version — no gain, reverted.  What would move it: probabilities in
+//     TMEM instead of registers (row pass: 272 + 136 + 64 columns), 16 element-wise warps, dV as a label-batched N = 256 GEMM.
 #include "vit_attn_tc.cuh"
 
 namespace sb {
@@ -177,8 +192,8 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     auto issue_g = [&](int c) {
       const int st = g_n % 3;
       if (c == 0) {
-        if (g_p == 0) mbar_wait_spin(&bar_kv[g_ul & 1], (g_ul >> 1) & 1);
-        mbar_wait_spin(&bar_do[st], (g_n / 3) & 1);
+        if (g_p == 0) mbar_wait(&bar_kv[g_ul & 1], (g_ul >> 1) & 1);
+        mbar_wait(&bar_do[st], (g_n / 3) & 1);
         tc_fence_after();
       }
       if (c == 0 || nB) {
@@ -217,15 +232,15 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       // dO stage (n + 2) % 3 held item n - 1, whose G chunks were both consumed (bar_p waits of the previous iteration)
       if (n + 2 < N) load_do();
       __syncwarp();
-      mbar_wait_spin(&bar_p[0], n & 1);  // chunk 0 of the strip holds packed dS(n)
+      mbar_wait(&bar_p[0], n & 1);  // chunk 0 of the strip holds packed dS(n)
       tc_trace(a, 0, 0, n);
-      if (n >= 2) mbar_wait_spin(&bar_e[n & 1], ((n - 2) >> 1) & 1);  // accumulator n & 1 drained by the epilogue of item n - 2
+      if (n >= 2) mbar_wait(&bar_e[n & 1], ((n - 2) >> 1) & 1);  // accumulator n & 1 drained by the epilogue of item n - 2
       tc_fence_after();
       tc_trace(a, 0, 1, n);
       issue_q(n, m_ul, 0);
       if (n + 1 < N) issue_g(0);  // in issue order behind dQ(n, 0): may overwrite chunk 0
       tc_trace(a, 0, 2, n);
-      mbar_wait_spin(&bar_p[1], n & 1);
+      mbar_wait(&bar_p[1], n & 1);
       tc_fence_after();
       tc_trace(a, 0, 3, n);
       issue_q(n, m_ul, 1);
@@ -233,7 +248,7 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       tc_trace(a, 0, 4, n);
       if (m_p == 0 && n > 0) {
         // unit m_ul has started; the previous unit's K / V buffer is free once dQ(n - 1) has completed (long ago)
-        mbar_wait_spin(&bar_o[(n - 1) & 1], ((n - 1) >> 1) & 1);
+        mbar_wait(&bar_o[(n - 1) & 1], ((n - 1) >> 1) & 1);
         if (leader && m_ul + 1 < n_my) load_kv(m_ul + 1);
         __syncwarp();
       }
@@ -249,7 +264,7 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const size_t o_stride = size_t(a.B) * T * S3;    // dqkv16 rows: label p -> p + 1
     uint32_t arow[T3_NCH][8];  // this thread's half of its probability row (kept across the P labels of a unit)
     auto epilogue = [&](int m, __half* orow, bool valid) {
-      mbar_wait_spin(&bar_o[m & 1], (m >> 1) & 1);
+      mbar_wait(&bar_o[m & 1], (m >> 1) & 1);
       tc_fence_after();
       uint32_t o[32];
       tmem_ld_32x32b_x32(t_row + uint32_t(((m & 1) ? TC_COL_O2 : TC_COL_O) + 32 * half), o);
@@ -295,7 +310,7 @@ attn_bwd_row_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       }
 
       if (q == 0) tc_trace(a, 0, 5 + 5 * half, n);  // loop top
-      mbar_wait_spin(&bar_s[half], n & 1);
+      mbar_wait(&bar_s[half], n & 1);
       tc_fence_after();
       if (q == 0) tc_trace(a, 0, 6 + 5 * half, n);  // G chunk seen
       // TMEM loads run one 16-column chunk ahead of the arithmetic (two register buffers)
@@ -447,8 +462,8 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     int g_n = 0, g_p = 0, g_ul = 0;  // G issue position
     auto issue_g = [&](int c) {
       if (c == 0) {
-        if (g_p == 0) mbar_wait_spin(bar_kv, g_ul & 1);
-        mbar_wait_spin(&bar_do[g_n & 1], (g_n >> 1) & 1);
+        if (g_p == 0) mbar_wait(bar_kv, g_ul & 1);
+        mbar_wait(&bar_do[g_n & 1], (g_n >> 1) & 1);
         tc_fence_after();
       }
       if (c == 0 || nB) {
@@ -486,15 +501,15 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     int m_p = 0, m_ul = 0;
     for (int n = 0; n < N; ++n) {
       const bool more = n + 1 < N, boundary = m_p + 1 == P;
-      mbar_wait_spin(&bar_p[0], n & 1);
+      mbar_wait(&bar_p[0], n & 1);
       tc_trace(a, 1, 0, n);
-      if (n >= 1) mbar_wait_spin(bar_e, (n - 1) & 1);  // dK / dV accumulators drained by the epilogues of item n - 1
+      if (n >= 1) mbar_wait(bar_e, (n - 1) & 1);  // dK / dV accumulators drained by the epilogues of item n - 1
       tc_fence_after();
       tc_trace(a, 1, 1, n);
       issue_kv(n, 0);
       if (more && !boundary) issue_g(0);
       tc_trace(a, 1, 2, n);
-      mbar_wait_spin(&bar_p[1], n & 1);
+      mbar_wait(&bar_p[1], n & 1);
       tc_fence_after();
       tc_trace(a, 1, 3, n);
       issue_kv(n, 1);
@@ -502,7 +517,7 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       tc_trace(a, 1, 4, n);
       // dO stage n & 1 (B operand of dV(n)) and, at a unit boundary, Q / V / the probability tile are free once item n's
       // MMAs have completed; the next item's G chunks are already queued behind them
-      mbar_wait_spin(bar_o, n & 1);
+      mbar_wait(bar_o, n & 1);
       tc_fence_after();
       tc_trace(a, 1, 15, n);
       if (n + 2 < N) load_do();
@@ -546,7 +561,7 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       optr = a.dqkv16 + (size_t(b) * T + jc) * S3 + (half ? 2 * d : d) + h * TC_HD;
     };
     auto epilogue = [&](int m, __half* orow, float* wrow, bool ok) {
-      mbar_wait_spin(bar_o, m & 1);  // item m's MMAs are complete (and, transitively, both halves' s_w partial sums are visible)
+      mbar_wait(bar_o, m & 1);  // item m's MMAs are complete (and, transitively, both halves' s_w partial sums are visible)
       tc_fence_after();
       float wsum = 0.f;
       if (half == 0) wsum = (s_w[(m & 1) * 256 + jj] + s_w[(m & 1) * 256 + 128 + jj]) * invH;
@@ -588,7 +603,7 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         have_next = true;
       }
       if (p == 0) {
-        mbar_wait_spin(bar_kv, ul & 1);  // the tile is read with ordinary loads: every thread acquires the TMA writes
+        mbar_wait(bar_kv, ul & 1);  // the tile is read with ordinary loads: every thread acquires the TMA writes
 #pragma unroll
         for (int cc = 0; cc < T3_NCH; ++cc) {
           if (c0 + cc < c1) {
@@ -607,7 +622,7 @@ attn_bwd_col_tc3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         }
       }
       if (q == 0) tc_trace(a, 1, 5 + 5 * half, n);  // loop top (after the next item's scalar fetch / unit set-up)
-      mbar_wait_spin(&bar_s[half], n & 1);
+      mbar_wait(&bar_s[half], n & 1);
       tc_fence_after();
       if (q == 0) tc_trace(a, 1, 6 + 5 * half, n);  // G^T chunk seen
       const uint32_t dr_addr = order_after_wait(smem_u32(s_dr + (n & 1) * TC_MAX_T));
