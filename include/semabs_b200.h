@@ -263,6 +263,11 @@ int semabs_conv3d(const void* x16, int32_t a_splits, const void* w16, int32_t w_
 int semabs_ncdhw_to_ndhwc(const float* x, float* y, int32_t N, int64_t S, int32_t C, int32_t Cpad, int32_t groups,
                           double* stats, void* stream);
 int semabs_ndhwc_to_ncdhw(const float* x, float* y, int32_t N, int64_t S, int32_t C, void* stream);
+/* final_conv (nn.Conv3d(f_maps[0], out_channels, 1), unet3d.py:565 / 619) fused with the conversion back to NCDHW (inference
+ * path): x16 [N,S,splits*C_in] fp16 rows [hi | lo], w [C_out,C_in] fp32, bias [C_out] or null -> y [N,C_out,S] fp32; fp32 FMAs.
+ * C_in in {16, 32, 64}. */
+int semabs_final_conv1x1_ncdhw(const void* x16, int32_t splits, const float* w, const float* bias, float* y, int32_t N, int64_t S,
+                               int32_t C_in, int32_t C_out, void* stream);
 
 /* nn.GroupNorm apply (unet3d.py:78-83; biased variance, eps 1e-5, affine): x raw fp32 [N,S,C] + stats ->
  * y16 [N,S,splits*C] (planar == 0) or the chunk-planar layout [N][splits*C/8][S][8] consumed by

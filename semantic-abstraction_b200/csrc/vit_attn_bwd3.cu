@@ -36,6 +36,9 @@
 //     loops instead of try_wait, and a separate TMA-issue warp were each built and measured: 0.60 / 1.89 ms against 0.56 /
 //     1.76 ms (row / column) for this version — no gain, reverted.  What would move it: probabilities in
 //     TMEM instead of registers (row pass: 272 + 136 + 64 columns), 16 element-wise warps, dV as a label-batched N = 256 GEMM.
+//   * a tail without resident Q / K / V tiles (two CTAs per SM: dO stages + the ds of all labels in shared memory, Q / K rows
+//     read from global in the final reductions) was built too: 0.60 + 0.35 ms against 0.79 ms for the second generation's
+//     tail kernel — the global-latency-bound reductions cost more than the occupancy gained; reverted.
 #include "vit_attn_tc.cuh"
 
 namespace sb {
@@ -686,6 +689,12 @@ extern "C" int semabs_attn_bwd_tc3(const void* qkv16, int32_t ld_qkv, const void
                                    const void* dO16, int32_t ld_do, const float* r, float* delta_ws, float* wpart,
                                    void* dqkv16, int32_t P, int32_t B, int32_t T, int32_t H, int32_t splits,
                                    int32_t positive_only, int32_t need_dqkv, void* stream) {
+  // one label per unit: the row pass's K / V look-ahead (next unit loaded one unit ahead into the other buffer) would have to
+  // be issued before the current unit has released that buffer — the second generation handles the (rare: ragged label
+  // chunks) case
+  if (P == 1)
+    return semabs_attn_bwd_tc2(qkv16, ld_qkv, probs16, ld_p16, o32, dO16, ld_do, r, delta_ws, wpart, dqkv16, P, B, T, H, splits,
+                               positive_only, need_dqkv, stream);
   SB_REQUIRE(qkv16 && probs16 && o32 && dO16 && r && delta_ws && wpart, "semabs_attn_bwd_tc3: null pointer");
   SB_REQUIRE(!need_dqkv || dqkv16, "semabs_attn_bwd_tc3: dqkv16 missing");
   SB_REQUIRE(P > 0 && B > 0 && T > 0 && H > 0 && T <= TC_MAX_T, "semabs_attn_bwd_tc3: bad shape (T <= %d)", TC_MAX_T);

@@ -326,6 +326,13 @@ def ndhwc_to_ncdhw(x, y, *, N, S, C):
     check(lib().semabs_ndhwc_to_ncdhw(ptr(x), ptr(y), i32(N), _i64(S), i32(C), stream_ptr()))
 
 
+def final_conv1x1_ncdhw(x16, w, bias, y, *, N, S, C_in, C_out, splits):
+    """final 1x1x1 convolution + channels-last -> NCDHW in one pass (see semabs_final_conv1x1_ncdhw)."""
+    CALL_PROFILE.note("semabs_final_conv1x1_ncdhw", bytes=N * S * (2 * splits * C_in + 4 * C_out), flops=2.0 * N * S * C_in * C_out)
+    check(lib().semabs_final_conv1x1_ncdhw(ptr(x16), i32(splits), ptr(w), ptr(bias), ptr(y), i32(N), _i64(S), i32(C_in), i32(C_out),
+                                           stream_ptr()))
+
+
 def groupnorm_apply(x, stats, gamma, beta, y16, *, N, S, C, C_real, groups, splits=1, planar=False):
     CALL_PROFILE.note("semabs_groupnorm_apply", bytes=N * S * C * (4 + 2 * splits))
     check(lib().semabs_groupnorm_apply(ptr(x), ptr(stats), ptr(gamma), ptr(beta), ptr(y16), i32(N), _i64(S), i32(C),

@@ -203,6 +203,7 @@ class ResidualUNet3D(nn.Module):
         fw = self.final_conv.weight
         pk["final.w"] = _split_pack(fw.detach().to(device, F32).reshape(fw.shape[0], fw.shape[1]), s)
         pk["final.b"] = self.final_conv.bias.detach().to(device, F32).contiguous()
+        pk["final.w32"] = fw.detach().to(device, F32).reshape(fw.shape[0], fw.shape[1]).contiguous()
         self._pack, self._pack_key = pk, key
         return pk
 
@@ -303,7 +304,7 @@ class ResidualUNet3D(nn.Module):
         self.kernel_launches += 1 + 3 * N
         return out32, out16
 
-    def forward_channels_last(self, x_raw, x_stats, N, dims, dev, tape=None):
+    def forward_channels_last(self, x_raw, x_stats, N, dims, dev, tape=None, ncdhw_out=None):
         """Core of Abstract3DUNet.forward (unet3d.py:596-621) on channels-last buffers. x_raw [N,S,Cpad] fp32 with
         its GroupNorm statistics. Returns the final conv output, channels-last fp32 [N,S,out_channels]."""
         pk = self._packed(dev)
@@ -354,6 +355,12 @@ class ResidualUNet3D(nn.Module):
             _, cur16 = self._res_block(pk, f"dec{j}", dec.basic_module, up, ust, N=N, dims=dims, c_in_pad=c_out,
                                        c_in_real=c_out, lvl=lvl, dev=dev, want32=False, want16=True, tape=tape)
         D, H, W = dims
+        if ncdhw_out is not None and tape is None and self.f_maps[0] in (16, 32, 64) and self.out_channels <= 256:
+            # inference: final_conv and the conversion back to NCDHW in one pass (no channels-last fp32 copy of the output)
+            ops.final_conv1x1_ncdhw(cur16, pk["final.w32"], pk["final.b"], ncdhw_out, N=N, S=D * H * W, C_in=self.f_maps[0],
+                                    C_out=self.out_channels, splits=s)
+            self.kernel_launches += 1
+            return None
         out = self._alloc(tape, "final_cl", "final.out", (N, D * H * W, self.out_channels), F32, dev)
         if tape is not None:
             tape.meta = dict(N=N, dims0=dims, dev=dev)
@@ -381,8 +388,10 @@ class ResidualUNet3D(nn.Module):
         st = self._buf("l0_pst", (N, 8, 2), F64, dev)
         st.zero_()
         ops.ncdhw_to_ndhwc(x, raw, N=N, S=S, C=C, Cpad=cpad, groups=g_in, stats=st)
-        out_cl = self.forward_channels_last(raw, st, N, (D, H, W), dev)
         y = torch.empty(N, self.out_channels, D, H, W, device=dev)
-        ops.ndhwc_to_ncdhw(out_cl, y, N=N, S=S, C=self.out_channels)
-        self.kernel_launches += 2
+        out_cl = self.forward_channels_last(raw, st, N, (D, H, W), dev, ncdhw_out=y)
+        if out_cl is not None:
+            ops.ndhwc_to_ncdhw(out_cl, y, N=N, S=S, C=self.out_channels)
+            self.kernel_launches += 1
+        self.kernel_launches += 1
         return y

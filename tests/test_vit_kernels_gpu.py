@@ -119,7 +119,8 @@ def test_attn_bwd(T, H, impl):
     assert (got - ref).abs().max().item() < 4e-3 * scale, ((got - ref).abs().max().item(), scale)
 
 
-@pytest.mark.parametrize("B,T,H,P", [(12, 257, 16, 3), (40, 50, 12, 5), (7, 257, 16, 16)])
+@pytest.mark.parametrize("B,T,H,P", [(12, 257, 16, 3), (40, 50, 12, 5), (7, 257, 16, 16), (29, 257, 16, 5), (64, 257, 16, 1),
+                                     (29, 257, 16, 2), (3, 257, 16, 33)])
 def test_attn_bwd_pipelined_matches_second_generation_over_unit_boundaries(B, T, H, P):
     """More units than SMs, so every CTA of the chunk-pipelined passes (vit_attn_bwd3.cu) crosses unit boundaries (K / V double
     buffer, probability reload, accumulator hand-over).  The first version of these kernels did the same arithmetic in the

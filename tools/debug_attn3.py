@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from semabs_b200 import ops
 dev = "cuda"
-for (B, T, H, P) in [(40, 50, 12, 5), (7, 257, 16, 16), (12, 257, 16, 3)]:
+for (B, T, H, P) in [(29, 257, 16, 5), (64, 257, 16, 1), (29, 257, 16, 1), (64, 257, 16, 5)]:
     g = torch.Generator(device=dev).manual_seed(B * T + P)
     d = H * 64
     qkv = torch.randn(B * T, 3 * d, device=dev, generator=g)
