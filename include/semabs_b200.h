@@ -298,6 +298,11 @@ int semabs_conv3d_halo_fused(const void* x16_planar, int32_t a_splits, const voi
                              int32_t C_in, int32_t precise, const float* bias_cls, const float* residual, const void* res_planar,
                              int32_t relu, float* out32, void* out16, int32_t o16_splits, void* out_planar, double* stats,
                              int32_t groups, void* stream);
+/* The fold itself, for every sample in one launch: w [32][32][27] fp32 (conv.weight of a 32 -> 32 channel convolution), gamma /
+ * beta [32] and stats (per sample stats_stride doubles: [groups][2] = sum, sum of squares over S voxels x 32 / groups channels) ->
+ * w_img [N][55296] fp16 (ops.pack_halo_weights layout of W * gamma * rstd, hi | lo rows) and bias_cls [N][27][32] fp32. */
+int semabs_fold_groupnorm_halo(const float* w, const float* gamma, const float* beta, const double* stats, int32_t stats_stride,
+                               int32_t N, int64_t S, int32_t groups, void* w_img, float* bias_cls, void* stream);
 /* Debug aid of the pair kernel: copies and clears its barrier time-out records (up to 64 x 8 int32); returns their number. */
 int semabs_debug_halo_pair_dump(int32_t* out512);
 

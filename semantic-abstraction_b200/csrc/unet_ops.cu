@@ -134,6 +134,71 @@ __global__ void __launch_bounds__(256) final_conv1x1_ncdhw_kernel(const __half* 
   }
 }
 
+// ---- GroupNorm folded into the consuming 3x3x3 convolution (32 -> 32 channels, inference, see conv3d_halo2.cu) -------------
+// GroupNorm(x)[c] = a_c x_c + b_c per (sample, channel) with a = gamma rstd, b = beta - mean a, so
+//   conv_W(GroupNorm(x)) = conv_{W a}(x) + sum over the taps that fall inside the grid of (W b).
+// One launch writes, for every sample, the halo kernel's resident weight image of W a (ops.pack_halo_weights layout, hi | lo
+// rows) and the 27-entry border-class bias table.  Statistics arithmetic = gn_apply_kernel's (fp64 mean / variance, eps 1e-5).
+constexpr int FOLD_C = 32;
+constexpr int FOLD_IMG_HALFS = 2 * 27 * 2 * 4 * 2 * 8 * 8;  // [half][tap][kb][row group][kc][row][elem]
+__global__ void __launch_bounds__(256) fold_groupnorm_halo_kernel(const float* __restrict__ w /*[32][32][27]*/, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, const double* __restrict__ stats,
+                                                                  int stats_stride, int groups, double inv_count, __half* __restrict__ img,
+                                                                  float* __restrict__ bias_cls /*[N][27][32]*/) {
+  __shared__ float s_a[FOLD_C], s_b[FOLD_C];
+  __shared__ float s_wb[FOLD_C * 27];  // sum_ci W[co][ci][tap] b[ci]
+  const int n = blockIdx.x, cpg = FOLD_C / groups;
+  if (threadIdx.x < FOLD_C) {
+    const int c = threadIdx.x, g = c / cpg;
+    const double mean = stats[size_t(n) * stats_stride + 2 * g] * inv_count;
+    double var = stats[size_t(n) * stats_stride + 2 * g + 1] * inv_count - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = float(1.0 / sqrt(var + 1e-5));
+    const float a = rstd * gamma[c];
+    s_a[c] = a, s_b[c] = beta[c] - float(mean) * a;
+  }
+  __syncthreads();
+  __half* im = img + size_t(n) * FOLD_IMG_HALFS;
+  // weight image: the (co, ci, tap) index space in gridDim.y slices; the bias table is block (n, 0)'s
+  const int total = FOLD_C * FOLD_C * 27, per = (total + gridDim.y - 1) / gridDim.y;
+  const int lo_idx = blockIdx.y * per, hi_idx = min(total, lo_idx + per);
+  for (int idx = lo_idx + threadIdx.x; idx < hi_idx; idx += blockDim.x) {
+    const int tap = idx % 27, ci = (idx / 27) % FOLD_C, co = idx / (27 * FOLD_C);
+    const float v = w[idx] * s_a[ci];
+    const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+    const int h = co >> 4, r16 = co & 15, kb = ci >> 4, kc = (ci & 15) >> 3, e = ci & 7;
+    const size_t base = (size_t(h) * 27 + tap) * 2 + kb;
+    // rows 0-15 of a half: W_hi of its 16 output channels, rows 16-31: W_lo
+    im[((((base * 4 + (r16 >> 3)) * 2 + kc) * 8) + (r16 & 7)) * 8 + e] = hi;
+    im[((((base * 4 + 2 + (r16 >> 3)) * 2 + kc) * 8) + (r16 & 7)) * 8 + e] = lo;
+  }
+  if (blockIdx.y != 0) return;
+  for (int idx = threadIdx.x; idx < FOLD_C * 27; idx += blockDim.x) {
+    const int tap = idx % 27, co = idx / 27;
+    float acc = 0.f;
+    for (int ci = 0; ci < FOLD_C; ++ci) acc = fmaf(w[(co * FOLD_C + ci) * 27 + tap], s_b[ci], acc);
+    s_wb[idx] = acc;
+  }
+  __syncthreads();
+  // border classes per axis: 0 = first voxel (taps 1, 2 inside), 1 = interior (all), 2 = last voxel (taps 0, 1)
+  for (int idx = threadIdx.x; idx < 27 * FOLD_C; idx += blockDim.x) {
+    const int co = idx % FOLD_C, cls = idx / FOLD_C;
+    const int cz = cls / 9, cy = (cls / 3) % 3, cx = cls % 3;
+    float acc = 0.f;
+    for (int tz = 0; tz < 3; ++tz) {
+      if ((cz == 0 && tz == 0) || (cz == 2 && tz == 2)) continue;
+      for (int ty = 0; ty < 3; ++ty) {
+        if ((cy == 0 && ty == 0) || (cy == 2 && ty == 2)) continue;
+        for (int tx = 0; tx < 3; ++tx) {
+          if ((cx == 0 && tx == 0) || (cx == 2 && tx == 2)) continue;
+          acc += s_wb[co * 27 + (tz * 3 + ty) * 3 + tx];
+        }
+      }
+    }
+    bias_cls[(size_t(n) * 27 + cls) * FOLD_C + co] = acc;
+  }
+}
+
 // ---- GroupNorm apply: raw fp32 channels-last + (sum, sumsq) -> normalised fp16 (hi | lo) ------------------
 // torch.nn.GroupNorm semantics (unet3d.py:78-83): biased variance over (C/G) x D x H x W, eps 1e-5, affine.
 __global__ void __launch_bounds__(EW_THREADS)
@@ -258,6 +323,19 @@ extern "C" int semabs_final_conv1x1_ncdhw(const void* x16, int32_t splits, const
     }
     final_conv1x1_ncdhw_kernel<64><<<grid, 256, sm, st>>>(x, splits, w, bias, y, S, C_out);
   }
+  SB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int semabs_fold_groupnorm_halo(const float* w, const float* gamma, const float* beta, const double* stats,
+                                          int32_t stats_stride, int32_t N, int64_t S, int32_t groups, void* w_img, float* bias_cls,
+                                          void* stream) {
+  SB_REQUIRE(w && gamma && beta && stats && w_img && bias_cls && N > 0 && S > 0, "semabs_fold_groupnorm_halo: null pointer");
+  SB_REQUIRE(groups >= 1 && groups <= 8 && FOLD_C % groups == 0 && stats_stride >= 2 * groups,
+             "semabs_fold_groupnorm_halo: unsupported grouping %d / stride %d", groups, stats_stride);
+  const double inv_count = 1.0 / (double(S) * double(FOLD_C / groups));
+  fold_groupnorm_halo_kernel<<<dim3(N, 16), 256, 0, (cudaStream_t)stream>>>(w, gamma, beta, stats, stats_stride, groups, inv_count, (__half*)w_img,
+                                                                    bias_cls);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -364,6 +364,13 @@ def conv3d_halo_fused(x16_planar, w_img, *, D, H, C_in, a_splits, w_splits, prec
     )
 
 
+def fold_groupnorm_halo(w, gamma, beta, stats, w_img, bias_cls, *, N, S, groups):
+    """Per-sample halo weight images of W * gamma * rstd + border-class bias tables, one launch (see semabs_fold_groupnorm_halo)."""
+    assert stats.dim() == 3 and stats.is_contiguous() and stats.shape[0] == N
+    check(lib().semabs_fold_groupnorm_halo(ptr(w), ptr(gamma), ptr(beta), ptr(stats), i32(stats.shape[1] * stats.shape[2]), i32(N),
+                                           _i64(S), i32(groups), ptr(w_img), ptr(bias_cls), stream_ptr()))
+
+
 def set_halo_pair(enable: bool) -> None:
     """CTA-pair variant of the halo-resident convolution on / off (default on); see semabs_set_halo_pair."""
     check(lib().semabs_set_halo_pair(i32(int(enable))))

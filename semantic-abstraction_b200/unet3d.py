@@ -110,10 +110,10 @@ class ResidualUNet3D(nn.Module):
         self.use_halo = True  # halo-resident conv kernel at the 128-wide level (conv3d_halo.cu)
         # inference, 128-wide level, 32 channels, precise mode: conv2 / conv3 of a block consume the RAW output of their producer
         # (written chunk-planar hi | lo by its epilogue) with the GroupNorm folded into per-sample weights + a border-class bias
-        # (semabs_conv3d_halo_fused) instead of a GroupNorm-apply pass over an fp32 copy.  Off by default: measured on B200 it
-        # moves 46.0 instead of 49.4 GB per 4-grid forward but is not faster (29.2 vs 27.7 ms) while the per-sample weight fold
-        # runs as ~300 small torch kernels
-        self.fold_groupnorm = False
+        # (semabs_conv3d_halo_fused) instead of a GroupNorm-apply pass over an fp32 copy; the fold is one kernel launch per
+        # convolution for all samples (semabs_fold_groupnorm_halo)
+        self.fold_groupnorm = True
+        self.folded_blocks = 0  # residual blocks that took the folded path (tests)
         encoders = []
         for i, out_f in enumerate(f_maps):
             encoders.append(Encoder(in_channels if i == 0 else f_maps[i - 1], out_f, apply_pooling=i > 0,
@@ -250,27 +250,16 @@ class ResidualUNet3D(nn.Module):
                                        c_in_pad=c_in_pad, c_in_real=c_in_real, c_out=c_out)
         return out32, out16
 
-    # border classes of the folded GroupNorm shift: along one axis, first voxel -> taps {1, 2} inside, interior -> all, last -> {0, 1}
-    _TAP_VALID = ((0.0, 1.0, 1.0), (1.0, 1.0, 1.0), (1.0, 1.0, 0.0))
 
-    def _fold_gn(self, w, gamma, beta, stats, S, groups, s):
+    def _fold_gn(self, key, w, gamma, beta, stats, S, groups):
         """GroupNorm(x) = a x + b per (sample, channel) with a = gamma rstd, b = beta - mean a, so conv(GroupNorm(x)) =
-        conv_{W a}(x) + sum over the taps that fall inside the grid of (W b): -> (weight images [N, 2 halves, ...] of W a,
-        bias table [N, 27 border classes, C_out]).  Same statistics arithmetic as gn_apply_kernel (fp64 mean / variance, eps
-        1e-5, fp32 scale / shift)."""
+        conv_{W a}(x) + sum over the taps that fall inside the grid of (W b): -> (weight images [N, ...] of W a,
+        bias table [N, 27 border classes, C_out]), one kernel launch for all samples (semabs_fold_groupnorm_halo)."""
         N = stats.shape[0]
-        co, ci = w.shape[:2]
-        cpg = ci // groups
-        cnt = float(S) * cpg
-        mean = stats[:, :groups, 0] / cnt
-        var = (stats[:, :groups, 1] / cnt - mean * mean).clamp_min(0.0)
-        rstd = (1.0 / torch.sqrt(var + 1e-5)).float()
-        a = rstd.repeat_interleave(cpg, dim=1) * gamma[None, :ci]
-        b = beta[None, :ci] - mean.float().repeat_interleave(cpg, dim=1) * a
-        imgs = torch.stack([ops.pack_halo_weights(w * a[n].view(1, ci, 1, 1, 1), s) for n in range(N)])
-        T = torch.einsum("oczyx,nc->nozyx", w, b)
-        M = torch.tensor(self._TAP_VALID, device=w.device)
-        bias = torch.einsum("nozyx,az,by,cx->nabco", T, M, M, M).reshape(N, 27, co).contiguous()
+        imgs = self._buf(f"{key}_img", (N, 55296), F16, w.device)
+        bias = self._buf(f"{key}_bias", (N, 27, 32), F32, w.device)
+        ops.fold_groupnorm_halo(w, gamma, beta, stats, imgs, bias, N=N, S=S, groups=groups)
+        self.kernel_launches += 1
         return imgs, bias
 
     def _res_block_folded(self, pk, prefix, blk, x_raw, x_stats, *, N, dims, c_in_pad, c_in_real, lvl, dev, want32, want16):
@@ -292,16 +281,17 @@ class ResidualUNet3D(nn.Module):
         kw = dict(D=D, H=H, a_splits=2, w_splits=2, precise=True)
         for n in range(N):
             ops.conv3d_halo_fused(xn_n[n], pk[f"{prefix}.wh1"], C_in=c_in_pad, relu=True, out_planar=o1p[n], stats=st[0, n], groups=g2, **kw)
-        w2, bias2 = self._fold_gn(pk[f"{prefix}.wraw2"], pk[f"{prefix}.g2"], pk[f"{prefix}.b2"], st[0], S, g2, 2)
+        w2, bias2 = self._fold_gn(f"l{lvl}_f2", pk[f"{prefix}.wraw2"], pk[f"{prefix}.g2"], pk[f"{prefix}.b2"], st[0], S, g2)
         for n in range(N):
             ops.conv3d_halo_fused(o1p[n], w2[n], C_in=c, bias_cls=bias2[n], relu=True, out_planar=o2p[n], stats=st[1, n], groups=g3, **kw)
-        w3, bias3 = self._fold_gn(pk[f"{prefix}.wraw3"], pk[f"{prefix}.g3"], pk[f"{prefix}.b3"], st[1], S, g3, 2)
+        w3, bias3 = self._fold_gn(f"l{lvl}_f3", pk[f"{prefix}.wraw3"], pk[f"{prefix}.g3"], pk[f"{prefix}.b3"], st[1], S, g3)
         out32 = self._buf(f"l{lvl}_out32", (N, S, c), F32, dev) if want32 else None
         out16 = self._buf(f"l{lvl}_out16", (N, S, 2 * c), F16, dev) if want16 else None
         for n in range(N):
             ops.conv3d_halo_fused(o2p[n], w3[n], C_in=c, bias_cls=bias3[n], res_planar=o1p[n], relu=True,
                                   out32=out32[n] if want32 else None, out16=out16[n] if want16 else None, o16_splits=2, **kw)
         self.kernel_launches += 1 + 3 * N
+        self.folded_blocks += 1
         return out32, out16
 
     def forward_channels_last(self, x_raw, x_stats, N, dims, dev, tape=None, ncdhw_out=None):
