@@ -48,6 +48,7 @@ struct ConvParams {
   int o16_splits;
   double* stats;             // [N, G, 2] (sum, sumsq) or null
   int groups;                // G of the consumer GroupNorm
+  int stages;                // depth of the operand ring actually used (<= ConvCfg::STAGES; fewer = several CTAs per SM)
 };
 
 // FUSED (precise mode): the three precision terms x_hi W_hi + x_hi W_lo + x_lo W_hi run as TWO stages per (tap, K block)
@@ -76,9 +77,10 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   using Cfg = ConvCfg<BN, KB, FUSED>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  const int STG = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STG * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STG;
+  uint64_t* tmem_full = empty_bar + STG;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -93,7 +95,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    for (int s = 0; s < STG; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -146,7 +148,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tma_load_5d(sA, &tmA, &full_bar[stage], h * p.C_in + kb * KB, x0 + dx, y0 + dy, z0 + dz, n0);
                 tma_load_2d(sB, &tmB, &full_bar[stage], wk_hi + kb * KB, nb * BN);
                 if (h == 0) tma_load_2d(sB + Cfg::B_BYTES_RAW, &tmB, &full_bar[stage], wk_lo + kb * KB, nb * BN);
-                if (++stage == Cfg::STAGES) {
+                if (++stage == STG) {
                   stage = 0;
                   phase ^= 1;
                 }
@@ -167,7 +169,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES_RAW);
                 tma_load_5d(sA, &tmA, &full_bar[stage], a_off + kb * KB, x0 + dx, y0 + dy, z0 + dz, n0);
                 tma_load_2d(sB, &tmB, &full_bar[stage], wk + kb * KB, nb * BN);
-                if (++stage == Cfg::STAGES) {
+                if (++stage == STG) {
                   stage = 0;
                   phase ^= 1;
                 }
@@ -203,7 +205,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < KB / 16; ++k)
             umma_f16_elect(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), id, (ks | k) != 0, leader);
           umma_commit_elect(&empty_bar[stage], leader);
-          if (++stage == Cfg::STAGES) {
+          if (++stage == STG) {
             stage = 0;
             phase ^= 1;
           }
@@ -371,8 +373,26 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
     configured = true;
   }
   const int num_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n * p.n_tiles_out;
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  conv3d_igemm_kernel<BN, KB, FUSED><<<grid, CONV_THREADS, Cfg::TOTAL, st>>>(tmA, tmB, p);
+  // Short tap lists over big grids with narrow tiles (the parity classes of the transposed convolution into the 128^3 level)
+  // are not tensor-bound (ncu: 5 us per 128-voxel tile whatever the tap count, 2-18 % tensor pipe, ~2 TB/s of strided 128-byte
+  // rows): a 4-stage ring leaves room for two CTAs per SM (shared memory and 2 x TMEM_COLS <= 512), so two tiles' epilogues and
+  // operand loads overlap: 275 -> 230 us per class.  (BN = 64, the 64^3 level: 80 -> 98 us, not taken.  What these launches
+  // want is one pass over all eight classes — input read once, contiguous output rows)
+  ConvParams q = p;
+  int per_sm = 1;
+  q.stages = Cfg::STAGES;
+  if (BN <= 32 && p.ntaps <= 8 && 2 * Cfg::TMEM_COLS <= 512 && num_tiles >= 4 * num_sms()) {
+    for (int s = 4; s >= 2; --s) {
+      if (s < Cfg::STAGES && s * Cfg::STAGE_BYTES + 1536 <= 112 * 1024) {
+        q.stages = s, per_sm = 2;
+        break;
+      }
+    }
+  }
+  const int smem_bytes = q.stages * Cfg::STAGE_BYTES + 512 + 1024;
+  const int cap = per_sm * num_sms();
+  const int grid = num_tiles < cap ? num_tiles : cap;
+  conv3d_igemm_kernel<BN, KB, FUSED><<<grid, CONV_THREADS, smem_bytes, st>>>(tmA, tmB, q);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -76,7 +76,10 @@ def test_unet_full_size_batch_independence():
     x = torch.randn(4, 32, 128, 128, 128, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
     y = m(x).clone()
     assert torch.isfinite(y).all()
-    assert _maxrel(m(x), y) < 1e-6  # run-to-run stable (the only order-dependent arithmetic: fp64 atomics of the GroupNorm statistics)
+    # run-to-run stable: the only order-dependent arithmetic is the fp64 atomics of the GroupNorm statistics; with the GroupNorm
+    # folded into the level-0 convolutions their last-bit differences reach the weights (fp16 hi | lo images of W gamma rstd):
+    # measured 1.1e-6
+    assert _maxrel(m(x), y) < 5e-6
     y2 = m(x[2:3].contiguous())
     err = _maxrel(y2, y[2:3])
     assert err < 1e-5, err  # GroupNorm is per sample: a grid must not see its batch neighbours
