@@ -1,0 +1,337 @@
+// Transposed 3-D convolution (ConvTranspose3d k3 s2 p1 called with output_size = 2x, reference unet3d.py:428-440) into a
+// 32-channel level, ALL EIGHT output-parity classes in one pass (the decoder's skip sum and bias in the epilogue, the next
+// GroupNorm's statistics accumulated on the way: Upsampling.forward + summation joining, unet3d.py:385-396).
+//
+// Why: the per-class launches of conv3d.cu (8 x 230-280 us into the 128^3 level) are not tensor-bound — ncu: 5 us per
+// 128-voxel tile whatever the tap count, 2-18 % tensor pipe, ~2 TB/s of 128-byte rows at a stride of two voxels, the input
+// level read eight times.  One output voxel (2z + pz, 2y + py, 2x + px) is
+//     sum over input shifts s <= p (componentwise, s in {0,1}^3) of  W[k = p + 1 - 2s] x[z + sz, y + sy, x + sx],
+// so a tile of 128 INPUT voxels needs 8 shifted activation boxes, and shift s serves every class p >= s.  Here:
+//   * accumulator = 8 classes x 32 channels = 256 TMEM columns (two buffers = all of TMEM), class c = pz*4 + py*2 + px at
+//     columns [32c, 32c + 32);
+//   * one pipeline stage = (precision pass, shift, 64-channel K block): the shifted box (TMA, out-of-bounds = zero) + the weight
+//     slices of the classes using that shift stacked along N; the MMA warp issues one tcgen05.mma per run of consecutive
+//     classes (shift 0: N = 256; 27 (class, tap) pairs in 14 instructions instead of 27 N = 32 ones — an N = 32 instruction costs
+//     40 cycles, an N = 256 one 128);
+//   * epilogue thread = input voxel: its 8 output voxels x 32 channels, the two px neighbours being adjacent 128-byte rows.
+// Input read once, output and skip tensor touched once, contiguously per (z, y) output row pair.
+#include "../../include/semabs_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sb {
+
+constexpr int CT_THREADS = 256;
+constexpr int CT_KB = 64;                    // input channels per stage (one 128-byte swizzle row)
+constexpr int CT_CO = 32;                    // output channels (one class = 32 accumulator columns)
+constexpr int CT_A_BYTES = 128 * CT_KB * 2;  // 16 KB
+constexpr int CT_SLICE = CT_CO * CT_KB * 2;  // 4 KB: one class's weight slice of a K block
+constexpr int CT_STAGE = CT_A_BYTES + 8 * CT_SLICE;
+constexpr int CT_STAGES = 4;
+constexpr int CT_SMEM = CT_STAGES * CT_STAGE + 512 + 1024;
+
+struct ConvTParams {
+  int N, D, H, W;  // input grid
+  int C_in;
+  int npass;
+  int8_t pass_a[3], pass_w[3];
+  int bw, bh, bd, bn;
+  int tiles_w, tiles_h, tiles_d, tiles_n;
+  const float* bias;      // [32] or null
+  const float* residual;  // [N, 2D, 2H, 2W, 32] or null (the encoder feature of the output level)
+  float* out32;           // [N, 2D, 2H, 2W, 32]
+  double* stats;          // [N, G, 2] or null
+  int groups;
+};
+
+__global__ void __launch_bounds__(CT_THREADS, 1)
+convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ ConvTParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + CT_STAGES * CT_STAGE);
+  uint64_t* empty_bar = full_bar + CT_STAGES;
+  uint64_t* tmem_full = empty_bar + CT_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
+  const int kblocks = p.C_in / CT_KB;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < CT_STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
+    for (int a = 0; a < 2; ++a) mbar_init(&tmem_full[a], 1), mbar_init(&tmem_empty[a], 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int t, int& x0, int& y0, int& z0, int& n0) {
+    int s = t;
+    x0 = (s % p.tiles_w) * p.bw;
+    s /= p.tiles_w;
+    y0 = (s % p.tiles_h) * p.bh;
+    s /= p.tiles_h;
+    z0 = (s % p.tiles_d) * p.bd;
+    s /= p.tiles_d;
+    n0 = s * p.bn;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int x0, y0, z0, n0;
+        decode(t, x0, y0, z0, n0);
+        for (int ps = 0; ps < p.npass; ++ps) {
+          const int a_off = p.pass_a[ps] * p.C_in, w_off = p.pass_w[ps] * 27;
+          for (int s = 0; s < 8; ++s) {
+            const int sz = (s >> 2) & 1, sy = (s >> 1) & 1, sx = s & 1;
+            const int ncls = 8 >> (sz + sy + sx);  // classes p >= s
+            for (int kb = 0; kb < kblocks; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sA = smem + stage * CT_STAGE;
+              uint8_t* sB = sA + CT_A_BYTES;
+              mbar_arrive_expect_tx(&full_bar[stage], CT_A_BYTES + ncls * CT_SLICE);
+              tma_load_5d(sA, &tmA, &full_bar[stage], a_off + kb * CT_KB, x0 + sx, y0 + sy, z0 + sz, n0);
+              int idx = 0;
+              for (int c = 0; c < 8; ++c) {
+                if ((c & s) != s) continue;
+                // tap of class (pz, py, px) under shift (sz, sy, sx): k = p + 1 - 2 s per axis
+                const int kz = ((c >> 2) & 1) + 1 - 2 * sz, ky = ((c >> 1) & 1) + 1 - 2 * sy, kx = (c & 1) + 1 - 2 * sx;
+                tma_load_2d(sB + idx * CT_SLICE, &tmB, &full_bar[stage], (w_off + (kz * 3 + ky) * 3 + kx) * p.C_in + kb * CT_KB, 0);
+                ++idx;
+              }
+              if (++stage == CT_STAGES) stage = 0, phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint64_t desc0 = make_smem_desc(0, 16, 1024, SW_128B) + (smem_u32(smem) >> 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      bool first = true;
+      for (int ps = 0; ps < p.npass; ++ps) {
+        for (int s = 0; s < 8; ++s) {
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t da = desc0 + uint32_t(stage) * uint32_t(CT_STAGE >> 4);
+            const uint64_t db0 = da + uint32_t(CT_A_BYTES >> 4);
+            // runs of consecutive classes among {c : c & s == s}; their slices are stacked in class order
+            int pos = 0, c = 0;
+            while (c < 8) {
+              if ((c & s) != s) {
+                ++c;
+                continue;
+              }
+              int len = 1;
+              while (c + len < 8 && ((c + len) & s) == s) ++len;
+              const uint32_t idesc = make_idesc_f16(128, CT_CO * len);
+              const uint64_t db = db0 + uint32_t(pos) * uint32_t(CT_SLICE >> 4);
+#pragma unroll
+              for (int k = 0; k < CT_KB / 16; ++k)
+                umma_f16_elect(d_tmem + uint32_t(c * CT_CO), da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, !(first && k == 0), leader);
+              pos += len, c += len;
+            }
+            first = false;  // the very first stage is shift 0: one N = 256 run initialises every column
+            umma_commit_elect(&empty_bar[stage], leader);
+            if (++stage == CT_STAGES) stage = 0, phase ^= 1;
+          }
+        }
+      }
+      umma_commit_elect(&tmem_full[acc], leader);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row of the tile = input voxel
+    const int lw = r % p.bw, lh = (r / p.bw) % p.bh, ld = (r / (p.bw * p.bh)) % p.bd, ln = r / (p.bw * p.bh * p.bd);
+    const int Do = 2 * p.D, Ho = 2 * p.H, Wo = 2 * p.W;
+    constexpr int MAXG = 8;
+    float gs[MAXG], gq[MAXG];
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i) gs[i] = gq[i] = 0.f;
+    int stat_n = -1;
+    const int cpg = p.stats ? CT_CO / p.groups : 16;  // channels per group (power of two, 2..32)
+    auto flush = [&]() {
+      if (stat_n < 0) return;
+#pragma unroll
+      for (int i = 0; i < MAXG; ++i) {
+        if (i < p.groups) {
+          const float s = warp_sum(gs[i]), s2 = warp_sum(gq[i]);
+          if (lane == 0) {
+            double* dst = p.stats + (size_t(stat_n) * p.groups + i) * 2;
+            atomicAdd(dst, double(s));
+            atomicAdd(dst + 1, double(s2));
+          }
+        }
+        gs[i] = gq[i] = 0.f;
+      }
+    };
+    float bias_r[CT_CO];
+#pragma unroll
+    for (int j = 0; j < CT_CO; ++j) bias_r[j] = p.bias ? p.bias[j] : 0.f;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int x0, y0, z0, n0;
+      decode(t, x0, y0, z0, n0);
+      const int n = n0 + ln, z = z0 + ld, y = y0 + lh, x = x0 + lw;
+      const bool ok = n < p.N;
+      const int n_w = __shfl_sync(0xffffffffu, n, 0);  // warp-uniform (rows per sample are a multiple of 32, or one sample per tile)
+      if (p.stats && n_w != stat_n) {
+        flush();
+        stat_n = n_w < p.N ? n_w : -1;
+      }
+      auto ovox = [&](int c) -> size_t {
+        return ((size_t(n) * Do + (2 * z + ((c >> 2) & 1))) * Ho + (2 * y + ((c >> 1) & 1))) * Wo + (2 * x + (c & 1));
+      };
+      // the skip rows do not depend on the accumulator: class 0's row is requested before the MMAs are awaited, class c + 1's
+      // while class c is processed
+      float4 rs_cur[8], rs_nxt[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rs_cur[j] = rs_nxt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.residual && ok) {
+        const float* row = p.residual + ovox(0) * CT_CO;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rs_cur[j] = *reinterpret_cast<const float4*>(row + 4 * j);
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        if (p.residual && ok && c + 1 < 8) {
+          const float* row = p.residual + ovox(c + 1) * CT_CO;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rs_nxt[j] = *reinterpret_cast<const float4*>(row + 4 * j);
+        }
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 256 + c * CT_CO), rr);
+        tc_wait_ld();
+        if (ok) {
+          float v[CT_CO];
+#pragma unroll
+          for (int j = 0; j < CT_CO; j += 4) {
+            const float4 b = rs_cur[j >> 2];
+            v[j] = __uint_as_float(rr[j]) + bias_r[j] + b.x, v[j + 1] = __uint_as_float(rr[j + 1]) + bias_r[j + 1] + b.y;
+            v[j + 2] = __uint_as_float(rr[j + 2]) + bias_r[j + 2] + b.z, v[j + 3] = __uint_as_float(rr[j + 3]) + bias_r[j + 3] + b.w;
+          }
+          float* o = p.out32 + ovox(c) * CT_CO;
+#pragma unroll
+          for (int j = 0; j < CT_CO; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (p.stats) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              float ps[8], pq[8];
+              group_sums16(*reinterpret_cast<const float(*)[16]>(&v[16 * half]), cpg, ps, pq);
+              const int per = cpg >= 16 ? 1 : 16 / cpg;             // groups inside 16 channels
+              const int first = cpg >= 32 ? 0 : (16 * half) / cpg;  // first group of this half
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                if (k < per) {
+#pragma unroll
+                  for (int i = 0; i < MAXG; ++i)
+                    if (i == first + k) gs[i] += ps[k], gq[i] += pq[k];
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rs_cur[j] = rs_nxt[j];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (p.stats) flush();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" int semabs_conv_transpose3d_s2(const void* x16, int32_t a_splits, const void* w16, int32_t w_splits, int32_t N, int32_t D,
+                                          int32_t H, int32_t W, int32_t C_in, int32_t C_out, int32_t precise, const float* bias,
+                                          const float* residual, float* out32, double* stats, int32_t groups, void* stream) {
+  SB_REQUIRE(x16 && w16 && out32, "semabs_conv_transpose3d_s2: null pointer");
+  SB_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "semabs_conv_transpose3d_s2: bad grid");
+  SB_REQUIRE(C_out == CT_CO && C_in % CT_KB == 0, "semabs_conv_transpose3d_s2: C_in %% 64 == 0 and C_out == 32 only (got %d -> %d)", C_in, C_out);
+  SB_REQUIRE(!precise || (a_splits == 2 && w_splits == 2), "semabs_conv_transpose3d_s2: precise mode needs hi/lo activations and weights");
+  SB_REQUIRE(!stats || (groups > 0 && groups <= 8 && CT_CO % groups == 0 && CT_CO / groups >= 2), "semabs_conv_transpose3d_s2: bad GroupNorm groups");
+  ConvTParams p{};
+  p.N = N, p.D = D, p.H = H, p.W = W, p.C_in = C_in;
+  if (precise) {
+    p.npass = 3;
+    p.pass_a[0] = 0, p.pass_w[0] = 0, p.pass_a[1] = 1, p.pass_w[1] = 0, p.pass_a[2] = 0, p.pass_w[2] = 1;
+  } else {
+    p.npass = 1, p.pass_a[0] = 0, p.pass_w[0] = 0;
+  }
+  p.bw = W < 128 ? W : 128;
+  p.bh = H < 128 / p.bw ? H : 128 / p.bw;
+  p.bd = D < 128 / (p.bw * p.bh) ? D : 128 / (p.bw * p.bh);
+  p.bn = 128 / (p.bw * p.bh * p.bd);
+  SB_REQUIRE(p.bw * p.bh * p.bd * p.bn == 128 && W % p.bw == 0 && H % p.bh == 0 && D % p.bd == 0,
+             "semabs_conv_transpose3d_s2: grid %dx%dx%d cannot be tiled into 128-voxel boxes", D, H, W);
+  SB_REQUIRE(p.bn == 1 || (p.bw * p.bh * p.bd) % 32 == 0, "semabs_conv_transpose3d_s2: grid too small (needs >= 32 voxels)");
+  p.tiles_w = W / p.bw, p.tiles_h = H / p.bh, p.tiles_d = D / p.bd, p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.bias = bias, p.residual = residual, p.out32 = out32, p.stats = stats, p.groups = groups;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t C = uint64_t(a_splits) * C_in;
+    uint64_t dims[5] = {C, uint64_t(W), uint64_t(H), uint64_t(D), uint64_t(N)};
+    uint64_t str[4] = {C * 2, C * 2 * W, C * 2 * W * H, C * 2 * W * H * D};
+    uint32_t box[5] = {uint32_t(CT_KB), uint32_t(p.bw), uint32_t(p.bh), uint32_t(p.bd), uint32_t(p.bn)};
+    if (int rc = make_tmap_f16(&tmA, x16, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  }
+  {
+    const uint64_t K = uint64_t(w_splits) * 27 * C_in;
+    uint64_t dims[2] = {K, uint64_t(C_out)};
+    uint64_t str[1] = {K * 2};
+    uint32_t box[2] = {uint32_t(CT_KB), uint32_t(CT_CO)};
+    if (int rc = make_tmap_f16(&tmB, w16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  }
+  static bool configured = false;
+  if (!configured) {
+    SB_CHECK_CUDA(cudaFuncSetAttribute(convt_allparity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
+    configured = true;
+  }
+  const int num_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  convt_allparity_kernel<<<grid, CT_THREADS, CT_SMEM, (cudaStream_t)stream>>>(tmA, tmB, p);
+  SB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

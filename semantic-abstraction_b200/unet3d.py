@@ -114,6 +114,7 @@ class ResidualUNet3D(nn.Module):
         # convolution for all samples (semabs_fold_groupnorm_halo)
         self.fold_groupnorm = True
         self.folded_blocks = 0  # residual blocks that took the folded path (tests)
+        self.fuse_transposed = True  # transposed convolution into a 32-channel level: eight parity classes in one launch
         encoders = []
         for i, out_f in enumerate(f_maps):
             encoders.append(Encoder(in_channels if i == 0 else f_maps[i - 1], out_f, apply_pooling=i > 0,
@@ -335,12 +336,18 @@ class ResidualUNet3D(nn.Module):
             ust.zero_()
             g1 = dec.basic_module.conv1.num_groups
             assert sdims == (2 * D, 2 * H, 2 * W), "ConvTranspose3d(output_size) path expects exact 2x up-sampling"
-            for parity in range(8):
-                # Upsampling.forward + summation joining (unet3d.py:385-396, 438-440)
-                ops.conv3d(cur16, pk[f"dec{j}.up_w"], kind=ops.CONV_TRANSPOSE_PARITY, parity=parity, N=N, D=D, H=H, W=W,
-                           C_in=c_in, C_out=c_out, a_splits=s, w_splits=s, precise=self.precise, bias=pk[f"dec{j}.up_b"],
-                           residual=skip, out32=up, stats=ust, groups=g1)
-            self.kernel_launches += 8
+            # Upsampling.forward + summation joining (unet3d.py:385-396, 438-440)
+            if self.fuse_transposed and c_out == 32 and c_in % 64 == 0 and D * H * W * N >= 32:
+                # into a 32-channel level: all eight output-parity classes in one pass (conv3d_convt.cu)
+                ops.conv_transpose3d_s2(cur16, pk[f"dec{j}.up_w"], N=N, D=D, H=H, W=W, C_in=c_in, C_out=c_out, a_splits=s, w_splits=s,
+                                        precise=self.precise, bias=pk[f"dec{j}.up_b"], residual=skip, out32=up, stats=ust, groups=g1)
+                self.kernel_launches += 1
+            else:
+                for parity in range(8):
+                    ops.conv3d(cur16, pk[f"dec{j}.up_w"], kind=ops.CONV_TRANSPOSE_PARITY, parity=parity, N=N, D=D, H=H, W=W,
+                               C_in=c_in, C_out=c_out, a_splits=s, w_splits=s, precise=self.precise, bias=pk[f"dec{j}.up_b"],
+                               residual=skip, out32=up, stats=ust, groups=g1)
+                self.kernel_launches += 8
             dims = sdims
             _, cur16 = self._res_block(pk, f"dec{j}", dec.basic_module, up, ust, N=N, dims=dims, c_in_pad=c_out,
                                        c_in_real=c_out, lvl=lvl, dev=dev, want32=False, want16=True, tape=tape)

@@ -96,6 +96,39 @@ def test_conv_transpose(N, D, Ci, Co):
     assert torch.allclose(stats, st_ref, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("N,D,Ci,groups", [(1, 8, 64, 8), (2, 4, 128, 8), (3, 4, 64, 1), (1, 16, 64, 2)])
+def test_conv_transpose_all_parities_one_launch(N, D, Ci, groups):
+    """semabs_conv_transpose3d_s2 (conv3d_convt.cu: eight output-parity classes per tile of 128 input voxels, weight slices of
+    the classes sharing an input shift stacked along N) against torch's ConvTranspose3d and against the eight per-class launches."""
+    from semabs_b200 import ops
+
+    Co = 32
+    g = torch.Generator(device=dev).manual_seed(D + Ci + groups)
+    x = torch.randn(N, Ci, D, D, D, device=dev, generator=g)
+    w = torch.randn(Ci, Co, 3, 3, 3, device=dev, generator=g) / (8 * Ci) ** 0.5
+    b = torch.randn(Co, device=dev, generator=g)
+    skip = torch.randn(N, 2 * D, 2 * D, 2 * D, Co, device=dev, generator=g)
+    wp = _pack(w.permute(1, 2, 3, 4, 0).reshape(Co, -1), 2)
+    out = torch.full((N, 2 * D, 2 * D, 2 * D, Co), float("nan"), device=dev)
+    stats = torch.zeros(N, groups, 2, device=dev, dtype=torch.float64)
+    ops.conv_transpose3d_s2(_cl(x, 2), wp, N=N, D=D, H=D, W=D, C_in=Ci, C_out=Co, a_splits=2, w_splits=2, precise=True, bias=b,
+                            residual=skip, out32=out, stats=stats, groups=groups)
+    ref = F.conv_transpose3d(x, w, b, stride=2, padding=1, output_padding=1).permute(0, 2, 3, 4, 1) + skip
+    assert _maxrel(out, ref) < 2e-5, _maxrel(out, ref)
+    r = ref.reshape(N, -1, groups, Co // groups)
+    st_ref = torch.stack([r.double().sum(dim=(1, 3)), (r.double() ** 2).sum(dim=(1, 3))], dim=-1)
+    assert torch.allclose(stats, st_ref, rtol=1e-5, atol=1e-5)
+    out8 = torch.full_like(out, float("nan"))
+    for parity in range(8):
+        ops.conv3d(_cl(x, 2), wp, kind=ops.CONV_TRANSPOSE_PARITY, parity=parity, N=N, D=D, H=D, W=D, C_in=Ci, C_out=Co,
+                   a_splits=2, w_splits=2, precise=True, bias=b, residual=skip, out32=out8)
+    assert _maxrel(out, out8) < 2e-6, _maxrel(out, out8)  # same products, different accumulation order
+    # no bias / skip / statistics
+    out2 = torch.full_like(out, float("nan"))
+    ops.conv_transpose3d_s2(_cl(x, 2), wp, N=N, D=D, H=D, W=D, C_in=Ci, C_out=Co, a_splits=2, w_splits=2, precise=True, out32=out2)
+    assert _maxrel(out2, ref - skip - b) < 2e-5
+
+
 def test_groupnorm_pool_layout():
     from semabs_b200 import ops
 
