@@ -612,7 +612,7 @@ def bench_voxel(dev, world, dist, pk, C=32, N=4, steps=5, warmup=3):
                 ev_out[b].record(s_out)
         torch.cuda.synchronize()
 
-    run_e2e(2)
+    run_e2e(6)  # warm-up: both input buffers seen twice (the second sight of a buffer captures its CUDA graph)
     t0 = time.perf_counter()
     run_e2e(K)
     e2e = K * N / (time.perf_counter() - t0) * world

@@ -13,6 +13,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Tuple
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -115,6 +117,11 @@ class ResidualUNet3D(nn.Module):
         self.fold_groupnorm = True
         self.folded_blocks = 0  # residual blocks that took the folded path (tests)
         self.fuse_transposed = True  # transposed convolution into a 32-channel level: eight parity classes in one launch
+        # inference forward replayed as a CUDA graph (see _forward_graphed); SEMABS_UNET_GRAPH=0 = eager launches (A/B runs)
+        self.use_cuda_graph = os.environ.get("SEMABS_UNET_GRAPH", "1") != "0"
+        self._graphs: Dict[Tuple, tuple] = {}
+        self._graph_seen: set = set()
+        self._pack_gen = 0
         encoders = []
         for i, out_f in enumerate(f_maps):
             encoders.append(Encoder(in_channels if i == 0 else f_maps[i - 1], out_f, apply_pooling=i > 0,
@@ -141,6 +148,8 @@ class ResidualUNet3D(nn.Module):
                 del self._ws[k]
             t = torch.empty(key[1], dtype=dtype, device=device)
             self._ws[key] = t
+            self._graphs.clear()  # captured launches hold workspace addresses: a replaced buffer invalidates every graph
+            self._graph_seen.clear()
         return t
 
     def _bwd(self):
@@ -206,6 +215,7 @@ class ResidualUNet3D(nn.Module):
         pk["final.b"] = self.final_conv.bias.detach().to(device, F32).contiguous()
         pk["final.w32"] = fw.detach().to(device, F32).reshape(fw.shape[0], fw.shape[1]).contiguous()
         self._pack, self._pack_key = pk, key
+        self._pack_gen += 1
         return pk
 
     # ------------------------------------------------------------------------------------------------
@@ -374,10 +384,51 @@ class ResidualUNet3D(nn.Module):
             from .unet3d_bwd import _UNetFn  # training: the same kernels + a tape, backward in unet3d_bwd.py
 
             return _UNetFn.apply(x, self, *self.parameters())
-        N, C, D, H, W = x.shape
-        assert C == self.in_channels
-        dev = x.device
+        assert x.shape[1] == self.in_channels
         x = x.contiguous().float()
+        from ._lib import CALL_PROFILE
+
+        if self.use_cuda_graph and not CALL_PROFILE.on and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graphed(x)
+        return self._forward_eager(x)
+
+    def _forward_graphed(self, x: torch.Tensor) -> torch.Tensor:
+        """Inference forward as a CUDA-graph replay.  One forward is ~350 launches of 10-2000 us kernels: on a busy host the Python /
+        ctypes side (20-40 us per launch) is slower than the GPU (measured: 26 ms of kernels, 40-57 ms per forward in some runs).
+        Graphs are keyed on everything a captured launch bakes in: input pointer and shape, the weight pack (rebuilt when a
+        parameter changes), the path switches.  Workspaces are the module's cached buffers, so their addresses are stable; the
+        output lives in the graph's pool and a copy is returned."""
+        dev = x.device
+        self._packed(dev)  # (re)build the weight pack outside the capture; its identity is part of the key
+        key = (x.data_ptr(), tuple(x.shape), str(dev), self._pack_gen, self.precise, self.use_halo, self.fold_groupnorm, self.fuse_transposed)
+        entry = self._graphs.get(key)
+        if entry is None:
+            if key not in self._graph_seen:
+                # first sight of this (input buffer, shape): run eagerly — a caller that passes a fresh tensor every time must not
+                # pay a capture per call; the second call with the same buffer captures
+                y = self._forward_eager(x)  # (may allocate workspaces, which clears the seen set: add the key afterwards)
+                if len(self._graph_seen) >= 16:
+                    self._graph_seen.clear()
+                self._graph_seen.add(key)
+                return y
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            torch.cuda.synchronize(dev)
+            self._forward_eager(x)  # allocates every workspace of this shape (a new buffer drops all graphs, see _buf)
+            torch.cuda.synchronize(dev)
+            l0 = self.kernel_launches
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                y_static = self._forward_eager(x)
+            entry = (graph, y_static, x, self.kernel_launches - l0)  # (x kept alive: its address is baked into the graph)
+            self._graphs[key] = entry
+        entry[0].replay()
+        self.kernel_launches += entry[3]
+        return entry[1].clone()
+
+    def _forward_eager(self, x: torch.Tensor) -> torch.Tensor:
+        N, C, D, H, W = x.shape
+        dev = x.device
         S = D * H * W
         cpad = _pad16(C)
         g_in = self.encoders[0].basic_module.conv1.num_groups
