@@ -266,7 +266,7 @@ int semabs_ndhwc_to_ncdhw(const float* x, float* y, int32_t N, int64_t S, int32_
 /* ConvTranspose3d(k = 3, s = 2, p = 1, output_size = 2x) + bias + skip sum (Upsampling.forward + summation joining, unet3d.py:
  * 385-396, 428-440) with all eight output-parity classes in ONE launch (conv3d_convt.cu): x16 [N,D,H,W,a_splits*C_in] fp16, w16 as
  * for semabs_conv3d kind 2 ([C_out, w_splits*27*C_in]), residual / out32 [N,2D,2H,2W,C_out] fp32, stats [N,groups,2] of the output
- * (optional).  C_out == 32 and C_in % 64 == 0 (the transposed convolution into a 32-channel level); other shapes: 8 x kind 2. */
+ * (optional; channels per group a power of two >= 4).  C_out % 32 == 0 and C_in % 64 == 0; other shapes: 8 x kind 2. */
 int semabs_conv_transpose3d_s2(const void* x16, int32_t a_splits, const void* w16, int32_t w_splits, int32_t N, int32_t D, int32_t H,
                                int32_t W, int32_t C_in, int32_t C_out, int32_t precise, const float* bias, const float* residual,
                                float* out32, double* stats, int32_t groups, void* stream);

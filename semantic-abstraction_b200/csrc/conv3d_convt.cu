@@ -34,7 +34,8 @@ constexpr int CT_SMEM = CT_STAGES * CT_STAGE + CT_TR_BYTES + 512 + 1024;
 
 struct ConvTParams {
   int N, D, H, W;  // input grid
-  int C_in;
+  int C_in, C_out;
+  int n_cb;        // C_out / 32 channel blocks: tile = (128 input voxels, one block of 32 output channels)
   int npass;
   int8_t pass_a[3], pass_w[3];
   int bw, bh, bd, bn;
@@ -59,7 +60,7 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
+  const int num_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n * p.n_cb;
   const int kblocks = p.C_in / CT_KB;
 
   if (warp == 0 && lane == 0) {
@@ -80,8 +81,10 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto decode = [&](int t, int& x0, int& y0, int& z0, int& n0) {
-    int s = t;
+  // tile id -> (channel block fastest: neighbouring CTAs share the activation boxes in L2, then w, h, d, n)
+  auto decode = [&](int t, int& cb, int& x0, int& y0, int& z0, int& n0) {
+    cb = t % p.n_cb;
+    int s = t / p.n_cb;
     x0 = (s % p.tiles_w) * p.bw;
     s /= p.tiles_w;
     y0 = (s % p.tiles_h) * p.bh;
@@ -96,8 +99,8 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int x0, y0, z0, n0;
-        decode(t, x0, y0, z0, n0);
+        int cb, x0, y0, z0, n0;
+        decode(t, cb, x0, y0, z0, n0);
         for (int ps = 0; ps < p.npass; ++ps) {
           const int a_off = p.pass_a[ps] * p.C_in, w_off = p.pass_w[ps] * 27;
           for (int s = 0; s < 8; ++s) {
@@ -114,7 +117,7 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 if ((c & s) != s) continue;
                 // tap of class (pz, py, px) under shift (sz, sy, sx): k = p + 1 - 2 s per axis
                 const int kz = ((c >> 2) & 1) + 1 - 2 * sz, ky = ((c >> 1) & 1) + 1 - 2 * sy, kx = (c & 1) + 1 - 2 * sx;
-                tma_load_2d(sB + idx * CT_SLICE, &tmB, &full_bar[stage], (w_off + (kz * 3 + ky) * 3 + kx) * p.C_in + kb * CT_KB, 0);
+                tma_load_2d(sB + idx * CT_SLICE, &tmB, &full_bar[stage], (w_off + (kz * 3 + ky) * 3 + kx) * p.C_in + kb * CT_KB, cb * CT_CO);
                 ++idx;
               }
               if (++stage == CT_STAGES) stage = 0, phase ^= 1;
@@ -177,8 +180,8 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     float gs[MAXG], gq[MAXG];
 #pragma unroll
     for (int i = 0; i < MAXG; ++i) gs[i] = gq[i] = 0.f;
-    int stat_n = -1;
-    const int cpg = p.stats ? CT_CO / p.groups : 16;  // channels per group (power of two, 2..32)
+    int stat_n = -1, stat_cb = -1;
+    const int cpg = p.stats ? p.C_out / p.groups : 16;  // channels per group (power of two >= 2)
     auto flush = [&]() {
       if (stat_n < 0) return;
 #pragma unroll
@@ -195,8 +198,13 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     };
     float bias_r[CT_CO];
+    int bias_cb = -1;
+    auto load_bias = [&](int cb) {
+      if (cb == bias_cb) return;
+      bias_cb = cb;
 #pragma unroll
-    for (int j = 0; j < CT_CO; ++j) bias_r[j] = p.bias ? p.bias[j] : 0.f;
+      for (int j = 0; j < CT_CO; ++j) bias_r[j] = p.bias ? p.bias[cb * CT_CO + j] : 0.f;
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
     // Coalesced path (32 lanes = 32 consecutive x of one input row, i.e. box width % 32 == 0): the two px classes of a thread
@@ -207,7 +215,7 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const bool coalesced = (p.bw % 32) == 0;
     float* tr = tr_base + (warp - 4) * 32 * CT_TR_PITCH;
     const int my_col = lane & 15;                               // float4 column of this lane in the transposed domain
-    const int my_g = p.stats ? (4 * (my_col & 7)) / cpg : 0;    // its GroupNorm group (cpg is a multiple of 4 here)
+    int my_g = 0;                                               // its GroupNorm group in the current channel block
     float cs = 0.f, cq = 0.f;                                   // statistics of this lane's group (coalesced path)
     auto flush_coalesced = [&]() {
       if (stat_n < 0) return;
@@ -224,15 +232,17 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     };
     if (coalesced) {
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int x0, y0, z0, n0;
-        decode(t, x0, y0, z0, n0);
+        int cb, x0, y0, z0, n0;
+        decode(t, cb, x0, y0, z0, n0);
+        load_bias(cb);
         const int n = n0 + ln, z = z0 + ld, y = y0 + lh, x = x0 + lw;
         const int n_w = __shfl_sync(0xffffffffu, n, 0), z_w = __shfl_sync(0xffffffffu, z, 0), y_w = __shfl_sync(0xffffffffu, y, 0);
         const int x_w = __shfl_sync(0xffffffffu, x, 0);
         const bool ok = n_w < p.N;  // warp-uniform
-        if (p.stats && n_w != stat_n) {
+        if (p.stats && (n_w != stat_n || cb != stat_cb)) {
           flush_coalesced();
-          stat_n = ok ? n_w : -1;
+          stat_n = ok ? n_w : -1, stat_cb = cb;
+          my_g = (cb * CT_CO + 4 * (my_col & 7)) / cpg;  // (cpg is a multiple of 4 on this path)
         }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -243,9 +253,10 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const size_t row0 = ((size_t(n_w) * Do + (2 * z_w + pz)) * Ho + (2 * y_w + py)) * Wo + 2 * x_w;
           float4 rq[16];
           if (p.residual && ok) {
-            const float4* src = reinterpret_cast<const float4*>(p.residual + row0 * CT_CO);
+            // float4 (k, lane) of the warp's 64 output rows: row (k * 32 + lane) / 8, 16-byte column (k * 32 + lane) % 8 of this channel block
+            const float* src = p.residual + row0 * p.C_out + cb * CT_CO + 4 * (lane & 7);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) rq[k] = src[k * 32 + lane];
+            for (int k = 0; k < 16; ++k) rq[k] = *reinterpret_cast<const float4*>(src + size_t(4 * k + (lane >> 3)) * p.C_out);
           }
           uint32_t rr[64];
           tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 256 + (2 * cp2) * CT_CO), *reinterpret_cast<uint32_t(*)[32]>(&rr[0]));
@@ -258,12 +269,12 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                                                                __uint_as_float(rr[j + 2]) + bias_r[(j + 2) & 31], __uint_as_float(rr[j + 3]) + bias_r[(j + 3) & 31]);
           __syncwarp();
           if (ok) {
-            float4* dst = reinterpret_cast<float4*>(p.out32 + row0 * CT_CO);
+            float* dst = p.out32 + row0 * p.C_out + cb * CT_CO + 4 * (lane & 7);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
               float4 v = *reinterpret_cast<const float4*>(tr + (2 * k + (lane >> 4)) * CT_TR_PITCH + 4 * my_col);
               if (p.residual) v.x += rq[k].x, v.y += rq[k].y, v.z += rq[k].z, v.w += rq[k].w;
-              dst[k * 32 + lane] = v;
+              *reinterpret_cast<float4*>(dst + size_t(4 * k + (lane >> 3)) * p.C_out) = v;
               cs += (v.x + v.y) + (v.z + v.w);
               cq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
             }
@@ -279,8 +290,9 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (p.stats) flush_coalesced();
     } else
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      int x0, y0, z0, n0;
-      decode(t, x0, y0, z0, n0);
+      int cb, x0, y0, z0, n0;
+      decode(t, cb, x0, y0, z0, n0);
+      load_bias(cb);
       const int n = n0 + ln, z = z0 + ld, y = y0 + lh, x = x0 + lw;
       const bool ok = n < p.N;
       const int n_w = __shfl_sync(0xffffffffu, n, 0);  // warp-uniform (rows per sample are a multiple of 32, or one sample per tile)
@@ -297,7 +309,7 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
       for (int j = 0; j < 8; ++j) rs_cur[j] = rs_nxt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.residual && ok) {
-        const float* row = p.residual + ovox(0) * CT_CO;
+        const float* row = p.residual + ovox(0) * p.C_out + cb * CT_CO;
 #pragma unroll
         for (int j = 0; j < 8; ++j) rs_cur[j] = *reinterpret_cast<const float4*>(row + 4 * j);
       }
@@ -306,7 +318,7 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         if (p.residual && ok && c + 1 < 8) {
-          const float* row = p.residual + ovox(c + 1) * CT_CO;
+          const float* row = p.residual + ovox(c + 1) * p.C_out + cb * CT_CO;
 #pragma unroll
           for (int j = 0; j < 8; ++j) rs_nxt[j] = *reinterpret_cast<const float4*>(row + 4 * j);
         }
@@ -321,7 +333,7 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             v[j] = __uint_as_float(rr[j]) + bias_r[j] + b.x, v[j + 1] = __uint_as_float(rr[j + 1]) + bias_r[j + 1] + b.y;
             v[j + 2] = __uint_as_float(rr[j + 2]) + bias_r[j + 2] + b.z, v[j + 3] = __uint_as_float(rr[j + 3]) + bias_r[j + 3] + b.w;
           }
-          float* o = p.out32 + ovox(c) * CT_CO;
+          float* o = p.out32 + ovox(c) * p.C_out + cb * CT_CO;
 #pragma unroll
           for (int j = 0; j < CT_CO; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           if (p.stats) {
@@ -330,7 +342,7 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               float ps[8], pq[8];
               group_sums16(*reinterpret_cast<const float(*)[16]>(&v[16 * half]), cpg, ps, pq);
               const int per = cpg >= 16 ? 1 : 16 / cpg;             // groups inside 16 channels
-              const int first = cpg >= 32 ? 0 : (16 * half) / cpg;  // first group of this half
+              const int first = (cb * CT_CO + 16 * half) / cpg;    // first group of this half
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 if (k < per) {
@@ -371,11 +383,12 @@ extern "C" int semabs_conv_transpose3d_s2(const void* x16, int32_t a_splits, con
                                           const float* residual, float* out32, double* stats, int32_t groups, void* stream) {
   SB_REQUIRE(x16 && w16 && out32, "semabs_conv_transpose3d_s2: null pointer");
   SB_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "semabs_conv_transpose3d_s2: bad grid");
-  SB_REQUIRE(C_out == CT_CO && C_in % CT_KB == 0, "semabs_conv_transpose3d_s2: C_in %% 64 == 0 and C_out == 32 only (got %d -> %d)", C_in, C_out);
+  SB_REQUIRE(C_out % CT_CO == 0 && C_in % CT_KB == 0, "semabs_conv_transpose3d_s2: C_in %% 64 == 0 and C_out %% 32 == 0 only (got %d -> %d)", C_in, C_out);
   SB_REQUIRE(!precise || (a_splits == 2 && w_splits == 2), "semabs_conv_transpose3d_s2: precise mode needs hi/lo activations and weights");
-  SB_REQUIRE(!stats || (groups > 0 && groups <= 8 && CT_CO % groups == 0 && CT_CO / groups >= 2), "semabs_conv_transpose3d_s2: bad GroupNorm groups");
+  SB_REQUIRE(!stats || (groups > 0 && groups <= 8 && C_out % groups == 0 && (C_out / groups) % 4 == 0 && ((C_out / groups) & (C_out / groups - 1)) == 0),
+             "semabs_conv_transpose3d_s2: channels per GroupNorm group must be a power of two >= 4");
   ConvTParams p{};
-  p.N = N, p.D = D, p.H = H, p.W = W, p.C_in = C_in;
+  p.N = N, p.D = D, p.H = H, p.W = W, p.C_in = C_in, p.C_out = C_out, p.n_cb = C_out / CT_CO;
   if (precise) {
     p.npass = 3;
     p.pass_a[0] = 0, p.pass_w[0] = 0, p.pass_a[1] = 1, p.pass_w[1] = 0, p.pass_a[2] = 0, p.pass_w[2] = 1;
@@ -411,7 +424,7 @@ extern "C" int semabs_conv_transpose3d_s2(const void* x16, int32_t a_splits, con
     SB_CHECK_CUDA(cudaFuncSetAttribute(convt_allparity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
     configured = true;
   }
-  const int num_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
+  const int num_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n * p.n_cb;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   convt_allparity_kernel<<<grid, CT_THREADS, CT_SMEM, (cudaStream_t)stream>>>(tmA, tmB, p);
   SB_CHECK_CUDA(cudaGetLastError());

@@ -318,7 +318,7 @@ def conv3d(x16, w16, *, kind, N, D, H, W, C_in, C_out, a_splits=1, w_splits=1, p
 
 def conv_transpose3d_s2(x16, w16, *, N, D, H, W, C_in, C_out, a_splits, w_splits, precise, bias=None, residual=None, out32=None,
                         stats=None, groups=0):
-    """Transposed convolution (k3 s2 p1, output 2x) with all eight parity classes in one launch; C_out == 32, C_in % 64 == 0."""
+    """Transposed convolution (k3 s2 p1, output 2x) with all eight parity classes in one launch; C_out % 32 == 0, C_in % 64 == 0."""
     CALL_PROFILE.note("semabs_conv_transpose3d_s2", flops=2.0 * N * D * H * W * 27 * C_in * C_out)
     check(
         lib().semabs_conv_transpose3d_s2(

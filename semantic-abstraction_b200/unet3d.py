@@ -347,8 +347,8 @@ class ResidualUNet3D(nn.Module):
             g1 = dec.basic_module.conv1.num_groups
             assert sdims == (2 * D, 2 * H, 2 * W), "ConvTranspose3d(output_size) path expects exact 2x up-sampling"
             # Upsampling.forward + summation joining (unet3d.py:385-396, 438-440)
-            if self.fuse_transposed and c_out == 32 and c_in % 64 == 0 and D * H * W * N >= 32:
-                # into a 32-channel level: all eight output-parity classes in one pass (conv3d_convt.cu)
+            if self.fuse_transposed and c_out in (32, 64) and c_in % 64 == 0 and D * H * W * N >= 32 and (c_out // g1) % 4 == 0:
+                # into the 32- / 64-channel levels (the big grids): all eight output-parity classes in one pass (conv3d_convt.cu)
                 ops.conv_transpose3d_s2(cur16, pk[f"dec{j}.up_w"], N=N, D=D, H=H, W=W, C_in=c_in, C_out=c_out, a_splits=s, w_splits=s,
                                         precise=self.precise, bias=pk[f"dec{j}.up_b"], residual=skip, out32=up, stats=ust, groups=g1)
                 self.kernel_launches += 1

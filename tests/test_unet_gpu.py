@@ -96,13 +96,13 @@ def test_conv_transpose(N, D, Ci, Co):
     assert torch.allclose(stats, st_ref, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("N,D,Ci,groups", [(1, 8, 64, 8), (2, 4, 128, 8), (3, 4, 64, 1), (1, 16, 64, 2)])
-def test_conv_transpose_all_parities_one_launch(N, D, Ci, groups):
+@pytest.mark.parametrize("N,D,Ci,groups,Co", [(1, 8, 64, 8, 32), (2, 4, 128, 8, 32), (3, 4, 64, 1, 32), (1, 16, 64, 2, 32),
+                                              (1, 8, 128, 8, 64), (2, 32, 64, 4, 64), (1, 4, 64, 2, 128)])
+def test_conv_transpose_all_parities_one_launch(N, D, Ci, groups, Co):
     """semabs_conv_transpose3d_s2 (conv3d_convt.cu: eight output-parity classes per tile of 128 input voxels, weight slices of
     the classes sharing an input shift stacked along N) against torch's ConvTranspose3d and against the eight per-class launches."""
     from semabs_b200 import ops
 
-    Co = 32
     g = torch.Generator(device=dev).manual_seed(D + Ci + groups)
     x = torch.randn(N, Ci, D, D, D, device=dev, generator=g)
     w = torch.randn(Ci, Co, 3, 3, 3, device=dev, generator=g) / (8 * Ci) ** 0.5
