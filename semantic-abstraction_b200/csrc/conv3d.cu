@@ -61,9 +61,12 @@ struct ConvCfg {
   static constexpr int B_BYTES_RAW = BN * KB * 2;
   static constexpr int B_BYTES = ((FUSED ? 2 : 1) * B_BYTES_RAW + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
+  // epilogue transpose staging (coalesced path, BN <= 64): 4 warps x 32 voxel rows x (BN + 4) floats
+  static constexpr int TR_PITCH = BN + 4;
+  static constexpr int TR_BYTES = BN <= 64 ? 4 * 32 * TR_PITCH * 4 : 0;
+  static constexpr int STAGES_RAW = (192 * 1024 - TR_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 512 + 1024;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + TR_BYTES + 512 + 1024;
   static constexpr uint64_t SWZ = (KB == 64) ? SW_128B : (KB == 32 ? SW_64B : SW_32B);
   static constexpr uint32_t SBO = 8 * KB * 2;  // 8 rows of one swizzle atom
   static constexpr int ACC_COLS = (FUSED ? 2 : 1) * BN;  // columns of one accumulator buffer
@@ -78,7 +81,8 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STG = p.stages;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STG * Cfg::STAGE_BYTES);
+  float* tr_base = reinterpret_cast<float*>(smem + STG * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STG * Cfg::STAGE_BYTES + Cfg::TR_BYTES);
   uint64_t* empty_bar = full_bar + STG;
   uint64_t* tmem_full = empty_bar + STG;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -245,6 +249,110 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     };
     int acc = 0;
     uint32_t acc_phase = 0;
+    // Coalesced epilogue (BN <= 64, unit output stride, 32 lanes = 32 consecutive x of one grid row): the accumulator rows (+ bias)
+    // go through a per-warp shared-memory transpose, then residual add, ReLU, statistics and the stores run with 4 BN bytes of
+    // every voxel row contiguous across BN / 4 lanes.  Row-per-thread float4 accesses touch 32 lines per instruction: measured
+    // ~5 us per 128 voxels x 32 channels in every kernel that used them — the 64-channel 64^3 convolutions spent 13.5 us per tile
+    // with 7 us of MMAs.
+    if (BN <= 64 && p.os == 1 && (p.bw % 32) == 0 && (!p.stats || (cpg % 4) == 0)) {
+      constexpr int Q = (BN <= 64 ? BN : 64) / 4;  // float4 columns per voxel row of this tile (4, 8 or 16: divides 32)
+      constexpr int VPI = 32 / Q;                  // voxel rows covered by one warp instruction
+      constexpr int PITCH = Cfg::TR_PITCH;
+      float* tr = tr_base + (warp - 4) * 32 * PITCH;
+      const int my_col = lane % Q, my_sub = lane / Q;
+      float cs = 0.f, cq = 0.f;
+      int my_g = 0;
+      auto flush_c = [&]() {
+        if (stat_n < 0) return;
+        __syncwarp();
+        if (lane < 16) tr[lane] = 0.f;
+        __syncwarp();
+        atomicAdd(&tr[2 * my_g], cs);
+        atomicAdd(&tr[2 * my_g + 1], cq);
+        __syncwarp();
+        if (lane < 2 * p.groups && (tr[lane] != 0.f)) atomicAdd(p.stats + size_t(stat_n) * p.groups * 2 + lane, double(tr[lane]));
+        __syncwarp();
+        cs = cq = 0.f;
+      };
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int nb, x0, y0, z0, n0;
+        decode(t, nb, x0, y0, z0, n0);
+        const int n = n0 + ln, z = z0 + ld, y = y0 + lh, x = x0 + lw;
+        const int n_w = __shfl_sync(0xffffffffu, n, 0);
+        const bool ok = n_w < p.N;  // warp-uniform: the 32 lanes share (n, z, y)
+        if (p.stats && (n_w != stat_n || nb != stat_nb)) {
+          flush_c();
+          stat_n = ok ? n_w : -1, stat_nb = nb;
+          my_g = (nb * BN + 4 * my_col) / cpg;
+        }
+        // first voxel row of the warp: lanes are consecutive x
+        const size_t row_w = ((size_t(n_w) * p.Do + __shfl_sync(0xffffffffu, z, 0)) * p.Ho + __shfl_sync(0xffffffffu, y, 0)) * p.Wo +
+                             __shfl_sync(0xffffffffu, x, 0);
+        float4 rq[Q];
+        if (p.residual && ok) {
+          const float* src = p.residual + (row_w + my_sub) * p.C_out + nb * BN + 4 * my_col;
+#pragma unroll
+          for (int k = 0; k < Q; ++k) rq[k] = *reinterpret_cast<const float4*>(src + size_t(k * VPI) * p.C_out);
+        }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        float* mine = tr + lane * PITCH;
+#pragma unroll
+        for (int c = 0; c < BN / 16; ++c) {
+          uint32_t rr[16], r2[16];
+          tmem_ld_32x32b_x16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * Cfg::ACC_COLS + c * 16), rr);
+          if (FUSED) tmem_ld_32x32b_x16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * Cfg::ACC_COLS + BN + c * 16), r2);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 v;
+            v.x = FUSED ? __uint_as_float(rr[j]) + __uint_as_float(r2[j]) : __uint_as_float(rr[j]);
+            v.y = FUSED ? __uint_as_float(rr[j + 1]) + __uint_as_float(r2[j + 1]) : __uint_as_float(rr[j + 1]);
+            v.z = FUSED ? __uint_as_float(rr[j + 2]) + __uint_as_float(r2[j + 2]) : __uint_as_float(rr[j + 2]);
+            v.w = FUSED ? __uint_as_float(rr[j + 3]) + __uint_as_float(r2[j + 3]) : __uint_as_float(rr[j + 3]);
+            *reinterpret_cast<float4*>(mine + c * 16 + j) = v;
+          }
+        }
+        // the accumulator has been read: hand the TMEM buffer back before the global-memory phase
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        if (ok) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + nb * BN + 4 * my_col);
+          const size_t col = size_t(nb) * BN + 4 * my_col;
+#pragma unroll
+          for (int k = 0; k < Q; ++k) {
+            const int vrow = k * VPI + my_sub;  // voxel row within the warp
+            float4 v = *reinterpret_cast<const float4*>(tr + vrow * PITCH + 4 * my_col);
+            v.x += b4.x, v.y += b4.y, v.z += b4.z, v.w += b4.w;
+            if (p.residual) v.x += rq[k].x, v.y += rq[k].y, v.z += rq[k].z, v.w += rq[k].w;
+            if (p.relu) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+            const size_t orow = row_w + vrow;
+            if (p.out32) *reinterpret_cast<float4*>(p.out32 + orow * p.C_out + col) = v;
+            if (p.out16) {
+              __half* o = p.out16 + orow * size_t(p.o16_splits) * p.C_out + col;
+              const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+              uint2 u;
+              u.x = *reinterpret_cast<const uint32_t*>(&h0), u.y = *reinterpret_cast<const uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(o) = u;
+              if (p.o16_splits == 2) {
+                const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+                u.x = *reinterpret_cast<const uint32_t*>(&l0), u.y = *reinterpret_cast<const uint32_t*>(&l1);
+                *reinterpret_cast<uint2*>(o + p.C_out) = u;
+              }
+            }
+            cs += (v.x + v.y) + (v.z + v.w);
+            cq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+          }
+        }
+        __syncwarp();  // the staging rows are rewritten by the next tile
+      }
+      if (p.stats) flush_c();
+    } else
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int nb, x0, y0, z0, n0;
       decode(t, nb, x0, y0, z0, n0);
@@ -353,7 +461,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (p.stats) flush();
+    if (p.stats && stat_n >= 0) flush();
   }
 
   tc_fence_before();
@@ -383,13 +491,13 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   q.stages = Cfg::STAGES;
   if (BN <= 32 && p.ntaps <= 8 && 2 * Cfg::TMEM_COLS <= 512 && num_tiles >= 4 * num_sms()) {
     for (int s = 4; s >= 2; --s) {
-      if (s < Cfg::STAGES && s * Cfg::STAGE_BYTES + 1536 <= 112 * 1024) {
+      if (s < Cfg::STAGES && s * Cfg::STAGE_BYTES + Cfg::TR_BYTES + 1536 <= 112 * 1024) {
         q.stages = s, per_sm = 2;
         break;
       }
     }
   }
-  const int smem_bytes = q.stages * Cfg::STAGE_BYTES + 512 + 1024;
+  const int smem_bytes = q.stages * Cfg::STAGE_BYTES + Cfg::TR_BYTES + 512 + 1024;
   const int cap = per_sm * num_sms();
   const int grid = num_tiles < cap ? num_tiles : cap;
   conv3d_igemm_kernel<BN, KB, FUSED><<<grid, CONV_THREADS, smem_bytes, st>>>(tmA, tmB, q);
