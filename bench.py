@@ -78,10 +78,13 @@ def _release():
 
 
 def measured_traffic():
-    """DRAM bytes from the committed ncu captures (profiles/r01_traffic.json, made with the commands in its `source` fields);
-    bench.py itself never runs under a profiler."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    return json.load(open(p)) if os.path.exists(p) else {}
+    """DRAM bytes from the committed ncu captures (profiles/rNN_traffic.json of the latest round, made with the commands in its
+    `source` fields); bench.py itself never runs under a profiler."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p))
+    return {}
 
 
 def peaks():
