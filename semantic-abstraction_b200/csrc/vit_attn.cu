@@ -1,3 +1,7 @@
+// STATUS (round 2): of this file the product path uses `semabs_attn_fwd` for the text tower (T = 77, causal) and
+// `attn_bwd_cls_kernel` (class-token-only backward of the top block).  The mma.sync backward passes below are the fall-back for
+// T > 272 and the cross-check of the tcgen05 generations (tests/test_vit_kernels_gpu.py impl "mma"); the image tower runs on
+// vit_attn_tc.cu (forward) and vit_attn_bwd3.cu (backward).
 // Multi-head attention of the CLIP transformers: forward that materialises the softmax probabilities (the
 // reference keeps them through a hook, CLIP/clip/auxiliary.py:307-337) and the hand-written backward that yields,
 // for P stacked label cotangents, the per-head relevance term  sum_i r_i * relu(dA ⊙ A)[i, :]  of
