@@ -263,13 +263,19 @@ int semabs_conv3d(const void* x16, int32_t a_splits, const void* w16, int32_t w_
 int semabs_ncdhw_to_ndhwc(const float* x, float* y, int32_t N, int64_t S, int32_t C, int32_t Cpad, int32_t groups,
                           double* stats, void* stream);
 int semabs_ndhwc_to_ncdhw(const float* x, float* y, int32_t N, int64_t S, int32_t C, void* stream);
+/* Module input straight into the halo convolution's operand layout: x [N,C,S] fp32 -> y16 [N][2 Cpad / 8][S][8] fp16 (hi chunks,
+ * then lo chunks; channels >= C zero) + the first GroupNorm's statistics (inference path with that GroupNorm folded into conv1). */
+int semabs_ncdhw_to_planar(const float* x, void* y16, int32_t N, int64_t S, int32_t C, int32_t Cpad, int32_t groups, double* stats,
+                           void* stream);
 /* ConvTranspose3d(k = 3, s = 2, p = 1, output_size = 2x) + bias + skip sum (Upsampling.forward + summation joining, unet3d.py:
  * 385-396, 428-440) with all eight output-parity classes in ONE launch (conv3d_convt.cu): x16 [N,D,H,W,a_splits*C_in] fp16, w16 as
  * for semabs_conv3d kind 2 ([C_out, w_splits*27*C_in]), residual / out32 [N,2D,2H,2W,C_out] fp32, stats [N,groups,2] of the output
- * (optional; channels per group a power of two >= 4).  C_out % 32 == 0 and C_in % 64 == 0; other shapes: 8 x kind 2. */
+ * (optional; channels per group a power of two >= 4); out_planar (optional, W % 32 == 0): the same values as chunk-planar fp16 hi | lo
+ * [N][2 C_out / 8][8 D H W][8] = the operand layout of semabs_conv3d_halo(_fused); one of out32 / out_planar may be null.
+ * C_out % 32 == 0 and C_in % 64 == 0; other shapes: 8 x kind 2. */
 int semabs_conv_transpose3d_s2(const void* x16, int32_t a_splits, const void* w16, int32_t w_splits, int32_t N, int32_t D, int32_t H,
                                int32_t W, int32_t C_in, int32_t C_out, int32_t precise, const float* bias, const float* residual,
-                               float* out32, double* stats, int32_t groups, void* stream);
+                               float* out32, void* out_planar, double* stats, int32_t groups, void* stream);
 /* final_conv (nn.Conv3d(f_maps[0], out_channels, 1), unet3d.py:565 / 619) fused with the conversion back to NCDHW (inference
  * path): x16 [N,S,splits*C_in] fp16 rows [hi | lo], w [C_out,C_in] fp32, bias [C_out] or null -> y [N,C_out,S] fp32; fp32 FMAs.
  * C_in in {16, 32, 64}. */

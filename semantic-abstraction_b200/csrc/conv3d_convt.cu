@@ -42,7 +42,8 @@ struct ConvTParams {
   int tiles_w, tiles_h, tiles_d, tiles_n;
   const float* bias;      // [32] or null
   const float* residual;  // [N, 2D, 2H, 2W, 32] or null (the encoder feature of the output level)
-  float* out32;           // [N, 2D, 2H, 2W, 32]
+  float* out32;           // [N, 2D, 2H, 2W, C_out] or null
+  __half* out_planar;     // [N][2 C_out / 8 chunks: hi then lo][8 D H W voxels][8] fp16 = the halo convolution's operand layout, or null
   double* stats;          // [N, G, 2] or null
   int groups;
 };
@@ -269,12 +270,35 @@ convt_allparity_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                                                                __uint_as_float(rr[j + 2]) + bias_r[(j + 2) & 31], __uint_as_float(rr[j + 3]) + bias_r[(j + 3) & 31]);
           __syncwarp();
           if (ok) {
-            float* dst = p.out32 + row0 * p.C_out + cb * CT_CO + 4 * (lane & 7);
+            float* dst = p.out32 ? p.out32 + row0 * p.C_out + cb * CT_CO + 4 * (lane & 7) : nullptr;
+            // chunk-planar hi | lo copy (the operand of a following halo convolution with folded GroupNorm): an even / odd lane
+            // pair holds the 8 channels of one 16-byte chunk; the even lane stores the hi halves, the odd lane the lo halves
+            const size_t s_out = size_t(Do) * Ho * Wo;
+            __half* pl = nullptr;
+            if (p.out_planar) {
+              const int chunk = cb * (CT_CO / 8) + ((lane & 7) >> 1) + ((lane & 1) ? p.C_out / 8 : 0);
+              pl = p.out_planar + (size_t(n_w) * (2 * p.C_out / 8) + chunk) * s_out * 8 + (row0 - size_t(n_w) * s_out) * 8;
+            }
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
               float4 v = *reinterpret_cast<const float4*>(tr + (2 * k + (lane >> 4)) * CT_TR_PITCH + 4 * my_col);
               if (p.residual) v.x += rq[k].x, v.y += rq[k].y, v.z += rq[k].z, v.w += rq[k].w;
-              *reinterpret_cast<float4*>(dst + size_t(4 * k + (lane >> 3)) * p.C_out) = v;
+              if (dst) *reinterpret_cast<float4*>(dst + size_t(4 * k + (lane >> 3)) * p.C_out) = v;
+              if (p.out_planar) {  // (warp-uniform)
+                float4 o;
+                o.x = __shfl_xor_sync(0xffffffffu, v.x, 1), o.y = __shfl_xor_sync(0xffffffffu, v.y, 1);
+                o.z = __shfl_xor_sync(0xffffffffu, v.z, 1), o.w = __shfl_xor_sync(0xffffffffu, v.w, 1);
+                const float4 f0 = (lane & 1) ? o : v, f1 = (lane & 1) ? v : o;  // channels 8c .. 8c+3, 8c+4 .. 8c+7
+                __align__(16) __half2 h[4];
+                h[0] = __floats2half2_rn(f0.x, f0.y), h[1] = __floats2half2_rn(f0.z, f0.w);
+                h[2] = __floats2half2_rn(f1.x, f1.y), h[3] = __floats2half2_rn(f1.z, f1.w);
+                if (lane & 1) {
+                  const float2 a0 = __half22float2(h[0]), a1 = __half22float2(h[1]), a2 = __half22float2(h[2]), a3 = __half22float2(h[3]);
+                  h[0] = __floats2half2_rn(f0.x - a0.x, f0.y - a0.y), h[1] = __floats2half2_rn(f0.z - a1.x, f0.w - a1.y);
+                  h[2] = __floats2half2_rn(f1.x - a2.x, f1.y - a2.y), h[3] = __floats2half2_rn(f1.z - a3.x, f1.w - a3.y);
+                }
+                *reinterpret_cast<uint4*>(pl + size_t(4 * k + (lane >> 3)) * 8) = *reinterpret_cast<const uint4*>(h);
+              }
               cs += (v.x + v.y) + (v.z + v.w);
               cq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
             }
@@ -380,8 +404,9 @@ using namespace sb;
 
 extern "C" int semabs_conv_transpose3d_s2(const void* x16, int32_t a_splits, const void* w16, int32_t w_splits, int32_t N, int32_t D,
                                           int32_t H, int32_t W, int32_t C_in, int32_t C_out, int32_t precise, const float* bias,
-                                          const float* residual, float* out32, double* stats, int32_t groups, void* stream) {
-  SB_REQUIRE(x16 && w16 && out32, "semabs_conv_transpose3d_s2: null pointer");
+                                          const float* residual, float* out32, void* out_planar, double* stats, int32_t groups,
+                                          void* stream) {
+  SB_REQUIRE(x16 && w16 && (out32 || out_planar), "semabs_conv_transpose3d_s2: null pointer");
   SB_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "semabs_conv_transpose3d_s2: bad grid");
   SB_REQUIRE(C_out % CT_CO == 0 && C_in % CT_KB == 0, "semabs_conv_transpose3d_s2: C_in %% 64 == 0 and C_out %% 32 == 0 only (got %d -> %d)", C_in, C_out);
   SB_REQUIRE(!precise || (a_splits == 2 && w_splits == 2), "semabs_conv_transpose3d_s2: precise mode needs hi/lo activations and weights");
@@ -403,7 +428,9 @@ extern "C" int semabs_conv_transpose3d_s2(const void* x16, int32_t a_splits, con
              "semabs_conv_transpose3d_s2: grid %dx%dx%d cannot be tiled into 128-voxel boxes", D, H, W);
   SB_REQUIRE(p.bn == 1 || (p.bw * p.bh * p.bd) % 32 == 0, "semabs_conv_transpose3d_s2: grid too small (needs >= 32 voxels)");
   p.tiles_w = W / p.bw, p.tiles_h = H / p.bh, p.tiles_d = D / p.bd, p.tiles_n = (N + p.bn - 1) / p.bn;
-  p.bias = bias, p.residual = residual, p.out32 = out32, p.stats = stats, p.groups = groups;
+  p.bias = bias, p.residual = residual, p.out32 = out32, p.out_planar = (__half*)out_planar, p.stats = stats, p.groups = groups;
+  SB_REQUIRE(!out_planar || (p.bw % 32 == 0 && C_out % 8 == 0), "semabs_conv_transpose3d_s2: the planar output needs a grid width that is a multiple of 32");
+  SB_REQUIRE(out32 || p.bw % 32 == 0, "semabs_conv_transpose3d_s2: out32 missing");
   CUtensorMap tmA, tmB;
   {
     const uint64_t C = uint64_t(a_splits) * C_in;

@@ -61,6 +61,50 @@ ncdhw_to_ndhwc_kernel(const float* __restrict__ x, float* __restrict__ y, long l
   }
 }
 
+// ---- NCDHW fp32 -> chunk-planar fp16 hi | lo [N][2 Cpad / 8][S][8] + statistics ------------------------------
+// The operand layout of the halo convolution, written straight from the module input (inference with the first GroupNorm folded
+// into conv1): no channels-last fp32 copy, no GroupNorm-apply pass.  Thread = (voxel, 8-channel chunk), voxels fastest across
+// the CTA so that both the plane reads and the 16-byte chunk writes are contiguous.
+__global__ void __launch_bounds__(EW_THREADS)
+ncdhw_to_planar_kernel(const float* __restrict__ x, __half* __restrict__ y, long long S, int C, int Cpad, int groups,
+                       double* __restrict__ stats) {
+  __shared__ float sm[16];
+  if (threadIdx.x < 16) sm[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int qpc = Cpad / 8;            // chunks per voxel
+  const int vpb = EW_THREADS / qpc;    // voxels per CTA iteration
+  const int vl = threadIdx.x % vpb, cq = threadIdx.x / vpb, c = 8 * cq;
+  const float* xn = x + size_t(n) * C * S;
+  __half* hi = y + (size_t(n) * 2 * qpc + cq) * S * 8;
+  __half* lo = y + (size_t(n) * 2 * qpc + qpc + cq) * S * 8;
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;  // channels c .. c+3 and c+4 .. c+7
+  for (long long v = (long long)blockIdx.x * vpb + vl; v < S; v += (long long)gridDim.x * vpb) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = c + j < C ? xn[size_t(c + j) * S + v] : 0.f;
+    __align__(16) __half2 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+      const float2 b = __half22float2(h[j]);
+      l[j] = __floats2half2_rn(f[2 * j] - b.x, f[2 * j + 1] - b.y);
+    }
+    *reinterpret_cast<uint4*>(hi + v * 8) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + v * 8) = *reinterpret_cast<const uint4*>(l);
+    s0 += (f[0] + f[1]) + (f[2] + f[3]), q0 += (f[0] * f[0] + f[1] * f[1]) + (f[2] * f[2] + f[3] * f[3]);
+    s1 += (f[4] + f[5]) + (f[6] + f[7]), q1 += (f[4] * f[4] + f[5] * f[5]) + (f[6] * f[6] + f[7] * f[7]);
+  }
+  if (stats) {
+    const int cpg = groups == 1 ? Cpad : C / groups;  // (a multiple of 4: the host checks)
+    const int g0 = min(c / cpg, groups - 1), g1 = min((c + 4) / cpg, groups - 1);
+    atomicAdd(&sm[2 * g0], s0), atomicAdd(&sm[2 * g0 + 1], q0);
+    atomicAdd(&sm[2 * g1], s1), atomicAdd(&sm[2 * g1 + 1], q1);
+    __syncthreads();
+    if (threadIdx.x < 2 * groups) atomicAdd(stats + size_t(n) * groups * 2 + threadIdx.x, double(sm[threadIdx.x]));
+  }
+}
+
 // ---- channels-last fp32 -> NCDHW fp32 -------------------------------------------------------------------
 __global__ void __launch_bounds__(EW_THREADS)
 ndhwc_to_ncdhw_kernel(const float* __restrict__ x, float* __restrict__ y, long long S, int C) {
@@ -291,6 +335,19 @@ extern "C" int semabs_ncdhw_to_ndhwc(const float* x, float* y, int32_t N, int64_
   const int vpb = EW_THREADS / (Cpad / 4);
   dim3 grid(ew_grid(S, vpb), N);
   ncdhw_to_ndhwc_kernel<<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, y, S, C, Cpad, groups, stats);
+  SB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int semabs_ncdhw_to_planar(const float* x, void* y16, int32_t N, int64_t S, int32_t C, int32_t Cpad, int32_t groups,
+                                      double* stats, void* stream) {
+  SB_REQUIRE(x && y16 && N > 0 && S > 0 && C > 0 && Cpad >= C, "semabs_ncdhw_to_planar: bad arguments");
+  SB_REQUIRE(Cpad % 8 == 0 && EW_THREADS % (Cpad / 8) == 0 && Cpad <= 64, "semabs_ncdhw_to_planar: unsupported channel count %d", Cpad);
+  SB_REQUIRE(!stats || (groups >= 1 && groups <= 8 && (groups == 1 || (C % groups == 0 && (C / groups) % 4 == 0))),
+             "semabs_ncdhw_to_planar: unsupported GroupNorm grouping");
+  const int vpb = EW_THREADS / (Cpad / 8);
+  dim3 grid(ew_grid(S, vpb), N);
+  ncdhw_to_planar_kernel<<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, (__half*)y16, S, C, Cpad, groups, stats);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

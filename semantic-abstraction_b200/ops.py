@@ -317,13 +317,13 @@ def conv3d(x16, w16, *, kind, N, D, H, W, C_in, C_out, a_splits=1, w_splits=1, p
 
 
 def conv_transpose3d_s2(x16, w16, *, N, D, H, W, C_in, C_out, a_splits, w_splits, precise, bias=None, residual=None, out32=None,
-                        stats=None, groups=0):
+                        out_planar=None, stats=None, groups=0):
     """Transposed convolution (k3 s2 p1, output 2x) with all eight parity classes in one launch; C_out % 32 == 0, C_in % 64 == 0."""
     CALL_PROFILE.note("semabs_conv_transpose3d_s2", flops=2.0 * N * D * H * W * 27 * C_in * C_out)
     check(
         lib().semabs_conv_transpose3d_s2(
             ptr(x16), i32(a_splits), ptr(w16), i32(w_splits), i32(N), i32(D), i32(H), i32(W), i32(C_in), i32(C_out), i32(int(precise)),
-            ptr(bias), ptr(residual), ptr(out32), ptr(stats), i32(groups), stream_ptr(),
+            ptr(bias), ptr(residual), ptr(out32), ptr(out_planar), ptr(stats), i32(groups), stream_ptr(),
         )
     )
 
@@ -331,6 +331,11 @@ def conv_transpose3d_s2(x16, w16, *, N, D, H, W, C_in, C_out, a_splits, w_splits
 def ncdhw_to_ndhwc(x, y, *, N, S, C, Cpad, groups=1, stats=None):
     CALL_PROFILE.note("semabs_ncdhw_to_ndhwc", bytes=N * S * (C + Cpad) * 4)
     check(lib().semabs_ncdhw_to_ndhwc(ptr(x), ptr(y), i32(N), _i64(S), i32(C), i32(Cpad), i32(groups), ptr(stats), stream_ptr()))
+
+
+def ncdhw_to_planar(x, y16, *, N, S, C, Cpad, groups=1, stats=None):
+    CALL_PROFILE.note("semabs_ncdhw_to_planar", bytes=N * S * (C * 4 + Cpad * 4))
+    check(lib().semabs_ncdhw_to_planar(ptr(x), ptr(y16), i32(N), _i64(S), i32(C), i32(Cpad), i32(groups), ptr(stats), stream_ptr()))
 
 
 def ndhwc_to_ncdhw(x, y, *, N, S, C):

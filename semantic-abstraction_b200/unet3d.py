@@ -220,17 +220,17 @@ class ResidualUNet3D(nn.Module):
 
     # ------------------------------------------------------------------------------------------------
     def _res_block(self, pk, prefix, blk: ExtResNetBlock, x_raw, x_stats, *, N, dims, c_in_pad, c_in_real, lvl, dev,
-                   want32: bool, want16: bool, tape=None):
+                   want32: bool, want16: bool, tape=None, x_planar=None):
         """ExtResNetBlock.forward (unet3d.py:243-259): o1 = relu(conv(gn(x))); o2 = relu(conv(gn(o1)));
         out = relu(conv(gn(o2)) + o1). Returns (out32 | None, out16 | None)."""
         D, H, W = dims
         S = D * H * W
         s = 2 if self.precise else 1
         c_out = blk.conv1.conv.out_channels
-        if (tape is None and self.fold_groupnorm and self.use_halo and self.precise and W == 128 and c_out == 32 and c_in_pad in (16, 32)
-                and blk.conv2.num_groups * 2 <= 32 and H % 2 == 0 and f"{prefix}.wraw2" in pk):
+        if self._folds(pk, prefix, blk, tape, dims, c_in_pad):
             return self._res_block_folded(pk, prefix, blk, x_raw, x_stats, N=N, dims=dims, c_in_pad=c_in_pad, c_in_real=c_in_real,
-                                          lvl=lvl, dev=dev, want32=want32, want16=want16)
+                                          lvl=lvl, dev=dev, want32=want32, want16=want16, x_planar=x_planar)
+        assert x_planar is None, "a planar raw input is only produced for blocks that fold their first GroupNorm"
         xn = self._buf(f"l{lvl}_xn", (N, S, s * max(c_in_pad, c_out)), F16, dev)
         o1 = self._alloc(tape, f"l{lvl}_o1", f"{prefix}.o1", (N, S, c_out), F32, dev)
         o2 = self._alloc(tape, f"l{lvl}_o2", f"{prefix}.o2", (N, S, c_out), F32, dev)
@@ -262,6 +262,18 @@ class ResidualUNet3D(nn.Module):
         return out32, out16
 
 
+    def _folds(self, pk, prefix, blk, tape, dims, c_in_pad) -> bool:
+        """This residual block runs with its GroupNorms folded into the halo convolutions (inference, 128-wide level, 32 channels)."""
+        D, H, W = dims
+        return (tape is None and self.fold_groupnorm and self.use_halo and self.precise and W == 128 and H % 2 == 0
+                and blk.conv1.conv.out_channels == 32 and c_in_pad in (16, 32) and blk.conv2.num_groups * 2 <= 32
+                and f"{prefix}.wraw2" in pk)
+
+    def _folds_input(self, pk, prefix, blk, tape, dims, c_in_pad, c_in_real) -> bool:
+        """... and also its FIRST GroupNorm: the producer then writes the raw block input chunk-planar hi | lo itself."""
+        return (self._folds(pk, prefix, blk, tape, dims, c_in_pad) and c_in_pad == 32 and c_in_real == 32 and f"{prefix}.wraw1" in pk
+                and (32 // blk.conv1.num_groups) % 4 == 0)
+
     def _fold_gn(self, key, w, gamma, beta, stats, S, groups):
         """GroupNorm(x) = a x + b per (sample, channel) with a = gamma rstd, b = beta - mean a, so conv(GroupNorm(x)) =
         conv_{W a}(x) + sum over the taps that fall inside the grid of (W b): -> (weight images [N, ...] of W a,
@@ -273,25 +285,34 @@ class ResidualUNet3D(nn.Module):
         self.kernel_launches += 1
         return imgs, bias
 
-    def _res_block_folded(self, pk, prefix, blk, x_raw, x_stats, *, N, dims, c_in_pad, c_in_real, lvl, dev, want32, want16):
-        """ExtResNetBlock.forward at the 128-wide level with 32 channels, inference: conv1 reads GroupNorm-applied x (its
-        producer is not a halo convolution), conv2 / conv3 read the raw planar output of conv1 / conv2 with folded GroupNorm;
-        o1 / o2 exist only as chunk-planar hi | lo fp16, the residual of conv3 is read from o1's planar copy."""
+    def _res_block_folded(self, pk, prefix, blk, x_raw, x_stats, *, N, dims, c_in_pad, c_in_real, lvl, dev, want32, want16,
+                          x_planar=None):
+        """ExtResNetBlock.forward at the 128-wide level with 32 channels, inference: conv2 / conv3 read the raw planar output of
+        conv1 / conv2 with folded GroupNorm; o1 / o2 exist only as chunk-planar hi | lo fp16, the residual of conv3 is read from
+        o1's planar copy.  conv1 reads either a GroupNorm-applied copy of x_raw (fp32 channels-last) or, when its producer wrote
+        the raw input chunk-planar itself (x_planar), that tensor with the first GroupNorm folded as well."""
         D, H, W = dims
         S = D * H * W
         c = 32
         g2, g3 = blk.conv2.num_groups, blk.conv3.num_groups
-        xn = self._buf(f"l{lvl}_xn", (N, S, 2 * max(c_in_pad, c)), F16, dev)
         o1p = self._buf(f"l{lvl}_o1p", (N, 2 * c * S), F16, dev)
         o2p = self._buf(f"l{lvl}_o2p", (N, 2 * c * S), F16, dev)
         st = self._buf(f"l{lvl}_st", (2, N, 8, 2), F64, dev)
         st.zero_()
-        ops.groupnorm_apply(x_raw, x_stats, pk[f"{prefix}.g1"], pk[f"{prefix}.b1"], xn, N=N, S=S, C=c_in_pad, C_real=c_in_real,
-                            groups=blk.conv1.num_groups, splits=2, planar=True)
-        xn_n = xn.view(N, -1)
         kw = dict(D=D, H=H, a_splits=2, w_splits=2, precise=True)
-        for n in range(N):
-            ops.conv3d_halo_fused(xn_n[n], pk[f"{prefix}.wh1"], C_in=c_in_pad, relu=True, out_planar=o1p[n], stats=st[0, n], groups=g2, **kw)
+        if x_planar is not None:
+            w1, bias1 = self._fold_gn(f"l{lvl}_f1", pk[f"{prefix}.wraw1"], pk[f"{prefix}.g1"], pk[f"{prefix}.b1"], x_stats, S,
+                                      blk.conv1.num_groups)
+            xp = x_planar.view(N, -1)
+            for n in range(N):
+                ops.conv3d_halo_fused(xp[n], w1[n], C_in=c, bias_cls=bias1[n], relu=True, out_planar=o1p[n], stats=st[0, n], groups=g2, **kw)
+        else:
+            xn = self._buf(f"l{lvl}_xn", (N, S, 2 * max(c_in_pad, c)), F16, dev)
+            ops.groupnorm_apply(x_raw, x_stats, pk[f"{prefix}.g1"], pk[f"{prefix}.b1"], xn, N=N, S=S, C=c_in_pad, C_real=c_in_real,
+                                groups=blk.conv1.num_groups, splits=2, planar=True)
+            xn_n = xn.view(N, -1)
+            for n in range(N):
+                ops.conv3d_halo_fused(xn_n[n], pk[f"{prefix}.wh1"], C_in=c_in_pad, relu=True, out_planar=o1p[n], stats=st[0, n], groups=g2, **kw)
         w2, bias2 = self._fold_gn(f"l{lvl}_f2", pk[f"{prefix}.wraw2"], pk[f"{prefix}.g2"], pk[f"{prefix}.b2"], st[0], S, g2)
         for n in range(N):
             ops.conv3d_halo_fused(o1p[n], w2[n], C_in=c, bias_cls=bias2[n], relu=True, out_planar=o2p[n], stats=st[1, n], groups=g3, **kw)
@@ -305,7 +326,7 @@ class ResidualUNet3D(nn.Module):
         self.folded_blocks += 1
         return out32, out16
 
-    def forward_channels_last(self, x_raw, x_stats, N, dims, dev, tape=None, ncdhw_out=None):
+    def forward_channels_last(self, x_raw, x_stats, N, dims, dev, tape=None, ncdhw_out=None, x_planar=None):
         """Core of Abstract3DUNet.forward (unet3d.py:596-621) on channels-last buffers. x_raw [N,S,Cpad] fp32 with
         its GroupNorm statistics. Returns the final conv output, channels-last fp32 [N,S,out_channels]."""
         pk = self._packed(dev)
@@ -329,7 +350,7 @@ class ResidualUNet3D(nn.Module):
             last = i == L - 1
             out32, out16 = self._res_block(pk, f"enc{i}", enc.basic_module, cur_raw, cur_stats, N=N, dims=dims,
                                            c_in_pad=c_pad, c_in_real=c_real, lvl=i, dev=dev, want32=not last,
-                                           want16=last, tape=tape)
+                                           want16=last, tape=tape, x_planar=x_planar if i == 0 else None)
             c_pad = c_real = self.f_maps[i]
             if not last:
                 feats.insert(0, (out32, dims))
@@ -341,16 +362,25 @@ class ResidualUNet3D(nn.Module):
             D, H, W = dims  # input grid of the transposed conv
             c_in, c_out = self.f_maps[lvl + 1], self.f_maps[lvl]
             S_out = sdims[0] * sdims[1] * sdims[2]
-            up = self._alloc(tape, f"l{lvl}_up", f"dec{j}.up", (N, S_out, c_out), F32, dev)
-            ust = self._alloc(tape, f"l{lvl}_ust", f"dec{j}.ust", (N, 8, 2), F64, dev)
-            ust.zero_()
             g1 = dec.basic_module.conv1.num_groups
             assert sdims == (2 * D, 2 * H, 2 * W), "ConvTranspose3d(output_size) path expects exact 2x up-sampling"
+            fused_t = self.fuse_transposed and c_out in (32, 64) and c_in % 64 == 0 and D * H * W * N >= 32 and (c_out // g1) % 4 == 0
+            # the block that consumes the up-sampled tensor folds its first GroupNorm too when the transposed convolution can hand
+            # it the raw tensor chunk-planar (hi | lo): then no fp32 copy of it exists at all
+            up_planar = None
+            if fused_t and (2 * W) % 32 == 0 and self._folds_input(pk, f"dec{j}", dec.basic_module, tape, sdims, c_out, c_out):
+                up_planar = self._buf(f"l{lvl}_upp", (N, 2 * c_out * S_out), F16, dev)
+                up = None
+            else:
+                up = self._alloc(tape, f"l{lvl}_up", f"dec{j}.up", (N, S_out, c_out), F32, dev)
+            ust = self._alloc(tape, f"l{lvl}_ust", f"dec{j}.ust", (N, 8, 2), F64, dev)
+            ust.zero_()
             # Upsampling.forward + summation joining (unet3d.py:385-396, 438-440)
-            if self.fuse_transposed and c_out in (32, 64) and c_in % 64 == 0 and D * H * W * N >= 32 and (c_out // g1) % 4 == 0:
+            if fused_t:
                 # into the 32- / 64-channel levels (the big grids): all eight output-parity classes in one pass (conv3d_convt.cu)
                 ops.conv_transpose3d_s2(cur16, pk[f"dec{j}.up_w"], N=N, D=D, H=H, W=W, C_in=c_in, C_out=c_out, a_splits=s, w_splits=s,
-                                        precise=self.precise, bias=pk[f"dec{j}.up_b"], residual=skip, out32=up, stats=ust, groups=g1)
+                                        precise=self.precise, bias=pk[f"dec{j}.up_b"], residual=skip, out32=up, out_planar=up_planar,
+                                        stats=ust, groups=g1)
                 self.kernel_launches += 1
             else:
                 for parity in range(8):
@@ -360,7 +390,7 @@ class ResidualUNet3D(nn.Module):
                 self.kernel_launches += 8
             dims = sdims
             _, cur16 = self._res_block(pk, f"dec{j}", dec.basic_module, up, ust, N=N, dims=dims, c_in_pad=c_out,
-                                       c_in_real=c_out, lvl=lvl, dev=dev, want32=False, want16=True, tape=tape)
+                                       c_in_real=c_out, lvl=lvl, dev=dev, want32=False, want16=True, tape=tape, x_planar=up_planar)
         D, H, W = dims
         if ncdhw_out is not None and tape is None and self.f_maps[0] in (16, 32, 64) and self.out_channels <= 256:
             # inference: final_conv and the conversion back to NCDHW in one pass (no channels-last fp32 copy of the output)
@@ -432,12 +462,19 @@ class ResidualUNet3D(nn.Module):
         S = D * H * W
         cpad = _pad16(C)
         g_in = self.encoders[0].basic_module.conv1.num_groups
-        raw = self._buf("l0_in", (N, S, cpad), F32, dev)
         st = self._buf("l0_pst", (N, 8, 2), F64, dev)
         st.zero_()
-        ops.ncdhw_to_ndhwc(x, raw, N=N, S=S, C=C, Cpad=cpad, groups=g_in, stats=st)
+        raw = xp = None
+        pk = self._packed(dev)
+        if self._folds_input(pk, "enc0", self.encoders[0].basic_module, None, (D, H, W), cpad, C):
+            # the first block folds its first GroupNorm: the module input goes straight into the halo kernel's operand layout
+            xp = self._buf("l0_inp", (N, 2 * cpad * S), F16, dev)
+            ops.ncdhw_to_planar(x, xp, N=N, S=S, C=C, Cpad=cpad, groups=g_in, stats=st)
+        else:
+            raw = self._buf("l0_in", (N, S, cpad), F32, dev)
+            ops.ncdhw_to_ndhwc(x, raw, N=N, S=S, C=C, Cpad=cpad, groups=g_in, stats=st)
         y = torch.empty(N, self.out_channels, D, H, W, device=dev)
-        out_cl = self.forward_channels_last(raw, st, N, (D, H, W), dev, ncdhw_out=y)
+        out_cl = self.forward_channels_last(raw, st, N, (D, H, W), dev, ncdhw_out=y, x_planar=xp)
         if out_cl is not None:
             ops.ndhwc_to_ncdhw(out_cl, y, N=N, S=S, C=self.out_channels)
             self.kernel_launches += 1
