@@ -35,7 +35,7 @@ IMG = 336
 IMAGES_PER_STEP = 8
 # tiles per engine call: the reference's `tile_batch_size` kwarg (a memory knob there, default 32, no effect on results);
 # 95 = 285 / 3 keeps every GEMM's M dimension large and leaves no ragged last batch
-TILE_BATCH = 95
+TILE_BATCH = int(os.environ.get("SEMABS_TILE_BATCH", "95"))  # tiles per engine pass (285 = 3 x 95); env override for A/B runs
 MODEL = "ViT-L/14"
 # algorithmic work (SURVEY.md §8d / BASELINE.md §3): per tile 162.0 GF forward + 89.1 GF backward per label
 GF_FWD_TILE, GF_BWD_TILE_LABEL = 162.0, 89.1
