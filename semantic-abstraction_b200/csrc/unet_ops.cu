@@ -141,40 +141,51 @@ __global__ void __launch_bounds__(256) final_conv1x1_ncdhw_kernel(const __half* 
   for (int i = threadIdx.x; i < C_out; i += blockDim.x) s_w[C_out * CIN + i] = bias ? bias[i] : 0.f;
   __syncthreads();
   const int n = blockIdx.y;
-  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= S) return;
-  const __half* row = x16 + (size_t(n) * S + v) * size_t(splits) * CIN;
-  float x[CIN];
+  // persistent blocks (the weights are staged once per block), two voxels per thread and step: every broadcast weight load
+  // feeds two FMAs.  v and v + 256 so that the plane stores of both stay coalesced.
+  for (long long v0 = (long long)blockIdx.x * 512 + threadIdx.x; v0 < S; v0 += (long long)gridDim.x * 512) {
+    const long long v1 = v0 + 256;
+    const bool two = v1 < S;
+    float x[2][CIN];
 #pragma unroll
-  for (int c = 0; c < CIN; c += 8) {
-    const uint4 uh = *reinterpret_cast<const uint4*>(row + c);
-    const __half2* h2 = reinterpret_cast<const __half2*>(&uh);
+    for (int u = 0; u < 2; ++u) {
+      const __half* row = x16 + (size_t(n) * S + (u == 0 || two ? v0 + 256 * u : v0)) * size_t(splits) * CIN;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = __half22float2(h2[e]);
-      x[c + 2 * e] = f.x, x[c + 2 * e + 1] = f.y;
-    }
-    if (splits == 2) {
-      const uint4 ul = *reinterpret_cast<const uint4*>(row + CIN + c);
-      const __half2* l2 = reinterpret_cast<const __half2*>(&ul);
+      for (int c = 0; c < CIN; c += 8) {
+        const uint4 uh = *reinterpret_cast<const uint4*>(row + c);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&uh);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(l2[e]);
-        x[c + 2 * e] += f.x, x[c + 2 * e + 1] += f.y;
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h2[e]);
+          x[u][c + 2 * e] = f.x, x[u][c + 2 * e + 1] = f.y;
+        }
+        if (splits == 2) {
+          const uint4 ul = *reinterpret_cast<const uint4*>(row + CIN + c);
+          const __half2* l2 = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(l2[e]);
+            x[u][c + 2 * e] += f.x, x[u][c + 2 * e + 1] += f.y;
+          }
+        }
       }
     }
-  }
-  float* yn = y + size_t(n) * C_out * S + v;
-  for (int o = 0; o < C_out; ++o) {
-    const float4* wo = reinterpret_cast<const float4*>(s_w + o * CIN);
-    float a0 = s_w[C_out * CIN + o], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float* yn = y + size_t(n) * C_out * S + v0;
+    for (int o = 0; o < C_out; ++o) {
+      const float4* wo = reinterpret_cast<const float4*>(s_w + o * CIN);
+      const float bo = s_w[C_out * CIN + o];
+      float a0 = bo, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = bo, b1 = 0.f, b2 = 0.f, b3 = 0.f;
 #pragma unroll
-    for (int c = 0; c < CIN / 4; ++c) {
-      const float4 w4 = wo[c];
-      a0 = fmaf(w4.x, x[4 * c], a0), a1 = fmaf(w4.y, x[4 * c + 1], a1);
-      a2 = fmaf(w4.z, x[4 * c + 2], a2), a3 = fmaf(w4.w, x[4 * c + 3], a3);
+      for (int c = 0; c < CIN / 4; ++c) {
+        const float4 w4 = wo[c];
+        a0 = fmaf(w4.x, x[0][4 * c], a0), a1 = fmaf(w4.y, x[0][4 * c + 1], a1);
+        a2 = fmaf(w4.z, x[0][4 * c + 2], a2), a3 = fmaf(w4.w, x[0][4 * c + 3], a3);
+        b0 = fmaf(w4.x, x[1][4 * c], b0), b1 = fmaf(w4.y, x[1][4 * c + 1], b1);
+        b2 = fmaf(w4.z, x[1][4 * c + 2], b2), b3 = fmaf(w4.w, x[1][4 * c + 3], b3);
+      }
+      yn[size_t(o) * S] = (a0 + a1) + (a2 + a3);
+      if (two) yn[size_t(o) * S + 256] = (b0 + b1) + (b2 + b3);
     }
-    yn[size_t(o) * S] = (a0 + a1) + (a2 + a3);
   }
 }
 
@@ -366,7 +377,8 @@ extern "C" int semabs_final_conv1x1_ncdhw(const void* x16, int32_t splits, const
   SB_REQUIRE(splits == 1 || splits == 2, "semabs_final_conv1x1_ncdhw: splits must be 1 or 2");
   SB_REQUIRE((C_in == 16 || C_in == 32 || C_in == 64) && C_out >= 1 && C_out <= 256,
              "semabs_final_conv1x1_ncdhw: unsupported channels %d -> %d", C_in, C_out);
-  dim3 grid((unsigned)((S + 255) / 256), N);
+  const long long want = (S + 511) / 512, cap = 8LL * num_sms();
+  dim3 grid((unsigned)(want < cap ? want : cap), N);
   const size_t sm = size_t(C_out) * (C_in + 1) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   const __half* x = (const __half*)x16;
