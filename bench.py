@@ -754,7 +754,9 @@ def bench_train(dev, rank, world, pk, C=16, num_descs=16, steps=2, warmup=2, pre
             "unet_kernel_launches_per_step": launches_per_step,
             "loss_trajectory": loss_values, "unet_algorithmic_tflops": tf, "tensor_frac": tf / world / pk["tflops"],
             "peak_memory_gb": peak_gb,
-            "note": "gradient all-reduce: one flat NCCL all-reduce after backward" if world > 1 else "single GPU: no collective"}
+            "note": ("gradient all-reduce: one NCCL bucket per UNet level, started from the backward pass as the level's weight "
+                     "gradients are queued (train.GradientBuckets); the few parameters outside the UNet in one flat call after "
+                     "backward") if world > 1 else "single GPU: no collective"}
 
 
 if __name__ == "__main__":

@@ -663,22 +663,27 @@ struct AttnClsArgs {
   int positive_only, need_dqkv;
 };
 
-__global__ void __launch_bounds__(256) attn_bwd_cls_kernel(AttnClsArgs a) {
+// (Two CTAs per SM: the kernel is a latency-bound walk over the 257 keys of a (label, sequence, head) per warp — round 2 ncu
+// showed 2.2 ms per launch with 8 warps per SM; Q_0 is no longer replicated in every lane, which was 64 of ~170 registers.)
+__global__ void __launch_bounds__(256, 2) attn_bwd_cls_kernel(AttnClsArgs a) {
   const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (gw >= a.P * a.B * a.H) return;
   const int h = gw % a.H, pb = gw / a.H, b = pb % a.B;
   const int T = a.T, d = a.d;
   const __half* base = a.qkv16 + size_t(b) * T * a.ldq + h * HD;
-  // dO_0 and Q_0 (64 values each) replicated in registers
-  float dO[HD], q0[HD];
+  // dO_0 (64 values) replicated in registers for the dot products; of Q_0 a lane only needs its own channel pair
+  float dO[HD];
+  float q0a, q0b, doa, dob;
   {
     const __half2* g2 = reinterpret_cast<const __half2*>(a.dO16 + size_t(pb) * a.ld_do + h * HD);
     const __half2* q2 = reinterpret_cast<const __half2*>(base);
 #pragma unroll
     for (int e = 0; e < HD / 2; ++e) {
-      const float2 x = __half22float2(g2[e]), y = __half22float2(q2[e]);
-      dO[2 * e] = x.x, dO[2 * e + 1] = x.y, q0[2 * e] = y.x, q0[2 * e + 1] = y.y;
+      const float2 x = __half22float2(g2[e]);
+      dO[2 * e] = x.x, dO[2 * e + 1] = x.y;
     }
+    const float2 y = __half22float2(q2[lane]), x = __half22float2(g2[lane]);
+    q0a = y.x, q0b = y.y, doa = x.x, dob = x.y;
   }
   const __half* Arow = a.probs16 + size_t(b * a.H + h) * T * a.ldp;  // query row 0
   const float r0 = a.r[size_t(pb) * T];
@@ -690,12 +695,18 @@ __global__ void __launch_bounds__(256) attn_bwd_cls_kernel(AttnClsArgs a) {
     const int j = c * 32 + lane;
     G[c] = 0.f, A[c] = 0.f;
     if (j < T) {
-      const __half2* v2 = reinterpret_cast<const __half2*>(base + size_t(j) * a.ldq + 2 * d);
+      // every lane reads its own key row: 16-byte loads, so a warp load costs 32 L1 wavefronts per 8 channels, not per 2
+      const uint4* v4 = reinterpret_cast<const uint4*>(base + size_t(j) * a.ldq + 2 * d);
       float acc = 0.f;
 #pragma unroll
-      for (int e = 0; e < HD / 2; ++e) {
-        const float2 v = __half22float2(v2[e]);
-        acc = fmaf(dO[2 * e], v.x, acc), acc = fmaf(dO[2 * e + 1], v.y, acc);
+      for (int e = 0; e < HD / 8; ++e) {
+        const uint4 u = __ldg(v4 + e);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+          acc = fmaf(dO[8 * e + 2 * q], v.x, acc), acc = fmaf(dO[8 * e + 2 * q + 1], v.y, acc);
+        }
       }
       G[c] = acc;
       A[c] = __half2float(Arow[j]);
@@ -721,10 +732,6 @@ __global__ void __launch_bounds__(256) attn_bwd_cls_kernel(AttnClsArgs a) {
     // One key row per step, the warp's 32 lanes across the 64 head channels (one half2 each): every store below is a
     // whole 128-byte row segment.  (The first version let each lane write its own rows 4 bytes at a time: 32 partial
     // sectors per warp store, 5.8 ms per launch for 2.4 GB of output.)
-    float q0a = 0.f, q0b = 0.f, doa = 0.f, dob = 0.f;
-#pragma unroll
-    for (int e = 0; e < HD / 2; ++e)
-      if (e == lane) q0a = q0[2 * e], q0b = q0[2 * e + 1], doa = dO[2 * e], dob = dO[2 * e + 1];
     float dq0 = 0.f, dq1 = 0.f;
 #pragma unroll
     for (int c = 0; c < JMAX; ++c) {

@@ -11,6 +11,7 @@ SURVEY.md §8f), `train_step` mirrors the train branch of `utils.loop` (utils.py
 from __future__ import annotations
 
 import ctypes as C
+import os
 import struct
 from typing import Iterable, List, Optional
 
@@ -92,8 +93,9 @@ def train_step(net, batch: dict, get_losses_fn, optimizer, grad_max_norm: float 
     memory; `gradnorm` is reported as what utils.compute_grad_norm would see AFTER the reference's in-place clip)."""
     stats, _ = get_losses_fn(net=net, batch=batch, **kwargs)
     optimizer.zero_grad(set_to_none=True)
-    stats["loss"].backward()
-    all_reduce_gradients(net.parameters())
+    with GradientBuckets() as buckets:
+        stats["loss"].backward()
+    all_reduce_gradients(net.parameters(), skip=buckets.reduced)
     if isinstance(optimizer, Lamb):
         optimizer.step(max_grad_norm=grad_max_norm)
         total = optimizer.last_grad_norm
@@ -220,16 +222,75 @@ class Lamb(torch.optim.Optimizer):
         return loss
 
 
-def all_reduce_gradients(parameters: Iterable[torch.Tensor], world_size: Optional[int] = None):
+class GradientBuckets:
+    """Per-level gradient buckets, all-reduced while the backward pass is still running (the overlap
+    DistributedDataParallel's reducer gives the reference at utils.py:255-258).  `with GradientBuckets():` around
+    `loss.backward()` makes the UNet's backward (unet3d_bwd._UNetFn) hand over the weight gradients of each resolution
+    level as soon as that level's weight-gradient kernels are queued: one flat NCCL all-reduce per level, asynchronous
+    (NCCL's stream waits for the producing kernels, the compute stream carries on with the next level), joined once at
+    the end of the node's backward.  The node then returns the AVERAGED gradients, and `reduced` names the parameters
+    `all_reduce_gradients` must leave alone.  Inactive (a no-op context) without an initialised process group, with one
+    rank, or with SEMABS_GRAD_BUCKETS=0.  Every rank runs the same levels in the same order, so the collectives match."""
+
+    _active: Optional["GradientBuckets"] = None
+
+    def __init__(self, world_size: Optional[int] = None):
+        on = dist.is_available() and dist.is_initialized() and os.environ.get("SEMABS_GRAD_BUCKETS", "1") != "0"
+        self.world = (world_size or dist.get_world_size()) if on else 1
+        self.enabled = on and self.world > 1
+        self.pending: list = []
+        self.reduced: set = set()
+        self.n_buckets = 0
+
+    def __enter__(self):
+        if self.enabled:
+            GradientBuckets._active = self
+        return self
+
+    def __exit__(self, *exc):
+        GradientBuckets._active = None
+        assert not self.pending or exc[0] is not None, "GradientBuckets: a bucket was submitted but never joined"
+        return False
+
+    @staticmethod
+    def active() -> Optional["GradientBuckets"]:
+        return GradientBuckets._active
+
+    def submit(self, grads: dict, keys: list):
+        """Start the all-reduce of grads[k] for k in keys (one flat bucket)."""
+        if not keys:
+            return
+        flat = torch.cat([grads[k].reshape(-1) for k in keys])
+        work = dist.all_reduce(flat, async_op=True)
+        self.pending.append((work, flat, keys))
+        self.n_buckets += 1
+
+    def join(self, grads: dict):
+        """Wait for every bucket (stream-side on NCCL) and replace grads[k] by views of the averaged buckets."""
+        for work, flat, keys in self.pending:
+            work.wait()
+            flat.mul_(1.0 / self.world)
+            off = 0
+            for k in keys:
+                n = grads[k].numel()
+                grads[k] = flat[off : off + n].view_as(grads[k])
+                off += n
+                self.reduced.add(k)
+        self.pending.clear()
+
+
+def all_reduce_gradients(parameters: Iterable[torch.Tensor], world_size: Optional[int] = None, skip=()):
     """Data-parallel gradient averaging over NCCL (what DistributedDataParallel(find_unused_parameters=True) does at
     utils.py:255-258): one flat bucket per call.  A parameter that has a gradient on ANY rank ends up with the averaged
     gradient on EVERY rank (ranks without one contribute zeros); a parameter unused everywhere keeps grad None on all
     ranks — so LAMB's skip decision (arm/optim/lamb.py:71-72) is identical across ranks and the replicas stay in sync
-    (SURVEY.md §8e).  The reference sets NCCL_P2P_DISABLE=1 (utils.py:132); we do not."""
+    (SURVEY.md §8e).  The reference sets NCCL_P2P_DISABLE=1 (utils.py:132); we do not.  The UNet's parameters normally
+    arrive here already averaged (GradientBuckets, overlapped with the backward pass) and are passed in `skip`."""
     if not (dist.is_available() and dist.is_initialized()):
         return
     world = world_size or dist.get_world_size()
-    ps = list(parameters)
+    done = {id(p) for p in skip}  # already averaged by GradientBuckets during backward
+    ps = [p for p in parameters if id(p) not in done]
     if not ps:
         return
     dev = ps[0].device

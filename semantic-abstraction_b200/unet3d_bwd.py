@@ -212,9 +212,20 @@ class UNetBackward:
 
     # ---- whole network ----------------------------------------------------------------------------------------
     @torch.no_grad()
-    def backward(self, tape: Tape, d_out_cl: torch.Tensor, need_dx: bool = True):
+    def backward(self, tape: Tape, d_out_cl: torch.Tensor, need_dx: bool = True, buckets=None):
         """d_out_cl: gradient of the channels-last output [N, S, out_channels] (true scale). Returns
-        (dx channels-last [N, S, Cpad_in] or None, {parameter: gradient})."""
+        (dx channels-last [N, S, Cpad_in] or None, {parameter: gradient}).  `buckets` (train.GradientBuckets): the weight
+        gradients of each resolution level are handed to it as soon as they are queued, so their all-reduce overlaps
+        the levels still to come; the caller joins."""
+        n_sent = 0
+
+        def hand_over():
+            nonlocal n_sent
+            if buckets is not None:
+                keys = list(grads)[n_sent:]
+                buckets.submit(grads, keys)
+                n_sent += len(keys)
+
         u = self.unet
         N, dims0, dev = tape.meta["N"], tape.meta["dims0"], tape.meta["dev"]
         pk, fpk = self._packed(dev), u._packed(dev)
@@ -325,6 +336,7 @@ class UNetBackward:
             ops.absmax_f32(d_low, a_l)
             g_cur = _Grad(d_low, s_up, a_l)
             u.kernel_launches += 16
+            hand_over()
 
         # encoders, deepest first
         dx_in = None
@@ -354,6 +366,7 @@ class UNetBackward:
                 u.kernel_launches += 1
             else:
                 dx_in = d_in
+            hand_over()
         return dx_in, grads
 
 
@@ -391,7 +404,10 @@ class _UNetFn(torch.autograd.Function):
         ops.ncdhw_to_ndhwc(dy.contiguous().float(), dy_cl, N=N, S=S, C=co, Cpad=co)
         bw = unet._bwd()
         need_dx = ctx.needs_input_grad[0]
-        dx_cl, grads = bw.backward(tape, dy_cl, need_dx=need_dx)
+        from .train import GradientBuckets
+
+        buckets = GradientBuckets.active()
+        dx_cl, grads = bw.backward(tape, dy_cl, need_dx=need_dx, buckets=buckets)
         bw.release(tape)
         dx = None
         if need_dx:
@@ -403,4 +419,6 @@ class _UNetFn(torch.autograd.Function):
                 full = torch.empty(N, cpad, D, H, W, device=dev)
                 ops.ndhwc_to_ncdhw(dx_cl, full, N=N, S=S, C=cpad)
                 dx = full[:, :C].contiguous()
+        if buckets is not None:
+            buckets.join(grads)
         return (dx, None) + tuple(grads.get(p) for p in ctx.params)

@@ -152,8 +152,9 @@ def loop(net, loader, pbar, get_losses_fn: Callable, logger=None, optimizer=None
         if optimizer:
             stats, detailed = get_losses_fn(net=net, batch=batch, **kwargs)
             optimizer.zero_grad(set_to_none=True)
-            stats["loss"].backward()
-            _train.all_reduce_gradients(net.parameters())
+            with _train.GradientBuckets() as buckets:
+                stats["loss"].backward()
+            _train.all_reduce_gradients(net.parameters(), skip=buckets.reduced)
             if isinstance(optimizer, Lamb):
                 optimizer.step(max_grad_norm=grad_max_norm)
                 total = optimizer.last_grad_norm
