@@ -107,7 +107,11 @@ class _FeatureVolumeFn(torch.autograd.Function):
         unet = net.vol_feature_extractor
         bw = unet._bwd()
         dev = d_out.device
-        dx_cl, grads = bw.backward(tape, d_out.contiguous().float(), need_dx=net.use_pts_feat_extractor)
+        from .train import GradientBuckets
+
+        buckets = GradientBuckets.active()  # data-parallel training: per-level all-reduce overlapped with this backward
+        dx_cl, grads = bw.backward(tape, d_out.contiguous().float(), need_dx=net.use_pts_feat_extractor, buckets=buckets)
+        n_unet = len(grads)
         if net.use_pts_feat_extractor:
             ex = tape.extra
             N, npts, F, P, cpad = ex["N"], ex["npts"], ex["F"], ex["P"], ex["cpad"]
@@ -129,6 +133,9 @@ class _FeatureVolumeFn(torch.autograd.Function):
             grads[l2.weight], grads[l2.bias] = _linear_grads(scratch, npt, off_d2, Hd, 8, Hd, dev)
             grads[l0.weight], grads[l0.bias] = _linear_grads(scratch, npt, off_d1, Hd, 0, 3 + F, dev)
         bw.release(tape)
+        if buckets is not None:
+            buckets.submit(grads, list(grads)[n_unet:])  # the point MLP: one last small bucket
+            buckets.join(grads)
         return (None, None, None) + tuple(grads.get(p) for p in ctx.params)
 
 
