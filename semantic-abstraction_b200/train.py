@@ -234,7 +234,8 @@ class GradientBuckets:
 
     _active: Optional["GradientBuckets"] = None
 
-    def __init__(self, world_size: Optional[int] = None):
+    def __init__(self, world_size: Optional[int] = None, keep_local: bool = False):
+        self.local: Optional[dict] = {} if keep_local else None  # debugging: this rank's own gradients, before the reduce
         on = dist.is_available() and dist.is_initialized() and os.environ.get("SEMABS_GRAD_BUCKETS", "1") != "0"
         self.world = (world_size or dist.get_world_size()) if on else 1
         self.enabled = on and self.world > 1
@@ -261,6 +262,8 @@ class GradientBuckets:
         if not keys:
             return
         flat = torch.cat([grads[k].reshape(-1) for k in keys])
+        if self.local is not None:
+            self.local.update((k, grads[k].clone()) for k in keys)
         work = dist.all_reduce(flat, async_op=True)
         self.pending.append((work, flat, keys))
         self.n_buckets += 1

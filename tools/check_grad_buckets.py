@@ -34,11 +34,13 @@ def gradients(dev, rank, mode):
                  out_of_bounds_pts=torch.zeros(B, P, n_out, dtype=torch.bool, device=dev),
                  out_of_frustum_pts_mask=torch.zeros(B, P, n_out, dtype=torch.bool, device=dev), patch_labels=[("a",), ("b",)])
     stats, _ = train.get_losses_ovssc(m, batch)
-    with train.GradientBuckets() as gb:
+    with train.GradientBuckets(keep_local=True) as gb:
         stats["loss"].backward()
-    local = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None and p not in gb.reduced}
+    names = {p: n for n, p in m.named_parameters()}
+    local = {names[p]: t for p, t in (gb.local or {}).items()}  # bucketed parameters: this rank's own gradient
+    local.update({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None and p not in gb.reduced})
     train.all_reduce_gradients(m.parameters(), skip=gb.reduced)
-    return {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}, gb.n_buckets, len(gb.reduced), len(local)
+    return {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}, local, gb.n_buckets, len(gb.reduced)
 
 
 def main():
@@ -46,11 +48,26 @@ def main():
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
-    g_flat, nb0, nr0, _ = gradients(dev, rank, "0")
-    g_bkt, nb1, nr1, n_rest = gradients(dev, rank, "1")
-    assert (nb0, nr0) == (0, 0) and nb1 > 1 and nr1 > 0, (nb0, nr0, nb1, nr1)
-    assert g_flat.keys() == g_bkt.keys()
-    worst = max(((g_bkt[k] - g_flat[k]).norm() / g_flat[k].norm().clamp_min(1e-30)).item() for k in g_flat)
+    # The same backward pass, so no run-to-run spread enters (two runs of the backward differ by ~1e-5, and by ~2e-3 in the
+    # rare run where one ReLU input sits within rounding noise of zero — tools/debug_bwd_determinism.py): the gradients
+    # the step ends up with must be the mean over ranks of the gradients each rank computed.
+    world_t = float(world)
+    worst, worst_key = 0.0, ""
+    counts = {}
+    for mode in ("0", "1"):
+        g_avg, local, nb, nr = gradients(dev, rank, mode)
+        counts[mode] = (nb, nr, len(local) - nr)
+        for k in sorted(g_avg):
+            parts = [torch.empty_like(local[k]) for _ in range(world)]
+            dist.all_gather(parts, local[k].contiguous())
+            mean = torch.stack(parts).sum(0) / world_t
+            d = ((g_avg[k] - mean).norm() / mean.norm().clamp_min(1e-30)).item()
+            if d > worst:
+                worst, worst_key = d, f"{k} (buckets {'on' if mode == '1' else 'off'})"
+        if mode == "1":
+            g_bkt = g_avg
+    (nb0, nr0, _), (nb1, nr1, n_rest) = counts["0"], counts["1"]
+    assert (nb0, nr0) == (0, 0) and nb1 > 1 and nr1 > 0, counts
     # every rank must hold the same averaged gradients
     sig = torch.stack([g_bkt[k].double().sum() for k in sorted(g_bkt)])
     all_sig = [torch.empty_like(sig) for _ in range(world)]
@@ -63,9 +80,10 @@ def main():
         res[mode] = bench.bench_train(dev, rank, world, pk, steps=3, warmup=2)
     if rank == 0:
         print(json.dumps({"world": world, "buckets": nb1, "bucketed_parameters": nr1, "flat_parameters": n_rest,
-                          "worst_rel_diff_vs_flat": worst, "ranks_identical": same,
+                          "worst_rel_diff_vs_mean_of_rank_gradients": worst, "worst_tensor": worst_key,
+                          "ranks_identical": same,
                           "train_ms_flat": res["0"].get("ms_per_step"), "train_ms_buckets": res["1"].get("ms_per_step")}))
-    assert worst < 1e-5 and same
+    assert worst <= (0.0 if world == 2 else 1e-6) and same
     dist.destroy_process_group()
 
 
