@@ -38,6 +38,9 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 
 // ---- device math -----------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
+// ex2.approx + rcp.approx (2 MUFU + 3 FP32 instructions; relative error ~1e-6 over the QuickGELU input range, against ~25
+// instructions of expf + IEEE division): for epilogues whose warps are issue / latency bound (gemm_epilogue.cuh)
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // QuickGELU (reference: CLIP/clip/model_explainability.py:197-199): x * sigmoid(1.702 x)
 __device__ __forceinline__ float quick_gelu(float x) { return x * sigmoidf_precise(1.702f * x); }
 __device__ __forceinline__ float quick_gelu_grad(float x) {

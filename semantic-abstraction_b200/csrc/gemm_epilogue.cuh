@@ -115,7 +115,9 @@ __device__ __forceinline__ void gemm_epilogue_tile(const EpiParams& ep, uint32_t
           // one sigmoid gives both the activation and (for the backward sweep) its derivative
 #pragma unroll
           for (int j = 0; j < CW; j += 2) {
-            const float s0 = sigmoidf_precise(1.702f * v[j]), s1 = sigmoidf_precise(1.702f * v[j + 1]);
+            // (fast sigmoid: with expf + IEEE division the 16 sigmoids of a chunk were 60 % of the kernel's instructions and
+            // the epilogue warps, two per scheduler, could not keep up with the K = 1024 main loop: tensor pipe 56 %)
+            const float s0 = sigmoidf_fast(1.702f * v[j]), s1 = sigmoidf_fast(1.702f * v[j + 1]);
             h[j >> 1] = __floats2half2_rn(s0 + 1.702f * v[j] * s0 * (1.0f - s0), s1 + 1.702f * v[j + 1] * s1 * (1.0f - s1));
             v[j] *= s0, v[j + 1] *= s1;
           }
