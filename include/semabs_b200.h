@@ -152,6 +152,11 @@ int semabs_attn_bwd_tc3(const void* qkv16, int32_t ld_qkv, const void* probs16, 
 /* Debug aid of semabs_attn_bwd_tc3: device buffer of 2 x 16 x 64 int64 that the next launches fill with clock64 time stamps of
  * CTA 0's pipeline events (tools/attn_trace.py prints the timeline); null = off (default). */
 int semabs_debug_attn_trace(long long* device_buf);
+/* Same for semabs_attn_fwd_tc: 64 int64 slots, clock64 stamps of the CTA in the middle of the grid (slot 0 = start, 1 + 8 t ..
+ * 7 + 8 t = softmax warp 4 in MMA tile t: before / after the wait for S, after the max pass, after the exp pass, after the
+ * normalise-and-pack pass, after the wait for O, after the stores; 31 = TMEM freed; 32 + 4 w .. 34 + 4 w = SIMT tail warp w:
+ * start, K / V in shared memory, row done). */
+int semabs_debug_attn_fwd_trace(long long* device_buf);
 
 /* Known-answer hook for the two tcgen05 operand forms the attention kernels add to the GEMM's (A operand in TMEM,
  * MN-major B in shared memory): D[128,64] = A16[128,Kd] * B16[Kd,64], Kd % 16 == 0, Kd <= 256; lbo / sbo are the

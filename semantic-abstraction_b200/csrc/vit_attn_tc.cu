@@ -100,7 +100,13 @@ struct AttnFwdTcArgs {
   int o_splits;
   int T, H, d, causal;
   int in_splits;    // qkv16 rows are [hi (3d) | lo (3d)] when 2
+  const __half* qkv16;  // the same matrix the tensor map describes: the SIMT tail rows read their query row directly
+  int ldq;
+  long long* trace;     // debug (semabs_debug_attn_fwd_trace): clock64 stamps of one late CTA; null in production
 };
+__device__ __forceinline__ void fwd_trace(const AttnFwdTcArgs& a, int slot, int lane) {
+  if (a.trace && blockIdx.x == gridDim.x / 2 && lane == 0) a.trace[slot] = clock64();
+}
 
 struct TcSmem {
   static constexpr int Q_HI = 0;
@@ -110,8 +116,153 @@ struct TcSmem {
   static constexpr int V_HI = K_LO + TC_KV_BYTES;
   static constexpr int V_LO = V_HI + TC_KV_BYTES;
   static constexpr int BARS = V_LO + TC_KV_BYTES;
-  static constexpr int TOTAL = BARS + 128 + 1024;
+  static constexpr int TAIL = BARS + 128;  // float [8 + 3 x 64]: maxima, sums and partial outputs of the three tail warps
+  static constexpr int TOTAL = TAIL + 1024 + 1024;
 };
+
+// The query row past the last full 128-row tile (T = 257 = 2 x 128 + 1: as a third MMA tile the class-token-plus-256-patch
+// sequence's last row cost as much as 128 rows, a third of the kernel) on the three warps that were idle anyway: warp w takes
+// the keys [96 w, 96 w + 96), the three combine maximum, sum and partial output through shared memory.  K / V are read from the
+// TMA-written tiles (128-byte swizzle: the 16-byte chunk c of row r sits at chunk c ^ (r & 7); two boxes of 136 rows) with
+// explicit shared-space loads (the generic form ran ~10x slower here).  Timeline: semabs_debug_attn_fwd_trace.
+__device__ __forceinline__ uint32_t tc_kv_row(uint32_t base, int j) {
+  return base + uint32_t((j / TC_BOX_ROWS) * TC_BOX_BYTES + (j % TC_BOX_ROWS) * 128);
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
+  uint4 v;
+  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void tail_warps_sync() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+// 8 fp16 hi (+ lo) values of one swizzled 16-byte chunk -> fp32
+__device__ __forceinline__ void tc_chunk_f32(uint32_t hi_row, uint32_t lo_row, int pos, bool split, float (&x)[8]) {
+  const uint4 u = lds128u(hi_row + (pos << 4));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[t]));
+    x[2 * t] = f.x, x[2 * t + 1] = f.y;
+  }
+  if (split) {
+    const uint4 ul = lds128u(lo_row + (pos << 4));
+    const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wl[t]));
+      x[2 * t] += f.x, x[2 * t + 1] += f.y;
+    }
+  }
+}
+constexpr int TC_TAIL_GROUPS = 3;  // 32-key groups per tail warp: 3 warps x 3 x 32 = 288 >= TC_MAX_T
+__device__ __noinline__ void attn_fwd_tail_row(uint32_t smem, float* scratch, const AttnFwdTcArgs& a, int bh, int row0, int h, int i,
+                                               int w, int lane, int k_hi, int k_lo, int v_hi, int v_lo) {
+  const int T = a.T, d = a.d;
+  const bool split = a.in_splits == 2;
+  constexpr float LOG2E = 1.4426950408889634f;
+  constexpr int G = TC_TAIL_GROUPS;
+  const __half* qrow = a.qkv16 + size_t(row0 + i) * a.ldq + h * TC_HD;
+  float q[TC_HD];
+#pragma unroll
+  for (int e = 0; e < TC_HD / 2; ++e) {
+    float2 x = __half22float2(reinterpret_cast<const __half2*>(qrow)[e]);
+    if (split) {
+      const float2 y = __half22float2(reinterpret_cast<const __half2*>(qrow + 3 * d)[e]);
+      x.x += y.x, x.y += y.y;
+    }
+    q[2 * e] = x.x, q[2 * e + 1] = x.y;
+  }
+  const int jmax = a.causal ? (i + 1 < T ? i + 1 : T) : T;
+  float p[G];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int j = (w * G + g) * 32 + lane;
+    p[g] = -INFINITY;
+    if (j < jmax) {
+      const uint32_t kh = tc_kv_row(smem + k_hi, j), kl = tc_kv_row(smem + k_lo, j);
+      const int sw = (j % TC_BOX_ROWS) & 7;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};  // four chains: a single one is 64 dependent FMAs per key
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        float x[8];
+        tc_chunk_f32(kh, kl, ch ^ sw, split, x);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[t] = fmaf(q[8 * ch + 2 * t], x[2 * t], acc[t]), acc[t] = fmaf(q[8 * ch + 2 * t + 1], x[2 * t + 1], acc[t]);
+      }
+      p[g] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+      mx = fmaxf(mx, p[g]);
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) scratch[w] = mx;
+  tail_warps_sync();
+  mx = fmaxf(fmaxf(scratch[0], scratch[1]), scratch[2]);
+  const float mb = mx * LOG2E;
+  float sum = 0.f;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    p[g] = ((w * G + g) * 32 + lane < jmax) ? fast_exp2(fmaf(p[g], LOG2E, -mb)) : 0.f;
+    sum += p[g];
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) scratch[4 + w] = sum;
+  tail_warps_sync();
+  const float inv = 1.0f / ((scratch[4] + scratch[5]) + scratch[6]);
+  __half* prow = a.probs16 ? a.probs16 + (size_t(bh) * T + i) * a.ldp : nullptr;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    p[g] *= inv;
+    const int j = (w * G + g) * 32 + lane;
+    if (prow && j < a.ldp) prow[j] = __float2half_rn(p[g]);
+    if (!split) p[g] = __half2float(__float2half_rn(p[g]));  // the MMA path feeds P V with fp16 probabilities when the operands are single
+  }
+  // partial O_i = sum over this warp's keys of p_j V_j: every lane sums its own keys over all 64 channels (64 independent
+  // chains, conflict-free 16-byte row reads), then a reduce-scatter over the warp leaves channels 2 lane, 2 lane + 1 in `lane`
+  float v[TC_HD];
+#pragma unroll
+  for (int e = 0; e < TC_HD; ++e) v[e] = 0.f;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int j = (w * G + g) * 32 + lane;
+    if (j < jmax) {
+      const uint32_t vh = tc_kv_row(smem + v_hi, j), vl = tc_kv_row(smem + v_lo, j);
+      const int sw = (j % TC_BOX_ROWS) & 7;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        float x[8];
+        tc_chunk_f32(vh, vl, ch ^ sw, split, x);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[8 * ch + t] = fmaf(p[g], x[t], v[8 * ch + t]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 16, n = TC_HD; m >= 1; m >>= 1, n >>= 1) {
+    const bool up = (lane & m) != 0;  // this lane keeps the upper half of its n values, its partner the lower half
+#pragma unroll
+    for (int e = 0; e < n / 2; ++e) {
+      const float send = up ? v[e] : v[e + n / 2];
+      const float keep = up ? v[e + n / 2] : v[e];
+      v[e] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+  *reinterpret_cast<float2*>(scratch + 8 + w * TC_HD + 2 * lane) = make_float2(v[0], v[1]);
+  tail_warps_sync();
+  if (w != 0) return;
+  const float2 p0 = *reinterpret_cast<const float2*>(scratch + 8 + 2 * lane);
+  const float2 p1 = *reinterpret_cast<const float2*>(scratch + 8 + TC_HD + 2 * lane);
+  const float2 p2 = *reinterpret_cast<const float2*>(scratch + 8 + 2 * TC_HD + 2 * lane);
+  const float o0 = (p0.x + p1.x) + p2.x, o1 = (p0.y + p1.y) + p2.y;
+  const size_t row = size_t(row0) + i;
+  if (a.o32) *reinterpret_cast<float2*>(a.o32 + row * d + h * TC_HD + 2 * lane) = make_float2(o0, o1);
+  if (a.o16) {
+    uint32_t hi, lo;
+    split_pack(o0, o1, hi, lo);
+    __half* dst = a.o16 + row * size_t(a.o_splits) * d + h * TC_HD + 2 * lane;
+    *reinterpret_cast<uint32_t*>(dst) = hi;
+    if (a.o_splits == 2) *reinterpret_cast<uint32_t*>(dst + d) = lo;
+  }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnFwdTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -124,7 +275,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_fwd_tc_kernel(const __grid
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
   const int T = a.T, d = a.d;
   const int row0 = b * T;
-  const int n_mt = (T + 127) / 128;
+  // a single row beyond the last full 128-row tile goes to the otherwise idle warps 1..3
+  const int n_tail = (T > 128 && (T & 127) == 1) ? 1 : 0;
+  const int n_mt = n_tail ? T / 128 : (T + 127) / 128;
   const int ncol = (T + 15) & ~15;
   const int n1 = ncol < 256 ? ncol : 256, n2 = ncol - n1;
   const bool split = a.in_splits == 2;
@@ -139,6 +292,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_fwd_tc_kernel(const __grid
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  if (warp == 4) fwd_trace(a, 0, lane);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -202,7 +356,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_fwd_tc_kernel(const __grid
       }
       umma_commit_elect(bar_o, leader);
     }
-  } else if (warp >= 4) {
+  } else if (warp <= 3) {
+    if (n_tail) {
+      fwd_trace(a, 32 + 4 * (warp - 1), lane);
+      mbar_wait(bar_kv, 0);  // K / V of the whole sequence are in shared memory
+      fwd_trace(a, 33 + 4 * (warp - 1), lane);
+      attn_fwd_tail_row(smem_u32(smem), reinterpret_cast<float*>(smem + TcSmem::TAIL), a, bh, row0, h, n_mt * 128, warp - 1, lane,
+                        TcSmem::K_HI, TcSmem::K_LO, TcSmem::V_HI, TcSmem::V_LO);
+      fwd_trace(a, 34 + 4 * (warp - 1), lane);
+    }
+  } else {
     // ===== softmax + epilogue: thread = query row =====
     const int q = warp & 3;
     const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16);
@@ -211,8 +374,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_fwd_tc_kernel(const __grid
       const int i = mt * 128 + q * 32 + lane;
       const bool valid = i < T;
       const int jmax = a.causal ? (i < T ? i + 1 : T) : T;  // keys [0, jmax) take part
+      if (warp == 4) fwd_trace(a, 1 + 8 * mt, lane);
       mbar_wait(bar_s, mt & 1);
       tc_fence_after();
+      if (warp == 4) fwd_trace(a, 2 + 8 * mt, lane);
       // pass 1: row maximum
       float mx = -INFINITY;
       for (int c = 0; c < ncol; c += 16) {
@@ -224,6 +389,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_fwd_tc_kernel(const __grid
           if (c + e < jmax) mx = fmaxf(mx, __uint_as_float(r[e]));
       }
       // pass 2: e = exp(s - max) kept in place, row sum
+      if (warp == 4) fwd_trace(a, 3 + 8 * mt, lane);
       const float mb = mx * LOG2E;
       float sum = 0.f;
       for (int c = 0; c < ncol; c += 16) {
@@ -239,6 +405,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_fwd_tc_kernel(const __grid
         tmem_st_32x32b_x16(t_row + uint32_t(TC_COL_S + c), r);
       }
       tc_wait_st();
+      if (warp == 4) fwd_trace(a, 4 + 8 * mt, lane);
       // pass 3: normalise, write probabilities to HBM, pack fp16 hi / lo A operands over the strip (32 columns at a
       // time: the packed words of a 32-column chunk land inside the same 32 columns)
       const float inv = 1.0f / sum;
@@ -270,9 +437,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_fwd_tc_kernel(const __grid
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p);
+      if (warp == 4) fwd_trace(a, 5 + 8 * mt, lane);
       // epilogue
       mbar_wait(bar_o, mt & 1);
       tc_fence_after();
+      if (warp == 4) fwd_trace(a, 6 + 8 * mt, lane);
       uint32_t o[64];
       tmem_ld_32x32b_x32(t_row + uint32_t(TC_COL_O), *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
       tmem_ld_32x32b_x32(t_row + uint32_t(TC_COL_O + 32), *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
@@ -299,6 +468,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_fwd_tc_kernel(const __grid
           }
         }
       }
+      if (warp == 4) fwd_trace(a, 7 + 8 * mt, lane);
     }
   }
   tc_fence_before();
@@ -306,6 +476,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_fwd_tc_kernel(const __grid
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+    fwd_trace(a, 31, lane);
   }
 }
 
@@ -882,6 +1053,12 @@ extern "C" int semabs_selftest_ts_mma(const void* A16, const void* B16, float* D
   return 0;
 }
 
+static long long* g_attn_fwd_trace = nullptr;
+extern "C" int semabs_debug_attn_fwd_trace(long long* device_buf) {
+  g_attn_fwd_trace = device_buf;
+  return 0;
+}
+
 extern "C" int semabs_attn_fwd_tc(const void* qkv16, int32_t in_splits, void* probs16, int32_t ld_p16, float* o32, void* o16,
                                   int32_t o_splits, int32_t B, int32_t T, int32_t H, int32_t causal, void* stream) {
   SB_REQUIRE(qkv16 && (o32 || o16) && B > 0 && T > 0 && H > 0, "semabs_attn_fwd_tc: bad arguments");
@@ -891,7 +1068,7 @@ extern "C" int semabs_attn_fwd_tc(const void* qkv16, int32_t in_splits, void* pr
   const int d = H * TC_HD;
   CUtensorMap tm;
   if (int rc = make_qkv_tmap(&tm, qkv16, (long long)B * T, (long long)in_splits * 3 * d)) return rc;
-  AttnFwdTcArgs a{(__half*)probs16, ld_p16, o32, (__half*)o16, o_splits, T, H, d, causal, in_splits};
+  AttnFwdTcArgs a{(__half*)probs16, ld_p16, o32, (__half*)o16, o_splits, T, H, d, causal, in_splits, (const __half*)qkv16, in_splits * 3 * d, g_attn_fwd_trace};
   static bool configured = false;
   if (!configured) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::TOTAL));

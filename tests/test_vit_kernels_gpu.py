@@ -230,7 +230,9 @@ def test_tcgen05_tmem_a_operand_and_mn_major_b():
 
 
 @pytest.mark.parametrize("T,H,causal,splits", [(50, 12, False, 2), (257, 16, False, 2), (77, 8, True, 2), (257, 16, False, 1),
-                                               (197, 12, False, 2), (128, 4, False, 2), (129, 4, True, 2)])
+                                               (197, 12, False, 2), (128, 4, False, 2), (129, 4, True, 2),
+                                               # rows beyond the last full 128-row tile ride on SIMT warps (1, 2 or 3 of them)
+                                               (130, 4, False, 1), (131, 4, True, 2), (259, 2, False, 2), (132, 4, False, 2)])
 def test_attn_fwd_tc(T, H, causal, splits):
     from semabs_b200 import ops
 

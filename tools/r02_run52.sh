@@ -1,0 +1,3 @@
+#!/bin/bash
+SPLITS=2 timeout 300 python tools/attn_fwd_trace.py 2>&1 | grep -v Warn | tail -9
+bash tools/r02_run50.sh
