@@ -519,18 +519,26 @@ attn_bwd_col_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 constexpr int TAIL_PITCH = 72;                       // halfs per staged row (64 + 8 pad = 144 B)
 constexpr int TAIL_ROWS = 264;                       // >= T (<= 257 + ...) rounded up
 constexpr int TAIL_TILE_BYTES = TAIL_ROWS * TAIL_PITCH * 2;
+// Two groups of 8 warps per CTA, each on its own labels (p = group, group + 2, ...) with its own dO tile, scratch and named
+// barrier: the per-label work is a chain of five short barrier-separated phases, latency-bound with two warps per scheduler
+// (7.2 k cycles per label for ~2.8 k cycles of instructions); the second group fills the other half of every stall and the
+// next label's dO lands while the group finishes the phases that no longer read the tile.
+constexpr int TAIL_GROUPS = 2;
+constexpr int TAIL_THREADS = TAIL_GROUPS * TC_SIMT;
 struct TailSmem {
-  static constexpr int Q = 0, K = Q + TAIL_TILE_BYTES, V = K + TAIL_TILE_BYTES, DO = V + TAIL_TILE_BYTES;  // DO: 2 stages
-  static constexpr int DS = DO + 2 * TAIL_TILE_BYTES; // float [2][TAIL_ROWS]: ds and a (column part) / ds (row part)
-  static constexpr int RED = DS + 2 * TAIL_ROWS * 4;  // float [8 segments][3][64] partial sums
-  static constexpr int WRED = RED + 8 * 3 * 64 * 4;   // float [8] warp partials of the relevance sum
-  static constexpr int TOTAL = WRED + 64;
+  static constexpr int Q = 0, K = Q + TAIL_TILE_BYTES, V = K + TAIL_TILE_BYTES, DO = V + TAIL_TILE_BYTES;  // DO: one tile per group
+  static constexpr int DS = DO + TAIL_GROUPS * TAIL_TILE_BYTES;  // per group float [2][TAIL_ROWS]: ds and a (column part) / ds (row part)
+  static constexpr int RED = DS + TAIL_GROUPS * 2 * TAIL_ROWS * 4;   // per group float [8 segments][3][64] partial sums
+  static constexpr int WRED = RED + TAIL_GROUPS * 8 * 3 * 64 * 4;    // per group float [8] warp partials of the relevance sum
+  static constexpr int TOTAL = WRED + TAIL_GROUPS * 32;
 };
+static_assert(TailSmem::TOTAL + 16 <= 227 * 1024, "tail kernel shared memory");
+__device__ __forceinline__ void tail_group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(TC_SIMT) : "memory"); }
 
 // rows [0, T) x 64 halfs -> padded shared rows, 16 bytes per cp.async (no register round trip: every copy of the tile is
 // in flight at once; the first version staged through registers and spent 41 % of the kernel waiting on those loads)
-__device__ __forceinline__ void tail_stage_async(__half* dst, const __half* src, int ld, int T, int tid) {
-  for (int idx = tid; idx < T * 8; idx += TC_SIMT) {
+__device__ __forceinline__ void tail_stage_async(__half* dst, const __half* src, int ld, int T, int tid, int nthreads = TC_SIMT) {
+  for (int idx = tid; idx < T * 8; idx += nthreads) {
     const int r = idx >> 3, c = idx & 7;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + r * TAIL_PITCH + c * 8)),
                  "l"(src + size_t(r) * ld + c * 8)
@@ -554,17 +562,19 @@ __device__ __forceinline__ float tail_dot64(const __half* x, const __half* y) { 
   return acc0 + acc1;
 }
 
-__global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArgs a) {
+__global__ void __launch_bounds__(TAIL_THREADS, 1) attn_bwd_tail2_kernel(AttnBwdTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 15) & ~uintptr_t(15));
+  const int grp = threadIdx.x / TC_SIMT;                   // label group of this thread
+  const int tid = threadIdx.x % TC_SIMT, warp = tid >> 5, lane = tid & 31;  // indices inside the group
   __half* sQ = reinterpret_cast<__half*>(smem + TailSmem::Q);
   __half* sK = reinterpret_cast<__half*>(smem + TailSmem::K);
   __half* sV = reinterpret_cast<__half*>(smem + TailSmem::V);
-  float* s_ds = reinterpret_cast<float*>(smem + TailSmem::DS);
+  __half* sG = reinterpret_cast<__half*>(smem + TailSmem::DO + grp * TAIL_TILE_BYTES);
+  float* s_ds = reinterpret_cast<float*>(smem + TailSmem::DS) + grp * 2 * TAIL_ROWS;
   float* s_av = s_ds + TAIL_ROWS;
-  float* s_red = reinterpret_cast<float*>(smem + TailSmem::RED);
-  float* s_wred = reinterpret_cast<float*>(smem + TailSmem::WRED);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* s_red = reinterpret_cast<float*>(smem + TailSmem::RED) + grp * 8 * 192;
+  float* s_wred = reinterpret_cast<float*>(smem + TailSmem::WRED) + grp * 8;
   const int T = a.T, d = a.d;
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
   const int x0 = a.n_full * 128;  // n_tail == 1
@@ -572,11 +582,10 @@ __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArg
   const __half* Ab = a.probs16 + size_t(bh) * T * a.ldp;
   const size_t ld = size_t(a.splits) * 3 * d;
   auto dO_of = [&](int p) { return a.dO16 + size_t(p * a.B + b) * T * a.ld_do + h * TC_HD; };
-  auto sG_of = [&](int p) { return reinterpret_cast<__half*>(smem + TailSmem::DO + (p & 1) * TAIL_TILE_BYTES); };
-  tail_stage_async(sQ, qkv, a.ldq, T, tid);
-  tail_stage_async(sK, qkv + d, a.ldq, T, tid);
-  tail_stage_async(sV, qkv + 2 * d, a.ldq, T, tid);
-  tail_stage_async(sG_of(0), dO_of(0), a.ld_do, T, tid);
+  tail_stage_async(sQ, qkv, a.ldq, T, threadIdx.x, TAIL_THREADS);
+  tail_stage_async(sK, qkv + d, a.ldq, T, threadIdx.x, TAIL_THREADS);
+  tail_stage_async(sV, qkv + 2 * d, a.ldq, T, threadIdx.x, TAIL_THREADS);
+  if (grp < a.P) tail_stage_async(sG, dO_of(grp), a.ld_do, T, tid);
   // probability column x0 (rows i) and row x0 (columns j) of this head: per-thread registers, rows tid and tid + 256
   const int r1 = tid + TC_SIMT;
   const float acol0 = tid < T ? __half2float(Ab[size_t(tid) * a.ldp + x0]) : 0.f;
@@ -586,9 +595,10 @@ __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArg
   const int cp = tid & 31, seg = tid >> 5;  // reduction layout: channel pair (2 cp, 2 cp + 1) x 8 row segments
   const int rows_per_seg = (T + 7) / 8;
   const int i_beg = seg * rows_per_seg, i_end = min(T, (seg + 1) * rows_per_seg);
-  for (int p = 0; p < a.P; ++p) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();  // Q / K / V (staged by all threads) and each group's first dO tile are visible
+  for (int p = grp; p < a.P; p += TAIL_GROUPS) {
     const int pb = p * a.B + b;
-    const __half* sG = sG_of(p);
     const float* dl = a.delta + (size_t(pb) * a.H + h) * T;
     const float* rp = a.r + size_t(pb) * T;
     // per-label scalars: in flight while the staged tile lands
@@ -597,9 +607,11 @@ __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArg
     if (a.need_dqkv) {
       dv0 = tid < T ? dl[tid] : 0.f, dv1 = r1 < T ? dl[r1] : 0.f, dx0 = dl[x0];
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();  // label p's dO (and, first pass, Q / K / V) visible; every reader of stage (p+1)&1 (label p-1) is done
-    if (p + 1 < a.P) tail_stage_async(sG_of(p + 1), dO_of(p + 1), a.ld_do, T, tid);  // overlaps this label's arithmetic
+    if (p != grp) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      tail_group_sync(grp);  // label p's dO visible; the group's scratch of label p - 2 is consumed
+    }
+    const bool more = p + TAIL_GROUPS < a.P;
     // ---- column part, scalars: thread = query row(s) tid, tid + 256
     float wsum = 0.f;
     {
@@ -621,14 +633,17 @@ __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArg
     }
     wsum = warp_sum(wsum);
     if (lane == 0) s_wred[warp] = wsum;
-    __syncthreads();
+    tail_group_sync(grp);
     if (tid == 0) {
       float s = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) s += s_wred[k];
       a.wpart[(size_t(pb) * a.H + h) * T + x0] = s / a.H;
     }
-    if (!a.need_dqkv) continue;  // (block-uniform)
+    if (!a.need_dqkv) {  // (block-uniform) the tile is free: every thread of the group passed the barrier after its last read
+      if (more) tail_stage_async(sG, dO_of(p + TAIL_GROUPS), a.ld_do, T, tid);
+      continue;
+    }
     // ---- column part, vectors: dK_x0 = sum_i ds_i Q_i ; dV_x0 = sum_i a_i dO_i
     {
       float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
@@ -643,14 +658,15 @@ __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArg
       float* rd = s_red + seg * 192;
       rd[2 * cp] = k0, rd[2 * cp + 1] = k1, rd[64 + 2 * cp] = v0, rd[64 + 2 * cp + 1] = v1;
     }
-    __syncthreads();  // s_ds / s_av consumed; s_red (dK, dV) written
+    tail_group_sync(grp);  // s_ds / s_av consumed; s_red (dK, dV) written
     // ---- row part, scalars: thread = key(s) j = tid, tid + 256
     {
       const __half* g0 = sG + x0 * TAIL_PITCH;
       if (tid < T) s_ds[tid] = arow0 * (tail_dot64(g0, sV + tid * TAIL_PITCH) - dx0);
       if (r1 < T) s_ds[r1] = arow1 * (tail_dot64(g0, sV + r1 * TAIL_PITCH) - dx0);
     }
-    __syncthreads();
+    tail_group_sync(grp);
+    if (more) tail_stage_async(sG, dO_of(p + TAIL_GROUPS), a.ld_do, T, tid);  // nobody reads the tile again: lands during the rest
     {
       float q0 = 0.f, q1 = 0.f;
 #pragma unroll 4
@@ -662,7 +678,7 @@ __global__ void __launch_bounds__(TC_SIMT, 1) attn_bwd_tail2_kernel(AttnBwdTcArg
       float* rd = s_red + seg * 192;
       rd[128 + 2 * cp] = q0, rd[128 + 2 * cp + 1] = q1;
     }
-    __syncthreads();
+    tail_group_sync(grp);
     if (tid < 96) {  // 3 vectors (dK, dV, dQ) x 32 channel pairs
       const int vec = tid >> 5, c2 = tid & 31;
       float s0 = 0.f, s1 = 0.f;
@@ -694,7 +710,7 @@ int launch_attn_tail2(const AttnBwdTcArgs& a, cudaStream_t st) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tail2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TailSmem::TOTAL + 16));
     configured = true;
   }
-  attn_bwd_tail2_kernel<<<a.B * a.H, TC_SIMT, TailSmem::TOTAL + 16, st>>>(a);
+  attn_bwd_tail2_kernel<<<a.B * a.H, TAIL_THREADS, TailSmem::TOTAL + 16, st>>>(a);
   SB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -752,7 +768,7 @@ extern "C" int semabs_attn_bwd_tc2(const void* qkv16, int32_t ld_qkv, const void
   attn_bwd_col_tc2_kernel<<<grid, TC_BWD_THREADS, ColSmem::TOTAL, st>>>(tm_qkv, tm_do, tm_pr, a);
   SB_CHECK_CUDA(cudaGetLastError());
   if (a.n_tail) {
-    attn_bwd_tail2_kernel<<<B * H, TC_SIMT, TailSmem::TOTAL + 16, st>>>(a);
+    attn_bwd_tail2_kernel<<<B * H, TAIL_THREADS, TailSmem::TOTAL + 16, st>>>(a);
     SB_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
