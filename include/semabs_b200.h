@@ -119,7 +119,9 @@ int semabs_attn_fwd(const float* qkv, float* probs, void* probs16, int32_t ld_p1
 
 /* Same operator on tcgen05 / TMEM (vit_attn_tc.cu) for T <= 272: qkv16 [B*T, in_splits*3d] fp16 — the QKV GEMM's
  * out_f16 with out_f16_splits = in_splits, i.e. rows [hi(3d) | lo(3d)], q pre-scaled — instead of fp32 qkv.  With
- * in_splits = 2 both products run as hi*hi + lo*hi + hi*lo (fp32-grade).  probs16 pitch must be a multiple of 16. */
+ * in_splits = 2 both products run as hi*hi + lo*hi + hi*lo (fp32-grade).  probs16 pitch must be a multiple of 16.
+ * When T % 128 == 1 (ViT-L/14: 257 tokens) the last query row is computed by three SIMT warps from the K / V tiles in
+ * shared memory instead of a third 128-row MMA tile; its results obey the same tolerances. */
 int semabs_attn_fwd_tc(const void* qkv16, int32_t in_splits, void* probs16, int32_t ld_p16, float* o32, void* o16,
                        int32_t o_splits, int32_t B, int32_t T, int32_t H, int32_t causal, void* stream);
 
